@@ -1,0 +1,160 @@
+"""Capped-protein PDB -> packed dipeptide / ACE-NME fragments (+ whole-protein force map).
+
+A compact restatement of the reference's one-off fragmentation tables, far enough to produce real
+``FragmentData`` geometry for the four example proteins:
+
+* residue windows: ``/root/reference/src/Fragmentation/basefrag.py:44-167`` (``get_fragments_index``)
+* cap-hydrogen choice and first-approximation placement on the acceptor->removed-atom ray at the sum
+  of covalent radii: ``src/Fragmentation/distancefrag.py:365-504`` and ``:34-54``
+* ACE-NME k shares its 12 positions with dipeptides k+1 (leading cap group) and k (trailing cap group):
+  ``distancefrag.py:286-307``
+* interleaved packing dipeptide 0, ACE-NME 0, dipeptide 1, ...: ``distancefrag.py:250-284``
+* signed force map (+ dipeptide atoms, - ACE-NME atoms, added hydrogens dropped):
+  ``distancefrag.py:335-353``, ``src/Calculators/combiner.py:38-39``
+
+Not restated (out of scope for the ViSNet hot path): the AMBER atom
+permutation (``seq_dict.pkl``), the LBFGS relaxation of the added hydrogens, CYX-CYX fused pairs.
+ViSNet is permutation-equivariant, so atom order inside a fragment does not change energies/forces.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import List, Tuple
+
+import numpy as np
+
+from .fragment_data import FragmentData
+
+_Z = {"H": 1, "C": 6, "N": 7, "O": 8, "S": 16}
+_RCOV = {"C": 0.76, "N": 0.71, "H": 0.31}   # distancefrag.py:383-388
+
+
+@dataclass
+class CappedProtein:
+    names: List[str]        # atom names (CA, HA, ...)
+    resnames: List[str]
+    resnums: np.ndarray     # 1-based, contiguous
+    elements: List[str]
+    positions: np.ndarray   # [n,3] float64 Angstrom
+
+    def __len__(self):
+        return len(self.names)
+
+
+def read_pdb(path: str) -> CappedProtein:
+    names, resn, resi, elem, xyz = [], [], [], [], []
+    with open(path) as fh:
+        for line in fh:
+            if not line.startswith(("ATOM", "HETATM")):
+                continue
+            names.append(line[12:16].strip())
+            resn.append(line[17:20].strip())
+            resi.append(int(line[22:26]))
+            xyz.append((float(line[30:38]), float(line[38:46]), float(line[46:54])))
+            e = line[76:78].strip() if len(line) >= 78 else ""
+            elem.append(e if e else names[-1][0])
+    resi = np.asarray(resi)
+    resi = resi - resi.min() + 1
+    return CappedProtein(names, resn, resi, elem, np.asarray(xyz, dtype=np.float64))
+
+
+@dataclass
+class ProteinMap:
+    """Whole-protein reduction map: F_prot[dst_atom] += sign * F_frag[src_atom]; E = sum sign_g * E_g."""
+    n_protein: int
+    src_atom: np.ndarray    # int32 [M] index into the packed fragment atoms
+    dst_atom: np.ndarray    # int32 [M] index into the protein
+    sign: np.ndarray        # float32 [M]
+    frag_sign: np.ndarray   # float32 [G] (+1 dipeptide, -1 ACE-NME)
+
+
+def _cap_h(pos, acceptor, removed, acc_elem):
+    d = pos[removed] - pos[acceptor]
+    d = d / np.linalg.norm(d)
+    return pos[acceptor] + d * (_RCOV[acc_elem] + _RCOV["H"])
+
+
+def fragment_protein(prot: CappedProtein) -> Tuple[FragmentData, ProteinMap]:
+    R = int(prot.resnums.max())
+    assert len(set(prot.resnums.tolist())) == R, "residue numbers are not continuous"
+    nd, na = R - 2, R - 3
+    if nd < 2:
+        raise NotImplementedError("3 or fewer residues (incl. caps): run un-fragmented (--mode visnet)")
+    by_res = {r: [i for i in range(len(prot)) if prot.resnums[i] == r] for r in range(1, R + 1)}
+
+    def pick(r, pred):
+        return [i for i in by_res[r] if pred(prot.names[i])]
+
+    def atom(r, name):
+        hit = [i for i in by_res[r] if prot.names[i] == name]
+        return hit[0] if hit else None
+
+    is_ca = lambda n: n == "CA" or n.startswith("HA")
+    P = prot.positions
+
+    # leading (ACE-like) and trailing (NME-like) cap groups per junction
+    def lead_group(r):
+        """Atoms dipeptide (centre r+1) takes from residue r: [(protein index | None, element, xyz)]."""
+        if prot.resnames[by_res[r][0]] == "ACE":
+            return [(i, prot.elements[i], P[i]) for i in by_res[r]]
+        out = [(i, prot.elements[i], P[i]) for i in pick(r, lambda n: is_ca(n) or n in ("C", "O"))]
+        ca = atom(r, "CA")
+        out.append((None, "H", _cap_h(P, ca, atom(r, "N"), "C")))
+        if prot.resnames[by_res[r][0]] != "GLY":
+            out.append((None, "H", _cap_h(P, ca, atom(r, "CB"), "C")))
+        return out
+
+    def trail_group(r):
+        """Atoms dipeptide (centre r-1) takes from residue r."""
+        if prot.resnames[by_res[r][0]] == "NME":
+            return [(i, prot.elements[i], P[i]) for i in by_res[r]]
+        out = [(i, prot.elements[i], P[i]) for i in pick(r, lambda n: is_ca(n) or n in ("N", "H"))]
+        ca = atom(r, "CA")
+        out.append((None, "H", _cap_h(P, ca, atom(r, "C"), "C")))
+        rn = prot.resnames[by_res[r][0]]
+        if rn != "GLY":
+            out.append((None, "H", _cap_h(P, ca, atom(r, "CB"), "C")))
+        if rn == "PRO":
+            out.append((None, "H", _cap_h(P, atom(r, "N"), atom(r, "CD"), "N")))
+        return out
+
+    frags = []  # (sign, [(prot_idx|None, elem, xyz)])
+    for k in range(nd):
+        centre = k + 2
+        atoms = lead_group(centre - 1) + [(i, prot.elements[i], P[i]) for i in by_res[centre]] + \
+            trail_group(centre + 1)
+        frags.append((+1.0, atoms))
+        if k < na:
+            # ACE-NME k: leading group of dipeptide k+1 (from residue k+2) + trailing group of dipeptide k (k+3)
+            frags.append((-1.0, lead_group(centre) + trail_group(centre + 1)))
+
+    z, pos, batch, start, end = [], [], [], [], []
+    src, dst, sgn, fsgn = [], [], [], []
+    off = 0
+    for g, (s, atoms) in enumerate(frags):
+        start.append(off)
+        for (pi, el, xyz) in atoms:
+            z.append(_Z[el])
+            pos.append(xyz)
+            batch.append(g)
+            if pi is not None:
+                src.append(off)
+                dst.append(pi)
+                sgn.append(s)
+            off += 1
+        end.append(off)
+        fsgn.append(s)
+    fd = FragmentData(np.asarray(z, dtype=np.int64), np.asarray(pos, dtype=np.float32),
+                      np.asarray(start, dtype=np.int64), np.asarray(end, dtype=np.int64),
+                      np.asarray(batch, dtype=np.int64))
+    pm = ProteinMap(len(prot), np.asarray(src, dtype=np.int32), np.asarray(dst, dtype=np.int32),
+                    np.asarray(sgn, dtype=np.float32), np.asarray(fsgn, dtype=np.float32))
+    return fd, pm
+
+
+def single_graph(z, pos) -> FragmentData:
+    """Un-fragmented mode (``visnet_calculator.py:142-148``): the whole input is one graph."""
+    n = len(z)
+    return FragmentData(np.asarray(z, dtype=np.int64), np.asarray(pos, dtype=np.float32),
+                        np.array([0], dtype=np.int64), np.array([n], dtype=np.int64),
+                        np.zeros((n,), dtype=np.int64))
