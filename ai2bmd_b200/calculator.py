@@ -1,0 +1,163 @@
+"""The reference's Calculator surface over the B200 engine.
+
+Mirrors, name for name, the classes of ``/root/reference/src/Calculators`` that sit on the hot path:
+
+* :class:`ViSNetModel`        <- ``visnet_calculator.py:22-75``  (``dl_potential_loader``, ``from_file``)
+* :func:`get_visnet_model`    <- ``visnet_calculator.py:184-204``
+* :class:`ViSNetCalculator`   <- ``visnet_calculator.py:121-155`` (un-fragmented ``--mode visnet``)
+* :class:`DipeptideBondedCombiner` <- ``combiner.py:11-41``
+* :class:`DLBondedCalculator` <- ``bonded.py:19-123`` (fragment-batch evaluation + combine)
+
+ASE is not a dependency: calculators expose ``calculate(atoms, ...)`` / ``get_potential_energy`` /
+``get_forces`` with ASE semantics (results cached while positions are unchanged,
+``src/Calculators/calculator.py:9-23``) for any ``atoms`` object with ``.numbers`` and ``.positions``.
+All compute goes through the C-ABI library; nothing here falls back to PyTorch or the CPU.
+"""
+from __future__ import annotations
+
+import os.path as osp
+from typing import Dict, Optional, Tuple
+
+import numpy as np
+
+from .engine import Engine
+from .fragment_data import FragmentData
+from .weights import load_state_dict
+
+
+def _device_index(device: str) -> int:
+    if device == "cpu":
+        raise RuntimeError("the B200 engine has no CPU path (device='cpu' requested)")
+    if not device.startswith("cuda"):
+        raise ValueError(f"Unrecognized device {device!r}")   # device_strategy.py:24-35
+    return int(device.split(":")[1]) if ":" in device else 0
+
+
+class ViSNetModel:
+    """Energy and forces of a packed fragment batch with the ViSNet potential on one B200."""
+
+    implemented_properties = ["energy", "forces"]
+
+    def __init__(self, state_dict: Dict[str, np.ndarray], device: str = "cuda:0"):
+        self.device = device
+        self.engine = Engine(state_dict, _device_index(device))
+        self._topo_key = None
+
+    @classmethod
+    def from_file(cls, **kwargs):
+        if "model_path" not in kwargs:
+            raise ValueError("model_path must be provided")
+        return cls(load_state_dict(kwargs["model_path"]), device=kwargs.get("device", "cuda:0"))
+
+    def _ensure_topology(self, frag: FragmentData):
+        z = np.ascontiguousarray(frag.z, dtype=np.int64)
+        batch = np.ascontiguousarray(frag.batch, dtype=np.int64)
+        key = (z.size, hash(z.tobytes()), hash(batch.tobytes()))
+        if key != self._topo_key:
+            self.engine.set_topology(z, batch, n_graphs=len(frag))
+            self._topo_key = key
+
+    def dl_potential_loader(self, frag_data: FragmentData) -> Tuple[np.ndarray, np.ndarray]:
+        """``FragmentData -> (e[G,1] float32 eV, f[N,3] float32 eV/A)`` as numpy arrays."""
+        self._ensure_topology(frag_data)
+        e, f = self.engine.forward_host(np.asarray(frag_data.pos, dtype=np.float32))
+        return e.reshape(-1, 1), f.reshape(-1, 3)
+
+
+_local_calc: Dict[str, ViSNetModel] = {}
+
+
+def get_visnet_model(model_path: str, device: str) -> ViSNetModel:
+    """One engine per (device, checkpoint); the reference's sub-process proxies
+    (``ViSNetAsyncModel``) are unnecessary because every engine is in-process and asynchronous."""
+    signature = f"{device}-{model_path}"
+    if signature not in _local_calc:
+        _local_calc[signature] = ViSNetModel.from_file(model_path=model_path, device=device)
+    return _local_calc[signature]
+
+
+class _CalculatorBase:
+    """Minimal ASE-style result cache (``Calculator.get_property`` + patched ``check_state``)."""
+
+    implemented_properties = ["energy", "forces"]
+
+    def __init__(self):
+        self.results: Dict[str, np.ndarray] = {}
+        self._cached_pos: Optional[np.ndarray] = None
+
+    def _changed(self, atoms) -> bool:
+        pos = np.asarray(atoms.positions)
+        return self._cached_pos is None or pos.shape != self._cached_pos.shape or not np.array_equal(pos, self._cached_pos)
+
+    def get_property(self, name, atoms):
+        if name not in self.implemented_properties:
+            raise NotImplementedError(name)
+        if self._changed(atoms) or name not in self.results:
+            self.calculate(atoms, [name], ["positions"])
+            self._cached_pos = np.array(atoms.positions, copy=True)
+        return self.results[name]
+
+    def get_potential_energy(self, atoms):
+        return self.get_property("energy", atoms)
+
+    def get_forces(self, atoms):
+        return self.get_property("forces", atoms)
+
+
+class ViSNetCalculator(_CalculatorBase):
+    """Feed the input through the ViSNet model without fragmentation (one graph)."""
+
+    def __init__(self, ckpt_path: str, ckpt_type: str, device: str = "cuda:0", is_root_calc=True, **kwargs):
+        super().__init__()
+        self.ckpt_path, self.ckpt_type, self.is_root_calc = ckpt_path, ckpt_type, is_root_calc
+        model_path = osp.join(ckpt_path, f"visnet-uni-{ckpt_type}.ckpt")
+        if not osp.exists(model_path) and osp.exists(ckpt_path) and osp.isfile(ckpt_path):
+            model_path = ckpt_path
+        self.device = device
+        self.model = get_visnet_model(model_path, device)
+
+    def calculate(self, atoms, properties, system_changes):
+        n = len(atoms.numbers)
+        data = FragmentData(np.asarray(atoms.numbers), np.asarray(atoms.positions).astype(np.float32),
+                            np.array([0], dtype=int), np.array([n], dtype=int), np.zeros((n,), dtype=int))
+        e, f = self.model.dl_potential_loader(data)
+        self.results = {"energy": e, "forces": f}
+
+
+class DipeptideBondedCombiner:
+    """E = sum E_dipeptide - sum E_ACE-NME ; F = scatter_sum(cat[F_dip, -F_AN][select], origin)."""
+
+    @staticmethod
+    def energy_combine(dipeptides_energies: np.ndarray, acenmes_energies: np.ndarray) -> np.ndarray:
+        return np.asarray(np.sum(dipeptides_energies, dtype=np.float32) - np.sum(acenmes_energies, dtype=np.float32))
+
+    @staticmethod
+    def forces_combine(num_atoms: int, dipeptides_forces, acenmes_forces, select_index, origin_index) -> np.ndarray:
+        forces = np.concatenate([dipeptides_forces, -acenmes_forces])[select_index]
+        out = np.zeros((num_atoms, 3), dtype=np.float32)
+        np.add.at(out, origin_index, forces)
+        return out
+
+
+class DLBondedCalculator:
+    """Fragment batch -> per-fragment (E, F) -> whole-protein (E, F).
+
+    ``calculate(fragments)`` keeps the reference's return signature (``bonded.py:51-100``).  The
+    whole-protein reduction can also run on the device through ``Engine.set_protein_map`` /
+    ``forward_protein_device`` (used by ``parallel.ShardedBondedCalculator`` for the multi-GPU path)."""
+
+    def __init__(self, ckpt_path: str, ckpt_type: str = "", device: str = "cuda:0", **kwargs):
+        model_path = osp.join(ckpt_path, f"visnet-uni-{ckpt_type}.ckpt") if ckpt_type else ckpt_path
+        self.models = [get_visnet_model(model_path, device)]
+        self.combiner = DipeptideBondedCombiner()
+
+    def calculate(self, fragments: FragmentData):
+        energy, forces = self.models[0].dl_potential_loader(fragments)
+        dip_e, an_e = (energy[s] for s in fragments.scalar_split())
+        dip_f, an_f = (forces[s] for s in fragments.vector_split())
+        return dip_e, dip_f, an_e, an_f
+
+    def combine(self, fragments: FragmentData, num_atoms: int, select_index, origin_index):
+        dip_e, dip_f, an_e, an_f = self.calculate(fragments)
+        return (self.combiner.energy_combine(dip_e, an_e),
+                self.combiner.forces_combine(num_atoms, dip_f, an_f, select_index, origin_index))

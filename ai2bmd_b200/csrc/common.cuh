@@ -1,0 +1,138 @@
+// Shared device helpers for the ViSNet sm_100a engine.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace vb {
+
+constexpr int D = 128;        // channels
+constexpr int H = 8;          // heads (head_dim 16)
+constexpr int NR = 32;        // radial basis functions
+constexpr int L = 6;          // interaction layers
+constexpr int KNB = 32;       // neighbour slots per atom (incl. self)
+constexpr int LDS_PAD = 4;    // smem row padding (floats) keeps rows 16 B aligned
+
+__device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }
+__device__ __forceinline__ float silu_(float x) { return x / (1.0f + expf(-x)); }
+// d/dx [x*sigmoid(x)] = s*(1 + x*(1-s))
+__device__ __forceinline__ float dsilu_(float x) {
+    float s = sigmoidf_(x);
+    return s * (1.0f + x * (1.0f - s));
+}
+
+__device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+__device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+__device__ __forceinline__ void st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
+__device__ __forceinline__ void red4(float* p, float4 v) { atomicAdd(reinterpret_cast<float4*>(p), v); }
+
+__device__ __forceinline__ float4 f4(float a, float b, float c, float d) { return make_float4(a, b, c, d); }
+__device__ __forceinline__ float4 f4s(float a) { return make_float4(a, a, a, a); }
+__device__ __forceinline__ float4 operator+(float4 a, float4 b) { return f4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w); }
+__device__ __forceinline__ float4 operator-(float4 a, float4 b) { return f4(a.x - b.x, a.y - b.y, a.z - b.z, a.w - b.w); }
+__device__ __forceinline__ float4 operator*(float4 a, float4 b) { return f4(a.x * b.x, a.y * b.y, a.z * b.z, a.w * b.w); }
+__device__ __forceinline__ float4 operator*(float4 a, float b) { return f4(a.x * b, a.y * b, a.z * b, a.w * b); }
+__device__ __forceinline__ float4 operator*(float b, float4 a) { return f4(a.x * b, a.y * b, a.z * b, a.w * b); }
+__device__ __forceinline__ float hsum4(float4 a) { return (a.x + a.y) + (a.z + a.w); }
+__device__ __forceinline__ float4 silu4(float4 a) { return f4(silu_(a.x), silu_(a.y), silu_(a.z), silu_(a.w)); }
+__device__ __forceinline__ float4 dsilu4(float4 a) { return f4(dsilu_(a.x), dsilu_(a.y), dsilu_(a.z), dsilu_(a.w)); }
+__device__ __forceinline__ float4 arr4(const float (&a)[4]) { return f4(a[0], a[1], a[2], a[3]); }
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+__device__ __forceinline__ float warp_min(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fminf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+// sum over the 4 lanes that share one attention head (lanes 4h..4h+3)
+__device__ __forceinline__ float quad_sum(float v) {
+    v += __shfl_xor_sync(0xffffffffu, v, 1);
+    v += __shfl_xor_sync(0xffffffffu, v, 2);
+    return v;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Warp-level fp32 GEMM micro-kernel.
+//   acc[r][0..3] += sum_k A[r][k] * W[k][lane*4 + 0..3]      r < R, k < K
+// A: shared memory, row-major, row stride LDA floats (16 B aligned rows), rows private to the warp
+//    (every lane reads the same address -> broadcast, no bank conflicts).
+// W: global memory, row-major [K][ldw]; the caller pre-offsets W to the first of the 128 columns this
+//    call produces.  Lanes read consecutive float4 -> one coalesced 512 B request per k.
+// ---------------------------------------------------------------------------------------------
+template <int R, int K, int LDA>
+__device__ __forceinline__ void warp_gemm(float (&acc)[R][4], const float* __restrict__ As,
+                                          const float* __restrict__ W, int ldw, int lane) {
+    const float* Wp = W + lane * 4;
+#pragma unroll 2
+    for (int k = 0; k < K; k += 4) {
+        const float4 w0 = ldg4(Wp + (size_t)(k + 0) * ldw);
+        const float4 w1 = ldg4(Wp + (size_t)(k + 1) * ldw);
+        const float4 w2 = ldg4(Wp + (size_t)(k + 2) * ldw);
+        const float4 w3 = ldg4(Wp + (size_t)(k + 3) * ldw);
+#pragma unroll
+        for (int r = 0; r < R; r++) {
+            const float4 a = ld4(As + r * LDA + k);
+            acc[r][0] = fmaf(a.x, w0.x, acc[r][0]); acc[r][1] = fmaf(a.x, w0.y, acc[r][1]);
+            acc[r][2] = fmaf(a.x, w0.z, acc[r][2]); acc[r][3] = fmaf(a.x, w0.w, acc[r][3]);
+            acc[r][0] = fmaf(a.y, w1.x, acc[r][0]); acc[r][1] = fmaf(a.y, w1.y, acc[r][1]);
+            acc[r][2] = fmaf(a.y, w1.z, acc[r][2]); acc[r][3] = fmaf(a.y, w1.w, acc[r][3]);
+            acc[r][0] = fmaf(a.z, w2.x, acc[r][0]); acc[r][1] = fmaf(a.z, w2.y, acc[r][1]);
+            acc[r][2] = fmaf(a.z, w2.z, acc[r][2]); acc[r][3] = fmaf(a.z, w2.w, acc[r][3]);
+            acc[r][0] = fmaf(a.w, w3.x, acc[r][0]); acc[r][1] = fmaf(a.w, w3.y, acc[r][1]);
+            acc[r][2] = fmaf(a.w, w3.z, acc[r][2]); acc[r][3] = fmaf(a.w, w3.w, acc[r][3]);
+        }
+    }
+}
+
+// Narrow variant: 64 output columns, 2 per lane (head blocks).  W row-major [K][ldw].
+template <int R, int K, int LDA>
+__device__ __forceinline__ void warp_gemm2(float (&acc)[R][2], const float* __restrict__ As,
+                                           const float* __restrict__ W, int ldw, int lane) {
+    const float* Wp = W + lane * 2;
+#pragma unroll 2
+    for (int k = 0; k < K; k += 4) {
+        const float2 w0 = __ldg(reinterpret_cast<const float2*>(Wp + (size_t)(k + 0) * ldw));
+        const float2 w1 = __ldg(reinterpret_cast<const float2*>(Wp + (size_t)(k + 1) * ldw));
+        const float2 w2 = __ldg(reinterpret_cast<const float2*>(Wp + (size_t)(k + 2) * ldw));
+        const float2 w3 = __ldg(reinterpret_cast<const float2*>(Wp + (size_t)(k + 3) * ldw));
+#pragma unroll
+        for (int r = 0; r < R; r++) {
+            const float4 a = ld4(As + r * LDA + k);
+            acc[r][0] = fmaf(a.x, w0.x, acc[r][0]); acc[r][1] = fmaf(a.x, w0.y, acc[r][1]);
+            acc[r][0] = fmaf(a.y, w1.x, acc[r][0]); acc[r][1] = fmaf(a.y, w1.y, acc[r][1]);
+            acc[r][0] = fmaf(a.z, w2.x, acc[r][0]); acc[r][1] = fmaf(a.z, w2.y, acc[r][1]);
+            acc[r][0] = fmaf(a.w, w3.x, acc[r][0]); acc[r][1] = fmaf(a.w, w3.y, acc[r][1]);
+        }
+    }
+}
+
+template <int R>
+__device__ __forceinline__ void acc_set_bias(float (&acc)[R][4], const float* __restrict__ b, int lane) {
+    const float4 bb = ldg4(b + lane * 4);
+#pragma unroll
+    for (int r = 0; r < R; r++) { acc[r][0] = bb.x; acc[r][1] = bb.y; acc[r][2] = bb.z; acc[r][3] = bb.w; }
+}
+template <int R>
+__device__ __forceinline__ void acc_zero(float (&acc)[R][4]) {
+#pragma unroll
+    for (int r = 0; r < R; r++) { acc[r][0] = 0.f; acc[r][1] = 0.f; acc[r][2] = 0.f; acc[r][3] = 0.f; }
+}
+
+// cosine cutoff and its derivative (utils.py:16-19), cutoff passed in
+__device__ __forceinline__ float cutoff_fn(float r, float rc) {
+    return (r < rc) ? 0.5f * (cosf(r * (3.14159265358979323846f / rc)) + 1.0f) : 0.0f;
+}
+__device__ __forceinline__ float cutoff_dfn(float r, float rc) {
+    const float w = 3.14159265358979323846f / rc;
+    return (r < rc) ? -0.5f * w * sinf(r * w) : 0.0f;
+}
+
+}  // namespace vb

@@ -1,0 +1,699 @@
+// Host side of the ViSNet sm_100a engine: workspace, launch sequence, CUDA-graph replay, C ABI.
+// See include/visnet_b200.h for the boundary each entry point replaces in the reference.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/visnet_b200.h"
+#include "k_edge.cuh"
+#include "k_graph_embed.cuh"
+#include "k_head.cuh"
+#include "k_node.cuh"
+
+using namespace vb;
+
+namespace {
+
+std::string g_create_error;
+
+#define CUDA_TRY(h, expr)                                                                            \
+    do {                                                                                             \
+        cudaError_t _e = (expr);                                                                     \
+        if (_e != cudaSuccess) {                                                                     \
+            (h)->set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+            return VB_ERR_CUDA;                                                                      \
+        }                                                                                            \
+    } while (0)
+
+__global__ void protein_scatter_kernel(int n_map, const int* __restrict__ src, const int* __restrict__ dst,
+                                       const float* __restrict__ sign, const float* __restrict__ forces,
+                                       float* __restrict__ ef) {
+    const int m = blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= n_map) return;
+    const float s = sign[m];
+    const int a = src[m], p = dst[m];
+    atomicAdd(ef + 3 * p + 0, s * forces[3 * a + 0]);
+    atomicAdd(ef + 3 * p + 1, s * forces[3 * a + 1]);
+    atomicAdd(ef + 3 * p + 2, s * forces[3 * a + 2]);
+}
+
+__global__ void protein_energy_kernel(int G, const float* __restrict__ fsign, const float* __restrict__ energy,
+                                      float* __restrict__ out) {
+    double s = 0.0;
+    for (int g = threadIdx.x; g < G; g += 32) s += (double)fsign[g] * (double)energy[g];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (threadIdx.x == 0) *out = (float)s;
+}
+
+}  // namespace
+
+struct vb_handle {
+    int device = 0;
+    int sm_count = 148;
+    std::string err;
+    std::mutex mu;
+    // weights
+    float* d_weights = nullptr;
+    ModelW mw{};
+    // topology / workspace
+    bool has_topology = false;
+    Workspace ws{};
+    char* arena = nullptr;
+    size_t arena_bytes = 0;
+    float* d_pos = nullptr;      // [N][3]
+    float* d_energy = nullptr;   // [G]
+    float* d_forces = nullptr;   // [N][3]
+    float *h_pos = nullptr, *h_energy = nullptr, *h_forces = nullptr;   // pinned staging
+    cudaStream_t own_stream = nullptr;
+    // protein map
+    int n_protein = 0, n_map = 0;
+    int *d_map_src = nullptr, *d_map_dst = nullptr;
+    float *d_map_sign = nullptr, *d_frag_sign = nullptr;
+    // options
+    int use_graph = 1, npw = 0, te_fwd = 0, te_bwd = 32;
+    // graph cache
+    cudaGraphExec_t graph_exec = nullptr;
+    int launches = 0;
+    std::vector<std::string> stage_names;
+
+    void set_error(const char* fmt, ...) {
+        char buf[1024];
+        va_list ap;
+        va_start(ap, fmt);
+        vsnprintf(buf, sizeof(buf), fmt, ap);
+        va_end(ap);
+        err = buf;
+    }
+    void drop_graph() {
+        if (graph_exec) { cudaGraphExecDestroy(graph_exec); graph_exec = nullptr; }
+    }
+};
+
+namespace {
+
+// ---- weight table ---------------------------------------------------------------------------------
+size_t layer_floats() {
+    size_t n = 0;
+#define X(name, count) n += (size_t)(count);
+    VB_LAYER_WEIGHTS(X)
+#undef X
+    return n;
+}
+size_t global_floats() {
+    size_t n = 0;
+#define X(name, count) n += (size_t)(count);
+    VB_GLOBAL_WEIGHTS(X)
+#undef X
+    return n;
+}
+size_t total_floats() { return global_floats() + (size_t)L * layer_floats(); }
+
+void bind_weights(ModelW& mw, const float* base) {
+    const float* p = base;
+#define X(name, count) mw.name = p; p += (size_t)(count);
+    VB_GLOBAL_WEIGHTS(X)
+#undef X
+    for (int l = 0; l < L; l++) {
+#define X(name, count) mw.layer[l].name = p; p += (size_t)(count);
+        VB_LAYER_WEIGHTS(X)
+#undef X
+    }
+}
+
+std::string build_manifest() {
+    std::string s;
+    char buf[128];
+#define X(name, count) snprintf(buf, sizeof(buf), "%s:%zu;", #name, (size_t)(count)); s += buf;
+    VB_GLOBAL_WEIGHTS(X)
+#undef X
+    for (int l = 0; l < L; l++) {
+#define X(name, count) snprintf(buf, sizeof(buf), "layer%d.%s:%zu;", l, #name, (size_t)(count)); s += buf;
+        VB_LAYER_WEIGHTS(X)
+#undef X
+    }
+    return s;
+}
+
+// ---- arena ------------------------------------------------------------------------------------------
+struct ArenaPlan {
+    size_t off = 0;
+    size_t take(size_t bytes) {
+        const size_t o = off;
+        off += (bytes + 255) & ~(size_t)255;
+        return o;
+    }
+};
+
+template <typename T>
+void carve(ArenaPlan& plan, char* base, T*& ptr, size_t count) {
+    const size_t o = plan.take(count * sizeof(T));
+    ptr = base ? reinterpret_cast<T*>(base + o) : nullptr;
+}
+
+void layout_workspace(vb_handle* h, char* base, ArenaPlan& plan, int*& z, int*& frag_of, int*& frag_start) {
+    Workspace& ws = h->ws;
+    const size_t N = ws.N, G = ws.G, E = ws.Ecap;
+    carve(plan, base, z, N);
+    carve(plan, base, frag_of, N);
+    carve(plan, base, frag_start, G + 1);
+    carve(plan, base, ws.deg, N);
+    carve(plan, base, ws.slots, N * KNB);
+    carve(plan, base, ws.rowptr, N + 1);
+    carve(plan, base, ws.esrc, E);
+    carve(plan, base, ws.edst, E);
+    carve(plan, base, ws.geom, E * 8);
+    carve(plan, base, ws.rbf, E * NR);
+    carve(plan, base, ws.eacc, E * 4);
+    carve(plan, base, ws.grbf, E * NR);
+    for (int l = 0; l <= L; l++) { carve(plan, base, ws.X[l], N * D); carve(plan, base, ws.V[l], N * 3 * D); }
+    for (int l = 0; l < L; l++) {
+        carve(plan, base, ws.F[l], E * D);
+        carve(plan, base, ws.VN[l], N * 3 * D);
+        carve(plan, base, ws.QKV[l], N * 3 * D);
+        carve(plan, base, ws.V123[l], N * 9 * D);
+        carve(plan, base, ws.VDOT[l], N * D);
+        carve(plan, base, ws.TU[l], N * 6 * D);
+        carve(plan, base, ws.O[l], N * 3 * D);
+    }
+    carve(plan, base, ws.XA, N * D);
+    carve(plan, base, ws.VA, N * 3 * D);
+    carve(plan, base, ws.GX, N * D);
+    carve(plan, base, ws.GVEC, N * 3 * D);
+    carve(plan, base, ws.GF, E * D);
+    carve(plan, base, ws.GXA, N * D);
+    carve(plan, base, ws.GQKV, N * 3 * D);
+    carve(plan, base, ws.GVNMSG, N * 3 * D);
+    carve(plan, base, ws.GTU, N * 6 * D);
+    carve(plan, base, ws.eatom, N);
+    carve(plan, base, h->d_pos, N * 3);
+    carve(plan, base, h->d_energy, G);
+    carve(plan, base, h->d_forces, N * 3);
+}
+
+// ---- launch sequence --------------------------------------------------------------------------------
+struct Launcher {
+    vb_handle* h;
+    cudaStream_t st;
+    int limit;          // stop after this many stages (debug); <0 = all
+    int count = 0;
+    bool record_names;
+    cudaError_t status = cudaSuccess;
+
+    bool next(const char* name) {
+        if (record_names) h->stage_names.push_back(name);
+        if (limit >= 0 && count >= limit) return false;
+        count++;
+        return true;
+    }
+    void check() {
+        if (status == cudaSuccess) status = cudaGetLastError();
+    }
+};
+
+template <int NPW>
+void launch_node_fwd(Launcher& Lc, int k) {
+    vb_handle* h = Lc.h;
+    NodeArgs a{k, h->mw, h->ws};
+    const int blocks = (h->ws.N + NODE_WARPS * NPW - 1) / (NODE_WARPS * NPW);
+    node_fwd_kernel<NPW><<<blocks, NODE_WARPS * 32, 0, Lc.st>>>(a);
+    Lc.check();
+}
+template <int NPW>
+void launch_node_bwd(Launcher& Lc, int k) {
+    vb_handle* h = Lc.h;
+    NodeArgs a{k, h->mw, h->ws};
+    const int blocks = (h->ws.N + NODE_WARPS * NPW - 1) / (NODE_WARPS * NPW);
+    node_bwd_kernel<NPW><<<blocks, NODE_WARPS * 32, node_bwd_smem_bytes<NPW>(), Lc.st>>>(a);
+    Lc.check();
+}
+template <int NPW>
+void launch_head(Launcher& Lc) {
+    vb_handle* h = Lc.h;
+    const int blocks = (h->ws.N + NODE_WARPS * NPW - 1) / (NODE_WARPS * NPW);
+    head_kernel<NPW><<<blocks, NODE_WARPS * 32, HeadSmem<NPW>::BYTES, Lc.st>>>(h->mw, h->ws);
+    Lc.check();
+}
+template <int TE, int NW>
+void launch_edge_fwd(Launcher& Lc, int l, int occ) {
+    vb_handle* h = Lc.h;
+    EdgeArgs a{l, h->mw, h->ws};
+    const int tiles = (h->ws.Ecap + TE - 1) / TE;
+    const int blocks = std::max(1, std::min(tiles, h->sm_count * occ));
+    edge_fwd_kernel<TE, NW><<<blocks, NW * 32, edge_fwd_smem_bytes<TE>(), Lc.st>>>(a);
+    Lc.check();
+}
+template <int TE, int NW>
+void launch_edge_bwd(Launcher& Lc, int l, int occ) {
+    vb_handle* h = Lc.h;
+    EdgeArgs a{l, h->mw, h->ws};
+    const int tiles = (h->ws.Ecap + TE - 1) / TE;
+    const int blocks = std::max(1, std::min(tiles, h->sm_count * occ));
+    edge_bwd_kernel<TE, NW><<<blocks, NW * 32, edge_bwd_smem_bytes<TE>(), Lc.st>>>(a);
+    Lc.check();
+}
+
+void node_fwd(Launcher& Lc, int k) { Lc.h->npw == 2 ? launch_node_fwd<2>(Lc, k) : launch_node_fwd<1>(Lc, k); }
+void node_bwd(Launcher& Lc, int k) { Lc.h->npw == 2 ? launch_node_bwd<2>(Lc, k) : launch_node_bwd<1>(Lc, k); }
+void head(Launcher& Lc) { Lc.h->npw == 2 ? launch_head<2>(Lc) : launch_head<1>(Lc); }
+void edge_fwd(Launcher& Lc, int l) {
+    if (Lc.h->te_fwd == 64) launch_edge_fwd<64, 8>(Lc, l, 2);
+    else launch_edge_fwd<32, 8>(Lc, l, 4);
+}
+void edge_bwd(Launcher& Lc, int l) {
+    if (Lc.h->te_bwd == 64) launch_edge_bwd<64, 8>(Lc, l, 1);
+    else launch_edge_bwd<32, 8>(Lc, l, 2);
+}
+
+// Enqueue one full evaluation (energy + forces) on Lc.st, reading h->d_pos, writing h->d_energy / d_forces.
+void enqueue_all(Launcher& Lc) {
+    vb_handle* h = Lc.h;
+    Workspace& ws = h->ws;
+    const int N = ws.N;
+    char name[64];
+    if (Lc.next("nbr_build")) {
+        nbr_build_kernel<<<(N + 127) / 128, 128, 0, Lc.st>>>(N, h->d_pos, ws.frag_of, ws.frag_start, h->mw.cutoff,
+                                                           ws.slots, ws.deg);
+        Lc.check();
+    }
+    if (Lc.next("rowptr_scan")) { rowptr_scan_kernel<<<1, 1024, 0, Lc.st>>>(N, ws.deg, ws.rowptr); Lc.check(); }
+    if (Lc.next("edge_geom")) { edge_geom_kernel<<<(N + 3) / 4, 128, 0, Lc.st>>>(N, h->d_pos, h->mw, ws); Lc.check(); }
+    if (Lc.next("embed_node")) { embed_node_kernel<<<(N + EMB_NB - 1) / EMB_NB, 128, 0, Lc.st>>>(h->mw, ws); Lc.check(); }
+    const int eblocks = std::max(1, std::min(ws.Ecap, h->sm_count * 16));
+    if (Lc.next("embed_edge")) { embed_edge_kernel<<<eblocks, 128, 0, Lc.st>>>(h->mw, ws); Lc.check(); }
+    for (int l = 0; l < L; l++) {
+        snprintf(name, sizeof(name), "node_fwd%d", l);
+        if (Lc.next(name)) node_fwd(Lc, l);
+        snprintf(name, sizeof(name), "edge_fwd%d", l);
+        if (Lc.next(name)) edge_fwd(Lc, l);
+    }
+    if (Lc.next("node_fwd6")) node_fwd(Lc, L);
+    if (Lc.next("head")) head(Lc);
+    if (Lc.next("energy_reduce")) {
+        energy_reduce_kernel<<<(ws.G + 3) / 4, 128, 0, Lc.st>>>(ws, h->mw.scalars, h->d_energy);
+        Lc.check();
+    }
+    for (int l = L - 1; l >= 0; l--) {
+        snprintf(name, sizeof(name), "node_bwd%d", l + 1);
+        if (Lc.next(name)) node_bwd(Lc, l + 1);
+        snprintf(name, sizeof(name), "edge_bwd%d", l);
+        if (Lc.next(name)) edge_bwd(Lc, l);
+    }
+    if (Lc.next("node_bwd0")) node_bwd(Lc, 0);
+    if (Lc.next("embed_edge_bwd")) { embed_edge_bwd_kernel<<<eblocks, 128, 0, Lc.st>>>(h->mw, ws); Lc.check(); }
+    if (Lc.next("forces_zero")) {
+        if (Lc.status == cudaSuccess) Lc.status = cudaMemsetAsync(h->d_forces, 0, sizeof(float) * 3 * N, Lc.st);
+    }
+    if (Lc.next("embed_node_bwd")) { embed_node_bwd_kernel<<<N, 128, 0, Lc.st>>>(h->mw, ws, h->d_forces); Lc.check(); }
+}
+
+template <typename K>
+cudaError_t opt_in_smem(K kernel, size_t bytes) {
+    return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+}
+
+int configure_kernels(vb_handle* h) {
+    CUDA_TRY(h, opt_in_smem(edge_fwd_kernel<32, 8>, edge_fwd_smem_bytes<32>()));
+    CUDA_TRY(h, opt_in_smem(edge_fwd_kernel<64, 8>, edge_fwd_smem_bytes<64>()));
+    CUDA_TRY(h, opt_in_smem(edge_bwd_kernel<32, 8>, edge_bwd_smem_bytes<32>()));
+    CUDA_TRY(h, opt_in_smem(edge_bwd_kernel<64, 8>, edge_bwd_smem_bytes<64>()));
+    CUDA_TRY(h, opt_in_smem(node_bwd_kernel<1>, node_bwd_smem_bytes<1>()));
+    CUDA_TRY(h, opt_in_smem(node_bwd_kernel<2>, node_bwd_smem_bytes<2>()));
+    CUDA_TRY(h, opt_in_smem(head_kernel<1>, HeadSmem<1>::BYTES));
+    CUDA_TRY(h, opt_in_smem(head_kernel<2>, HeadSmem<2>::BYTES));
+    return VB_OK;
+}
+
+int ensure_graph(vb_handle* h) {
+    if (h->graph_exec) return VB_OK;
+    cudaGraph_t graph = nullptr;
+    CUDA_TRY(h, cudaStreamBeginCapture(h->own_stream, cudaStreamCaptureModeThreadLocal));
+    Launcher Lc{h, h->own_stream, -1, 0, false};
+    enqueue_all(Lc);
+    cudaError_t e_end = cudaStreamEndCapture(h->own_stream, &graph);
+    if (Lc.status != cudaSuccess || e_end != cudaSuccess) {
+        h->set_error("graph capture failed: %s / %s", cudaGetErrorString(Lc.status), cudaGetErrorString(e_end));
+        if (graph) cudaGraphDestroy(graph);
+        return VB_ERR_CUDA;
+    }
+    cudaError_t e_inst = cudaGraphInstantiate(&h->graph_exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (e_inst != cudaSuccess) {
+        h->set_error("cudaGraphInstantiate failed: %s", cudaGetErrorString(e_inst));
+        h->graph_exec = nullptr;
+        return VB_ERR_CUDA;
+    }
+    return VB_OK;
+}
+
+// core evaluation on internal buffers, asynchronous on st
+int run_core(vb_handle* h, cudaStream_t st) {
+    if (h->use_graph) {
+        int rc = ensure_graph(h);
+        if (rc != VB_OK) return rc;
+        CUDA_TRY(h, cudaGraphLaunch(h->graph_exec, st));
+    } else {
+        Launcher Lc{h, st, -1, 0, false};
+        enqueue_all(Lc);
+        if (Lc.status != cudaSuccess) {
+            h->set_error("kernel launch failed: %s", cudaGetErrorString(Lc.status));
+            return VB_ERR_CUDA;
+        }
+    }
+    return VB_OK;
+}
+
+void choose_defaults(vb_handle* h) {
+    const int N = h->ws.N;
+    if (h->npw == 0) h->npw = (N > 4096) ? 2 : 1;
+    if (h->te_fwd == 0) h->te_fwd = ((long long)N * 17 / 64 >= 2LL * h->sm_count) ? 64 : 32;
+}
+
+}  // namespace
+
+// =====================================================================================================
+// C ABI
+// =====================================================================================================
+extern "C" {
+
+const char* vb_weight_manifest(void) {
+    static const std::string m = build_manifest();
+    return m.c_str();
+}
+
+const char* vb_last_error(const vb_handle* h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+int vb_create(const float* weights_host, size_t n_floats, const vb_hparams* hp, int device, vb_handle** out) {
+    if (!weights_host || !hp || !out) { g_create_error = "vb_create: null argument"; return VB_ERR_ARG; }
+    *out = nullptr;
+    if (hp->hidden_channels != D || hp->num_layers != L || hp->num_heads != H || hp->num_rbf != NR ||
+        hp->max_num_neighbors != KNB || !(hp->cutoff > 0.f)) {
+        g_create_error = "vb_create: hyper-parameters differ from the compiled specialisation (128/6/8/32/32)";
+        return VB_ERR_ARG;
+    }
+    if (n_floats != total_floats()) {
+        char buf[160];
+        snprintf(buf, sizeof(buf), "vb_create: weight blob has %zu floats, manifest needs %zu", n_floats, total_floats());
+        g_create_error = buf;
+        return VB_ERR_ARG;
+    }
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || device < 0 || device >= ndev) {
+        g_create_error = std::string("vb_create: no usable CUDA device (") + cudaGetErrorString(e) +
+                         "); this engine has no CPU fallback";
+        return VB_ERR_CUDA;
+    }
+    cudaDeviceProp prop;
+    cudaGetDeviceProperties(&prop, device);
+    if (prop.major < 10) {
+        g_create_error = "vb_create: device is not sm_100 class; the kernels are built for sm_100a only";
+        return VB_ERR_CUDA;
+    }
+    vb_handle* h = new vb_handle();
+    h->device = device;
+    h->sm_count = prop.multiProcessorCount;
+    auto fail = [&](int rc) { g_create_error = h->err; vb_destroy(h); return rc; };
+    if (cudaSetDevice(device) != cudaSuccess) { h->set_error("cudaSetDevice failed"); return fail(VB_ERR_CUDA); }
+    if (cudaMalloc(&h->d_weights, n_floats * sizeof(float)) != cudaSuccess) { h->set_error("weights alloc failed"); return fail(VB_ERR_ALLOC); }
+    if (cudaMemcpy(h->d_weights, weights_host, n_floats * sizeof(float), cudaMemcpyHostToDevice) != cudaSuccess) {
+        h->set_error("weights upload failed");
+        return fail(VB_ERR_CUDA);
+    }
+    bind_weights(h->mw, h->d_weights);
+    h->mw.cutoff = hp->cutoff;
+    if (cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking) != cudaSuccess) { h->set_error("stream create failed"); return fail(VB_ERR_CUDA); }
+    if (configure_kernels(h) != VB_OK) return fail(VB_ERR_CUDA);
+    if (const char* s = getenv("VB_USE_GRAPH")) h->use_graph = atoi(s);
+    if (const char* s = getenv("VB_NPW")) h->npw = atoi(s);
+    if (const char* s = getenv("VB_TE_FWD")) h->te_fwd = atoi(s);
+    if (const char* s = getenv("VB_TE_BWD")) h->te_bwd = atoi(s);
+    *out = h;
+    return VB_OK;
+}
+
+void vb_destroy(vb_handle* h) {
+    if (!h) return;
+    cudaSetDevice(h->device);
+    h->drop_graph();
+    if (h->own_stream) cudaStreamDestroy(h->own_stream);
+    cudaFree(h->d_weights);
+    cudaFree(h->arena);
+    cudaFree(h->d_map_src); cudaFree(h->d_map_dst); cudaFree(h->d_map_sign); cudaFree(h->d_frag_sign);
+    cudaFreeHost(h->h_pos); cudaFreeHost(h->h_energy); cudaFreeHost(h->h_forces);
+    delete h;
+}
+
+int vb_set_topology(vb_handle* h, int64_t n_atoms, int64_t n_graphs, const int64_t* z_host,
+                    const int64_t* batch_host, int64_t max_edges) {
+    if (!h) return VB_ERR_ARG;
+    std::lock_guard<std::mutex> lk(h->mu);
+    if (n_atoms <= 0 || n_graphs <= 0 || !z_host || !batch_host || n_atoms > (1 << 26)) {
+        h->set_error("vb_set_topology: bad sizes/pointers");
+        return VB_ERR_ARG;
+    }
+    std::vector<int> z(n_atoms), frag_of(n_atoms), frag_start(n_graphs + 1, 0);
+    for (int64_t i = 0; i < n_atoms; i++) {
+        if (z_host[i] < 0 || z_host[i] >= 100) { h->set_error("vb_set_topology: atomic number out of range [0,100)"); return VB_ERR_ARG; }
+        const int64_t g = batch_host[i];
+        if (g < 0 || g >= n_graphs || (i > 0 && g < batch_host[i - 1])) {
+            h->set_error("vb_set_topology: batch must be sorted with values in [0,G)");
+            return VB_ERR_ARG;
+        }
+        z[i] = (int)z_host[i];
+        frag_of[i] = (int)g;
+        frag_start[g + 1]++;
+    }
+    for (int64_t g = 0; g < n_graphs; g++) frag_start[g + 1] += frag_start[g];
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    h->drop_graph();
+    h->has_topology = false;
+    cudaFree(h->arena); h->arena = nullptr;
+    cudaFreeHost(h->h_pos); cudaFreeHost(h->h_energy); cudaFreeHost(h->h_forces);
+    h->h_pos = h->h_energy = h->h_forces = nullptr;
+    h->ws = Workspace{};
+    h->ws.N = (int)n_atoms;
+    h->ws.G = (int)n_graphs;
+    const int64_t worst = n_atoms * KNB;
+    h->ws.Ecap = (int)((max_edges > 0 && max_edges < worst) ? max_edges : worst);
+    int *dz = nullptr, *dfo = nullptr, *dfs = nullptr;
+    ArenaPlan dry;
+    layout_workspace(h, nullptr, dry, dz, dfo, dfs);
+    h->arena_bytes = dry.off;
+    if (cudaMalloc(&h->arena, h->arena_bytes) != cudaSuccess) {
+        cudaGetLastError();
+        h->set_error("vb_set_topology: workspace allocation of %zu bytes failed", h->arena_bytes);
+        h->arena = nullptr;
+        return VB_ERR_ALLOC;
+    }
+    ArenaPlan real;
+    layout_workspace(h, h->arena, real, dz, dfo, dfs);
+    h->ws.z = dz; h->ws.frag_of = dfo; h->ws.frag_start = dfs;
+    CUDA_TRY(h, cudaMemset(h->arena, 0, h->arena_bytes));
+    CUDA_TRY(h, cudaMemcpy(dz, z.data(), sizeof(int) * n_atoms, cudaMemcpyHostToDevice));
+    CUDA_TRY(h, cudaMemcpy(dfo, frag_of.data(), sizeof(int) * n_atoms, cudaMemcpyHostToDevice));
+    CUDA_TRY(h, cudaMemcpy(dfs, frag_start.data(), sizeof(int) * (n_graphs + 1), cudaMemcpyHostToDevice));
+    CUDA_TRY(h, cudaMallocHost(&h->h_pos, sizeof(float) * 3 * n_atoms));
+    CUDA_TRY(h, cudaMallocHost(&h->h_forces, sizeof(float) * 3 * n_atoms));
+    CUDA_TRY(h, cudaMallocHost(&h->h_energy, sizeof(float) * n_graphs));
+    choose_defaults(h);
+    // record stage names / launch count
+    h->stage_names.clear();
+    Launcher Lc{h, nullptr, 0, 0, true};
+    enqueue_all(Lc);
+    h->launches = (int)h->stage_names.size();
+    h->has_topology = true;
+    return VB_OK;
+}
+
+int vb_forward(vb_handle* h, const float* pos_dev, float* energy_dev, float* forces_dev, void* stream) {
+    if (!h) return VB_ERR_ARG;
+    std::lock_guard<std::mutex> lk(h->mu);
+    if (!h->has_topology) { h->set_error("vb_forward: call vb_set_topology first"); return VB_ERR_STATE; }
+    if (!pos_dev || !energy_dev || !forces_dev) { h->set_error("vb_forward: null buffer"); return VB_ERR_ARG; }
+    cudaStream_t st = (cudaStream_t)stream;
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    CUDA_TRY(h, cudaMemcpyAsync(h->d_pos, pos_dev, sizeof(float) * 3 * h->ws.N, cudaMemcpyDeviceToDevice, st));
+    int rc = run_core(h, st);
+    if (rc != VB_OK) return rc;
+    CUDA_TRY(h, cudaMemcpyAsync(energy_dev, h->d_energy, sizeof(float) * h->ws.G, cudaMemcpyDeviceToDevice, st));
+    CUDA_TRY(h, cudaMemcpyAsync(forces_dev, h->d_forces, sizeof(float) * 3 * h->ws.N, cudaMemcpyDeviceToDevice, st));
+    return VB_OK;
+}
+
+int vb_forward_host(vb_handle* h, const float* pos_host, float* energy_host, float* forces_host) {
+    if (!h) return VB_ERR_ARG;
+    std::lock_guard<std::mutex> lk(h->mu);
+    if (!h->has_topology) { h->set_error("vb_forward_host: call vb_set_topology first"); return VB_ERR_STATE; }
+    if (!pos_host || !energy_host || !forces_host) { h->set_error("vb_forward_host: null buffer"); return VB_ERR_ARG; }
+    const int N = h->ws.N, G = h->ws.G;
+    cudaStream_t st = h->own_stream;
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    memcpy(h->h_pos, pos_host, sizeof(float) * 3 * N);
+    CUDA_TRY(h, cudaMemcpyAsync(h->d_pos, h->h_pos, sizeof(float) * 3 * N, cudaMemcpyHostToDevice, st));
+    int rc = run_core(h, st);
+    if (rc != VB_OK) return rc;
+    CUDA_TRY(h, cudaMemcpyAsync(h->h_energy, h->d_energy, sizeof(float) * G, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(h, cudaMemcpyAsync(h->h_forces, h->d_forces, sizeof(float) * 3 * N, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(h, cudaStreamSynchronize(st));
+    memcpy(energy_host, h->h_energy, sizeof(float) * G);
+    memcpy(forces_host, h->h_forces, sizeof(float) * 3 * N);
+    return VB_OK;
+}
+
+int vb_set_protein_map(vb_handle* h, int64_t n_protein_atoms, int64_t n_map, const int32_t* src_atom_host,
+                       const int32_t* dst_atom_host, const float* sign_host, const float* frag_sign_host) {
+    if (!h) return VB_ERR_ARG;
+    std::lock_guard<std::mutex> lk(h->mu);
+    if (!h->has_topology) { h->set_error("vb_set_protein_map: call vb_set_topology first"); return VB_ERR_STATE; }
+    if (n_protein_atoms <= 0 || n_map < 0 || !frag_sign_host || (n_map > 0 && (!src_atom_host || !dst_atom_host || !sign_host))) {
+        h->set_error("vb_set_protein_map: bad arguments");
+        return VB_ERR_ARG;
+    }
+    for (int64_t m = 0; m < n_map; m++) {
+        if (src_atom_host[m] < 0 || src_atom_host[m] >= h->ws.N || dst_atom_host[m] < 0 || dst_atom_host[m] >= n_protein_atoms) {
+            h->set_error("vb_set_protein_map: index out of range at entry %lld", (long long)m);
+            return VB_ERR_ARG;
+        }
+    }
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    cudaFree(h->d_map_src); cudaFree(h->d_map_dst); cudaFree(h->d_map_sign); cudaFree(h->d_frag_sign);
+    h->d_map_src = h->d_map_dst = nullptr; h->d_map_sign = h->d_frag_sign = nullptr;
+    const size_t nm = (size_t)std::max<int64_t>(n_map, 1);
+    CUDA_TRY(h, cudaMalloc(&h->d_map_src, sizeof(int) * nm));
+    CUDA_TRY(h, cudaMalloc(&h->d_map_dst, sizeof(int) * nm));
+    CUDA_TRY(h, cudaMalloc(&h->d_map_sign, sizeof(float) * nm));
+    CUDA_TRY(h, cudaMalloc(&h->d_frag_sign, sizeof(float) * h->ws.G));
+    if (n_map > 0) {
+        CUDA_TRY(h, cudaMemcpy(h->d_map_src, src_atom_host, sizeof(int) * n_map, cudaMemcpyHostToDevice));
+        CUDA_TRY(h, cudaMemcpy(h->d_map_dst, dst_atom_host, sizeof(int) * n_map, cudaMemcpyHostToDevice));
+        CUDA_TRY(h, cudaMemcpy(h->d_map_sign, sign_host, sizeof(float) * n_map, cudaMemcpyHostToDevice));
+    }
+    CUDA_TRY(h, cudaMemcpy(h->d_frag_sign, frag_sign_host, sizeof(float) * h->ws.G, cudaMemcpyHostToDevice));
+    h->n_protein = (int)n_protein_atoms;
+    h->n_map = (int)n_map;
+    return VB_OK;
+}
+
+int vb_forward_protein(vb_handle* h, const float* pos_dev, float* ef_prot_dev, void* stream) {
+    if (!h) return VB_ERR_ARG;
+    std::lock_guard<std::mutex> lk(h->mu);
+    if (!h->has_topology || h->n_protein <= 0) { h->set_error("vb_forward_protein: topology / protein map not set"); return VB_ERR_STATE; }
+    if (!pos_dev || !ef_prot_dev) { h->set_error("vb_forward_protein: null buffer"); return VB_ERR_ARG; }
+    cudaStream_t st = (cudaStream_t)stream;
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    CUDA_TRY(h, cudaMemcpyAsync(h->d_pos, pos_dev, sizeof(float) * 3 * h->ws.N, cudaMemcpyDeviceToDevice, st));
+    int rc = run_core(h, st);
+    if (rc != VB_OK) return rc;
+    CUDA_TRY(h, cudaMemsetAsync(ef_prot_dev, 0, sizeof(float) * (3 * (size_t)h->n_protein + 1), st));
+    if (h->n_map > 0)
+        protein_scatter_kernel<<<(h->n_map + 255) / 256, 256, 0, st>>>(h->n_map, h->d_map_src, h->d_map_dst,
+                                                                      h->d_map_sign, h->d_forces, ef_prot_dev);
+    protein_energy_kernel<<<1, 32, 0, st>>>(h->ws.G, h->d_frag_sign, h->d_energy, ef_prot_dev + 3 * (size_t)h->n_protein);
+    CUDA_TRY(h, cudaGetLastError());
+    return VB_OK;
+}
+
+int vb_get_edges(vb_handle* h, int32_t* slots_host, int32_t* deg_host) {
+    if (!h) return VB_ERR_ARG;
+    std::lock_guard<std::mutex> lk(h->mu);
+    if (!h->has_topology || !slots_host || !deg_host) { h->set_error("vb_get_edges: bad state/arguments"); return VB_ERR_STATE; }
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    CUDA_TRY(h, cudaDeviceSynchronize());
+    CUDA_TRY(h, cudaMemcpy(slots_host, h->ws.slots, sizeof(int) * (size_t)h->ws.N * KNB, cudaMemcpyDeviceToHost));
+    CUDA_TRY(h, cudaMemcpy(deg_host, h->ws.deg, sizeof(int) * (size_t)h->ws.N, cudaMemcpyDeviceToHost));
+    return VB_OK;
+}
+
+int vb_launches_per_forward(const vb_handle* h) { return h ? h->launches : 0; }
+
+int vb_set_option(vb_handle* h, const char* key, int64_t value) {
+    if (!h || !key) return VB_ERR_ARG;
+    std::lock_guard<std::mutex> lk(h->mu);
+    const std::string k(key);
+    if (k == "use_graph") h->use_graph = (int)value;
+    else if (k == "npw" && (value == 1 || value == 2)) h->npw = (int)value;
+    else if (k == "te_fwd" && (value == 32 || value == 64)) h->te_fwd = (int)value;
+    else if (k == "te_bwd" && (value == 32 || value == 64)) h->te_bwd = (int)value;
+    else { h->set_error("vb_set_option: unknown key or bad value: %s", key); return VB_ERR_ARG; }
+    h->drop_graph();
+    return VB_OK;
+}
+
+int vb_num_stages(const vb_handle* h) { return h ? (int)h->stage_names.size() : 0; }
+const char* vb_stage_name(const vb_handle* h, int stage) {
+    if (!h || stage < 0 || stage >= (int)h->stage_names.size()) return "";
+    return h->stage_names[stage].c_str();
+}
+
+int vb_debug_run(vb_handle* h, const float* pos_dev, int n_stages) {
+    if (!h) return VB_ERR_ARG;
+    std::lock_guard<std::mutex> lk(h->mu);
+    if (!h->has_topology || !pos_dev) { h->set_error("vb_debug_run: bad state/arguments"); return VB_ERR_STATE; }
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    CUDA_TRY(h, cudaMemcpy(h->d_pos, pos_dev, sizeof(float) * 3 * h->ws.N, cudaMemcpyDeviceToDevice));
+    Launcher Lc{h, h->own_stream, n_stages, 0, false};
+    enqueue_all(Lc);
+    if (Lc.status != cudaSuccess) { h->set_error("debug launch failed: %s", cudaGetErrorString(Lc.status)); return VB_ERR_CUDA; }
+    CUDA_TRY(h, cudaStreamSynchronize(h->own_stream));
+    return VB_OK;
+}
+
+int64_t vb_debug_read(vb_handle* h, const char* name, int layer, void* host_dst, int64_t cap_bytes) {
+    if (!h || !name || !host_dst) return VB_ERR_ARG;
+    std::lock_guard<std::mutex> lk(h->mu);
+    if (!h->has_topology) return VB_ERR_STATE;
+    const Workspace& ws = h->ws;
+    const size_t N = ws.N, E = ws.Ecap, G = ws.G;
+    const void* src = nullptr;
+    size_t bytes = 0;
+    const std::string k(name);
+    auto lay = [&](int hi) { return layer >= 0 && layer < hi; };
+#define BUF(key, ptr, count, elt) if (k == key) { src = (ptr); bytes = (size_t)(count) * (elt); }
+    if (k == "X" && lay(L + 1)) { src = ws.X[layer]; bytes = N * D * 4; }
+    else if (k == "V" && lay(L + 1)) { src = ws.V[layer]; bytes = N * 3 * D * 4; }
+    else if (k == "F" && lay(L)) { src = ws.F[layer]; bytes = E * D * 4; }
+    else if (k == "VN" && lay(L)) { src = ws.VN[layer]; bytes = N * 3 * D * 4; }
+    else if (k == "QKV" && lay(L)) { src = ws.QKV[layer]; bytes = N * 3 * D * 4; }
+    else if (k == "V123" && lay(L)) { src = ws.V123[layer]; bytes = N * 9 * D * 4; }
+    else if (k == "VDOT" && lay(L)) { src = ws.VDOT[layer]; bytes = N * D * 4; }
+    else if (k == "TU" && lay(L)) { src = ws.TU[layer]; bytes = N * 6 * D * 4; }
+    else if (k == "O" && lay(L)) { src = ws.O[layer]; bytes = N * 3 * D * 4; }
+    else BUF("XA", ws.XA, N * D, 4)
+    else BUF("VA", ws.VA, N * 3 * D, 4)
+    else BUF("GX", ws.GX, N * D, 4)
+    else BUF("GVEC", ws.GVEC, N * 3 * D, 4)
+    else BUF("GF", ws.GF, E * D, 4)
+    else BUF("GXA", ws.GXA, N * D, 4)
+    else BUF("GQKV", ws.GQKV, N * 3 * D, 4)
+    else BUF("GVNMSG", ws.GVNMSG, N * 3 * D, 4)
+    else BUF("GTU", ws.GTU, N * 6 * D, 4)
+    else BUF("geom", ws.geom, E * 8, 4)
+    else BUF("rbf", ws.rbf, E * NR, 4)
+    else BUF("eacc", ws.eacc, E * 4, 4)
+    else BUF("grbf", ws.grbf, E * NR, 4)
+    else BUF("esrc", ws.esrc, E, 4)
+    else BUF("edst", ws.edst, E, 4)
+    else BUF("rowptr", ws.rowptr, N + 1, 4)
+    else BUF("eatom", ws.eatom, N, 4)
+    else BUF("energy", h->d_energy, G, 4)
+    else BUF("forces", h->d_forces, N * 3, 4)
+#undef BUF
+    if (!src) { h->set_error("vb_debug_read: unknown buffer %s[%d]", name, layer); return VB_ERR_ARG; }
+    if ((int64_t)bytes > cap_bytes) bytes = (size_t)cap_bytes;
+    if (cudaSetDevice(h->device) != cudaSuccess || cudaDeviceSynchronize() != cudaSuccess ||
+        cudaMemcpy(host_dst, src, bytes, cudaMemcpyDeviceToHost) != cudaSuccess) {
+        h->set_error("vb_debug_read: copy failed: %s", cudaGetErrorString(cudaGetLastError()));
+        return VB_ERR_CUDA;
+    }
+    return (int64_t)bytes;
+}
+
+}  // extern "C"

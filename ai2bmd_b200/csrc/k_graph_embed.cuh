@@ -1,0 +1,349 @@
+// Neighbour build, edge geometry/RBF, neighbour + edge embedding (forward) and their adjoints.
+//   reference: utils.py:259-276 (Distance), :53-57 (ExpNormalSmearing), :16-19 (CosineCutoff),
+//              visnet_block.py:110-122, utils.py:296-317 (NeighborEmbedding), :331-337 (EdgeEmbedding)
+#pragma once
+#include "model.h"
+
+namespace vb {
+
+// ---------------------------------------------------------------------------------------------
+// K1: canonical radius graph.  One thread per target atom scans the atoms of its own fragment in
+// ascending index; d2 = fma(dz,dz, fma(dy,dy, dx*dx)) < rc^2 (strict), first 32 hits kept.
+// Bit-exact contract with oracle/radius_graph.c.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) nbr_build_kernel(int N, const float* __restrict__ pos,
+                                                        const int* __restrict__ frag_of,
+                                                        const int* __restrict__ frag_start, float rc,
+                                                        int* __restrict__ slots, int* __restrict__ deg) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    const int g = frag_of[i];
+    const int j0 = frag_start[g], j1 = frag_start[g + 1];
+    const float xi = pos[3 * i], yi = pos[3 * i + 1], zi = pos[3 * i + 2];
+    const float r2 = __fmul_rn(rc, rc);
+    int cnt = 0;
+    for (int j = j0; j < j1 && cnt < KNB; j++) {
+        const float dx = __fsub_rn(__ldg(pos + 3 * j), xi);
+        const float dy = __fsub_rn(__ldg(pos + 3 * j + 1), yi);
+        const float dz = __fsub_rn(__ldg(pos + 3 * j + 2), zi);
+        float d2 = __fmul_rn(dx, dx);
+        d2 = __fmaf_rn(dy, dy, d2);
+        d2 = __fmaf_rn(dz, dz, d2);
+        if (d2 < r2) slots[i * KNB + cnt++] = j;
+    }
+    for (int k = cnt; k < KNB; k++) slots[i * KNB + k] = -1;
+    deg[i] = cnt;
+}
+
+// K2: exclusive scan of deg -> rowptr (single block; N is small enough that this is latency only).
+__global__ void __launch_bounds__(1024) rowptr_scan_kernel(int N, const int* __restrict__ deg,
+                                                           int* __restrict__ rowptr) {
+    __shared__ int wsum[32];
+    __shared__ int carry_s;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) carry_s = 0;
+    __syncthreads();
+    for (int base = 0; base < N; base += 1024) {
+        const int i = base + tid;
+        const int v = (i < N) ? deg[i] : 0;
+        int incl = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
+        }
+        if (lane == 31) wsum[warp] = incl;
+        __syncthreads();
+        if (warp == 0) {
+            int w = wsum[lane];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int t = __shfl_up_sync(0xffffffffu, w, o);
+                if (lane >= o) w += t;
+            }
+            wsum[lane] = w;  // inclusive over warps
+        }
+        __syncthreads();
+        const int carry = carry_s;
+        const int excl = carry + (warp ? wsum[warp - 1] : 0) + incl - v;
+        if (i < N) rowptr[i] = excl;
+        __syncthreads();
+        if (tid == 1023) carry_s = carry + wsum[31];
+        __syncthreads();
+    }
+    if (tid == 0) rowptr[N] = carry_s;
+}
+
+// K3: per-edge geometry + RBF.  One warp per target atom, lane k = neighbour slot k.
+__global__ void __launch_bounds__(128) edge_geom_kernel(int N, const float* __restrict__ pos, ModelW mw,
+                                                        Workspace ws) {
+    const int lane = threadIdx.x & 31;
+    const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (i >= N) return;
+    const int dg = ws.deg[i];
+    const int e0 = ws.rowptr[i];
+    float r = 0.f, C = 0.f;
+    if (lane < dg) {
+        const int j = ws.slots[i * KNB + lane];
+        const int e = e0 + lane;
+        float dx = 0.f, dy = 0.f, dz = 0.f, inv_r = 0.f;
+        if (j != i) {
+            const float ex = __fsub_rn(pos[3 * j], pos[3 * i]);
+            const float ey = __fsub_rn(pos[3 * j + 1], pos[3 * i + 1]);
+            const float ez = __fsub_rn(pos[3 * j + 2], pos[3 * i + 2]);
+            const float s2 = __fadd_rn(__fadd_rn(__fmul_rn(ex, ex), __fmul_rn(ey, ey)), __fmul_rn(ez, ez));
+            r = __fsqrt_rn(s2);
+            dx = __fdiv_rn(ex, r); dy = __fdiv_rn(ey, r); dz = __fdiv_rn(ez, r);
+            inv_r = __fdiv_rn(1.0f, r);
+        }
+        C = cutoff_fn(r, mw.cutoff);
+        ws.esrc[e] = j;
+        ws.edst[e] = i;
+        st4(ws.geom + (size_t)e * 8, f4(r, C, dx, dy));
+        st4(ws.geom + (size_t)e * 8 + 4, f4(dz, inv_r, 0.f, 0.f));
+        st4(ws.eacc + (size_t)e * 4, f4s(0.f));
+    }
+    const float mu = __ldg(mw.rbf_means + lane), beta = __ldg(mw.rbf_betas + lane);
+    const float alpha = 5.0f / mw.cutoff;
+    for (int k = 0; k < dg; k++) {
+        const float rk = __shfl_sync(0xffffffffu, r, k);
+        const float Ck = __shfl_sync(0xffffffffu, C, k);
+        const float t = expf(-alpha * rk) - mu;
+        ws.rbf[(size_t)(e0 + k) * NR + lane] = Ck * expf(-beta * t * t);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// K4: neighbour embedding.  Block = 128 threads (thread = channel c), NB consecutive nodes per block.
+//   agg_i[c] = sum_{e->i, j!=i} (rbf_e . Wd[c,:] + bd[c]) * C_e * nb_emb[z_j][c]
+//   x_i = [emb[z_i] | agg_i] Wc^T + bc
+// ---------------------------------------------------------------------------------------------
+constexpr int EMB_NB = 8;
+__global__ void __launch_bounds__(128) embed_node_kernel(ModelW mw, Workspace ws) {
+    __shared__ float cat[EMB_NB][2 * D];
+    const int c = threadIdx.x;
+    const int n0 = blockIdx.x * EMB_NB;
+    float wd[NR];
+#pragma unroll
+    for (int k = 0; k < NR; k += 4) {
+        const float4 w = ldg4(mw.WdN + c * NR + k);
+        wd[k] = w.x; wd[k + 1] = w.y; wd[k + 2] = w.z; wd[k + 3] = w.w;
+    }
+    const float bd = __ldg(mw.bd + c);
+    for (int nd = 0; nd < EMB_NB; nd++) {
+        const int i = n0 + nd;
+        float acc = 0.f, x0 = 0.f;
+        if (i < ws.N) {
+            x0 = __ldg(mw.emb + ws.z[i] * D + c);
+            const int e1 = ws.rowptr[i + 1];
+            for (int e = ws.rowptr[i]; e < e1; e++) {
+                const int j = ws.esrc[e];
+                if (j == i) continue;
+                float dp = bd;
+#pragma unroll
+                for (int k = 0; k < NR; k += 4) {
+                    const float4 rb = ld4(ws.rbf + (size_t)e * NR + k);
+                    dp = fmaf(rb.x, wd[k], dp); dp = fmaf(rb.y, wd[k + 1], dp);
+                    dp = fmaf(rb.z, wd[k + 2], dp); dp = fmaf(rb.w, wd[k + 3], dp);
+                }
+                const float Ce = ws.geom[(size_t)e * 8 + 1];
+                acc = fmaf(dp * Ce, __ldg(mw.nb_emb + ws.z[j] * D + c), acc);
+            }
+        }
+        cat[nd][c] = x0;
+        cat[nd][D + c] = acc;
+    }
+    __syncthreads();
+    float out[EMB_NB];
+    const float bc = __ldg(mw.bc + c);
+#pragma unroll
+    for (int nd = 0; nd < EMB_NB; nd++) out[nd] = bc;
+    for (int k = 0; k < 2 * D; k++) {
+        const float w = __ldg(mw.WcT + k * D + c);
+#pragma unroll
+        for (int nd = 0; nd < EMB_NB; nd++) out[nd] = fmaf(cat[nd][k], w, out[nd]);
+    }
+#pragma unroll
+    for (int nd = 0; nd < EMB_NB; nd++)
+        if (n0 + nd < ws.N) ws.X[0][(size_t)(n0 + nd) * D + c] = out[nd];
+}
+
+// K5: edge embedding  f0_e[c] = (x_i[c] + x_j[c]) * (rbf_e . We[c,:] + be[c]).   thread = channel.
+__global__ void __launch_bounds__(128) embed_edge_kernel(ModelW mw, Workspace ws) {
+    const int c = threadIdx.x;
+    float we[NR];
+#pragma unroll
+    for (int k = 0; k < NR; k += 4) {
+        const float4 w = ldg4(mw.WeN + c * NR + k);
+        we[k] = w.x; we[k + 1] = w.y; we[k + 2] = w.z; we[k + 3] = w.w;
+    }
+    const float be = __ldg(mw.be + c);
+    const int E = ws.rowptr[ws.N];
+    const float* __restrict__ X = ws.X[0];
+    for (int e = blockIdx.x; e < E; e += gridDim.x) {
+        float ep = be;
+#pragma unroll
+        for (int k = 0; k < NR; k += 4) {
+            const float4 rb = ld4(ws.rbf + (size_t)e * NR + k);
+            ep = fmaf(rb.x, we[k], ep); ep = fmaf(rb.y, we[k + 1], ep);
+            ep = fmaf(rb.z, we[k + 2], ep); ep = fmaf(rb.w, we[k + 3], ep);
+        }
+        const int i = ws.edst[e], j = ws.esrc[e];
+        ws.F[0][(size_t)e * D + c] = (X[(size_t)i * D + c] + X[(size_t)j * D + c]) * ep;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// K14: adjoint of the edge embedding.  gf = dE/df0 (in ws.GF).
+//   gx_i += gf*ep, gx_j += gf*ep ; g_rbf[e][k] = sum_c gf*(x_i+x_j) * We[c][k]
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) embed_edge_bwd_kernel(ModelW mw, Workspace ws) {
+    __shared__ float gep_s[D];
+    __shared__ float part[4][NR];
+    const int c = threadIdx.x;
+    float we[NR];
+#pragma unroll
+    for (int k = 0; k < NR; k += 4) {
+        const float4 w = ldg4(mw.WeN + c * NR + k);
+        we[k] = w.x; we[k + 1] = w.y; we[k + 2] = w.z; we[k + 3] = w.w;
+    }
+    const float be = __ldg(mw.be + c);
+    const int E = ws.rowptr[ws.N];
+    const float* __restrict__ X = ws.X[0];
+    const int kk = c & 31, pp = c >> 5;   // reduction role: output k, channel quarter pp
+    for (int e = blockIdx.x; e < E; e += gridDim.x) {
+        float ep = be;
+#pragma unroll
+        for (int k = 0; k < NR; k += 4) {
+            const float4 rb = ld4(ws.rbf + (size_t)e * NR + k);
+            ep = fmaf(rb.x, we[k], ep); ep = fmaf(rb.y, we[k + 1], ep);
+            ep = fmaf(rb.z, we[k + 2], ep); ep = fmaf(rb.w, we[k + 3], ep);
+        }
+        const int i = ws.edst[e], j = ws.esrc[e];
+        const float gf = ws.GF[(size_t)e * D + c];
+        const float gfe = gf * ep;
+        atomicAdd(ws.GX + (size_t)i * D + c, gfe);
+        atomicAdd(ws.GX + (size_t)j * D + c, gfe);
+        __syncthreads();
+        gep_s[c] = gf * (X[(size_t)i * D + c] + X[(size_t)j * D + c]);
+        __syncthreads();
+        float s = 0.f;
+#pragma unroll 8
+        for (int q = 0; q < 32; q++) {
+            const int cc = pp * 32 + q;
+            s = fmaf(gep_s[cc], __ldg(mw.WeN + cc * NR + kk), s);
+        }
+        part[pp][kk] = s;
+        __syncthreads();
+        if (c < NR) ws.grbf[(size_t)e * NR + c] = (part[0][c] + part[1][c]) + (part[2][c] + part[3][c]);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// K15: adjoint of the neighbour embedding + geometry adjoint + force accumulation.
+// One block (128 threads) per target node i; needs the complete gx (all scatter-adds done).
+//   g_agg = (gx_i Wc)[128:256]
+//   per edge e->i (j != i): g_We = g_agg * nb[z_j]; gC += sum_c g_We*dp ; g_rbf[k] += sum_c g_We*C*Wd[c][k]
+//   g_r = gC*C'(r) + sum_k g_rbf[k]*drbf_k/dr ; g_ev = g_r d + (g_d - (g_d.d) d)/r
+//   dE/dpos_j += g_ev, dE/dpos_i -= g_ev ; forces = -dE/dpos
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) embed_node_bwd_kernel(ModelW mw, Workspace ws,
+                                                             float* __restrict__ forces) {
+    __shared__ float gx_s[D];
+    __shared__ float gwe_s[D];
+    __shared__ float part[4][NR];
+    __shared__ float red_s[4];
+    const int c = threadIdx.x, lane = c & 31, warp = c >> 5;
+    const int i = blockIdx.x;
+    if (i >= ws.N) return;
+    gx_s[c] = ws.GX[(size_t)i * D + c];
+    float wd[NR];
+#pragma unroll
+    for (int k = 0; k < NR; k += 4) {
+        const float4 w = ldg4(mw.WdN + c * NR + k);
+        wd[k] = w.x; wd[k + 1] = w.y; wd[k + 2] = w.z; wd[k + 3] = w.w;
+    }
+    const float bd = __ldg(mw.bd + c);
+    __syncthreads();
+    float g_agg = 0.f;
+    for (int k = 0; k < D; k++) g_agg = fmaf(gx_s[k], __ldg(mw.WcN + (size_t)k * 2 * D + D + c), g_agg);
+    const float alpha = 5.0f / mw.cutoff;
+    float fix = 0.f, fiy = 0.f, fiz = 0.f;   // accumulated -dE/dpos_i contributions (thread 0)
+    const int e1 = ws.rowptr[i + 1];
+    for (int e = ws.rowptr[i]; e < e1; e++) {
+        const int j = ws.esrc[e];
+        if (j == i) continue;     // self-loops carry no geometry and are masked out of the neighbour embedding
+        const float4 g0 = ld4(ws.geom + (size_t)e * 8);
+        const float4 g1 = ld4(ws.geom + (size_t)e * 8 + 4);
+        const float r = g0.x, Ce = g0.y, dx = g0.z, dy = g0.w, dz = g1.x, inv_r = g1.y;
+        float dp = bd;
+#pragma unroll
+        for (int k = 0; k < NR; k += 4) {
+            const float4 rb = ld4(ws.rbf + (size_t)e * NR + k);
+            dp = fmaf(rb.x, wd[k], dp); dp = fmaf(rb.y, wd[k + 1], dp);
+            dp = fmaf(rb.z, wd[k + 2], dp); dp = fmaf(rb.w, wd[k + 3], dp);
+        }
+        const float gwe = g_agg * __ldg(mw.nb_emb + ws.z[j] * D + c);
+        float gc = warp_sum(gwe * dp);
+        __syncthreads();                 // previous iteration finished reading gwe_s / part / red_s
+        gwe_s[c] = gwe * Ce;
+        if (lane == 0) red_s[warp] = gc;
+        __syncthreads();
+        {
+            const int kk = lane, pp = warp;
+            float s = 0.f;
+#pragma unroll 8
+            for (int q = 0; q < 32; q++) {
+                const int cc = pp * 32 + q;
+                s = fmaf(gwe_s[cc], __ldg(mw.WdN + cc * NR + kk), s);
+            }
+            part[pp][kk] = s;
+        }
+        __syncthreads();
+        if (warp == 0) {
+            const float4 ea = ld4(ws.eacc + (size_t)e * 4);
+            const float gC = ea.x + ((red_s[0] + red_s[1]) + (red_s[2] + red_s[3]));
+            const float grbf = ws.grbf[(size_t)e * NR + lane] +
+                               ((part[0][lane] + part[1][lane]) + (part[2][lane] + part[3][lane]));
+            const float mu = __ldg(mw.rbf_means + lane), beta = __ldg(mw.rbf_betas + lane);
+            const float ex = expf(-alpha * r);
+            const float t = ex - mu;
+            const float gk = expf(-beta * t * t);
+            const float dC = cutoff_dfn(r, mw.cutoff);
+            const float drbf = dC * gk + Ce * gk * (2.0f * beta * alpha) * t * ex;
+            const float g_r = gC * dC + warp_sum(grbf * drbf);
+            if (lane == 0) {
+                const float gdd = ea.y * dx + ea.z * dy + ea.w * dz;
+                const float gx_ = g_r * dx + (ea.y - gdd * dx) * inv_r;
+                const float gy_ = g_r * dy + (ea.z - gdd * dy) * inv_r;
+                const float gz_ = g_r * dz + (ea.w - gdd * dz) * inv_r;
+                // dE/dpos_j += g_ev  -> F_j -= g_ev ; dE/dpos_i -= g_ev -> F_i += g_ev
+                atomicAdd(forces + 3 * j, -gx_);
+                atomicAdd(forces + 3 * j + 1, -gy_);
+                atomicAdd(forces + 3 * j + 2, -gz_);
+                fix += gx_; fiy += gy_; fiz += gz_;
+            }
+        }
+    }
+    if (c == 0) {
+        atomicAdd(forces + 3 * i, fix);
+        atomicAdd(forces + 3 * i + 1, fiy);
+        atomicAdd(forces + 3 * i + 2, fiz);
+    }
+}
+
+// per-fragment energy: E_g = sum_a e_atom[a] + mean   (one warp per fragment; visnet.py:146-149).
+// The <= 44 per-atom terms are summed in double and rounded once, so the result does not depend on order.
+__global__ void __launch_bounds__(128) energy_reduce_kernel(Workspace ws, const float* __restrict__ scalars,
+                                                            float* __restrict__ energy) {
+    const int lane = threadIdx.x & 31;
+    const int g = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (g >= ws.G) return;
+    double s = 0.0;
+    for (int a = ws.frag_start[g] + lane; a < ws.frag_start[g + 1]; a += 32) s += (double)ws.eatom[a];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) energy[g] = (float)(s + (double)__ldg(scalars + 1));
+}
+
+}  // namespace vb

@@ -1,0 +1,187 @@
+"""ctypes binding of the C-ABI library ``libvisnet_b200.so`` (``include/visnet_b200.h``).
+
+PyTorch is used only as plumbing here (device tensors and streams owned by the caller); the binding
+itself passes raw pointers.  There is no CPU path: constructing an :class:`Engine` without a usable
+sm_100 device raises ``RuntimeError``, and a missing library raises at import of this module's users.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Dict, Optional, Tuple
+
+import numpy as np
+
+from . import build as _build
+from .weights import pack_weights
+
+_lib = None
+
+
+class _HParams(C.Structure):
+    _fields_ = [("hidden_channels", C.c_int32), ("num_layers", C.c_int32), ("num_heads", C.c_int32),
+                ("num_rbf", C.c_int32), ("max_num_neighbors", C.c_int32), ("cutoff", C.c_float)]
+
+
+# every symbol include/visnet_b200.h declares (tests check that the library exports each of them)
+EXPORTED_SYMBOLS = [
+    "vb_weight_manifest", "vb_create", "vb_destroy", "vb_last_error", "vb_set_topology", "vb_forward",
+    "vb_forward_host", "vb_set_protein_map", "vb_forward_protein", "vb_get_edges", "vb_launches_per_forward",
+    "vb_set_option", "vb_num_stages", "vb_stage_name", "vb_debug_run", "vb_debug_read",
+]
+
+
+def load_library(path: Optional[str] = None):
+    """Load (never build) the shared library; raises if it is missing -- there is no fallback."""
+    global _lib
+    if _lib is not None and path is None:
+        return _lib
+    path = path or _build.LIB_PATH
+    if not os.path.exists(path):
+        raise RuntimeError(f"{path} is missing: build it with `python -m ai2bmd_b200.build` "
+                           "(nvcc, sm_100a).  The engine has no CPU or PyTorch fallback.")
+    lib = C.CDLL(path)
+    vp, i64, i32 = C.c_void_p, C.c_int64, C.c_int32
+    lib.vb_weight_manifest.restype = C.c_char_p
+    lib.vb_weight_manifest.argtypes = []
+    lib.vb_create.restype = C.c_int
+    lib.vb_create.argtypes = [vp, C.c_size_t, C.POINTER(_HParams), C.c_int, C.POINTER(vp)]
+    lib.vb_destroy.restype = None
+    lib.vb_destroy.argtypes = [vp]
+    lib.vb_last_error.restype = C.c_char_p
+    lib.vb_last_error.argtypes = [vp]
+    lib.vb_set_topology.restype = C.c_int
+    lib.vb_set_topology.argtypes = [vp, i64, i64, vp, vp, i64]
+    lib.vb_forward.restype = C.c_int
+    lib.vb_forward.argtypes = [vp, vp, vp, vp, vp]
+    lib.vb_forward_host.restype = C.c_int
+    lib.vb_forward_host.argtypes = [vp, vp, vp, vp]
+    lib.vb_set_protein_map.restype = C.c_int
+    lib.vb_set_protein_map.argtypes = [vp, i64, i64, vp, vp, vp, vp]
+    lib.vb_forward_protein.restype = C.c_int
+    lib.vb_forward_protein.argtypes = [vp, vp, vp, vp]
+    lib.vb_get_edges.restype = C.c_int
+    lib.vb_get_edges.argtypes = [vp, vp, vp]
+    lib.vb_launches_per_forward.restype = C.c_int
+    lib.vb_launches_per_forward.argtypes = [vp]
+    lib.vb_set_option.restype = C.c_int
+    lib.vb_set_option.argtypes = [vp, C.c_char_p, i64]
+    lib.vb_num_stages.restype = C.c_int
+    lib.vb_num_stages.argtypes = [vp]
+    lib.vb_stage_name.restype = C.c_char_p
+    lib.vb_stage_name.argtypes = [vp, C.c_int]
+    lib.vb_debug_run.restype = C.c_int
+    lib.vb_debug_run.argtypes = [vp, vp, C.c_int]
+    lib.vb_debug_read.restype = i64
+    lib.vb_debug_read.argtypes = [vp, C.c_char_p, C.c_int, vp, i64]
+    if path == _build.LIB_PATH:
+        _lib = lib
+    return lib
+
+
+def weight_manifest() -> str:
+    return load_library().vb_weight_manifest().decode()
+
+
+class Engine:
+    """One engine per CUDA device (the reference keeps one ``ViSNetModel`` per device,
+    ``src/Calculators/bonded.py:40-44``)."""
+
+    def __init__(self, state_dict: Dict[str, np.ndarray], device: int = 0, cutoff: float = 5.0):
+        self.lib = load_library()
+        blob = pack_weights(state_dict, self.lib.vb_weight_manifest().decode())
+        hp = _HParams(128, 6, 8, 32, 32, cutoff)
+        handle = C.c_void_p()
+        rc = self.lib.vb_create(blob.ctypes.data, blob.size, C.byref(hp), int(device), C.byref(handle))
+        if rc != 0:
+            raise RuntimeError(f"vb_create failed ({rc}): {self.lib.vb_last_error(None).decode()}")
+        self.h = handle
+        self.device = int(device)
+        self.n_atoms = 0
+        self.n_graphs = 0
+        self.n_protein = 0
+
+    def _check(self, rc, what):
+        if rc < 0:
+            raise RuntimeError(f"{what} failed ({rc}): {self.lib.vb_last_error(self.h).decode()}")
+        return rc
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.vb_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- topology ----
+    def set_topology(self, z, batch, n_graphs: Optional[int] = None, max_edges: int = 0):
+        z = np.ascontiguousarray(z, dtype=np.int64)
+        batch = np.ascontiguousarray(batch, dtype=np.int64)
+        if z.shape != batch.shape or z.ndim != 1 or z.size == 0:
+            raise ValueError("z and batch must be non-empty 1-D arrays of equal length")
+        g = int(batch.max()) + 1 if n_graphs is None else int(n_graphs)
+        self._check(self.lib.vb_set_topology(self.h, z.size, g, z.ctypes.data, batch.ctypes.data, int(max_edges)),
+                    "vb_set_topology")
+        self.n_atoms, self.n_graphs = int(z.size), g
+
+    def set_protein_map(self, n_protein, src_atom, dst_atom, sign, frag_sign):
+        src_atom = np.ascontiguousarray(src_atom, dtype=np.int32)
+        dst_atom = np.ascontiguousarray(dst_atom, dtype=np.int32)
+        sign = np.ascontiguousarray(sign, dtype=np.float32)
+        frag_sign = np.ascontiguousarray(frag_sign, dtype=np.float32)
+        if frag_sign.size != self.n_graphs:
+            raise ValueError("frag_sign must have one entry per fragment")
+        self._check(self.lib.vb_set_protein_map(self.h, int(n_protein), src_atom.size, src_atom.ctypes.data,
+                                                dst_atom.ctypes.data, sign.ctypes.data, frag_sign.ctypes.data),
+                    "vb_set_protein_map")
+        self.n_protein = int(n_protein)
+
+    def set_option(self, key: str, value: int):
+        self._check(self.lib.vb_set_option(self.h, key.encode(), int(value)), "vb_set_option")
+
+    # ---- evaluation ----
+    def forward_host(self, pos: np.ndarray) -> Tuple[np.ndarray, np.ndarray]:
+        """Host arrays in, host arrays out (H2D / D2H inside the call)."""
+        pos = np.ascontiguousarray(pos, dtype=np.float32)
+        if pos.shape != (self.n_atoms, 3):
+            raise ValueError(f"pos must be [{self.n_atoms},3]")
+        e = np.empty((self.n_graphs,), dtype=np.float32)
+        f = np.empty((self.n_atoms, 3), dtype=np.float32)
+        self._check(self.lib.vb_forward_host(self.h, pos.ctypes.data, e.ctypes.data, f.ctypes.data), "vb_forward_host")
+        return e, f
+
+    def forward_device(self, pos_ptr: int, energy_ptr: int, forces_ptr: int, stream_ptr: int = 0):
+        """Raw device pointers (e.g. ``tensor.data_ptr()``) and a ``cudaStream_t``; asynchronous."""
+        self._check(self.lib.vb_forward(self.h, pos_ptr, energy_ptr, forces_ptr, stream_ptr), "vb_forward")
+
+    def forward_protein_device(self, pos_ptr: int, ef_ptr: int, stream_ptr: int = 0):
+        self._check(self.lib.vb_forward_protein(self.h, pos_ptr, ef_ptr, stream_ptr), "vb_forward_protein")
+
+    def get_edges(self) -> Tuple[np.ndarray, np.ndarray]:
+        slots = np.empty((self.n_atoms, 32), dtype=np.int32)
+        deg = np.empty((self.n_atoms,), dtype=np.int32)
+        self._check(self.lib.vb_get_edges(self.h, slots.ctypes.data, deg.ctypes.data), "vb_get_edges")
+        return slots, deg
+
+    @property
+    def launches_per_forward(self) -> int:
+        return int(self.lib.vb_launches_per_forward(self.h))
+
+    # ---- diagnostics ----
+    def stage_names(self):
+        return [self.lib.vb_stage_name(self.h, i).decode() for i in range(self.lib.vb_num_stages(self.h))]
+
+    def debug_run(self, pos_ptr: int, n_stages: int):
+        self._check(self.lib.vb_debug_run(self.h, pos_ptr, int(n_stages)), "vb_debug_run")
+
+    def debug_read(self, name: str, layer: int, shape, dtype=np.float32) -> np.ndarray:
+        out = np.empty(shape, dtype=dtype)
+        n = self._check(self.lib.vb_debug_read(self.h, name.encode(), int(layer), out.ctypes.data, out.nbytes),
+                        "vb_debug_read")
+        if n != out.nbytes:
+            raise RuntimeError(f"vb_debug_read({name}): got {n} bytes, wanted {out.nbytes}")
+        return out

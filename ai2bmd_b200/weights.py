@@ -1,0 +1,100 @@
+"""Checkpoint -> flat fp32 weight blob in the order of ``vb_weight_manifest()``.
+
+The checkpoint keys are the reference's (``/root/reference/src/ViSNet/model/visnet.py:73-93`` strips the
+leading ``model.``; tensor inventory in SURVEY.md App. B).  "T" entries are the transposed ``nn.Linear``
+weights ([in][out]) read by the forward GEMMs, "N" entries the native [out][in] layout read by the adjoint
+GEMMs; fused matrices ([q|k|v], [dk|dv|f], [w_trg|w_src]) are concatenated along the output dimension.
+"""
+from __future__ import annotations
+
+import re
+from typing import Dict
+
+import numpy as np
+
+D, L = 128, 6
+
+
+def load_state_dict(path: str) -> Dict[str, np.ndarray]:
+    """``.ckpt`` (Lightning checkpoint as shipped by the reference) or ``.npz`` (extracted state_dict)."""
+    if path.endswith(".npz"):
+        z = np.load(path)
+        return {k: np.asarray(z[k], dtype=np.float32) for k in z.files}
+    import torch
+    ck = torch.load(path, map_location="cpu", weights_only=True)
+    hp = ck.get("hyper_parameters", {})
+    if hp:
+        want = dict(embedding_dimension=128, num_layers=6, num_heads=8, num_rbf=32, lmax=1, max_num_neighbors=32,
+                    vecnorm_type="max_min", rbf_type="expnorm", activation="silu", attn_activation="silu")
+        for k, v in want.items():
+            if hp.get(k) != v:
+                raise ValueError(f"checkpoint hyper-parameter {k}={hp.get(k)!r} is not the supported {v!r}")
+    return {re.sub(r"^model\.", "", k): v.float().numpy() for k, v in ck["state_dict"].items()}
+
+
+def _named_arrays(sd: Dict[str, np.ndarray]) -> Dict[str, np.ndarray]:
+    f = lambda k: np.asarray(sd[k], dtype=np.float32)
+    rm = "representation_model."
+    o0, o1 = "output_model.output_network.0.", "output_model.output_network.1."
+    out: Dict[str, np.ndarray] = {}
+    out["emb"] = f(rm + "embedding.weight")
+    out["nb_emb"] = f(rm + "neighbor_embedding.embedding.weight")
+    out["rbf_means"] = f(rm + "distance_expansion.means")
+    out["rbf_betas"] = f(rm + "distance_expansion.betas")
+    out["WdN"] = f(rm + "neighbor_embedding.distance_proj.weight")
+    out["bd"] = f(rm + "neighbor_embedding.distance_proj.bias")
+    wc = f(rm + "neighbor_embedding.combine.weight")
+    out["WcT"], out["bc"], out["WcN"] = wc.T, f(rm + "neighbor_embedding.combine.bias"), wc
+    out["WeN"] = f(rm + "edge_embedding.edge_proj.weight")
+    out["be"] = f(rm + "edge_embedding.edge_proj.bias")
+    out["on_w"], out["on_b"] = f(rm + "out_norm.weight"), f(rm + "out_norm.bias")
+    out["von_w"] = f(rm + "vec_out_norm.weight")
+    for tag, pre in (("h0", o0), ("h1", o1)):
+        w1 = f(pre + "vec1_proj.weight")
+        out[f"{tag}_W1T"], out[f"{tag}_W1N"] = w1.T, w1
+        u0 = f(pre + "update_net.0.weight")
+        out[f"{tag}_U0T"], out[f"{tag}_b0"], out[f"{tag}_U0N"] = u0.T, f(pre + "update_net.0.bias"), u0
+    w2 = f(o0 + "vec2_proj.weight")
+    out["h0_W2T"], out["h0_W2N"] = w2.T, w2
+    u2 = f(o0 + "update_net.2.weight")
+    out["h0_U2T"], out["h0_b2"], out["h0_U2N"] = u2.T, f(o0 + "update_net.2.bias"), u2
+    out["h1_u2"] = f(o1 + "update_net.2.weight")[0]
+    out["h1_b2"] = np.array([f(o1 + "update_net.2.bias")[0], 0, 0, 0], dtype=np.float32)
+    out["atomref"] = f("prior_model.atomref.weight").reshape(-1)
+    out["scalars"] = np.array([float(sd["std"]), float(sd["mean"]), 0, 0], dtype=np.float32)
+    for l in range(L):
+        p = rm + f"vis_mp_layers.{l}."
+        last = l == L - 1
+        z = np.zeros((D, D), dtype=np.float32)
+        zb = np.zeros((D,), dtype=np.float32)
+        k = f"layer{l}."
+        out[k + "ln_w"], out[k + "ln_b"] = f(p + "layernorm.weight"), f(p + "layernorm.bias")
+        out[k + "vln_w"] = f(p + "vec_layernorm.weight")
+        wqkv = np.concatenate([f(p + "q_proj.weight"), f(p + "k_proj.weight"), f(p + "v_proj.weight")], 0)
+        out[k + "WqkvT"], out[k + "WqkvN"] = wqkv.T, wqkv
+        out[k + "bqkv"] = np.concatenate([f(p + "q_proj.bias"), f(p + "k_proj.bias"), f(p + "v_proj.bias")])
+        wv = f(p + "vec_proj.weight")
+        out[k + "WvecT"], out[k + "WvecN"] = wv.T, wv
+        wtu = np.concatenate([z if last else f(p + "w_trg_proj.weight"), z if last else f(p + "w_src_proj.weight")], 0)
+        out[k + "WtuT"], out[k + "WtuN"] = wtu.T, wtu
+        w1 = np.concatenate([f(p + "dk_proj.weight"), f(p + "dv_proj.weight"), z if last else f(p + "f_proj.weight")], 0)
+        out[k + "W1T"], out[k + "W1N"] = w1.T, w1
+        out[k + "b1"] = np.concatenate([f(p + "dk_proj.bias"), f(p + "dv_proj.bias"), zb if last else f(p + "f_proj.bias")])
+        ws = f(p + "s_proj.weight")
+        out[k + "WsT"], out[k + "bs"], out[k + "WsN"] = ws.T, f(p + "s_proj.bias"), ws
+        wo = f(p + "o_proj.weight")
+        out[k + "WoT"], out[k + "bo"], out[k + "WoN"] = wo.T, f(p + "o_proj.bias"), wo
+    return out
+
+
+def pack_weights(sd: Dict[str, np.ndarray], manifest: str) -> np.ndarray:
+    """Flatten per the library's manifest string ``name:count;...``; sizes are cross-checked."""
+    arrays = _named_arrays(sd)
+    parts = []
+    for item in manifest.strip(";").split(";"):
+        name, count = item.split(":")
+        a = np.ascontiguousarray(arrays[name], dtype=np.float32).reshape(-1)
+        if a.size != int(count):
+            raise ValueError(f"weight {name}: have {a.size} values, manifest wants {count}")
+        parts.append(a)
+    return np.concatenate(parts)

@@ -1,0 +1,137 @@
+"""Host-side logic: FragmentData semantics, fixtures, weight packing, C-ABI symbol table, loud failure."""
+import ctypes
+import os
+
+import numpy as np
+import pytest
+
+from ai2bmd_b200 import build as vbuild
+from ai2bmd_b200 import engine as vengine
+from ai2bmd_b200.calculator import DipeptideBondedCombiner
+from ai2bmd_b200.fragment_data import FragmentData, FragmentInfo
+from ai2bmd_b200.parallel import combine_local, partition_fragments, shard_protein_map
+from ai2bmd_b200.weights import pack_weights
+
+ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    vbuild.build()            # nvcc cross-compiles without a GPU
+    return vengine.load_library()
+
+
+def test_library_exports_every_declared_symbol(lib):
+    header = open(os.path.join(ROOT, "include", "visnet_b200.h")).read()
+    import re
+    declared = set(re.findall(r"\b(vb_[a-z_]+)\s*\(", header))
+    assert declared == set(vengine.EXPORTED_SYMBOLS)
+    for sym in declared:
+        assert hasattr(lib, sym), sym
+
+
+def test_weight_blob_matches_manifest(lib, real_weights):
+    manifest = lib.vb_weight_manifest().decode()
+    blob = pack_weights(real_weights, manifest)
+    total = sum(int(x.split(":")[1]) for x in manifest.strip(";").split(";"))
+    assert blob.dtype == np.float32 and blob.size == total
+    # spot-check the transposed / native pairs and the fused matrices
+    off = {}
+    o = 0
+    for item in manifest.strip(";").split(";"):
+        n, c = item.split(":")
+        off[n] = (o, int(c))
+        o += int(c)
+    get = lambda n, shape: blob[off[n][0]:off[n][0] + off[n][1]].reshape(shape)
+    wq = real_weights["representation_model.vis_mp_layers.2.q_proj.weight"]
+    assert np.array_equal(get("layer2.WqkvN", (384, 128))[:128], wq)
+    assert np.array_equal(get("layer2.WqkvT", (128, 384))[:, :128], wq.T)
+    assert np.array_equal(get("layer5.W1N", (384, 128))[256:], np.zeros((128, 128), np.float32))   # no f_proj in the last layer
+    assert np.array_equal(get("layer4.WtuN", (256, 128))[128:], real_weights["representation_model.vis_mp_layers.4.w_src_proj.weight"])
+    assert get("atomref", (100,))[6] == pytest.approx(-1027.537, abs=1e-2)
+
+
+def test_engine_fails_loudly_without_gpu(lib, real_weights):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(RuntimeError, match="no usable CUDA device|no CPU fallback"):
+        vengine.Engine(real_weights)
+    from ai2bmd_b200.calculator import ViSNetModel
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        ViSNetModel(real_weights, device="cpu")
+
+
+def test_create_rejects_bad_arguments(lib):
+    hp = vengine._HParams(256, 9, 8, 32, 32, 5.0)
+    h = ctypes.c_void_p()
+    blob = np.zeros(16, np.float32)
+    assert lib.vb_create(blob.ctypes.data, blob.size, ctypes.byref(hp), 0, ctypes.byref(h)) == -1
+    assert b"hyper-parameters" in lib.vb_last_error(None)
+    hp = vengine._HParams(128, 6, 8, 32, 32, 5.0)
+    assert lib.vb_create(blob.ctypes.data, blob.size, ctypes.byref(hp), 0, ctypes.byref(h)) == -1
+    assert b"manifest" in lib.vb_last_error(None)
+
+
+def test_fragment_data_slicing_and_splits(chig):
+    fd, _ = chig
+    assert len(fd) == 19 and fd.end[-1] == 391
+    sub = fd[2:5]
+    assert len(sub) == 3 and sub.start[0] == 0 and sub.batch[0] == 0 and sub.batch[-1] == 2
+    assert np.array_equal(sub.pos, fd.pos[fd.start[2]:fd.end[4]])
+    one = fd[1]
+    assert len(one) == 1 and len(one.z) == 12
+    dip, an = fd.scalar_split()
+    assert dip.sum() == 10 and an.sum() == 9 and dip[0] and an[1]
+    vd, va = fd.vector_split()
+    assert vd.sum() + va.sum() == 391 and va.sum() == 9 * 12
+    assert vd[:fd.end[0]].all() and va[fd.start[1]:fd.end[1]].all()
+    assert FragmentInfo.split(19) == (10, 9)
+    with pytest.raises(IndexError):
+        fd[3:3]
+
+
+def test_fixture_shapes_match_survey(golden_dir):
+    sizes = {"chig": (19, 391, 175), "trpcage": (39, 737, 281), "ww": (69, 1387, 571), "abd": (93, 1850, 746)}
+    for name, (g, n, p) in sizes.items():
+        f = np.load(os.path.join(golden_dir, f"fragments_{name}.npz"))
+        assert len(f["start"]) == g and len(f["z"]) == n and int(f["n_protein"]) == p
+        assert set(np.unique(f["z"])) <= {1, 6, 7, 8, 16}
+        assert ((f["end"] - f["start"])[1::2] == 12).all()                     # ACE-NME fragments
+        net = np.zeros(p)
+        np.add.at(net, f["dst_atom"], f["sign"])
+        assert (net == 1).all()                                                 # inclusion-exclusion covers every atom once
+
+
+def test_combiner_matches_signed_map(chig):
+    fd, pm = chig
+    rng = np.random.default_rng(0)
+    e = rng.normal(size=(len(fd), 1)).astype(np.float32)
+    f = rng.normal(size=(len(fd.z), 3)).astype(np.float32)
+    dip, an = fd.scalar_split()
+    vd, va = fd.vector_split()
+    # reference layout: [all dipeptide atoms | all ACE-NME atoms], select = real atoms, origin = protein index
+    order = np.concatenate([np.flatnonzero(vd), np.flatnonzero(va)])
+    inv = np.empty_like(order)
+    inv[order] = np.arange(len(order))
+    select, origin = inv[pm.src_atom], pm.dst_atom
+    F = DipeptideBondedCombiner.forces_combine(pm.n_protein, f[vd], f[va], select, origin)
+    E = DipeptideBondedCombiner.energy_combine(e[dip], e[an])
+    ef = combine_local(pm, e, f)
+    assert np.allclose(ef[:-1].reshape(-1, 3), F, atol=1e-5)
+    assert float(E) == pytest.approx(float(ef[-1]), abs=1e-4)
+
+
+@pytest.mark.parametrize("n_parts", [1, 2, 3, 4, 8, 32])
+def test_partition_is_contiguous_balanced_cover(chig, trpcage, n_parts):
+    for fd, pm in (chig, trpcage):
+        parts = partition_fragments(fd.start, fd.end, n_parts)
+        assert len(parts) == n_parts and parts[0][0] == 0 and parts[-1][1] == len(fd)
+        assert all(a[1] == b[0] for a, b in zip(parts, parts[1:]))
+        atoms = [int(fd.end[hi - 1] - fd.start[lo]) if hi > lo else 0 for lo, hi in parts]
+        assert sum(atoms) == int(fd.end[-1])
+        if n_parts <= 8:
+            assert max(atoms) <= int(fd.end[-1]) / n_parts + 36 + 12          # within one fragment of the ideal share
+        # shard maps partition the full map
+        total = sum(len(shard_protein_map(pm, fd, lo, hi).src_atom) for lo, hi in parts)
+        assert total == len(pm.src_atom)

@@ -1,0 +1,151 @@
+#!/usr/bin/env python
+"""Stage-by-stage parity of the CUDA engine against the hand-adjoint oracle (GPU box diagnostic).
+
+    python tools/stage_check.py [--weights real|random] [--frags chig] [--out gpurun_out/stage_check.txt]
+
+Runs the evaluation one launch at a time (``vb_debug_run``), reads the engine's internal buffers after
+each stage and compares them with the tensors of ``oracle/adjoint_ref.py`` (fp64).  The first stage whose
+relative error jumps is where a kernel bug lives.  Test infrastructure; not part of the product path.
+"""
+import argparse
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
+sys.path.insert(0, ROOT)
+
+from oracle import visnet_ref as O                      # noqa: E402
+from oracle.adjoint_ref import AdjointViSNet            # noqa: E402
+from ai2bmd_b200.engine import Engine                   # noqa: E402
+
+D, L = 128, 6
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--weights", default="real")
+    ap.add_argument("--frags", default="chig")
+    ap.add_argument("--max-frags", type=int, default=0)
+    ap.add_argument("--out", default="")
+    ap.add_argument("--opts", default="", help="comma list key=value for vb_set_option")
+    args = ap.parse_args()
+
+    g = np.load(os.path.join(ROOT, "tests", "golden", f"fragments_{args.frags}.npz"))
+    z, pos, batch = g["z"], g["pos"], g["batch"]
+    if args.max_frags:
+        keep = batch < args.max_frags
+        z, pos, batch = z[keep], pos[keep], batch[keep]
+    sd = O.load_state_dict(os.path.join(ROOT, "tests", "golden", "weights_2ef43f29.npz")) if args.weights == "real" \
+        else O.random_state_dict(int(args.weights) if args.weights.isdigit() else 0)
+    slots, deg = O.radius_graph_canonical(pos, batch)
+    ei = torch.from_numpy(O.slots_to_edge_index(slots, deg))
+    E, N = ei.shape[1], len(z)
+    adj = AdjointViSNet(O.OracleViSNet(sd, torch.float64))
+    Eo, Fo, S, B = adj.energy_and_forces(z, pos, batch, ei)
+    S = {k: v.numpy() for k, v in S.items()}
+    B = {k: v.numpy() for k, v in B.items()}
+
+    eng = Engine({k: v.numpy() for k, v in sd.items()}, 0)
+    eng.set_topology(z, batch)
+    for kv in filter(None, args.opts.split(",")):
+        k, v = kv.split("=")
+        eng.set_option(k, int(v))
+    names = eng.stage_names()
+    dpos = torch.from_numpy(pos).cuda()
+    lines = []
+
+    def report(stage, what, got, ref):
+        ref = np.asarray(ref, dtype=np.float64)
+        got = np.asarray(got, dtype=np.float64).reshape(ref.shape)
+        err = np.abs(got - ref).max() if ref.size else 0.0
+        mag = np.abs(ref).max() if ref.size else 0.0
+        rel = err / mag if mag > 0 else err
+        flag = "  <<<<<<" if (not np.isfinite(err)) or rel > 2e-3 else ""
+        lines.append(f"{stage:16s} {what:14s} maxabs {err:10.3e}  ref {mag:10.3e}  rel {rel:9.2e}{flag}")
+
+    def rd(name, layer, shape):
+        return eng.debug_read(name, layer, shape)
+
+    def cat(*xs):
+        return np.concatenate(xs, axis=-1)
+
+    for si, st in enumerate(names):
+        eng.debug_run(dpos.data_ptr(), si + 1)
+        if st == "nbr_build":
+            s2, d2 = eng.get_edges()
+            lines.append(f"{st:16s} neighbour list identical: {bool((s2 == slots).all() and (d2 == deg).all())}")
+        elif st == "rowptr_scan":
+            rp = rd("rowptr", 0, (N + 1,)).view(np.int32)
+            lines.append(f"{st:16s} rowptr ok: {bool((rp == np.concatenate([[0], np.cumsum(deg)])).all())}")
+        elif st == "edge_geom":
+            ge = rd("geom", 0, (N * 32, 8))[:E]
+            report(st, "r", ge[:, 0], S["r"]); report(st, "C", ge[:, 1], S["C"]); report(st, "d", ge[:, 2:5], S["d"])
+            report(st, "rbf", rd("rbf", 0, (N * 32, 32))[:E], S["rbf"])
+            es, ed = rd("esrc", 0, (N * 32,)).view(np.int32)[:E], rd("edst", 0, (N * 32,)).view(np.int32)[:E]
+            lines.append(f"{st:16s} edge_index ok: {bool((es == ei[0].numpy()).all() and (ed == ei[1].numpy()).all())}")
+        elif st == "embed_node":
+            report(st, "x_emb", rd("X", 0, (N, D)), S["x_emb"])
+        elif st == "embed_edge":
+            report(st, "f0", rd("F", 0, (N * 32, D))[:E], S["f_in0"])
+        elif st.startswith("node_fwd"):
+            k = int(st[8:])
+            if k >= 1:
+                report(st, f"x_in{k}", rd("X", k, (N, D)), S[f"x_in{k}"] if k < L else S["x_out"])
+                report(st, f"vec_in{k}", rd("V", k, (N, 3, D)), S[f"vec_in{k}"] if k < L else S["vec_out"])
+                report(st, f"o{k-1}", rd("O", k - 1, (N, 3 * D)), S[f"o{k-1}"])
+            if k < L:
+                report(st, "vn", rd("VN", k, (N, 3, D)), S[f"vn{k}"])
+                report(st, "qkv", rd("QKV", k, (N, 3 * D)), cat(S[f"q{k}"], S[f"k{k}"], S[f"v{k}"]))
+                report(st, "v123", rd("V123", k, (N, 3, 3 * D)), cat(S[f"v1{k}"], S[f"v2{k}"], S[f"v3{k}"]))
+                report(st, "vdot", rd("VDOT", k, (N, D)), S[f"vdot{k}"])
+                if k < L - 1:
+                    report(st, "tu", rd("TU", k, (N, 3, 2 * D)), cat(S[f"t{k}"], S[f"u{k}"]))
+        elif st.startswith("edge_fwd"):
+            l = int(st[8:])
+            report(st, "xa", rd("XA", 0, (N, D)), S[f"xa{l}"])
+            report(st, "va", rd("VA", 0, (N, 3, D)), S[f"va{l}"])
+            if l < L - 1:
+                report(st, f"f_in{l+1}", rd("F", l + 1, (N * 32, D))[:E], S[f"f_in{l+1}"])
+        elif st == "head":
+            report(st, "e_atom", rd("eatom", 0, (N,)), S["e_atom"][:, 0])
+            report(st, "gx_out", rd("GX", 0, (N, D)), B["gx_out"])
+            report(st, "gvec_out", rd("GVEC", 0, (N, 3, D)), B["gvec_out"])
+        elif st == "energy_reduce":
+            report(st, "E", rd("energy", 0, (eng.n_graphs,)), S["E"][:, 0])
+        elif st.startswith("node_bwd"):
+            k = int(st[8:])
+            if k <= L - 1:
+                report(st, f"gx_in{k}", rd("GX", 0, (N, D)), B[f"gx_in{k}"])
+                report(st, f"gvec_in{k}", rd("GVEC", 0, (N, 3, D)), B[f"gvec_in{k}"])
+            if k >= 1:
+                report(st, f"g_xa{k-1}", rd("GXA", 0, (N, D)), B[f"g_xa{k-1}"])
+        elif st.startswith("edge_bwd"):
+            l = int(st[8:])
+            report(st, f"gf_in{l}", rd("GF", 0, (N * 32, D))[:E], B[f"gf_in{l}"])
+            report(st, "g_qkv", rd("GQKV", 0, (N, 3 * D)), cat(B[f"g_q{l}"], B[f"g_k{l}"], B[f"g_v{l}"]))
+            report(st, "g_vn_msg", rd("GVNMSG", 0, (N, 3, D)), B[f"g_vn_msg{l}"])
+            if l < L - 1:
+                report(st, "g_tu", rd("GTU", 0, (N, 3, 2 * D)), cat(B[f"g_t{l}"], B[f"g_u{l}"]))
+        elif st == "embed_edge_bwd":
+            report(st, "gx_emb", rd("GX", 0, (N, D)), B["gx_emb"])
+        elif st == "embed_node_bwd":
+            ea = rd("eacc", 0, (N * 32, 4))[:E]
+            report(st, "g_d", ea[:, 1:4] * S["mask"][:, None], B["g_d"] * S["mask"][:, None])
+            report(st, "forces", rd("forces", 0, (N, 3)), B["forces"])
+    # full evaluation through the public host entry
+    e, f = eng.forward_host(pos)
+    report("forward_host", "E", e, S["E"][:, 0])
+    report("forward_host", "forces", f, B["forces"])
+    text = "\n".join(lines)
+    print(text)
+    if args.out:
+        os.makedirs(os.path.dirname(args.out), exist_ok=True)
+        with open(args.out, "w") as fh:
+            fh.write(text + "\n")
+
+
+if __name__ == "__main__":
+    main()
