@@ -206,10 +206,12 @@ struct Launcher {
     int count = 0;
     bool record_names;
     cudaError_t status = cudaSuccess;
+    std::vector<cudaEvent_t>* events = nullptr;   // optional: one event recorded before every stage
 
     bool next(const char* name) {
         if (record_names) h->stage_names.push_back(name);
         if (limit >= 0 && count >= limit) return false;
+        if (events && count < (int)events->size()) cudaEventRecord((*events)[count], st);
         count++;
         return true;
     }
@@ -644,6 +646,40 @@ int vb_debug_run(vb_handle* h, const float* pos_dev, int n_stages) {
     if (Lc.status != cudaSuccess) { h->set_error("debug launch failed: %s", cudaGetErrorString(Lc.status)); return VB_ERR_CUDA; }
     CUDA_TRY(h, cudaStreamSynchronize(h->own_stream));
     return VB_OK;
+}
+
+int vb_profile_stages(vb_handle* h, const float* pos_dev, int n_iter, float* ms_per_stage_host) {
+    if (!h) return VB_ERR_ARG;
+    std::lock_guard<std::mutex> lk(h->mu);
+    if (!h->has_topology || !pos_dev || !ms_per_stage_host || n_iter <= 0) { h->set_error("vb_profile_stages: bad state/arguments"); return VB_ERR_STATE; }
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    const int ns = (int)h->stage_names.size();
+    std::vector<cudaEvent_t> ev(ns + 1);
+    for (auto& e : ev) CUDA_TRY(h, cudaEventCreate(&e));
+    std::vector<double> acc(ns, 0.0);
+    CUDA_TRY(h, cudaMemcpy(h->d_pos, pos_dev, sizeof(float) * 3 * h->ws.N, cudaMemcpyDeviceToDevice));
+    int rc = VB_OK;
+    for (int it = 0; it < n_iter + 1 && rc == VB_OK; it++) {      // iteration 0 is an untimed warm-up
+        Launcher Lc{h, h->own_stream, -1, 0, false};
+        Lc.events = &ev;
+        enqueue_all(Lc);
+        cudaEventRecord(ev[ns], h->own_stream);
+        if (Lc.status != cudaSuccess || cudaStreamSynchronize(h->own_stream) != cudaSuccess) {
+            h->set_error("vb_profile_stages: launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+            rc = VB_ERR_CUDA;
+            break;
+        }
+        if (it == 0) continue;
+        for (int s = 0; s < ns; s++) {
+            float ms = 0.f;
+            cudaEventElapsedTime(&ms, ev[s], ev[s + 1]);
+            acc[s] += ms;
+        }
+    }
+    for (auto& e : ev) cudaEventDestroy(e);
+    if (rc == VB_OK)
+        for (int s = 0; s < ns; s++) ms_per_stage_host[s] = (float)(acc[s] / n_iter);
+    return rc;
 }
 
 int64_t vb_debug_read(vb_handle* h, const char* name, int layer, void* host_dst, int64_t cap_bytes) {

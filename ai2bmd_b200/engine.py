@@ -27,7 +27,7 @@ class _HParams(C.Structure):
 EXPORTED_SYMBOLS = [
     "vb_weight_manifest", "vb_create", "vb_destroy", "vb_last_error", "vb_set_topology", "vb_forward",
     "vb_forward_host", "vb_set_protein_map", "vb_forward_protein", "vb_get_edges", "vb_launches_per_forward",
-    "vb_set_option", "vb_num_stages", "vb_stage_name", "vb_debug_run", "vb_debug_read",
+    "vb_set_option", "vb_num_stages", "vb_stage_name", "vb_debug_run", "vb_debug_read", "vb_profile_stages",
 ]
 
 
@@ -72,6 +72,8 @@ def load_library(path: Optional[str] = None):
     lib.vb_stage_name.argtypes = [vp, C.c_int]
     lib.vb_debug_run.restype = C.c_int
     lib.vb_debug_run.argtypes = [vp, vp, C.c_int]
+    lib.vb_profile_stages.restype = C.c_int
+    lib.vb_profile_stages.argtypes = [vp, vp, C.c_int, vp]
     lib.vb_debug_read.restype = i64
     lib.vb_debug_read.argtypes = [vp, C.c_char_p, C.c_int, vp, i64]
     if path == _build.LIB_PATH:
@@ -177,6 +179,13 @@ class Engine:
 
     def debug_run(self, pos_ptr: int, n_stages: int):
         self._check(self.lib.vb_debug_run(self.h, pos_ptr, int(n_stages)), "vb_debug_run")
+
+    def profile_stages(self, pos_ptr: int, n_iter: int = 5):
+        """[(stage name, ms)] -- per-launch device time measured with CUDA events inside the library."""
+        names = self.stage_names()
+        ms = np.zeros(len(names), dtype=np.float32)
+        self._check(self.lib.vb_profile_stages(self.h, pos_ptr, int(n_iter), ms.ctypes.data), "vb_profile_stages")
+        return list(zip(names, ms.tolist()))
 
     def debug_read(self, name: str, layer: int, shape, dtype=np.float32) -> np.ndarray:
         out = np.empty(shape, dtype=dtype)

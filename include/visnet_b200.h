@@ -93,6 +93,9 @@ int vb_num_stages(const vb_handle* h);
 const char* vb_stage_name(const vb_handle* h, int stage);
 /* Run only the first n_stages launches of an evaluation, synchronously (no graph). */
 int vb_debug_run(vb_handle* h, const float* pos_dev, int n_stages);
+/* Per-launch device time (ms, CUDA events on the launching stream, average of n_iter eager evaluations after
+ * one warm-up) for each of the vb_num_stages() launches; used by bench.py for the live roofline numbers. */
+int vb_profile_stages(vb_handle* h, const float* pos_dev, int n_iter, float* ms_per_stage_host);
 /* Copy an internal buffer to the host.  name: "X","V","F","VN","QKV","V123","VDOT","TU","O" (per layer),
  * "XA","VA","GX","GVEC","GF","GXA","GQKV","GVNMSG","GTU","geom","rbf","eacc","grbf","esrc","edst","rowptr",
  * "eatom","energy","forces".  Returns the number of bytes copied (<= cap_bytes) or a negative status. */

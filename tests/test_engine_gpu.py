@@ -1,0 +1,269 @@
+"""Parity of the CUDA engine (through the C ABI) with the oracle and the committed golden vectors.
+
+Stated tolerances (fp32 end to end; the reference's own scatter atomics are order-nondeterministic at this
+level, and the fp32 oracle itself sits 3e-3 eV / 9e-6 eV/A from the fp64 anchor on these inputs):
+  neighbour lists  bit-exact
+  energy/fragment  |dE| <= max(4e-3 eV, 2 ulp(E))
+  forces           |dF| <= 5e-5 eV/A + 2e-5 * max|F|
+"""
+import numpy as np
+import pytest
+import torch
+
+from ai2bmd_b200.calculator import DLBondedCalculator, DipeptideBondedCombiner, ViSNetCalculator, ViSNetModel
+from ai2bmd_b200.engine import Engine
+from ai2bmd_b200.fixtures import load_fragments
+from ai2bmd_b200.fragment_data import FragmentData
+from ai2bmd_b200.parallel import combine_local
+from ai2bmd_b200.pdbfrag import single_graph
+from ai2bmd_b200.synth import synthetic_batch, synthetic_protein_map
+from oracle import visnet_ref as O
+
+pytestmark = pytest.mark.gpu
+
+
+def e_tol(e):
+    return np.maximum(4e-3, 2 * np.spacing(np.abs(e).astype(np.float32)))
+
+
+def f_tol(f):
+    return 5e-5 + 2e-5 * np.abs(f).max()
+
+
+@pytest.fixture(scope="module")
+def model(real_weights):
+    return ViSNetModel(real_weights, device="cuda:0")
+
+
+def _case(r, key):
+    z, pos, batch = r[f"{key}_z"], r[f"{key}_pos"], r[f"{key}_batch"]
+    g = int(batch.max()) + 1
+    start = np.searchsorted(batch, np.arange(g))
+    end = np.searchsorted(batch, np.arange(g), side="right")
+    return FragmentData(z, pos, start, end, batch)
+
+
+@pytest.mark.parametrize("name", ["chig", "trpcage", "ww", "abd"])
+def test_neighbour_list_bit_exact(model, name):
+    fd, _ = load_fragments(name)
+    model.dl_potential_loader(fd)
+    slots, deg = model.engine.get_edges()
+    s_ref, d_ref = O.radius_graph_canonical(fd.pos, fd.batch)
+    assert np.array_equal(deg, d_ref)
+    assert np.array_equal(slots, s_ref)
+
+
+def test_neighbour_cap_32_bit_exact(model, reference_outputs):
+    fd = _case(reference_outputs, "dense44")
+    model.dl_potential_loader(fd)
+    slots, deg = model.engine.get_edges()
+    assert np.array_equal(slots, reference_outputs["dense44_slots"]) and deg.max() == 32
+
+
+@pytest.mark.parametrize("key", ["c1_ala", "chig", "trpcage"])
+def test_parity_with_reference_golden_vectors(model, reference_outputs, key):
+    """Golden vectors were produced by the reference's own model source (tests/golden/make_golden.py)."""
+    r = reference_outputs
+    e, f = model.dl_potential_loader(_case(r, key))
+    assert e.shape == r[f"{key}_ref_e"].shape and f.shape == r[f"{key}_ref_f"].shape
+    assert e.dtype == np.float32 and f.dtype == np.float32
+    assert (np.abs(e - r[f"{key}_ref_e"]) <= e_tol(r[f"{key}_ref_e"])).all()
+    assert np.abs(f - r[f"{key}_ref_f"]).max() <= f_tol(r[f"{key}_ref_f"])
+    # and against the fp64 anchor
+    assert (np.abs(e - r[f"{key}_e64"]) <= e_tol(r[f"{key}_e64"])).all()
+    assert np.abs(f - r[f"{key}_f64"]).max() <= f_tol(r[f"{key}_f64"])
+
+
+def test_parity_dense_fragment(model, reference_outputs):
+    """Over-dense random fragment (deg capped at 32, forces O(1e2)): relative tolerance only."""
+    r = reference_outputs
+    e, f = model.dl_potential_loader(_case(r, "dense44"))
+    assert np.abs(f - r["dense44_f64"]).max() <= 2e-5 * np.abs(r["dense44_f64"]).max() + 5e-5
+    assert np.abs(e - r["dense44_e64"]).max() <= 2e-6 * np.abs(r["dense44_e64"]).max() + 4e-3
+
+
+@pytest.mark.parametrize("seed", [0, 7])
+def test_parity_random_weights(seed, chig):
+    fd, _ = chig
+    sub = fd[0:6]
+    sd = O.random_state_dict(seed)
+    oracle = O.OracleViSNet(sd, torch.float64)
+    e_ref, f_ref = oracle.energy_and_forces(sub.z, sub.pos, sub.batch)
+    m = ViSNetModel({k: v.numpy() for k, v in sd.items()}, device="cuda:0")
+    e, f = m.dl_potential_loader(sub)
+    assert (np.abs(e - e_ref.numpy()) <= e_tol(e_ref.numpy())).all()
+    assert np.abs(f - f_ref.numpy()).max() <= f_tol(f_ref.numpy())
+
+
+def test_edge_cases_tiny_graphs(real_weights):
+    """A single-atom graph (self-loop only), a 3-atom graph, and two atoms beyond the cutoff."""
+    z = np.array([8, 8, 1, 1, 6, 6], dtype=np.int64)
+    pos = np.array([[0, 0, 0], [10, 0, 0], [10.76, 0.59, 0], [9.24, 0.59, 0], [20, 0, 0], [26, 0, 0]], np.float32)
+    batch = np.array([0, 1, 1, 1, 2, 2], dtype=np.int64)
+    fd = FragmentData(z, pos, np.array([0, 1, 4]), np.array([1, 4, 6]), batch)
+    oracle = O.OracleViSNet({k: torch.from_numpy(v) for k, v in real_weights.items()}, torch.float64)
+    e_ref, f_ref = oracle.energy_and_forces(z, pos, batch)
+    e, f = ViSNetModel(real_weights, device="cuda:0").dl_potential_loader(fd)
+    assert np.isfinite(e).all() and np.isfinite(f).all()
+    assert (np.abs(e - e_ref.numpy()) <= e_tol(e_ref.numpy())).all()
+    assert np.abs(f - f_ref.numpy()).max() <= f_tol(f_ref.numpy())
+    assert np.abs(f[0]).max() == 0 and np.abs(f[4:]).max() == 0      # isolated atoms feel no force
+
+
+def test_batch_composition_independence(model, chig):
+    fd, _ = chig
+    e_all, f_all = model.dl_potential_loader(fd)
+    sub = fd[3:7]
+    e_sub, f_sub = model.dl_potential_loader(sub)
+    a0, a1 = fd.start[3], fd.end[6]
+    assert (np.abs(e_all[3:7] - e_sub) <= e_tol(e_sub)).all()
+    assert np.abs(f_all[a0:a1] - f_sub).max() <= 2e-5
+
+
+def test_graph_replay_equals_eager_and_tile_variants(real_weights, chig):
+    fd, _ = chig
+    eng = Engine(real_weights, 0)
+    eng.set_topology(fd.z, fd.batch)
+    e0, f0 = eng.forward_host(fd.pos)
+    e1, f1 = eng.forward_host(fd.pos)                 # graph replay
+    assert np.abs(f0 - f1).max() <= 1e-5 and np.abs(e0 - e1).max() <= 2e-3
+    for key, val in (("use_graph", 0), ("te_fwd", 64), ("te_bwd", 64), ("npw", 2)):
+        eng.set_option(key, val)
+        e2, f2 = eng.forward_host(fd.pos)
+        assert np.abs(f0 - f2).max() <= 2e-5 and (np.abs(e0 - e2) <= e_tol(e0)).all(), key
+    assert eng.launches_per_forward >= 30
+
+
+def test_device_pointer_entry_point(real_weights, chig):
+    fd, pm = chig
+    eng = Engine(real_weights, 0)
+    eng.set_topology(fd.z, fd.batch)
+    e_h, f_h = eng.forward_host(fd.pos)
+    pos = torch.from_numpy(fd.pos).cuda()
+    e = torch.empty(len(fd), device="cuda")
+    f = torch.empty(len(fd.z), 3, device="cuda")
+    eng.forward_device(pos.data_ptr(), e.data_ptr(), f.data_ptr(), torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    assert np.abs(e.cpu().numpy() - e_h).max() <= 2e-3 and np.abs(f.cpu().numpy() - f_h).max() <= 1e-5
+    # whole-protein reduction on the device == host restatement of the reference combiner
+    eng.set_protein_map(pm.n_protein, pm.src_atom, pm.dst_atom, pm.sign, pm.frag_sign)
+    ef = torch.empty(3 * pm.n_protein + 1, device="cuda")
+    eng.forward_protein_device(pos.data_ptr(), ef.data_ptr(), torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    ref = combine_local(pm, e_h, f_h)
+    assert np.abs(ef.cpu().numpy()[:-1] - ref[:-1]).max() <= 2e-5
+    assert abs(float(ef[-1]) - float(ref[-1])) <= 2e-2
+
+
+def test_bonded_calculator_surface(real_weights, chig, golden_dir):
+    import os
+    fd, pm = chig
+    calc = DLBondedCalculator(os.path.join(golden_dir, "weights_2ef43f29.npz"))
+    dip_e, dip_f, an_e, an_f = calc.calculate(fd)
+    assert dip_e.shape == (10, 1) and an_e.shape == (9, 1) and dip_f.shape[0] + an_f.shape[0] == 391
+    vd, va = fd.vector_split()
+    order = np.concatenate([np.flatnonzero(vd), np.flatnonzero(va)])
+    inv = np.empty_like(order)
+    inv[order] = np.arange(len(order))
+    F = DipeptideBondedCombiner.forces_combine(pm.n_protein, dip_f, an_f, inv[pm.src_atom], pm.dst_atom)
+    assert F.shape == (175, 3) and np.isfinite(F).all()
+    assert np.abs(F.sum(0)).max() < 5e-3            # net force on the protein vanishes (translation invariance)
+
+
+def test_unfragmented_calculator_ase_semantics(real_weights, reference_outputs, golden_dir):
+    import os
+    r = reference_outputs
+
+    class Atoms:
+        numbers = r["c1_ala_z"]
+        positions = r["c1_ala_pos"].astype(np.float64)
+
+    calc = ViSNetCalculator(os.path.join(golden_dir, "weights_2ef43f29.npz"), "", device="cuda:0")
+    e = calc.get_potential_energy(Atoms)
+    f = calc.get_forces(Atoms)                       # second property: served from the cache
+    assert e.shape == (1, 1) and f.shape == (22, 3)
+    assert np.abs(f - r["c1_ala_ref_f"]).max() <= f_tol(r["c1_ala_ref_f"])
+
+
+def test_errors_are_loud(real_weights, chig):
+    fd, _ = chig
+    eng = Engine(real_weights, 0)
+    buf = np.zeros((len(fd.z), 3), np.float32)
+    with pytest.raises(RuntimeError, match="vb_set_topology"):
+        eng._check(eng.lib.vb_forward_host(eng.h, buf.ctypes.data, buf.ctypes.data, buf.ctypes.data), "vb_forward_host")
+    with pytest.raises(RuntimeError, match="sorted"):
+        eng.set_topology(fd.z, fd.batch[::-1].copy())
+    eng.set_topology(fd.z, fd.batch)
+    with pytest.raises(ValueError):
+        eng.forward_host(fd.pos[:-1])
+
+
+# ---- full-size properties (config C4: 512 fragments, ~14k atoms): no oracle needed -------------------
+@pytest.fixture(scope="module")
+def c4(real_weights):
+    fd = synthetic_batch(512, seed=0)
+    eng = Engine(real_weights, 0)
+    eng.set_topology(fd.z, fd.batch)
+    e, f = eng.forward_host(fd.pos)
+    return fd, eng, e, f
+
+
+def test_fullsize_forces_sum_to_zero_per_fragment(c4):
+    fd, eng, e, f = c4
+    assert np.isfinite(e).all() and np.isfinite(f).all()
+    net = np.zeros((len(fd), 3))
+    np.add.at(net, fd.batch, f.astype(np.float64))
+    assert np.abs(net).max() <= 1e-3                  # translation invariance of every fragment energy
+    tq = np.zeros((len(fd), 3))
+    np.add.at(tq, fd.batch, np.cross(fd.pos.astype(np.float64), f.astype(np.float64)))
+    assert np.abs(tq).max() <= 1e-2                   # rotation invariance (no net torque)
+
+
+def test_fullsize_rigid_motion_equivariance(c4):
+    fd, eng, e, f = c4
+    rng = np.random.default_rng(5)
+    q, _ = np.linalg.qr(rng.normal(size=(3, 3)))
+    if np.linalg.det(q) < 0:
+        q[:, 0] *= -1
+    pos2 = (fd.pos.astype(np.float64) @ q.T + np.array([3.0, -2.0, 1.0])).astype(np.float32)
+    e2, f2 = eng.forward_host(pos2)
+    assert (np.abs(e2 - e) <= 3 * e_tol(e)).all()
+    assert np.abs(f2 - f @ q.T.astype(np.float32)).max() <= 3e-4      # fp32 positions re-rounded after the rotation
+
+
+def test_fullsize_fragment_order_independence(c4, real_weights):
+    fd, eng, e, f = c4
+    perm = np.random.default_rng(6).permutation(len(fd))
+    z, pos, batch, sizes = [], [], [], []
+    for g_new, g in enumerate(perm):
+        s, t = int(fd.start[g]), int(fd.end[g])
+        z.append(fd.z[s:t]); pos.append(fd.pos[s:t]); batch.append(np.full(t - s, g_new)); sizes.append(t - s)
+    eng2 = Engine(real_weights, 0)
+    eng2.set_topology(np.concatenate(z), np.concatenate(batch))
+    e2, f2 = eng2.forward_host(np.concatenate(pos))
+    assert (np.abs(e2 - e[perm]) <= e_tol(e[perm])).all()
+    offs = np.concatenate([[0], np.cumsum(sizes)])
+    for g_new, g in enumerate(perm[:64]):
+        assert np.abs(f2[offs[g_new]:offs[g_new + 1]] - f[fd.start[g]:fd.end[g]]).max() <= 3e-5
+
+
+def test_fullsize_subset_matches_oracle(c4, real_weights):
+    fd, eng, e, f = c4
+    sub = fd[100:104]
+    oracle = O.OracleViSNet({k: torch.from_numpy(v) for k, v in real_weights.items()}, torch.float64)
+    e_ref, f_ref = oracle.energy_and_forces(sub.z, sub.pos, sub.batch)
+    a0, a1 = fd.start[100], fd.end[103]
+    assert (np.abs(e[100:104] - e_ref.numpy()[:, 0]) <= e_tol(e_ref.numpy()[:, 0])).all()
+    assert np.abs(f[a0:a1] - f_ref.numpy()).max() <= f_tol(f_ref.numpy())
+
+
+def test_protein_reduction_fullsize(c4):
+    fd, eng, e, f = c4
+    pm = synthetic_protein_map(fd)
+    eng.set_protein_map(pm.n_protein, pm.src_atom, pm.dst_atom, pm.sign, pm.frag_sign)
+    pos = torch.from_numpy(fd.pos).cuda()
+    ef = torch.empty(3 * pm.n_protein + 1, device="cuda")
+    eng.forward_protein_device(pos.data_ptr(), ef.data_ptr(), torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    ref = combine_local(pm, e, f)
+    assert np.abs(ef.cpu().numpy()[:-1] - ref[:-1]).max() <= 5e-5
