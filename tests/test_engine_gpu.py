@@ -3,7 +3,8 @@
 Stated tolerances (fp32 end to end; the reference's own scatter atomics are order-nondeterministic at this
 level, and the fp32 oracle itself sits 3e-3 eV / 9e-6 eV/A from the fp64 anchor on these inputs):
   neighbour lists  bit-exact
-  energy/fragment  |dE| <= max(4e-3 eV, 2 ulp(E))
+  energy/fragment  |dE| <= max(4e-3 eV, 2 ulp(E)) against the fp64 anchor; 4 ulp(E) against fp32 golden vectors
+                   (both sides carry their own fp32 rounding of an O(2e4 eV) sum; 1 ulp = 2e-3 eV there)
   forces           |dF| <= 5e-5 eV/A + 2e-5 * max|F|
 """
 import numpy as np
@@ -22,8 +23,8 @@ from oracle import visnet_ref as O
 pytestmark = pytest.mark.gpu
 
 
-def e_tol(e):
-    return np.maximum(4e-3, 2 * np.spacing(np.abs(e).astype(np.float32)))
+def e_tol(e, ulps=2):
+    return np.maximum(4e-3, ulps * np.spacing(np.abs(e).astype(np.float32)))
 
 
 def f_tol(f):
@@ -67,7 +68,7 @@ def test_parity_with_reference_golden_vectors(model, reference_outputs, key):
     e, f = model.dl_potential_loader(_case(r, key))
     assert e.shape == r[f"{key}_ref_e"].shape and f.shape == r[f"{key}_ref_f"].shape
     assert e.dtype == np.float32 and f.dtype == np.float32
-    assert (np.abs(e - r[f"{key}_ref_e"]) <= e_tol(r[f"{key}_ref_e"])).all()
+    assert (np.abs(e - r[f"{key}_ref_e"]) <= e_tol(r[f"{key}_ref_e"], ulps=4)).all()
     assert np.abs(f - r[f"{key}_ref_f"]).max() <= f_tol(r[f"{key}_ref_f"])
     # and against the fp64 anchor
     assert (np.abs(e - r[f"{key}_e64"]) <= e_tol(r[f"{key}_e64"])).all()
