@@ -13,6 +13,7 @@
 
 #include "../../include/visnet_b200.h"
 #include "k_edge.cuh"
+#include "k_edge_tc.cuh"
 #include "k_graph_embed.cuh"
 #include "k_head.cuh"
 #include "k_node.cuh"
@@ -680,6 +681,33 @@ int vb_profile_stages(vb_handle* h, const float* pos_dev, int n_iter, float* ms_
     if (rc == VB_OK)
         for (int s = 0; s < ns; s++) ms_per_stage_host[s] = (float)(acc[s] / n_iter);
     return rc;
+}
+
+int vb_tc_selftest(int device, const float* a_host, const float* img_host, float* d_host, int reps, float* ms_out) {
+    // D[128][128] = A[128][128] * W^T through the tcgen05/TMEM/TMA pipeline of the tensor-core edge kernels.
+    if (!a_host || !img_host || !d_host || reps <= 0) return VB_ERR_ARG;
+    if (cudaSetDevice(device) != cudaSuccess) { g_create_error = "vb_tc_selftest: cudaSetDevice failed"; return VB_ERR_CUDA; }
+    float *dA = nullptr, *dI = nullptr, *dD = nullptr;
+    const size_t nA = (size_t)TC_TE * D * sizeof(float), nI = (size_t)(D / tc::SLAB_K) * tc::STAGE_BYTES;
+    cudaMalloc(&dA, nA); cudaMalloc(&dI, nI); cudaMalloc(&dD, nA);
+    cudaMemcpy(dA, a_host, nA, cudaMemcpyHostToDevice);
+    cudaMemcpy(dI, img_host, nI, cudaMemcpyHostToDevice);
+    cudaMemset(dD, 0, nA);
+    cudaFuncSetAttribute(tc_selftest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TcShared) + 1024);
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    cudaEventRecord(e0);
+    tc_selftest_kernel<<<1, TC_THREADS, sizeof(TcShared) + 1024>>>(dA, dI, dD, reps);
+    cudaEventRecord(e1);
+    cudaError_t err = cudaDeviceSynchronize();
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    if (ms_out) *ms_out = ms;
+    if (err == cudaSuccess) err = cudaMemcpy(d_host, dD, nA, cudaMemcpyDeviceToHost);
+    cudaFree(dA); cudaFree(dI); cudaFree(dD);
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    if (err != cudaSuccess) { g_create_error = std::string("vb_tc_selftest: ") + cudaGetErrorString(err); return VB_ERR_CUDA; }
+    return VB_OK;
 }
 
 int64_t vb_debug_read(vb_handle* h, const char* name, int layer, void* host_dst, int64_t cap_bytes) {

@@ -27,7 +27,7 @@ class _HParams(C.Structure):
 EXPORTED_SYMBOLS = [
     "vb_weight_manifest", "vb_create", "vb_destroy", "vb_last_error", "vb_set_topology", "vb_forward",
     "vb_forward_host", "vb_set_protein_map", "vb_forward_protein", "vb_get_edges", "vb_launches_per_forward",
-    "vb_set_option", "vb_num_stages", "vb_stage_name", "vb_debug_run", "vb_debug_read", "vb_profile_stages",
+    "vb_set_option", "vb_num_stages", "vb_stage_name", "vb_debug_run", "vb_debug_read", "vb_profile_stages", "vb_tc_selftest",
 ]
 
 
@@ -74,6 +74,8 @@ def load_library(path: Optional[str] = None):
     lib.vb_debug_run.argtypes = [vp, vp, C.c_int]
     lib.vb_profile_stages.restype = C.c_int
     lib.vb_profile_stages.argtypes = [vp, vp, C.c_int, vp]
+    lib.vb_tc_selftest.restype = C.c_int
+    lib.vb_tc_selftest.argtypes = [C.c_int, vp, vp, vp, C.c_int, vp]
     lib.vb_debug_read.restype = i64
     lib.vb_debug_read.argtypes = [vp, C.c_char_p, C.c_int, vp, i64]
     if path == _build.LIB_PATH:
@@ -194,3 +196,17 @@ class Engine:
         if n != out.nbytes:
             raise RuntimeError(f"vb_debug_read({name}): got {n} bytes, wanted {out.nbytes}")
         return out
+
+
+def tc_selftest(a: np.ndarray, w_nk: np.ndarray, reps: int = 1, device: int = 0):
+    """Run D = A @ W^T (A [128,128], W [128 out,128 in]) through the tcgen05 pipeline; returns (D, ms)."""
+    from .weights import tc_image
+    lib = load_library()
+    a = np.ascontiguousarray(a, dtype=np.float32)
+    img = tc_image(w_nk)
+    d = np.zeros((128, 128), dtype=np.float32)
+    ms = C.c_float(0)
+    rc = lib.vb_tc_selftest(int(device), a.ctypes.data, img.ctypes.data, d.ctypes.data, int(reps), C.byref(ms))
+    if rc != 0:
+        raise RuntimeError(f"vb_tc_selftest failed ({rc}): {lib.vb_last_error(None).decode()}")
+    return d, float(ms.value)

@@ -98,3 +98,31 @@ def pack_weights(sd: Dict[str, np.ndarray], manifest: str) -> np.ndarray:
             raise ValueError(f"weight {name}: have {a.size} values, manifest wants {count}")
         parts.append(a)
     return np.concatenate(parts)
+
+
+# ---- tensor-core weight images (tcgen05 path) -------------------------------------------------------------
+def round_tf32(x: np.ndarray) -> np.ndarray:
+    """Round-to-nearest (ties away) to tf32: keep 10 explicit mantissa bits (PTX ``cvt.rna.tf32.f32``)."""
+    b = np.ascontiguousarray(x, dtype=np.float32).view(np.uint32)
+    return ((b + np.uint32(0x1000)) & np.uint32(0xFFFFE000)).view(np.float32)
+
+
+def tc_image(w_nk: np.ndarray) -> np.ndarray:
+    """Shared-memory image of a GEMM chunk for ``tcgen05.mma`` (B operand, K-major, SWIZZLE_128B).
+
+    ``w_nk`` is [128 output columns][K] (K multiple of 32): D[m][n] = sum_k A[m][k] * w_nk[n][k].
+    Output: for every K-slab of 32 a 16 KB "hi" plane then a 16 KB "lo" plane (3xTF32 split); inside a plane
+    row n occupies bytes [n*128, n*128+128) and its 16-byte chunk c sits at chunk position c ^ (n & 7)."""
+    w = np.ascontiguousarray(w_nk, dtype=np.float32)
+    n, k = w.shape
+    assert n == 128 and k % 32 == 0
+    hi = round_tf32(w)
+    lo = round_tf32(w - hi)
+    rows = np.arange(128)
+    out = np.empty((k // 32, 2, 128, 8, 4), dtype=np.float32)
+    for s in range(k // 32):
+        for p, plane in enumerate((hi, lo)):
+            blk = plane[:, s * 32:(s + 1) * 32].reshape(128, 8, 4)
+            for c in range(8):
+                out[s, p, rows, c ^ (rows & 7), :] = blk[:, c, :]
+    return out.reshape(-1)

@@ -96,6 +96,9 @@ int vb_debug_run(vb_handle* h, const float* pos_dev, int n_stages);
 /* Per-launch device time (ms, CUDA events on the launching stream, average of n_iter eager evaluations after
  * one warm-up) for each of the vb_num_stages() launches; used by bench.py for the live roofline numbers. */
 int vb_profile_stages(vb_handle* h, const float* pos_dev, int n_iter, float* ms_per_stage_host);
+/* Self-test of the tcgen05/TMEM/TMA GEMM pipeline: d[128][128] = a[128][128] * W^T, W given as a tensor-core
+ * weight image (ai2bmd_b200.weights.tc_image); repeated `reps` times inside one launch; *ms_out = kernel time. */
+int vb_tc_selftest(int device, const float* a_host, const float* img_host, float* d_host, int reps, float* ms_out);
 /* Copy an internal buffer to the host.  name: "X","V","F","VN","QKV","V123","VDOT","TU","O" (per layer),
  * "XA","VA","GX","GVEC","GF","GXA","GQKV","GVNMSG","GTU","geom","rbf","eacc","grbf","esrc","edst","rowptr",
  * "eatom","energy","forces".  Returns the number of bytes copied (<= cap_bytes) or a negative status. */
