@@ -17,6 +17,7 @@
 #include "k_graph_embed.cuh"
 #include "k_head.cuh"
 #include "k_node.cuh"
+#include "k_node2.cuh"
 
 using namespace vb;
 
@@ -80,6 +81,8 @@ struct vb_handle {
     float *d_map_sign = nullptr, *d_frag_sign = nullptr;
     // options
     int use_graph = 1, npw = 0, te_fwd = 0, te_bwd = 32;
+    int node_impl = 1; // 0: warp-per-node kernels (k_node.cuh), 1: CTA-cooperative kernels (k_node2.cuh)
+    int edge_tc = 0;   // bit 0: forward edge stage on tcgen05, bit 1: adjoint edge stage on tcgen05
     // graph cache
     cudaGraphExec_t graph_exec = nullptr;
     int launches = 0;
@@ -263,10 +266,49 @@ void launch_edge_bwd(Launcher& Lc, int l, int occ) {
     Lc.check();
 }
 
-void node_fwd(Launcher& Lc, int k) { Lc.h->npw == 2 ? launch_node_fwd<2>(Lc, k) : launch_node_fwd<1>(Lc, k); }
-void node_bwd(Launcher& Lc, int k) { Lc.h->npw == 2 ? launch_node_bwd<2>(Lc, k) : launch_node_bwd<1>(Lc, k); }
+template <int NB>
+void launch_node_fwd2(Launcher& Lc, int k) {
+    vb_handle* h = Lc.h;
+    NodeArgs a{k, h->mw, h->ws};
+    node_fwd2_kernel<NB><<<(h->ws.N + NB - 1) / NB, N2_THREADS, sizeof(NodeFwd2Smem<NB>), Lc.st>>>(a);
+    Lc.check();
+}
+void launch_node_bwd2(Launcher& Lc, int k) {
+    vb_handle* h = Lc.h;
+    NodeArgs a{k, h->mw, h->ws};
+    node_bwd2_kernel<8><<<(h->ws.N + 7) / 8, N2_THREADS, sizeof(NodeBwd2Smem<8>), Lc.st>>>(a);
+    Lc.check();
+}
+void node_fwd(Launcher& Lc, int k) {
+    if (Lc.h->node_impl == 1) { Lc.h->npw == 2 ? launch_node_fwd2<16>(Lc, k) : launch_node_fwd2<8>(Lc, k); return; }
+    Lc.h->npw == 2 ? launch_node_fwd<2>(Lc, k) : launch_node_fwd<1>(Lc, k);
+}
+void node_bwd(Launcher& Lc, int k) {
+    if (Lc.h->node_impl == 1) { launch_node_bwd2(Lc, k); return; }
+    Lc.h->npw == 2 ? launch_node_bwd<2>(Lc, k) : launch_node_bwd<1>(Lc, k);
+}
 void head(Launcher& Lc) { Lc.h->npw == 2 ? launch_head<2>(Lc) : launch_head<1>(Lc); }
+void launch_edge_fwd_tc(Launcher& Lc, int l) {
+    vb_handle* h = Lc.h;
+    EdgeTcArgs a{};
+    a.layer = l; a.mw = h->mw; a.ws = h->ws;
+    const LayerW& lw = h->mw.layer[l];
+    const size_t chunk = 4 * 8192;
+    int n = 0;
+    a.jobs[n++] = TcJob{lw.tcW1, (int)TC_COL_D0, 0};                       // dk
+    a.jobs[n++] = TcJob{lw.tcW1 + chunk, (int)TC_COL_D1, 0};               // dv
+    if (l < L - 1) a.jobs[n++] = TcJob{lw.tcW1 + 2 * chunk, (int)TC_COL_D0, 0};   // f
+    a.jobs[n++] = TcJob{lw.tcWs, (int)TC_COL_D1, 0};                       // s1
+    a.jobs[n++] = TcJob{lw.tcWs + chunk, (int)TC_COL_D0, 0};               // s2
+    a.njobs = n;
+    const int tiles = (h->ws.Ecap + TC_TE - 1) / TC_TE;
+    const int blocks = std::max(1, std::min(tiles, h->sm_count));
+    edge_fwd_tc_kernel<<<blocks, TC2_THREADS, TC_SMEM_BYTES, Lc.st>>>(a);
+    Lc.check();
+}
+
 void edge_fwd(Launcher& Lc, int l) {
+    if (Lc.h->edge_tc & 1) { launch_edge_fwd_tc(Lc, l); return; }
     if (Lc.h->te_fwd == 64) launch_edge_fwd<64, 8>(Lc, l, 2);
     else launch_edge_fwd<32, 8>(Lc, l, 4);
 }
@@ -331,6 +373,10 @@ int configure_kernels(vb_handle* h) {
     CUDA_TRY(h, opt_in_smem(node_bwd_kernel<2>, node_bwd_smem_bytes<2>()));
     CUDA_TRY(h, opt_in_smem(head_kernel<1>, HeadSmem<1>::BYTES));
     CUDA_TRY(h, opt_in_smem(head_kernel<2>, HeadSmem<2>::BYTES));
+    CUDA_TRY(h, opt_in_smem(edge_fwd_tc_kernel, TC_SMEM_BYTES));
+    CUDA_TRY(h, opt_in_smem(node_fwd2_kernel<8>, sizeof(NodeFwd2Smem<8>)));
+    CUDA_TRY(h, opt_in_smem(node_fwd2_kernel<16>, sizeof(NodeFwd2Smem<16>)));
+    CUDA_TRY(h, opt_in_smem(node_bwd2_kernel<8>, sizeof(NodeBwd2Smem<8>)));
     return VB_OK;
 }
 
@@ -438,6 +484,8 @@ int vb_create(const float* weights_host, size_t n_floats, const vb_hparams* hp, 
     if (const char* s = getenv("VB_NPW")) h->npw = atoi(s);
     if (const char* s = getenv("VB_TE_FWD")) h->te_fwd = atoi(s);
     if (const char* s = getenv("VB_TE_BWD")) h->te_bwd = atoi(s);
+    if (const char* s = getenv("VB_EDGE_TC")) h->edge_tc = atoi(s);
+    if (const char* s = getenv("VB_NODE_IMPL")) h->node_impl = atoi(s);
     *out = h;
     return VB_OK;
 }
@@ -625,6 +673,8 @@ int vb_set_option(vb_handle* h, const char* key, int64_t value) {
     else if (k == "npw" && (value == 1 || value == 2)) h->npw = (int)value;
     else if (k == "te_fwd" && (value == 32 || value == 64)) h->te_fwd = (int)value;
     else if (k == "te_bwd" && (value == 32 || value == 64)) h->te_bwd = (int)value;
+    else if (k == "edge_tc" && value >= 0 && value <= 3) h->edge_tc = (int)value;
+    else if (k == "node_impl" && (value == 0 || value == 1)) h->node_impl = (int)value;
     else { h->set_error("vb_set_option: unknown key or bad value: %s", key); return VB_ERR_ARG; }
     h->drop_graph();
     return VB_OK;
@@ -693,11 +743,11 @@ int vb_tc_selftest(int device, const float* a_host, const float* img_host, float
     cudaMemcpy(dA, a_host, nA, cudaMemcpyHostToDevice);
     cudaMemcpy(dI, img_host, nI, cudaMemcpyHostToDevice);
     cudaMemset(dD, 0, nA);
-    cudaFuncSetAttribute(tc_selftest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TcShared) + 1024);
+    cudaFuncSetAttribute(tc_selftest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_BYTES);
     cudaEvent_t e0, e1;
     cudaEventCreate(&e0); cudaEventCreate(&e1);
     cudaEventRecord(e0);
-    tc_selftest_kernel<<<1, TC_THREADS, sizeof(TcShared) + 1024>>>(dA, dI, dD, reps);
+    tc_selftest_kernel<<<1, TC_THREADS, TC_SMEM_BYTES>>>(dA, dI, dD, reps);
     cudaEventRecord(e1);
     cudaError_t err = cudaDeviceSynchronize();
     float ms = 0.f;

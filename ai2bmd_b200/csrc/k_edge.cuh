@@ -155,7 +155,25 @@ __global__ void __launch_bounds__(NW * 32) edge_fwd_kernel(EdgeArgs a) {
                 const int lo = max(ws.rowptr[i], e0) - e0;
                 const int hi = min(ws.rowptr[i + 1], e0 + nvalid) - e0;
                 float xa = 0.f, va0 = 0.f, va1 = 0.f, va2 = 0.f;
-                for (int e = lo; e < hi; e++) {
+                int e = lo;
+                for (; e + 4 <= hi; e += 4) {                  // 12 independent gathers in flight
+                    float g[4][3];
+#pragma unroll
+                    for (int u = 0; u < 4; u++) {
+                        const size_t j3 = (size_t)meta.src[e + u] * 3;
+                        g[u][0] = VN[(j3 + 0) * D + c]; g[u][1] = VN[(j3 + 1) * D + c]; g[u][2] = VN[(j3 + 2) * D + c];
+                    }
+#pragma unroll
+                    for (int u = 0; u < 4; u++) {
+                        const float4 dd = meta.d[e + u];
+                        const float s1 = Ss[(e + u) * LE2 + c], s2 = Ss[(e + u) * LE2 + D + c];
+                        xa += Fs[(e + u) * LE1 + c];
+                        va0 += g[u][0] * s1 + s2 * dd.x;
+                        va1 += g[u][1] * s1 + s2 * dd.y;
+                        va2 += g[u][2] * s1 + s2 * dd.z;
+                    }
+                }
+                for (; e < hi; e++) {
                     const size_t j3 = (size_t)meta.src[e] * 3;
                     const float4 dd = meta.d[e];
                     const float s1 = Ss[e * LE2 + c], s2 = Ss[e * LE2 + D + c];

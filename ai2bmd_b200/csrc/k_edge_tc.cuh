@@ -44,12 +44,19 @@ struct TcShared {
     uint32_t tmem_base;
 };
 
+// the ring must start on a 1024 B boundary of the shared window (swizzle atom): align the dynamic block by hand
+__device__ __forceinline__ TcShared* tc_shared_base(uint8_t* raw) {
+    const uint32_t s = tc::smem_u32(raw);
+    return reinterpret_cast<TcShared*>(raw + (((s + 1023u) & ~1023u) - s));
+}
+constexpr size_t TC_SMEM_BYTES = sizeof(TcShared) + 1024;
+
 // one-time CTA setup: barriers + TMEM; returns the TMEM base address
-__device__ __forceinline__ uint32_t tc_setup(TcShared& sh, int njobs) {
+__device__ __forceinline__ uint32_t tc_setup(TcShared& sh, int njobs, int go_count = TC_TE) {
     const int warp = threadIdx.x >> 5;
     if (threadIdx.x == 0) {
         for (int s = 0; s < TC_STAGES; s++) { tc::mbar_init(&sh.b_full[s], 1); tc::mbar_init(&sh.b_empty[s], 1); }
-        for (int j = 0; j < njobs; j++) { tc::mbar_init(&sh.go[j], TC_TE); tc::mbar_init(&sh.done[j], 1); }
+        for (int j = 0; j < njobs; j++) { tc::mbar_init(&sh.go[j], go_count); tc::mbar_init(&sh.done[j], 1); }
         tc::fence_barrier_init();
     }
     if (warp == 4) tc::tmem_alloc(&sh.tmem_base, 512);
@@ -138,7 +145,7 @@ __device__ __forceinline__ void rows_sync() { asm volatile("bar.sync 1, 128;" ::
 __global__ void __launch_bounds__(TC_THREADS, 1) tc_selftest_kernel(const float* __restrict__ A, const float* __restrict__ img,
                                                                     float* __restrict__ Dout, int reps) {
     extern __shared__ __align__(1024) uint8_t dyn_raw[];
-    TcShared& sh = *reinterpret_cast<TcShared*>(dyn_raw);
+    TcShared& sh = *tc_shared_base(dyn_raw);
     __shared__ TcJob jobs[1];
     if (threadIdx.x == 0) jobs[0] = TcJob{img, (int)TC_COL_D0, 0};
     const uint32_t tmem = tc_setup(sh, 1);
@@ -174,6 +181,297 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_selftest_kernel(const float*
         }
     }
     tc_teardown(tmem);
+}
+
+}  // namespace vb
+
+
+// =====================================================================================================
+// Tensor-core edge stage, hybrid layout.
+//   * 8 compute warps keep the coalesced "lane owns 4 channels" layout of k_edge.cuh for every global
+//     gather / scatter / elementwise step (one 512 B request per node row per warp);
+//   * the five 128x128x128 contractions per tile run on tcgen05: the A operand is moved from the padded
+//     shared staging tile into TMEM (thread-per-row, 3xTF32 planes), the accumulator comes back the same way;
+//   * warp 8 lane 0 = TMA weight producer, warp 9 lane 0 = MMA issuer (tc_producer / tc_mma_issuer).
+// =====================================================================================================
+namespace vb {
+
+constexpr int TC2_CWARPS = 8;                       // compute warps
+constexpr int TC2_CTHREADS = TC2_CWARPS * 32;       // 256
+constexpr int TC2_THREADS = TC2_CTHREADS + 64;      // + producer warp + MMA warp
+constexpr int TC2_RPW = TC_TE / TC2_CWARPS;         // rows per compute warp in the coalesced phases (16)
+
+struct EdgeTcArgs {
+    int layer;
+    ModelW mw;
+    Workspace ws;
+    TcJob jobs[TC_MAXJOBS];
+    int njobs;
+};
+
+__device__ __forceinline__ void csync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+
+__device__ __forceinline__ uint32_t tc2_setup(TcShared& sh, int njobs) {
+    const int warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < TC_STAGES; s++) { tc::mbar_init(&sh.b_full[s], 1); tc::mbar_init(&sh.b_empty[s], 1); }
+        for (int j = 0; j < njobs; j++) { tc::mbar_init(&sh.go[j], TC2_CTHREADS); tc::mbar_init(&sh.done[j], 1); }
+        tc::fence_barrier_init();
+    }
+    if (warp == TC2_CWARPS) tc::tmem_alloc(&sh.tmem_base, 512);
+    tc::fence_before_sync();
+    __syncthreads();
+    tc::fence_after_sync();
+    return sh.tmem_base;
+}
+__device__ __forceinline__ void tc2_teardown(uint32_t tmem_base) {
+    tc::fence_before_sync();
+    __syncthreads();
+    if ((threadIdx.x >> 5) == TC2_CWARPS) tc::tmem_dealloc(tmem_base, 512);
+}
+
+// staging tile (fp32, row-major, padded) -> A operand planes in TMEM.  Compute warp w serves TMEM lane quarter
+// w&3 (rows 32*(w&3)..+31) and column half w>>2.
+__device__ __forceinline__ void tc2_tile_to_a(TcShared& sh, uint32_t tmem, int warp, int lane) {
+    const int row = (warp & 3) * 32 + lane, ch = (warp >> 2) * 64;
+    const uint32_t tl = tmem + ((uint32_t)((warp & 3) * 32) << 16);
+#pragma unroll
+    for (int c0 = 0; c0 < 64; c0 += 16) {
+        float v[16];
+#pragma unroll
+        for (int q = 0; q < 16; q += 4) {
+            const float4 x = ld4(&sh.tile[row][ch + c0 + q]);
+            v[q] = x.x; v[q + 1] = x.y; v[q + 2] = x.z; v[q + 3] = x.w;
+        }
+        tc::store_a16(tl + TC_COL_AHI, tl + TC_COL_ALO, ch + c0, v);
+    }
+}
+// accumulator (TMEM) -> staging tile
+__device__ __forceinline__ void tc2_d_to_tile(TcShared& sh, uint32_t tmem, uint32_t d_col, int warp, int lane) {
+    const int row = (warp & 3) * 32 + lane, ch = (warp >> 2) * 64;
+    const uint32_t tl = tmem + ((uint32_t)((warp & 3) * 32) << 16) + d_col;
+    uint32_t r[4][16];
+#pragma unroll
+    for (int b = 0; b < 4; b++) tc::tmem_ld16_nowait(tl + ch + b * 16, r[b]);
+    tc::wait_ld();
+#pragma unroll
+    for (int b = 0; b < 4; b++)
+#pragma unroll
+        for (int q = 0; q < 16; q += 4)
+            st4(&sh.tile[row][ch + b * 16 + q], f4(__uint_as_float(r[b][q]), __uint_as_float(r[b][q + 1]),
+                                                    __uint_as_float(r[b][q + 2]), __uint_as_float(r[b][q + 3])));
+}
+__device__ __forceinline__ void tc2_go(TcShared& sh, int j) {      // every compute thread
+    tc::wait_st();
+    tc::fence_before_sync();
+    tc::mbar_arrive(&sh.go[j]);
+}
+
+// ---------------------------------------------------------------------------------------------
+// forward (math and reference lines: see edge_fwd_kernel in k_edge.cuh)
+// job order: dk -> D0, dv -> D1, [f -> D0], s1 -> D1, s2 -> D0
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(TC2_THREADS, 1) edge_fwd_tc_kernel(const __grid_constant__ EdgeTcArgs a) {
+    extern __shared__ __align__(1024) uint8_t dyn_raw[];
+    TcShared& sh = *tc_shared_base(dyn_raw);
+    const Workspace& ws = a.ws;
+    const int l = a.layer;
+    const LayerW& lw = a.mw.layer[l];
+    const bool upd = (l < L - 1);
+    const int J_DK = 0, J_DV = 1, J_F = 2, J_S1 = upd ? 3 : 2, J_S2 = upd ? 4 : 3;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, col = lane * 4;
+    const int E = ws.rowptr[ws.N];
+    const int ntiles_total = (E + TC_TE - 1) / TC_TE;
+    const int my_tiles = ((int)blockIdx.x < ntiles_total) ? (ntiles_total - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+    const uint32_t tmem = tc2_setup(sh, a.njobs);
+
+    if (warp == TC2_CWARPS) {
+        if (lane == 0) tc_producer(sh, a.jobs, a.njobs, my_tiles);
+    } else if (warp == TC2_CWARPS + 1) {
+        if (lane == 0) tc_mma_issuer(sh, a.jobs, a.njobs, my_tiles, tmem);
+    } else {
+        const float* __restrict__ Fin = ws.F[l];
+        float* __restrict__ Fout = upd ? ws.F[l + 1] : nullptr;
+        const float* __restrict__ QKV = ws.QKV[l];
+        const float* __restrict__ VN = ws.VN[l];
+        const float* __restrict__ TU = ws.TU[l];
+        const int r0 = warp * TC2_RPW;
+        const int cch = threadIdx.x & (D - 1), grp = threadIdx.x >> 7;      // aggregation role: channel, target parity
+        for (int it = 0; it < my_tiles; it++) {
+            const uint32_t tpar = (uint32_t)(it & 1);
+            const int e0 = ((int)blockIdx.x + it * (int)gridDim.x) * TC_TE;
+            const int nvalid = min(TC_TE, E - e0);
+            // ---- load f tile + meta (coalesced) ----
+            for (int idx = threadIdx.x; idx < TC_TE * 32; idx += TC2_CTHREADS) {
+                const int row = idx >> 5, c4 = (idx & 31) * 4;
+                st4(&sh.tile[row][c4], row < nvalid ? ld4(Fin + (size_t)(e0 + row) * D + c4) : f4s(0.f));
+            }
+            load_edge_meta<TC_TE, TC2_CTHREADS>(sh.meta, ws, e0, nvalid);
+            csync();
+            tc2_tile_to_a(sh, tmem, warp, lane);
+            tc2_go(sh, J_DK);
+            tc2_go(sh, J_DV);
+            // ---- dk -> attention weights ----
+            float Areg[TC2_RPW];
+            tc::mbar_wait(&sh.done[J_DK], tpar);
+            tc::fence_after_sync();
+            csync();                                              // everyone finished reading f from the tile
+            tc2_d_to_tile(sh, tmem, TC_COL_D0, warp, lane);
+            tc::fence_before_sync();
+            csync();
+            {
+                const float4 bb = ldg4(lw.b1 + col);
+#pragma unroll
+                for (int r = 0; r < TC2_RPW; r++) {
+                    const int row = r0 + r;
+                    const float4 qi = ld4(QKV + (size_t)sh.meta.dst[row] * 3 * D + col);
+                    const float4 kj = ld4(QKV + (size_t)sh.meta.src[row] * 3 * D + D + col);
+                    const float av = quad_sum(hsum4(qi * kj * silu4(ld4(&sh.tile[row][col]) + bb)));
+                    Areg[r] = silu_(av) * sh.meta.C[row];
+                }
+            }
+            if (upd) { tc::fence_before_sync(); tc::mbar_arrive(&sh.go[J_F]); }     // D0 is free
+            // ---- dv -> message m (in place in the tile) ----
+            tc::mbar_wait(&sh.done[J_DV], tpar);
+            tc::fence_after_sync();
+            csync();
+            tc2_d_to_tile(sh, tmem, TC_COL_D1, warp, lane);
+            csync();
+            {
+                const float4 bb = ldg4(lw.b1 + D + col);
+#pragma unroll
+                for (int r = 0; r < TC2_RPW; r++) {
+                    const int row = r0 + r;
+                    const float4 vj = ld4(QKV + (size_t)sh.meta.src[row] * 3 * D + 2 * D + col);
+                    st4(&sh.tile[row][col], vj * silu4(ld4(&sh.tile[row][col]) + bb) * Areg[r]);
+                }
+            }
+            csync();
+            // ---- xa_i = sum_e m_e ----
+            {
+                const int i_first = sh.meta.dst[0], i_last = sh.meta.dst[nvalid - 1];
+                for (int i = i_first + grp; i <= i_last; i += 2) {
+                    const int q0 = ws.rowptr[i], q1 = ws.rowptr[i + 1];
+                    const int lo = max(q0, e0) - e0, hi = min(q1, e0 + nvalid) - e0;
+                    float xa = 0.f;
+                    for (int r = lo; r < hi; r++) xa += sh.tile[r][cch];
+                    if (q0 >= e0 && q1 <= e0 + nvalid) ws.XA[(size_t)i * D + cch] = xa;
+                    else atomicAdd(ws.XA + (size_t)i * D + cch, xa);
+                }
+            }
+            // ---- A = m, start s1 (-> D1) ----
+            if (upd) { tc::mbar_wait(&sh.done[J_F], tpar); tc::fence_after_sync(); }   // A planes no longer read
+            tc2_tile_to_a(sh, tmem, warp, lane);
+            tc2_go(sh, J_S1);
+            // ---- edge update from the f chunk (D0) ----
+            if (upd) {
+                csync();                                          // m tile fully consumed (xa + A copy)
+                tc2_d_to_tile(sh, tmem, TC_COL_D0, warp, lane);
+                tc::fence_before_sync();
+                csync();
+                const float4 bb = ldg4(lw.b1 + 2 * D + col);
+#pragma unroll 4
+                for (int r = 0; r < TC2_RPW; r++) {
+                    const int row = r0 + r;
+                    const size_t i3 = (size_t)sh.meta.dst[row] * 3, j3 = (size_t)sh.meta.src[row] * 3;
+                    const float4 dd = sh.meta.d[row];
+                    const float4 fp = silu4(ld4(&sh.tile[row][col]) + bb);
+                    float4 ti[3], uj[3];
+#pragma unroll
+                    for (int s = 0; s < 3; s++) {
+                        ti[s] = ld4(TU + (i3 + s) * 2 * D + col);
+                        uj[s] = ld4(TU + (j3 + s) * 2 * D + D + col);
+                    }
+                    const float4 a1 = ti[0] * dd.x + ti[1] * dd.y + ti[2] * dd.z;
+                    const float4 a2 = uj[0] * dd.x + uj[1] * dd.y + uj[2] * dd.z;
+                    const float4 wdot = (ti[0] - a1 * dd.x) * (uj[0] - a2 * dd.x) + (ti[1] - a1 * dd.y) * (uj[1] - a2 * dd.y) +
+                                        (ti[2] - a1 * dd.z) * (uj[2] - a2 * dd.z);
+                    if (row < nvalid)
+                        st4(Fout + (size_t)(e0 + row) * D + col, ld4(Fin + (size_t)(e0 + row) * D + col) + fp * wdot);
+                }
+            }
+            tc::fence_before_sync();
+            tc::mbar_arrive(&sh.go[J_S2]);                        // D0 is free (A = m already published by go[J_S1])
+            // ---- s1 (D1): va_i += sum_e vn_j * s1 ----
+            float bnd[2][3] = {{0.f, 0.f, 0.f}, {0.f, 0.f, 0.f}};
+            tc::mbar_wait(&sh.done[J_S1], tpar);
+            tc::fence_after_sync();
+            csync();
+            tc2_d_to_tile(sh, tmem, TC_COL_D1, warp, lane);
+            csync();
+            {
+                const float b = __ldg(lw.bs + cch);
+                const int i_first = sh.meta.dst[0], i_last = sh.meta.dst[nvalid - 1];
+                int nb = 0;
+                for (int i = i_first + grp; i <= i_last; i += 2) {
+                    const int q0 = ws.rowptr[i], q1 = ws.rowptr[i + 1];
+                    const int lo = max(q0, e0) - e0, hi = min(q1, e0 + nvalid) - e0;
+                    float v0 = 0.f, v1 = 0.f, v2 = 0.f;
+                    int r = lo;
+                    for (; r + 4 <= hi; r += 4) {              // 12 independent gathers in flight
+                        float g[4][3], s1[4];
+#pragma unroll
+                        for (int u = 0; u < 4; u++) {
+                            const size_t j3 = (size_t)sh.meta.src[r + u] * 3;
+                            g[u][0] = VN[(j3 + 0) * D + cch]; g[u][1] = VN[(j3 + 1) * D + cch]; g[u][2] = VN[(j3 + 2) * D + cch];
+                            s1[u] = silu_(sh.tile[r + u][cch] + b);
+                        }
+#pragma unroll
+                        for (int u = 0; u < 4; u++) { v0 += g[u][0] * s1[u]; v1 += g[u][1] * s1[u]; v2 += g[u][2] * s1[u]; }
+                    }
+                    for (; r < hi; r++) {
+                        const size_t j3 = (size_t)sh.meta.src[r] * 3;
+                        const float s1 = silu_(sh.tile[r][cch] + b);
+                        v0 += VN[(j3 + 0) * D + cch] * s1;
+                        v1 += VN[(j3 + 1) * D + cch] * s1;
+                        v2 += VN[(j3 + 2) * D + cch] * s1;
+                    }
+                    if (q0 >= e0 && q1 <= e0 + nvalid) {
+                        ws.VA[((size_t)i * 3 + 0) * D + cch] = v0;
+                        ws.VA[((size_t)i * 3 + 1) * D + cch] = v1;
+                        ws.VA[((size_t)i * 3 + 2) * D + cch] = v2;
+                    } else if (nb < 2) {
+                        bnd[nb][0] = v0; bnd[nb][1] = v1; bnd[nb][2] = v2;
+                        nb++;
+                    }
+                }
+            }
+            // ---- s2 (D0): va_i += sum_e s2 * d ----
+            tc::mbar_wait(&sh.done[J_S2], tpar);
+            tc::fence_after_sync();
+            csync();
+            tc2_d_to_tile(sh, tmem, TC_COL_D0, warp, lane);
+            tc::fence_before_sync();
+            csync();
+            {
+                const float b = __ldg(lw.bs + D + cch);
+                const int i_first = sh.meta.dst[0], i_last = sh.meta.dst[nvalid - 1];
+                int nb = 0;
+                for (int i = i_first + grp; i <= i_last; i += 2) {
+                    const int q0 = ws.rowptr[i], q1 = ws.rowptr[i + 1];
+                    const int lo = max(q0, e0) - e0, hi = min(q1, e0 + nvalid) - e0;
+                    float v0 = 0.f, v1 = 0.f, v2 = 0.f;
+                    for (int r = lo; r < hi; r++) {
+                        const float4 de = sh.meta.d[r];
+                        const float s2 = silu_(sh.tile[r][cch] + b);
+                        v0 += s2 * de.x; v1 += s2 * de.y; v2 += s2 * de.z;
+                    }
+                    if (q0 >= e0 && q1 <= e0 + nvalid) {
+                        ws.VA[((size_t)i * 3 + 0) * D + cch] += v0;
+                        ws.VA[((size_t)i * 3 + 1) * D + cch] += v1;
+                        ws.VA[((size_t)i * 3 + 2) * D + cch] += v2;
+                    } else if (nb < 2) {
+                        atomicAdd(ws.VA + ((size_t)i * 3 + 0) * D + cch, bnd[nb][0] + v0);
+                        atomicAdd(ws.VA + ((size_t)i * 3 + 1) * D + cch, bnd[nb][1] + v1);
+                        atomicAdd(ws.VA + ((size_t)i * 3 + 2) * D + cch, bnd[nb][2] + v2);
+                        nb++;
+                    }
+                }
+            }
+            csync();                                              // tile / meta free for the next tile
+        }
+    }
+    tc2_teardown(tmem);
 }
 
 }  // namespace vb

@@ -1,0 +1,296 @@
+// Per-node stages, CTA-cooperative version: a CTA of 8 warps owns NB consecutive nodes and spreads the
+// (weight chunk x 8-row block) GEMM units over its warps, so the critical path is ~3 units instead of the
+// 11 chunk-GEMMs a single warp walked through in k_node.cuh.  Same math, same buffers, same references
+// (visnet_block.py:237-250, 271-273; utils.py:200-228).
+#pragma once
+#include "k_node.cuh"
+
+namespace vb {
+
+constexpr int N2_WARPS = 8;
+constexpr int N2_THREADS = N2_WARPS * 32;
+constexpr int N2_RB = 8;                         // rows per GEMM unit
+
+template <int NB>
+struct NodeFwd2Smem {
+    static constexpr int LDA = D + LDS_PAD;       // 132
+    static constexpr int LDO = 3 * D + LDS_PAD;   // 388
+    float xs[NB][LDA];                            // xa rows, later LayerNorm(x) rows
+    float vs[3 * NB][LDA];                        // VecLayerNorm(vec) rows
+    float os[NB][LDO];                            // o_proj output rows
+};
+
+// ---------------------------------------------------------------------------------------------
+// forward node stage k (same contract as node_fwd_kernel)
+// ---------------------------------------------------------------------------------------------
+template <int NB>
+__global__ void __launch_bounds__(N2_THREADS) node_fwd2_kernel(NodeArgs a) {
+    using S = NodeFwd2Smem<NB>;
+    constexpr int LDA = S::LDA;
+    extern __shared__ __align__(16) float dyn_smem[];
+    S& sm = *reinterpret_cast<S*>(dyn_smem);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, col = lane * 4;
+    const int k = a.layer;
+    const Workspace& ws = a.ws;
+    const int n0 = blockIdx.x * NB;
+    const int nn = min(NB, ws.N - n0);            // valid nodes in this CTA
+
+    if (k >= 1) {
+        const LayerW& lw = a.mw.layer[k - 1];
+        for (int idx = threadIdx.x; idx < NB * 32; idx += N2_THREADS) {
+            const int nd = idx >> 5, c4 = (idx & 31) * 4;
+            st4(&sm.xs[nd][c4], nd < nn ? ld4(ws.XA + (size_t)(n0 + nd) * D + c4) : f4s(0.f));
+        }
+        __syncthreads();
+        // o = xa Wo^T + bo : units = 3 chunks x NB/8 row blocks
+        for (int u = warp; u < 3 * (NB / N2_RB); u += N2_WARPS) {
+            const int ch = u % 3, rb = u / 3;
+            float acc[N2_RB][4];
+            acc_set_bias<N2_RB>(acc, lw.bo + ch * D, lane);
+            warp_gemm<N2_RB, D, LDA>(acc, &sm.xs[rb * N2_RB][0], lw.WoT + ch * D, 3 * D, lane);
+#pragma unroll
+            for (int r = 0; r < N2_RB; r++) st4(&sm.os[rb * N2_RB + r][ch * D + col], arr4(acc[r]));
+        }
+        __syncthreads();
+    }
+    // per-node phase: residual update, LayerNorm, VecLayerNorm (warp per node)
+    for (int nd = warp; nd < NB; nd += N2_WARPS) {
+        const int node = n0 + nd;
+        const bool ok = nd < nn;
+        float4 x = f4s(0.f), vec[3] = {f4s(0.f), f4s(0.f), f4s(0.f)};
+        if (k >= 1) {
+            if (ok) {
+                const float4 o1 = ld4(&sm.os[nd][col]), o2 = ld4(&sm.os[nd][D + col]), o3 = ld4(&sm.os[nd][2 * D + col]);
+                float* orow = ws.O[k - 1] + (size_t)node * 3 * D;
+                st4(orow + col, o1); st4(orow + D + col, o2); st4(orow + 2 * D + col, o3);
+                x = ld4(ws.X[k - 1] + (size_t)node * D + col) + ld4(ws.VDOT[k - 1] + (size_t)node * D + col) * o2 + o3;
+                st4(ws.X[k] + (size_t)node * D + col, x);
+#pragma unroll
+                for (int s = 0; s < 3; s++) {
+                    const size_t r3 = (size_t)node * 3 + s;
+                    vec[s] = ld4(ws.V[k - 1] + r3 * D + col) + ld4(ws.V123[k - 1] + r3 * 3 * D + 2 * D + col) * o1 +
+                             ld4(ws.VA + r3 * D + col);
+                    st4(ws.V[k] + r3 * D + col, vec[s]);
+                }
+            }
+        } else if (ok) {
+            x = ld4(ws.X[0] + (size_t)node * D + col);
+        }
+        if (ok) {
+            st4(ws.XA + (size_t)node * D + col, f4s(0.f));
+#pragma unroll
+            for (int s = 0; s < 3; s++) st4(ws.VA + ((size_t)node * 3 + s) * D + col, f4s(0.f));
+        }
+        if (k < L) {
+            const LayerW& lw = a.mw.layer[k];
+            st4(&sm.xs[nd][col], ln_forward(x, lw.ln_w, lw.ln_b, lane));
+            float4 vn[3];
+            vecln_forward(vec, vn, lw.vln_w, lane);
+#pragma unroll
+            for (int s = 0; s < 3; s++) {
+                st4(&sm.vs[nd * 3 + s][col], vn[s]);
+                if (ok) st4(ws.VN[k] + ((size_t)node * 3 + s) * D + col, vn[s]);
+            }
+        }
+    }
+    if (k >= L) return;
+    __syncthreads();
+    const LayerW& lw = a.mw.layer[k];
+    // GEMM units: [0, UQ): qkv ; [UQ, UQ+UV): vec_proj ; then w_trg|w_src
+    constexpr int UQ = 3 * (NB / N2_RB), UV = 3 * (3 * NB / N2_RB), UT = 2 * (3 * NB / N2_RB);
+    const int nunits = UQ + UV + ((k < L - 1) ? UT : 0);
+    for (int u = warp; u < nunits; u += N2_WARPS) {
+        float acc[N2_RB][4];
+        if (u < UQ) {
+            const int ch = u % 3, rb = u / 3;
+            acc_set_bias<N2_RB>(acc, lw.bqkv + ch * D, lane);
+            warp_gemm<N2_RB, D, LDA>(acc, &sm.xs[rb * N2_RB][0], lw.WqkvT + ch * D, 3 * D, lane);
+#pragma unroll
+            for (int r = 0; r < N2_RB; r++) {
+                const int nd = rb * N2_RB + r;
+                if (nd < nn) st4(ws.QKV[k] + (size_t)(n0 + nd) * 3 * D + ch * D + col, arr4(acc[r]));
+            }
+        } else if (u < UQ + UV) {
+            const int v = u - UQ, ch = v % 3, rb = v / 3;
+            acc_zero<N2_RB>(acc);
+            warp_gemm<N2_RB, D, LDA>(acc, &sm.vs[rb * N2_RB][0], lw.WvecT + ch * D, 3 * D, lane);
+#pragma unroll
+            for (int r = 0; r < N2_RB; r++) {
+                const int row = rb * N2_RB + r;                  // = nd*3 + s
+                if (row / 3 < nn) st4(ws.V123[k] + ((size_t)n0 * 3 + row) * 3 * D + ch * D + col, arr4(acc[r]));
+            }
+        } else {
+            const int v = u - UQ - UV, ch = v % 2, rb = v / 2;
+            acc_zero<N2_RB>(acc);
+            warp_gemm<N2_RB, D, LDA>(acc, &sm.vs[rb * N2_RB][0], lw.WtuT + ch * D, 2 * D, lane);
+#pragma unroll
+            for (int r = 0; r < N2_RB; r++) {
+                const int row = rb * N2_RB + r;
+                if (row / 3 < nn) st4(ws.TU[k] + ((size_t)n0 * 3 + row) * 2 * D + ch * D + col, arr4(acc[r]));
+            }
+        }
+    }
+    __syncthreads();     // V123 rows of this CTA are visible block-wide
+    for (int nd = warp; nd < nn; nd += N2_WARPS) {
+        const size_t r3 = (size_t)(n0 + nd) * 3;
+        float4 vd = f4s(0.f);
+#pragma unroll
+        for (int s = 0; s < 3; s++) vd = vd + ld4(ws.V123[k] + (r3 + s) * 3 * D + col) * ld4(ws.V123[k] + (r3 + s) * 3 * D + D + col);
+        st4(ws.VDOT[k] + (size_t)(n0 + nd) * D + col, vd);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// backward node stage k (same contract as node_bwd_kernel).  K-split units: every (row block, 128-wide K
+// chunk) is one unit writing a partial [8][128] product into its own shared slot; slots are summed in a
+// fixed order afterwards (deterministic).
+// ---------------------------------------------------------------------------------------------
+template <int NB>
+struct NodeBwd2Smem {
+    static constexpr int LD3 = 3 * D + LDS_PAD;   // 388
+    static constexpr int LD2 = 2 * D + LDS_PAD;   // 260
+    static constexpr int NVB = 3 * NB / N2_RB;    // vector row blocks
+    static constexpr int NXB = NB / N2_RB;        // scalar row blocks
+    float gq[NB][LD3];                            // g_qkv rows -> later g_o rows
+    float gvp[3 * NB][LD3];                       // [g_vdot*v2 | g_vdot*v1 | gvec*o1] rows
+    float gtu[3 * NB][LD2];                       // [g_t | g_u] rows
+    float part_x[3][NB][D];                       // partial products of the scalar rows (3 K-chunks)
+    float part_v[5][3 * NB][D];                   // partial products of the vector rows (3 + 2 K-chunks)
+};
+
+template <int NB>
+__global__ void __launch_bounds__(N2_THREADS) node_bwd2_kernel(NodeArgs a) {
+    using S = NodeBwd2Smem<NB>;
+    constexpr int LD3 = S::LD3, LD2 = S::LD2;
+    extern __shared__ __align__(16) float dyn_smem[];
+    S& sm = *reinterpret_cast<S*>(dyn_smem);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, col = lane * 4;
+    const int k = a.layer;
+    const Workspace& ws = a.ws;
+    const int n0 = blockIdx.x * NB;
+    const int nn = min(NB, ws.N - n0);
+    const bool has_a = (k <= L - 1), has_b = (k >= 1);
+    const bool has_tu = (k < L - 1);
+    const float4 z4 = f4s(0.f);
+
+    if (has_a) {
+        const LayerW& lw = a.mw.layer[k];
+        // stage the A-operand rows (warp per node)
+        for (int nd = warp; nd < NB; nd += N2_WARPS) {
+            const int node = n0 + nd;
+            const bool ok = nd < nn;
+            const float4 gx = ok ? ld4(ws.GX + (size_t)node * D + col) : z4;
+            const float* orow = ws.O[k] + (size_t)node * 3 * D;
+            const float4 o1 = ok ? ld4(orow + col) : z4, o2 = ok ? ld4(orow + D + col) : z4;
+            const float4 g_vdot = gx * o2;
+            const float* gq = ws.GQKV + (size_t)node * 3 * D;
+            st4(&sm.gq[nd][col], ok ? ld4(gq + col) : z4);
+            st4(&sm.gq[nd][D + col], ok ? ld4(gq + D + col) : z4);
+            st4(&sm.gq[nd][2 * D + col], ok ? ld4(gq + 2 * D + col) : z4);
+#pragma unroll
+            for (int s = 0; s < 3; s++) {
+                const size_t r3 = (size_t)node * 3 + s;
+                const float* vrow = ws.V123[k] + r3 * 3 * D;
+                const float4 gv = ok ? ld4(ws.GVEC + r3 * D + col) : z4;
+                st4(&sm.gvp[nd * 3 + s][col], g_vdot * (ok ? ld4(vrow + D + col) : z4));
+                st4(&sm.gvp[nd * 3 + s][D + col], g_vdot * (ok ? ld4(vrow + col) : z4));
+                st4(&sm.gvp[nd * 3 + s][2 * D + col], gv * o1);
+                if (has_tu) {
+                    const float* gt = ws.GTU + r3 * 2 * D;
+                    st4(&sm.gtu[nd * 3 + s][col], ok ? ld4(gt + col) : z4);
+                    st4(&sm.gtu[nd * 3 + s][D + col], ok ? ld4(gt + D + col) : z4);
+                }
+            }
+        }
+        __syncthreads();
+        // units: scalar rows x 3 K-chunks (Wqkv) ; vector rows x (3 K-chunks Wvec + 2 K-chunks Wtu)
+        constexpr int UX = 3 * S::NXB;
+        const int kv = has_tu ? 5 : 3;
+        const int nunits = UX + kv * S::NVB;
+        for (int u = warp; u < nunits; u += N2_WARPS) {
+            float acc[N2_RB][4];
+            acc_zero<N2_RB>(acc);
+            if (u < UX) {
+                const int kc = u % 3, rb = u / 3;
+                warp_gemm<N2_RB, D, LD3>(acc, &sm.gq[rb * N2_RB][kc * D], lw.WqkvN + (size_t)kc * D * D, D, lane);
+#pragma unroll
+                for (int r = 0; r < N2_RB; r++) st4(&sm.part_x[kc][rb * N2_RB + r][col], arr4(acc[r]));
+            } else {
+                const int v = u - UX, kc = v % kv, rb = v / kv;
+                if (kc < 3) warp_gemm<N2_RB, D, LD3>(acc, &sm.gvp[rb * N2_RB][kc * D], lw.WvecN + (size_t)kc * D * D, D, lane);
+                else        warp_gemm<N2_RB, D, LD2>(acc, &sm.gtu[rb * N2_RB][(kc - 3) * D], lw.WtuN + (size_t)(kc - 3) * D * D, D, lane);
+#pragma unroll
+                for (int r = 0; r < N2_RB; r++) st4(&sm.part_v[kc][rb * N2_RB + r][col], arr4(acc[r]));
+            }
+        }
+        __syncthreads();
+    }
+    // per-node phase
+    for (int nd = warp; nd < NB; nd += N2_WARPS) {
+        const int node = n0 + nd;
+        const bool ok = nd < nn;
+        float4 gx = ok ? ld4(ws.GX + (size_t)node * D + col) : z4, gvec[3];
+#pragma unroll
+        for (int s = 0; s < 3; s++) gvec[s] = ok ? ld4(ws.GVEC + ((size_t)node * 3 + s) * D + col) : z4;
+        if (has_a && ok) {
+            const LayerW& lw = a.mw.layer[k];
+            const float4 gxn = (ld4(&sm.part_x[0][nd][col]) + ld4(&sm.part_x[1][nd][col])) + ld4(&sm.part_x[2][nd][col]);
+            float4 vin[3], gout[3], gv[3];
+#pragma unroll
+            for (int s = 0; s < 3; s++) {
+                const int row = nd * 3 + s;
+                float4 g = ld4(ws.GVNMSG + ((size_t)node * 3 + s) * D + col);
+                g = g + ((ld4(&sm.part_v[0][row][col]) + ld4(&sm.part_v[1][row][col])) + ld4(&sm.part_v[2][row][col]));
+                if (has_tu) g = g + (ld4(&sm.part_v[3][row][col]) + ld4(&sm.part_v[4][row][col]));
+                gout[s] = g;
+                vin[s] = ld4(ws.V[k] + ((size_t)node * 3 + s) * D + col);
+            }
+            vecln_backward(vin, gout, gv, lw.vln_w, lane);
+#pragma unroll
+            for (int s = 0; s < 3; s++) gvec[s] = gvec[s] + gv[s];
+            gx = gx + ln_backward(ld4(ws.X[k] + (size_t)node * D + col), gxn, lw.ln_w, lane);
+        }
+        if (ok) {
+            float* gq = ws.GQKV + (size_t)node * 3 * D;
+            st4(gq + col, z4); st4(gq + D + col, z4); st4(gq + 2 * D + col, z4);
+#pragma unroll
+            for (int s = 0; s < 3; s++) {
+                const size_t r3 = (size_t)node * 3 + s;
+                st4(ws.GVNMSG + r3 * D + col, z4);
+                st4(ws.GTU + r3 * 2 * D + col, z4);
+                st4(ws.GTU + r3 * 2 * D + D + col, z4);
+                st4(ws.GVEC + r3 * D + col, gvec[s]);
+            }
+            st4(ws.GX + (size_t)node * D + col, gx);
+        }
+        if (has_b) {
+            float4 go1 = z4;
+#pragma unroll
+            for (int s = 0; s < 3; s++)
+                go1 = go1 + gvec[s] * (ok ? ld4(ws.V123[k - 1] + ((size_t)node * 3 + s) * 3 * D + 2 * D + col) : z4);
+            __syncwarp();
+            st4(&sm.gq[nd][col], go1);
+            st4(&sm.gq[nd][D + col], gx * (ok ? ld4(ws.VDOT[k - 1] + (size_t)node * D + col) : z4));
+            st4(&sm.gq[nd][2 * D + col], gx);
+        }
+    }
+    if (!has_b) return;
+    __syncthreads();
+    {
+        const LayerW& lw = a.mw.layer[k - 1];
+        for (int u = warp; u < 3 * S::NXB; u += N2_WARPS) {
+            const int kc = u % 3, rb = u / 3;
+            float acc[N2_RB][4];
+            acc_zero<N2_RB>(acc);
+            warp_gemm<N2_RB, D, LD3>(acc, &sm.gq[rb * N2_RB][kc * D], lw.WoN + (size_t)kc * D * D, D, lane);
+#pragma unroll
+            for (int r = 0; r < N2_RB; r++) st4(&sm.part_x[kc][rb * N2_RB + r][col], arr4(acc[r]));
+        }
+    }
+    __syncthreads();
+    for (int nd = warp; nd < nn; nd += N2_WARPS)
+        st4(ws.GXA + (size_t)(n0 + nd) * D + col,
+            (ld4(&sm.part_x[0][nd][col]) + ld4(&sm.part_x[1][nd][col])) + ld4(&sm.part_x[2][nd][col]));
+}
+
+}  // namespace vb

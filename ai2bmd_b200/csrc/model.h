@@ -35,7 +35,12 @@ namespace vb {
     X(WtuT, D * 2 * D) X(WtuN, 2 * D * D)                    /* [w_trg|w_src] (zeros in the last layer) */ \
     X(W1T, D * 3 * D) X(b1, 3 * D) X(W1N, 3 * D * D)         /* [dk|dv|f] (f zeros in the last layer)   */ \
     X(WsT, D * 2 * D) X(bs, 2 * D) X(WsN, 2 * D * D)         /* s_proj [256,128]        */        \
-    X(WoT, D * 3 * D) X(bo, 3 * D) X(WoN, 3 * D * D)         /* o_proj [384,128]        */
+    X(WoT, D * 3 * D) X(bo, 3 * D) X(WoN, 3 * D * D)         /* o_proj [384,128]        */        \
+    /* tensor-core weight images (weights.py::tc_image): 128x128 chunks, 4 K-slabs x (hi 16 KB + lo 16 KB) */ \
+    X(tcW1, 3 * 4 * 8192)      /* forward  [dk | dv | f]   : 3 chunks                    */        \
+    X(tcWs, 2 * 4 * 8192)      /* forward  [s1 | s2]       : 2 chunks                    */        \
+    X(tcWsN, 2 * 4 * 8192)     /* adjoint  g_m = g_s Ws    : K-chunks s1-part, s2-part   */        \
+    X(tcW1N, 3 * 4 * 8192)     /* adjoint  g_f += g_P W1   : K-chunks dk, dv, f parts    */
 
 struct LayerW {
 #define X(name, count) const float* name;

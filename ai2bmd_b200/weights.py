@@ -84,6 +84,11 @@ def _named_arrays(sd: Dict[str, np.ndarray]) -> Dict[str, np.ndarray]:
         out[k + "WsT"], out[k + "bs"], out[k + "WsN"] = ws.T, f(p + "s_proj.bias"), ws
         wo = f(p + "o_proj.weight")
         out[k + "WoT"], out[k + "bo"], out[k + "WoN"] = wo.T, f(p + "o_proj.bias"), wo
+        # tensor-core images: forward chunks use W[n_out][k_in]; adjoint chunks use (W[k_out-chunk][n_in])^T
+        out[k + "tcW1"] = np.concatenate([tc_image(w1[c * D:(c + 1) * D]) for c in range(3)])
+        out[k + "tcWs"] = np.concatenate([tc_image(ws[c * D:(c + 1) * D]) for c in range(2)])
+        out[k + "tcWsN"] = np.concatenate([tc_image(ws[c * D:(c + 1) * D].T) for c in range(2)])
+        out[k + "tcW1N"] = np.concatenate([tc_image(w1[c * D:(c + 1) * D].T) for c in range(3)])
     return out
 
 
