@@ -67,27 +67,61 @@ __device__ __forceinline__ float quad_sum(float v) {
 // W: global memory, row-major [K][ldw]; the caller pre-offsets W to the first of the 128 columns this
 //    call produces.  Lanes read consecutive float4 -> one coalesced 512 B request per k.
 // ---------------------------------------------------------------------------------------------
+template <int R>
+__device__ __forceinline__ void warp_gemm_group(float (&acc)[R][4], const float* __restrict__ As, int lda, int k,
+                                                const float4 (&w)[4]) {
+#pragma unroll
+    for (int r = 0; r < R; r++) {
+        const float4 a = ld4(As + r * lda + k);
+        acc[r][0] = fmaf(a.x, w[0].x, acc[r][0]); acc[r][1] = fmaf(a.x, w[0].y, acc[r][1]);
+        acc[r][2] = fmaf(a.x, w[0].z, acc[r][2]); acc[r][3] = fmaf(a.x, w[0].w, acc[r][3]);
+        acc[r][0] = fmaf(a.y, w[1].x, acc[r][0]); acc[r][1] = fmaf(a.y, w[1].y, acc[r][1]);
+        acc[r][2] = fmaf(a.y, w[1].z, acc[r][2]); acc[r][3] = fmaf(a.y, w[1].w, acc[r][3]);
+        acc[r][0] = fmaf(a.z, w[2].x, acc[r][0]); acc[r][1] = fmaf(a.z, w[2].y, acc[r][1]);
+        acc[r][2] = fmaf(a.z, w[2].z, acc[r][2]); acc[r][3] = fmaf(a.z, w[2].w, acc[r][3]);
+        acc[r][0] = fmaf(a.w, w[3].x, acc[r][0]); acc[r][1] = fmaf(a.w, w[3].y, acc[r][1]);
+        acc[r][2] = fmaf(a.w, w[3].z, acc[r][2]); acc[r][3] = fmaf(a.w, w[3].w, acc[r][3]);
+    }
+}
+__device__ __forceinline__ void warp_gemm_loadw(float4 (&w)[4], const float* __restrict__ Wp, int ldw, int k) {
+    w[0] = ldg4(Wp + (size_t)(k + 0) * ldw);
+    w[1] = ldg4(Wp + (size_t)(k + 1) * ldw);
+    w[2] = ldg4(Wp + (size_t)(k + 2) * ldw);
+    w[3] = ldg4(Wp + (size_t)(k + 3) * ldw);
+}
+
+// Software-pipelined: the weight rows of the next k-groups are in flight while the current group is
+// multiplied (register ring of NBUF groups; NBUF = 4 for small R where the math does not cover L2 latency).
 template <int R, int K, int LDA>
 __device__ __forceinline__ void warp_gemm(float (&acc)[R][4], const float* __restrict__ As,
                                           const float* __restrict__ W, int ldw, int lane) {
+    static_assert(K % 16 == 0, "K must be a multiple of 16");
     const float* Wp = W + lane * 4;
-#pragma unroll 2
-    for (int k = 0; k < K; k += 4) {
-        const float4 w0 = ldg4(Wp + (size_t)(k + 0) * ldw);
-        const float4 w1 = ldg4(Wp + (size_t)(k + 1) * ldw);
-        const float4 w2 = ldg4(Wp + (size_t)(k + 2) * ldw);
-        const float4 w3 = ldg4(Wp + (size_t)(k + 3) * ldw);
-#pragma unroll
-        for (int r = 0; r < R; r++) {
-            const float4 a = ld4(As + r * LDA + k);
-            acc[r][0] = fmaf(a.x, w0.x, acc[r][0]); acc[r][1] = fmaf(a.x, w0.y, acc[r][1]);
-            acc[r][2] = fmaf(a.x, w0.z, acc[r][2]); acc[r][3] = fmaf(a.x, w0.w, acc[r][3]);
-            acc[r][0] = fmaf(a.y, w1.x, acc[r][0]); acc[r][1] = fmaf(a.y, w1.y, acc[r][1]);
-            acc[r][2] = fmaf(a.y, w1.z, acc[r][2]); acc[r][3] = fmaf(a.y, w1.w, acc[r][3]);
-            acc[r][0] = fmaf(a.z, w2.x, acc[r][0]); acc[r][1] = fmaf(a.z, w2.y, acc[r][1]);
-            acc[r][2] = fmaf(a.z, w2.z, acc[r][2]); acc[r][3] = fmaf(a.z, w2.w, acc[r][3]);
-            acc[r][0] = fmaf(a.w, w3.x, acc[r][0]); acc[r][1] = fmaf(a.w, w3.y, acc[r][1]);
-            acc[r][2] = fmaf(a.w, w3.z, acc[r][2]); acc[r][3] = fmaf(a.w, w3.w, acc[r][3]);
+    if constexpr (R <= 4) {
+        float4 w0[4], w1[4], w2[4], w3[4];
+        warp_gemm_loadw(w0, Wp, ldw, 0);
+        warp_gemm_loadw(w1, Wp, ldw, 4);
+        warp_gemm_loadw(w2, Wp, ldw, 8);
+#pragma unroll 1
+        for (int k = 0; k < K; k += 16) {
+            warp_gemm_loadw(w3, Wp, ldw, k + 12);
+            warp_gemm_group<R>(acc, As, LDA, k, w0);
+            if (k + 16 < K) warp_gemm_loadw(w0, Wp, ldw, k + 16);
+            warp_gemm_group<R>(acc, As, LDA, k + 4, w1);
+            if (k + 16 < K) warp_gemm_loadw(w1, Wp, ldw, k + 20);
+            warp_gemm_group<R>(acc, As, LDA, k + 8, w2);
+            if (k + 16 < K) warp_gemm_loadw(w2, Wp, ldw, k + 24);
+            warp_gemm_group<R>(acc, As, LDA, k + 12, w3);
+        }
+    } else {
+        float4 w0[4], w1[4];
+        warp_gemm_loadw(w0, Wp, ldw, 0);
+#pragma unroll 1
+        for (int k = 0; k < K; k += 8) {
+            warp_gemm_loadw(w1, Wp, ldw, k + 4);
+            warp_gemm_group<R>(acc, As, LDA, k, w0);
+            if (k + 8 < K) warp_gemm_loadw(w0, Wp, ldw, k + 8);
+            warp_gemm_group<R>(acc, As, LDA, k + 4, w1);
         }
     }
 }
@@ -97,7 +131,7 @@ template <int R, int K, int LDA>
 __device__ __forceinline__ void warp_gemm2(float (&acc)[R][2], const float* __restrict__ As,
                                            const float* __restrict__ W, int ldw, int lane) {
     const float* Wp = W + lane * 2;
-#pragma unroll 2
+#pragma unroll 4
     for (int k = 0; k < K; k += 4) {
         const float2 w0 = __ldg(reinterpret_cast<const float2*>(Wp + (size_t)(k + 0) * ldw));
         const float2 w1 = __ldg(reinterpret_cast<const float2*>(Wp + (size_t)(k + 1) * ldw));

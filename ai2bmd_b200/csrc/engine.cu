@@ -81,9 +81,11 @@ struct vb_handle {
     float *d_map_sign = nullptr, *d_frag_sign = nullptr;
     // options
     int use_graph = 1, npw = 0, te_fwd = 0, te_bwd = 32;
+    int npw_opt = 0, te_fwd_opt = 0, edge_tc_opt = -1;   // user choices (0 / -1 = choose by problem size)
     int node_impl = 1; // 0: warp-per-node kernels (k_node.cuh), 1: CTA-cooperative kernels (k_node2.cuh)
-    int edge_tc = 0;   // bit 0: forward edge stage on tcgen05, bit 1: adjoint edge stage on tcgen05
+    int edge_tc = -1;  // bit 0: forward edge stage on tcgen05, bit 1: adjoint edge stage on tcgen05; -1 = by size
     // graph cache
+    float* d_tc_scratch = nullptr;   // per-CTA scratch of the tensor-core adjoint edge kernel
     cudaGraphExec_t graph_exec = nullptr;
     int launches = 0;
     std::vector<std::string> stage_names;
@@ -312,7 +314,33 @@ void edge_fwd(Launcher& Lc, int l) {
     if (Lc.h->te_fwd == 64) launch_edge_fwd<64, 8>(Lc, l, 2);
     else launch_edge_fwd<32, 8>(Lc, l, 4);
 }
+void launch_edge_bwd_tc(Launcher& Lc, int l) {
+    vb_handle* h = Lc.h;
+    EdgeTcArgs a{};
+    a.layer = l; a.mw = h->mw; a.ws = h->ws;
+    const LayerW& lw = h->mw.layer[l];
+    const size_t chunk = 4 * 8192;
+    const bool upd = l < L - 1;
+    int n = 0;
+    a.jobs[n++] = TcJob{lw.tcW1, (int)TC_COL_D0, 0};                         // dk
+    a.jobs[n++] = TcJob{lw.tcW1 + chunk, (int)TC_COL_D1, 0};                 // dv
+    if (upd) a.jobs[n++] = TcJob{lw.tcW1 + 2 * chunk, (int)TC_COL_D0, 0};     // f
+    a.jobs[n++] = TcJob{lw.tcWs, (int)TC_COL_D1, 0};                         // s1
+    a.jobs[n++] = TcJob{lw.tcWs + chunk, (int)TC_COL_D0, 0};                 // s2
+    a.jobs[n++] = TcJob{lw.tcWsN, (int)TC_COL_D1, 0};                        // g_m  = g_s1' Ws[0:128]
+    a.jobs[n++] = TcJob{lw.tcWsN + chunk, (int)TC_COL_D1, 1};                //      + g_s2' Ws[128:256]
+    a.jobs[n++] = TcJob{lw.tcW1N + chunk, (int)TC_COL_D0, 0};                // g_f  = g_Pdv Wdv
+    a.jobs[n++] = TcJob{lw.tcW1N, (int)TC_COL_D0, 1};                        //      + g_Pdk Wdk
+    if (upd) a.jobs[n++] = TcJob{lw.tcW1N + 2 * chunk, (int)TC_COL_D0, 1};   //      + g_Pf  Wf
+    a.njobs = n;
+    const int tiles = (h->ws.Ecap + TC_TE - 1) / TC_TE;
+    const int blocks = std::max(1, std::min(tiles, h->sm_count));
+    edge_bwd_tc_kernel<<<blocks, TC2_THREADS, TC_SMEM_BYTES, Lc.st>>>(a, h->d_tc_scratch);
+    Lc.check();
+}
+
 void edge_bwd(Launcher& Lc, int l) {
+    if (Lc.h->edge_tc & 2) { launch_edge_bwd_tc(Lc, l); return; }
     if (Lc.h->te_bwd == 64) launch_edge_bwd<64, 8>(Lc, l, 1);
     else launch_edge_bwd<32, 8>(Lc, l, 2);
 }
@@ -374,6 +402,8 @@ int configure_kernels(vb_handle* h) {
     CUDA_TRY(h, opt_in_smem(head_kernel<1>, HeadSmem<1>::BYTES));
     CUDA_TRY(h, opt_in_smem(head_kernel<2>, HeadSmem<2>::BYTES));
     CUDA_TRY(h, opt_in_smem(edge_fwd_tc_kernel, TC_SMEM_BYTES));
+    CUDA_TRY(h, opt_in_smem(edge_bwd_tc_kernel, TC_SMEM_BYTES));
+    CUDA_TRY(h, cudaMalloc(&h->d_tc_scratch, sizeof(float) * (size_t)h->sm_count * 3 * TC_TE * D));
     CUDA_TRY(h, opt_in_smem(node_fwd2_kernel<8>, sizeof(NodeFwd2Smem<8>)));
     CUDA_TRY(h, opt_in_smem(node_fwd2_kernel<16>, sizeof(NodeFwd2Smem<16>)));
     CUDA_TRY(h, opt_in_smem(node_bwd2_kernel<8>, sizeof(NodeBwd2Smem<8>)));
@@ -421,8 +451,11 @@ int run_core(vb_handle* h, cudaStream_t st) {
 
 void choose_defaults(vb_handle* h) {
     const int N = h->ws.N;
+    h->npw = h->npw_opt; h->te_fwd = h->te_fwd_opt; h->edge_tc = h->edge_tc_opt;
     if (h->npw == 0) h->npw = (N > 4096) ? 2 : 1;
     if (h->te_fwd == 0) h->te_fwd = ((long long)N * 17 / 64 >= 2LL * h->sm_count) ? 64 : 32;
+    // tensor-core edge kernels own a whole SM per 128-edge tile: worth it once every SM gets several tiles
+    if (h->edge_tc < 0) h->edge_tc = ((long long)N * 17 / TC_TE >= 2LL * h->sm_count) ? 3 : 0;
 }
 
 }  // namespace
@@ -481,10 +514,10 @@ int vb_create(const float* weights_host, size_t n_floats, const vb_hparams* hp, 
     if (cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking) != cudaSuccess) { h->set_error("stream create failed"); return fail(VB_ERR_CUDA); }
     if (configure_kernels(h) != VB_OK) return fail(VB_ERR_CUDA);
     if (const char* s = getenv("VB_USE_GRAPH")) h->use_graph = atoi(s);
-    if (const char* s = getenv("VB_NPW")) h->npw = atoi(s);
-    if (const char* s = getenv("VB_TE_FWD")) h->te_fwd = atoi(s);
+    if (const char* s = getenv("VB_NPW")) h->npw_opt = atoi(s);
+    if (const char* s = getenv("VB_TE_FWD")) h->te_fwd_opt = atoi(s);
     if (const char* s = getenv("VB_TE_BWD")) h->te_bwd = atoi(s);
-    if (const char* s = getenv("VB_EDGE_TC")) h->edge_tc = atoi(s);
+    if (const char* s = getenv("VB_EDGE_TC")) h->edge_tc_opt = atoi(s);
     if (const char* s = getenv("VB_NODE_IMPL")) h->node_impl = atoi(s);
     *out = h;
     return VB_OK;
@@ -496,6 +529,7 @@ void vb_destroy(vb_handle* h) {
     h->drop_graph();
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
     cudaFree(h->d_weights);
+    cudaFree(h->d_tc_scratch);
     cudaFree(h->arena);
     cudaFree(h->d_map_src); cudaFree(h->d_map_dst); cudaFree(h->d_map_sign); cudaFree(h->d_frag_sign);
     cudaFreeHost(h->h_pos); cudaFreeHost(h->h_energy); cudaFreeHost(h->h_forces);
@@ -670,14 +704,27 @@ int vb_set_option(vb_handle* h, const char* key, int64_t value) {
     std::lock_guard<std::mutex> lk(h->mu);
     const std::string k(key);
     if (k == "use_graph") h->use_graph = (int)value;
-    else if (k == "npw" && (value == 1 || value == 2)) h->npw = (int)value;
-    else if (k == "te_fwd" && (value == 32 || value == 64)) h->te_fwd = (int)value;
+    else if (k == "npw" && (value == 1 || value == 2)) h->npw = h->npw_opt = (int)value;
+    else if (k == "te_fwd" && (value == 32 || value == 64)) h->te_fwd = h->te_fwd_opt = (int)value;
     else if (k == "te_bwd" && (value == 32 || value == 64)) h->te_bwd = (int)value;
-    else if (k == "edge_tc" && value >= 0 && value <= 3) h->edge_tc = (int)value;
+    else if (k == "edge_tc" && value >= 0 && value <= 3) h->edge_tc = h->edge_tc_opt = (int)value;
     else if (k == "node_impl" && (value == 0 || value == 1)) h->node_impl = (int)value;
     else { h->set_error("vb_set_option: unknown key or bad value: %s", key); return VB_ERR_ARG; }
     h->drop_graph();
     return VB_OK;
+}
+
+int64_t vb_get_option(const vb_handle* h, const char* key) {
+    if (!h || !key) return VB_ERR_ARG;
+    const std::string k(key);
+    if (k == "use_graph") return h->use_graph;
+    if (k == "npw") return h->npw;
+    if (k == "te_fwd") return h->te_fwd;
+    if (k == "te_bwd") return h->te_bwd;
+    if (k == "edge_tc") return h->edge_tc;
+    if (k == "node_impl") return h->node_impl;
+    if (k == "n_edges_capacity") return h->ws.Ecap;
+    return VB_ERR_ARG;
 }
 
 int vb_num_stages(const vb_handle* h) { return h ? (int)h->stage_names.size() : 0; }

@@ -20,7 +20,7 @@ namespace vb {
 
 constexpr int TC_TE = 128;           // edges per tile (= MMA M)
 constexpr int TC_STAGES = 4;
-constexpr int TC_MAXJOBS = 8;
+constexpr int TC_MAXJOBS = 12;
 constexpr int TC_THREADS = 192;
 constexpr int TC_LT = D + LDS_PAD;   // padded row length of the staging tile (132 floats)
 
@@ -42,6 +42,9 @@ struct TcShared {
     uint64_t go[TC_MAXJOBS];
     uint64_t done[TC_MAXJOBS];
     uint32_t tmem_base;
+    alignas(16) float eacc[TC_TE][4];   // per-edge adjoint scalars of the current tile: dE/dC, dE/dd[3]
+    float attn[TC_TE][H];               // adjoint kernel: attention pre-activation a_h per edge
+    float gattn[TC_TE][H];              // adjoint kernel: dE/da_h per edge
 };
 
 // the ring must start on a 1024 B boundary of the shared window (swizzle atom): align the dynamic block by hand
@@ -469,6 +472,322 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) edge_fwd_tc_kernel(const __gri
                 }
             }
             csync();                                              // tile / meta free for the next tile
+        }
+    }
+    tc2_teardown(tmem);
+}
+
+}  // namespace vb
+
+namespace vb {
+
+// ---------------------------------------------------------------------------------------------
+// adjoint (math and reference lines: see edge_bwd_kernel in k_edge.cuh)
+// jobs (upd):  0 dk->D0  1 dv->D1  2 f->D0  3 s1->D1  4 s2->D0  5 g3a->D1  6 g3b->D1(+)  7 g4dv->D0  8 g4dk->D0(+)  9 g4f->D0(+)
+// last layer:  0 dk->D0  1 dv->D1           2 s1->D1  3 s2->D0  4 g3a->D1  5 g3b->D1(+)  6 g4dv->D0  7 g4dk->D0(+)
+// scr = per-CTA global scratch [3][128][128] holding the pre-activations Pdk, Pdv, Pf (L2 resident), later
+// overwritten in place by their adjoints before those are staged as A operands.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(TC2_THREADS, 1) edge_bwd_tc_kernel(const __grid_constant__ EdgeTcArgs a, float* __restrict__ scratch) {
+    extern __shared__ __align__(1024) uint8_t dyn_raw[];
+    TcShared& sh = *tc_shared_base(dyn_raw);
+    const Workspace& ws = a.ws;
+    const int l = a.layer;
+    const LayerW& lw = a.mw.layer[l];
+    const bool upd = (l < L - 1);
+    const int o = upd ? 1 : 0;
+    const int J_DK = 0, J_DV = 1, J_F = 2, J_S1 = 2 + o, J_S2 = 3 + o, J_G3A = 4 + o, J_G3B = 5 + o, J_G4DV = 6 + o,
+              J_G4DK = 7 + o, J_G4F = 9;
+    const int J_LAST = upd ? J_G4F : J_G4DK;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, col = lane * 4;
+    const int E = ws.rowptr[ws.N];
+    const int ntiles_total = (E + TC_TE - 1) / TC_TE;
+    const int my_tiles = ((int)blockIdx.x < ntiles_total) ? (ntiles_total - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+    const uint32_t tmem = tc2_setup(sh, a.njobs);
+
+    if (warp == TC2_CWARPS) {
+        if (lane == 0) tc_producer(sh, a.jobs, a.njobs, my_tiles);
+    } else if (warp == TC2_CWARPS + 1) {
+        if (lane == 0) tc_mma_issuer(sh, a.jobs, a.njobs, my_tiles, tmem);
+    } else {
+        const float* __restrict__ Fin = ws.F[l];
+        const float* __restrict__ QKV = ws.QKV[l];
+        const float* __restrict__ VN = ws.VN[l];
+        const float* __restrict__ TU = ws.TU[l];
+        float* scr0 = scratch + (size_t)blockIdx.x * 3 * TC_TE * D;
+        float* scr1 = scr0 + TC_TE * D;
+        float* scr2 = scr1 + TC_TE * D;
+        const int r0 = warp * TC2_RPW;
+        const int cch = threadIdx.x & (D - 1), grp = threadIdx.x >> 7;
+        auto wait_done = [&](int j, uint32_t tpar) { tc::mbar_wait(&sh.done[j], tpar); tc::fence_after_sync(); };
+        auto stage_d = [&](uint32_t d_col) {           // accumulator -> tile, bracketed by CTA barriers
+            csync();
+            tc2_d_to_tile(sh, tmem, d_col, warp, lane);
+            tc::fence_before_sync();
+            csync();
+        };
+        for (int it = 0; it < my_tiles; it++) {
+            const uint32_t tpar = (uint32_t)(it & 1);
+            const int e0 = ((int)blockIdx.x + it * (int)gridDim.x) * TC_TE;
+            const int nvalid = min(TC_TE, E - e0);
+            for (int idx = threadIdx.x; idx < TC_TE * 32; idx += TC2_CTHREADS) {
+                const int row = idx >> 5, c4 = (idx & 31) * 4;
+                st4(&sh.tile[row][c4], row < nvalid ? ld4(Fin + (size_t)(e0 + row) * D + c4) : f4s(0.f));
+            }
+            load_edge_meta<TC_TE, TC2_CTHREADS>(sh.meta, ws, e0, nvalid);
+            csync();
+            tc2_tile_to_a(sh, tmem, warp, lane);
+            tc2_go(sh, J_DK);
+            tc2_go(sh, J_DV);
+            const int hd = lane >> 2;                           // head owned by this lane's 4 channels
+            // ---- recompute Pdk, attention pre-activation ----
+            wait_done(J_DK, tpar);
+            stage_d(TC_COL_D0);
+            {
+                const float4 bb = ldg4(lw.b1 + col);
+#pragma unroll
+                for (int r = 0; r < TC2_RPW; r++) {
+                    const int row = r0 + r;
+                    const float4 P = ld4(&sh.tile[row][col]) + bb;
+                    st4(scr0 + row * D + col, P);
+                    const float4 qi = ld4(QKV + (size_t)sh.meta.dst[row] * 3 * D + col);
+                    const float4 kj = ld4(QKV + (size_t)sh.meta.src[row] * 3 * D + D + col);
+                    const float av = quad_sum(hsum4(qi * kj * silu4(P)));
+                    if ((lane & 3) == 0) sh.attn[row][hd] = av;
+                }
+            }
+            if (upd) { tc::fence_before_sync(); tc::mbar_arrive(&sh.go[J_F]); }
+            // ---- recompute Pdv, message m ----
+            wait_done(J_DV, tpar);
+            stage_d(TC_COL_D1);
+            {
+                const float4 bb = ldg4(lw.b1 + D + col);
+#pragma unroll
+                for (int r = 0; r < TC2_RPW; r++) {
+                    const int row = r0 + r;
+                    const float4 P = ld4(&sh.tile[row][col]) + bb;
+                    st4(scr1 + row * D + col, P);
+                    const float4 vj = ld4(QKV + (size_t)sh.meta.src[row] * 3 * D + 2 * D + col);
+                    st4(&sh.tile[row][col], vj * silu4(P) * (silu_(sh.attn[row][hd]) * sh.meta.C[row]));
+                }
+            }
+            csync();
+            if (upd) wait_done(J_F, tpar);
+            tc2_tile_to_a(sh, tmem, warp, lane);               // A = m
+            tc2_go(sh, J_S1);
+            if (upd) {
+                stage_d(TC_COL_D0);
+                const float4 bb = ldg4(lw.b1 + 2 * D + col);
+#pragma unroll
+                for (int r = 0; r < TC2_RPW; r++) st4(scr2 + (r0 + r) * D + col, ld4(&sh.tile[r0 + r][col]) + bb);
+            }
+            tc::fence_before_sync();
+            tc::mbar_arrive(&sh.go[J_S2]);
+            // ---- s1 half: adjoint of M = vn_j*s1 (+ s2*d) ----
+            wait_done(J_S1, tpar);
+            stage_d(TC_COL_D1);
+            {
+                const float4 bb = ldg4(lw.bs + col);
+#pragma unroll 4
+                for (int r = 0; r < TC2_RPW; r++) {
+                    const int row = r0 + r;
+                    const size_t i3 = (size_t)sh.meta.dst[row] * 3, j3 = (size_t)sh.meta.src[row] * 3;
+                    const float4 sp = ld4(&sh.tile[row][col]) + bb;
+                    const float4 s1 = silu4(sp);
+                    const float4 gM0 = ld4(ws.GVEC + (i3 + 0) * D + col), gM1 = ld4(ws.GVEC + (i3 + 1) * D + col),
+                                 gM2 = ld4(ws.GVEC + (i3 + 2) * D + col);
+                    const float4 gs1 = gM0 * ld4(VN + (j3 + 0) * D + col) + gM1 * ld4(VN + (j3 + 1) * D + col) +
+                                       gM2 * ld4(VN + (j3 + 2) * D + col);
+                    if (row < nvalid) {
+                        red4(ws.GVNMSG + (j3 + 0) * D + col, gM0 * s1);
+                        red4(ws.GVNMSG + (j3 + 1) * D + col, gM1 * s1);
+                        red4(ws.GVNMSG + (j3 + 2) * D + col, gM2 * s1);
+                    }
+                    st4(&sh.tile[row][col], gs1 * dsilu4(sp));
+                }
+            }
+            csync();
+            wait_done(J_S2, tpar);                               // the s2 GEMM no longer reads A = m
+            tc2_tile_to_a(sh, tmem, warp, lane);               // A = g_Spre[:, 0:128]
+            tc2_go(sh, J_G3A);
+            // ---- s2 half ----
+            stage_d(TC_COL_D0);
+            {
+                const float4 bb = ldg4(lw.bs + D + col);
+#pragma unroll 4
+                for (int r = 0; r < TC2_RPW; r++) {
+                    const int row = r0 + r;
+                    const size_t i3 = (size_t)sh.meta.dst[row] * 3;
+                    const float4 dd = sh.meta.d[row];
+                    const float4 sp = ld4(&sh.tile[row][col]) + bb;
+                    const float4 s2 = silu4(sp);
+                    const float4 gM0 = ld4(ws.GVEC + (i3 + 0) * D + col), gM1 = ld4(ws.GVEC + (i3 + 1) * D + col),
+                                 gM2 = ld4(ws.GVEC + (i3 + 2) * D + col);
+                    const float gx_ = warp_sum(hsum4(gM0 * s2)), gy_ = warp_sum(hsum4(gM1 * s2)), gz_ = warp_sum(hsum4(gM2 * s2));
+                    if (lane == 0) { sh.eacc[row][1] = gx_; sh.eacc[row][2] = gy_; sh.eacc[row][3] = gz_; }
+                    st4(&sh.tile[row][col], (gM0 * dd.x + gM1 * dd.y + gM2 * dd.z) * dsilu4(sp));
+                }
+            }
+            csync();
+            wait_done(J_G3A, tpar);
+            tc2_tile_to_a(sh, tmem, warp, lane);               // A = g_Spre[:, 128:256]
+            tc2_go(sh, J_G3B);
+            // ---- g_m = g_xa_i + g_Spre Ws ; adjoint of m = v_j dv A ----
+            wait_done(J_G3B, tpar);
+            stage_d(TC_COL_D1);
+#pragma unroll 4
+            for (int r = 0; r < TC2_RPW; r++) {
+                const int row = r0 + r;
+                const size_t i = sh.meta.dst[row], j = sh.meta.src[row];
+                const float Ce = sh.meta.C[row];
+                const float av = sh.attn[row][hd], sa = silu_(av), A = sa * Ce;
+                const float4 gm = ld4(&sh.tile[row][col]) + ld4(ws.GXA + i * D + col);
+                const float4 vj = ld4(QKV + j * 3 * D + 2 * D + col);
+                const float4 pdv = ld4(scr1 + row * D + col);
+                const float4 dv = silu4(pdv);
+                if (row < nvalid) red4(ws.GQKV + j * 3 * D + 2 * D + col, gm * dv * A);
+                st4(&sh.tile[row][col], gm * vj * A * dsilu4(pdv));      // g_Pdv
+                const float gA = quad_sum(hsum4(gm * vj * dv));
+                if ((lane & 3) == 0) sh.gattn[row][hd] = gA * Ce * dsilu_(av);
+                const float gc = warp_sum((lane & 3) == 0 ? gA * sa : 0.f);
+                if (lane == 0) sh.eacc[row][0] = gc;
+            }
+            csync();
+            tc2_tile_to_a(sh, tmem, warp, lane);               // A = g_Pdv  (A free: g3b done)
+            tc2_go(sh, J_G4DV);
+            csync();
+            // ---- adjoint of a_h = sum q_i k_j dk ----
+#pragma unroll 4
+            for (int r = 0; r < TC2_RPW; r++) {
+                const int row = r0 + r;
+                const size_t i = sh.meta.dst[row], j = sh.meta.src[row];
+                const float4 pdk = ld4(scr0 + row * D + col);
+                const float4 dk = silu4(pdk);
+                const float4 qi = ld4(QKV + i * 3 * D + col), kj = ld4(QKV + j * 3 * D + D + col);
+                const float gav = sh.gattn[row][hd];
+                st4(&sh.tile[row][col], kj * dk * gav);                   // per-edge g_q contribution
+                if (row < nvalid) red4(ws.GQKV + j * 3 * D + D + col, qi * dk * gav);
+                st4(scr0 + row * D + col, qi * kj * gav * dsilu4(pdk));    // g_Pdk
+            }
+            csync();
+            {
+                const int i_first = sh.meta.dst[0], i_last = sh.meta.dst[nvalid - 1];
+                for (int i = i_first + grp; i <= i_last; i += 2) {
+                    const int q0 = ws.rowptr[i], q1 = ws.rowptr[i + 1];
+                    const int lo = max(q0, e0) - e0, hi = min(q1, e0 + nvalid) - e0;
+                    float gq = 0.f;
+                    for (int r = lo; r < hi; r++) gq += sh.tile[r][cch];
+                    if (q0 >= e0 && q1 <= e0 + nvalid) ws.GQKV[(size_t)i * 3 * D + cch] = gq;
+                    else atomicAdd(ws.GQKV + (size_t)i * 3 * D + cch, gq);
+                }
+            }
+            csync();
+            for (int idx = threadIdx.x; idx < TC_TE * 32; idx += TC2_CTHREADS) {
+                const int row = idx >> 5, c4 = (idx & 31) * 4;
+                st4(&sh.tile[row][c4], ld4(scr0 + row * D + c4));
+            }
+            csync();
+            wait_done(J_G4DV, tpar);
+            tc2_tile_to_a(sh, tmem, warp, lane);               // A = g_Pdk
+            tc2_go(sh, J_G4DK);
+            // ---- adjoint of the edge update ----
+            if (upd) {
+                csync();
+#pragma unroll 2
+                for (int r = 0; r < TC2_RPW; r++) {
+                    const int row = r0 + r;
+                    const bool ok = row < nvalid;
+                    const size_t i3 = (size_t)sh.meta.dst[row] * 3, j3 = (size_t)sh.meta.src[row] * 3;
+                    const float4 dd = sh.meta.d[row];
+                    const float4 gfn = ok ? ld4(ws.GF + (size_t)(e0 + row) * D + col) : f4s(0.f);
+                    const float4 pf = ld4(scr2 + row * D + col);
+                    const float4 fp = silu4(pf);
+                    float4 ti[3], uj[3];
+#pragma unroll
+                    for (int s = 0; s < 3; s++) {
+                        ti[s] = ld4(TU + (i3 + s) * 2 * D + col);
+                        uj[s] = ld4(TU + (j3 + s) * 2 * D + D + col);
+                    }
+                    const float dv3[3] = {dd.x, dd.y, dd.z};
+                    const float4 a1 = ti[0] * dd.x + ti[1] * dd.y + ti[2] * dd.z;
+                    const float4 a2 = uj[0] * dd.x + uj[1] * dd.y + uj[2] * dd.z;
+                    float4 w1[3], w2[3];
+#pragma unroll
+                    for (int s = 0; s < 3; s++) { w1[s] = ti[s] - a1 * dv3[s]; w2[s] = uj[s] - a2 * dv3[s]; }
+                    const float4 wdot = w1[0] * w2[0] + w1[1] * w2[1] + w1[2] * w2[2];
+                    const float4 gwd = gfn * fp;
+                    st4(&sh.tile[row][col], gwd);
+                    st4(scr2 + row * D + col, gfn * wdot * dsilu4(pf));       // g_Pf
+                    const float4 c1 = gwd * (w2[0] * dd.x + w2[1] * dd.y + w2[2] * dd.z);
+                    const float4 c2 = gwd * (w1[0] * dd.x + w1[1] * dd.y + w1[2] * dd.z);
+                    float gdl[3];
+#pragma unroll
+                    for (int s = 0; s < 3; s++) {
+                        const float4 gw1 = gwd * w2[s], gw2 = gwd * w1[s];
+                        if (ok) red4(ws.GTU + (j3 + s) * 2 * D + D + col, gw2 - c2 * dv3[s]);
+                        gdl[s] = warp_sum(hsum4(ti[s] * c1 + a1 * gw1 + uj[s] * c2 + a2 * gw2));
+                    }
+                    if (lane == 0) { sh.eacc[row][1] -= gdl[0]; sh.eacc[row][2] -= gdl[1]; sh.eacc[row][3] -= gdl[2]; }
+                }
+                csync();
+                {
+                    const int i_first = sh.meta.dst[0], i_last = sh.meta.dst[nvalid - 1];
+                    for (int i = i_first + grp; i <= i_last; i += 2) {
+                        const int q0 = ws.rowptr[i], q1 = ws.rowptr[i + 1];
+                        const int lo = max(q0, e0) - e0, hi = min(q1, e0 + nvalid) - e0;
+                        float gt0 = 0.f, gt1 = 0.f, gt2 = 0.f;
+                        for (int r = lo; r < hi; r++) {
+                            const size_t j3 = (size_t)sh.meta.src[r] * 3;
+                            const float4 dd = sh.meta.d[r];
+                            const float gw = sh.tile[r][cch];
+                            const float u0 = TU[(j3 + 0) * 2 * D + D + cch], u1 = TU[(j3 + 1) * 2 * D + D + cch],
+                                        u2 = TU[(j3 + 2) * 2 * D + D + cch];
+                            const float a2 = u0 * dd.x + u1 * dd.y + u2 * dd.z;
+                            const float w20 = u0 - a2 * dd.x, w21 = u1 - a2 * dd.y, w22 = u2 - a2 * dd.z;
+                            const float wd = w20 * dd.x + w21 * dd.y + w22 * dd.z;
+                            gt0 += gw * (w20 - wd * dd.x);
+                            gt1 += gw * (w21 - wd * dd.y);
+                            gt2 += gw * (w22 - wd * dd.z);
+                        }
+                        if (q0 >= e0 && q1 <= e0 + nvalid) {
+                            ws.GTU[((size_t)i * 3 + 0) * 2 * D + cch] = gt0;
+                            ws.GTU[((size_t)i * 3 + 1) * 2 * D + cch] = gt1;
+                            ws.GTU[((size_t)i * 3 + 2) * 2 * D + cch] = gt2;
+                        } else {
+                            atomicAdd(ws.GTU + ((size_t)i * 3 + 0) * 2 * D + cch, gt0);
+                            atomicAdd(ws.GTU + ((size_t)i * 3 + 1) * 2 * D + cch, gt1);
+                            atomicAdd(ws.GTU + ((size_t)i * 3 + 2) * 2 * D + cch, gt2);
+                        }
+                    }
+                }
+                csync();
+                for (int idx = threadIdx.x; idx < TC_TE * 32; idx += TC2_CTHREADS) {
+                    const int row = idx >> 5, c4 = (idx & 31) * 4;
+                    st4(&sh.tile[row][c4], ld4(scr2 + row * D + c4));
+                }
+                csync();
+                wait_done(J_G4DK, tpar);
+                tc2_tile_to_a(sh, tmem, warp, lane);           // A = g_Pf
+                tc2_go(sh, J_G4F);
+            }
+            // ---- g_f = g_f_next + [g_Pdk|g_Pdv|g_Pf] W1 ----
+            wait_done(J_LAST, tpar);
+            stage_d(TC_COL_D0);
+#pragma unroll 4
+            for (int r = 0; r < TC2_RPW; r++) {
+                const int row = r0 + r;
+                if (row < nvalid) {
+                    float* g = ws.GF + (size_t)(e0 + row) * D + col;
+                    float4 v = ld4(&sh.tile[row][col]);
+                    if (upd) v = v + ld4(g);
+                    st4(g, v);
+                }
+            }
+            if (threadIdx.x < nvalid) {
+                float* ea = ws.eacc + (size_t)(e0 + threadIdx.x) * 4;
+                st4(ea, ld4(ea) + ld4(&sh.eacc[threadIdx.x][0]));
+            }
+            csync();
         }
     }
     tc2_teardown(tmem);

@@ -158,6 +158,7 @@ __global__ void __launch_bounds__(128) embed_node_kernel(ModelW mw, Workspace ws
     const float bc = __ldg(mw.bc + c);
 #pragma unroll
     for (int nd = 0; nd < EMB_NB; nd++) out[nd] = bc;
+#pragma unroll 8
     for (int k = 0; k < 2 * D; k++) {
         const float w = __ldg(mw.WcT + k * D + c);
 #pragma unroll
@@ -266,6 +267,7 @@ __global__ void __launch_bounds__(128) embed_node_bwd_kernel(ModelW mw, Workspac
     const float bd = __ldg(mw.bd + c);
     __syncthreads();
     float g_agg = 0.f;
+#pragma unroll 8
     for (int k = 0; k < D; k++) g_agg = fmaf(gx_s[k], __ldg(mw.WcN + (size_t)k * 2 * D + D + c), g_agg);
     const float alpha = 5.0f / mw.cutoff;
     float fix = 0.f, fiy = 0.f, fiz = 0.f;   // accumulated -dE/dpos_i contributions (thread 0)

@@ -27,7 +27,7 @@ class _HParams(C.Structure):
 EXPORTED_SYMBOLS = [
     "vb_weight_manifest", "vb_create", "vb_destroy", "vb_last_error", "vb_set_topology", "vb_forward",
     "vb_forward_host", "vb_set_protein_map", "vb_forward_protein", "vb_get_edges", "vb_launches_per_forward",
-    "vb_set_option", "vb_num_stages", "vb_stage_name", "vb_debug_run", "vb_debug_read", "vb_profile_stages", "vb_tc_selftest",
+    "vb_set_option", "vb_get_option", "vb_num_stages", "vb_stage_name", "vb_debug_run", "vb_debug_read", "vb_profile_stages", "vb_tc_selftest",
 ]
 
 
@@ -66,6 +66,8 @@ def load_library(path: Optional[str] = None):
     lib.vb_launches_per_forward.argtypes = [vp]
     lib.vb_set_option.restype = C.c_int
     lib.vb_set_option.argtypes = [vp, C.c_char_p, i64]
+    lib.vb_get_option.restype = i64
+    lib.vb_get_option.argtypes = [vp, C.c_char_p]
     lib.vb_num_stages.restype = C.c_int
     lib.vb_num_stages.argtypes = [vp]
     lib.vb_stage_name.restype = C.c_char_p
@@ -146,6 +148,9 @@ class Engine:
 
     def set_option(self, key: str, value: int):
         self._check(self.lib.vb_set_option(self.h, key.encode(), int(value)), "vb_set_option")
+
+    def get_option(self, key: str) -> int:
+        return int(self.lib.vb_get_option(self.h, key.encode()))
 
     # ---- evaluation ----
     def forward_host(self, pos: np.ndarray) -> Tuple[np.ndarray, np.ndarray]:

@@ -321,7 +321,8 @@ def run_ours(args):
     roofline = {"bound": "hbm", "kernel": top[0], "kernel_ms": top[1], "algorithmic_bytes": ab,
                 "achieved": achieved, "peak": peak, "peak_kind": peak_kind, "unit": "GB/s",
                 "frac": (achieved / peak) if achieved else None, "traffic": None,
-                "note": "fp32 SIMT contractions dominate this kernel (compute-bound); workload is L2-resident at this size",
+                "note": "algorithmic bytes = SURVEY 8d fused lower bound for this launch; the kernel is contraction/latency bound, "
+                        "not HBM bound (see DESIGN.md); workloads below ~2k atoms are L2 resident",
                 "share_of_step": top[1] / total_ms,
                 "family_ms": {k: round(v, 4) for k, v in sorted(fam.items(), key=lambda x: -x[1])}}
 
@@ -351,7 +352,9 @@ def run_ours(args):
                    "parallelism": f"fragments sharded over {world} GPU(s), 1 NCCL all-reduce/step" if world > 1 else "single GPU",
                    "l2": "flushed (256 MiB write) before every timed step" if flush is not None else "warm",
                    "timing": "CUDA events around each step on the launching stream, max over ranks",
-                   "cuda_graph": True},
+                   "cuda_graph": True,
+                   "edge_kernels": "tcgen05 (TMEM accumulators, TMA weight ring, 3xTF32)" if shard.engine.get_option("edge_tc") == 3
+                                   else ("fp32 SIMT" if shard.engine.get_option("edge_tc") == 0 else f"mixed ({shard.engine.get_option('edge_tc')})")},
         "value_l2_warm": args.steps / float(t_warm.item()),
         "wall_s_timed_region": wall,
         "e2e": e2e,
