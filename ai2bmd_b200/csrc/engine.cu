@@ -188,6 +188,9 @@ void layout_workspace(vb_handle* h, char* base, ArenaPlan& plan, int*& z, int*& 
         carve(plan, base, ws.VDOT[l], N * D);
         carve(plan, base, ws.TU[l], N * 6 * D);
         carve(plan, base, ws.O[l], N * 3 * D);
+        carve(plan, base, ws.P1[l], E * 3 * D);
+        carve(plan, base, ws.SP[l], E * 2 * D);
+        carve(plan, base, ws.ATT[l], E * H);
     }
     carve(plan, base, ws.XA, N * D);
     carve(plan, base, ws.VA, N * 3 * D);
@@ -322,11 +325,6 @@ void launch_edge_bwd_tc(Launcher& Lc, int l) {
     const size_t chunk = 4 * 8192;
     const bool upd = l < L - 1;
     int n = 0;
-    a.jobs[n++] = TcJob{lw.tcW1, (int)TC_COL_D0, 0};                         // dk
-    a.jobs[n++] = TcJob{lw.tcW1 + chunk, (int)TC_COL_D1, 0};                 // dv
-    if (upd) a.jobs[n++] = TcJob{lw.tcW1 + 2 * chunk, (int)TC_COL_D0, 0};     // f
-    a.jobs[n++] = TcJob{lw.tcWs, (int)TC_COL_D1, 0};                         // s1
-    a.jobs[n++] = TcJob{lw.tcWs + chunk, (int)TC_COL_D0, 0};                 // s2
     a.jobs[n++] = TcJob{lw.tcWsN, (int)TC_COL_D1, 0};                        // g_m  = g_s1' Ws[0:128]
     a.jobs[n++] = TcJob{lw.tcWsN + chunk, (int)TC_COL_D1, 1};                //      + g_s2' Ws[128:256]
     a.jobs[n++] = TcJob{lw.tcW1N + chunk, (int)TC_COL_D0, 0};                // g_f  = g_Pdv Wdv
@@ -335,7 +333,7 @@ void launch_edge_bwd_tc(Launcher& Lc, int l) {
     a.njobs = n;
     const int tiles = (h->ws.Ecap + TC_TE - 1) / TC_TE;
     const int blocks = std::max(1, std::min(tiles, h->sm_count));
-    edge_bwd_tc_kernel<<<blocks, TC2_THREADS, TC_SMEM_BYTES, Lc.st>>>(a, h->d_tc_scratch);
+    edge_bwd_tc_kernel<<<blocks, TC2_THREADS, TC_SMEM_BYTES, Lc.st>>>(a);
     Lc.check();
 }
 
@@ -403,7 +401,7 @@ int configure_kernels(vb_handle* h) {
     CUDA_TRY(h, opt_in_smem(head_kernel<2>, HeadSmem<2>::BYTES));
     CUDA_TRY(h, opt_in_smem(edge_fwd_tc_kernel, TC_SMEM_BYTES));
     CUDA_TRY(h, opt_in_smem(edge_bwd_tc_kernel, TC_SMEM_BYTES));
-    CUDA_TRY(h, cudaMalloc(&h->d_tc_scratch, sizeof(float) * (size_t)h->sm_count * 3 * TC_TE * D));
+
     CUDA_TRY(h, opt_in_smem(node_fwd2_kernel<8>, sizeof(NodeFwd2Smem<8>)));
     CUDA_TRY(h, opt_in_smem(node_fwd2_kernel<16>, sizeof(NodeFwd2Smem<16>)));
     CUDA_TRY(h, opt_in_smem(node_bwd2_kernel<8>, sizeof(NodeBwd2Smem<8>)));
@@ -827,6 +825,9 @@ int64_t vb_debug_read(vb_handle* h, const char* name, int layer, void* host_dst,
     else if (k == "VDOT" && lay(L)) { src = ws.VDOT[layer]; bytes = N * D * 4; }
     else if (k == "TU" && lay(L)) { src = ws.TU[layer]; bytes = N * 6 * D * 4; }
     else if (k == "O" && lay(L)) { src = ws.O[layer]; bytes = N * 3 * D * 4; }
+    else if (k == "P1" && lay(L)) { src = ws.P1[layer]; bytes = E * 3 * D * 4; }
+    else if (k == "SP" && lay(L)) { src = ws.SP[layer]; bytes = E * 2 * D * 4; }
+    else if (k == "ATT" && lay(L)) { src = ws.ATT[layer]; bytes = E * H * 4; }
     else BUF("XA", ws.XA, N * D, 4)
     else BUF("VA", ws.VA, N * 3 * D, 4)
     else BUF("GX", ws.GX, N * D, 4)

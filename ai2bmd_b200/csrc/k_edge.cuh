@@ -84,6 +84,9 @@ __global__ void __launch_bounds__(NW * 32) edge_fwd_kernel(EdgeArgs a) {
     const float* __restrict__ QKV = ws.QKV[l];
     const float* __restrict__ VN = ws.VN[l];
     const float* __restrict__ TU = ws.TU[l];
+    float* __restrict__ P1 = ws.P1[l];
+    float* __restrict__ SP = ws.SP[l];
+    float* __restrict__ ATT = ws.ATT[l];
     const int r0 = warp * R;
 
     for (int e0 = blockIdx.x * TE; e0 < E; e0 += gridDim.x * TE) {
@@ -112,7 +115,10 @@ __global__ void __launch_bounds__(NW * 32) edge_fwd_kernel(EdgeArgs a) {
                 const float4 a2 = uj[0] * dd.x + uj[1] * dd.y + uj[2] * dd.z;
                 const float4 wdot = (ti[0] - a1 * dd.x) * (uj[0] - a2 * dd.x) + (ti[1] - a1 * dd.y) * (uj[1] - a2 * dd.y) +
                                     (ti[2] - a1 * dd.z) * (uj[2] - a2 * dd.z);
-                if (row < nvalid) st4(Fout + (size_t)(e0 + row) * D + col, ld4(Fs + row * LE1 + col) + fp * wdot);
+                if (row < nvalid) {
+                    st4(Fout + (size_t)(e0 + row) * D + col, ld4(Fs + row * LE1 + col) + fp * wdot);
+                    st4(P1 + (size_t)(e0 + row) * 3 * D + 2 * D + col, arr4(acc[r]));
+                }
             }
         }
         // ---- attention weight A_h = silu(sum_{c in h} q_i k_j dk) * C(r) ----
@@ -126,6 +132,10 @@ __global__ void __launch_bounds__(NW * 32) edge_fwd_kernel(EdgeArgs a) {
             const float4 kj = ld4(QKV + (size_t)meta.src[row] * 3 * D + D + col);
             const float av = quad_sum(hsum4(qi * kj * silu4(arr4(acc[r]))));
             Areg[r] = silu_(av) * meta.C[row];
+            if (row < nvalid) {
+                st4(P1 + (size_t)(e0 + row) * 3 * D + col, arr4(acc[r]));
+                if ((lane & 3) == 0) ATT[(size_t)(e0 + row) * H + (lane >> 2)] = av;
+            }
         }
         // ---- message m = v_j * dv * A  (overwrites this warp's rows of the f tile) ----
         acc_set_bias<R>(acc, lw.b1 + D, lane);
@@ -136,6 +146,7 @@ __global__ void __launch_bounds__(NW * 32) edge_fwd_kernel(EdgeArgs a) {
             const int row = r0 + r;
             const float4 vj = ld4(QKV + (size_t)meta.src[row] * 3 * D + 2 * D + col);
             st4(Fs + row * LE1 + col, vj * silu4(arr4(acc[r])) * Areg[r]);
+            if (row < nvalid) st4(P1 + (size_t)(e0 + row) * 3 * D + D + col, arr4(acc[r]));
         }
         __syncwarp();
         // ---- [s1|s2] = silu(m Ws^T + bs) ----
@@ -144,7 +155,10 @@ __global__ void __launch_bounds__(NW * 32) edge_fwd_kernel(EdgeArgs a) {
             acc_set_bias<R>(acc, lw.bs + ch * D, lane);
             warp_gemm<R, D, LE1>(acc, Fs + r0 * LE1, lw.WsT + ch * D, 2 * D, lane);
 #pragma unroll
-            for (int r = 0; r < R; r++) st4(Ss + (r0 + r) * LE2 + ch * D + col, silu4(arr4(acc[r])));
+            for (int r = 0; r < R; r++) {
+                st4(Ss + (r0 + r) * LE2 + ch * D + col, silu4(arr4(acc[r])));
+                if (r0 + r < nvalid) st4(SP + (size_t)(e0 + r0 + r) * 2 * D + ch * D + col, arr4(acc[r]));
+            }
         }
         __syncthreads();
         // ---- segmented reduction onto the targets present in this tile ----
@@ -193,11 +207,18 @@ __global__ void __launch_bounds__(NW * 32) edge_fwd_kernel(EdgeArgs a) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// adjoint
+// adjoint.  The forward stage left the pre-activations P1 = [Pdk|Pdv|Pf], SP = s_proj pre-activation and the
+// attention pre-activation ATT in HBM/L2, so the reverse sweep only runs the two adjoint contractions
+//   g_m = g_xa_i + g_Spre Ws            (K = 256)
+//   g_f = g_f_next + [g_Pdk|g_Pdv|g_Pf] W1   (K = 384, 256 in the last layer)
+// (measured: the stage is contraction bound, not HBM bound, so 2.5 KB/edge of stored state beats recomputing
+// five 128x128 contractions per edge tile).
 // ---------------------------------------------------------------------------------------------
+constexpr int LEQ = 2 * D + 2 * LDS_PAD;   // 264: g_Spre row (256) / later the two per-edge tiles g_q (0..127) and g_wdot (132..259)
+
 template <int TE>
 constexpr size_t edge_bwd_smem_bytes() {
-    return (size_t)TE * (3 * LE1 + LE3) * sizeof(float) + sizeof(EdgeMeta<TE>);
+    return (size_t)TE * (LEQ + LE3) * sizeof(float) + sizeof(EdgeMeta<TE>);
 }
 
 template <int TE, int NW>
@@ -205,75 +226,39 @@ __global__ void __launch_bounds__(NW * 32) edge_bwd_kernel(EdgeArgs a) {
     constexpr int R = TE / NW, NT = NW * 32;
     static_assert(TE % NW == 0 && NT % D == 0, "tile shape");
     extern __shared__ __align__(16) float dyn_smem[];
-    float* Fs = dyn_smem;                 // [TE][132]  f -> s_proj pre-act (cols 0..127) / its adjoint -> per-edge g_q
-    float* Ms = Fs + TE * LE1;            // [TE][132]  m -> per-edge g_wdot
-    float* Xs = Ms + TE * LE1;            // [TE][132]  s_proj pre-act (cols 128..255) / its adjoint
-    float* Ps = Xs + TE * LE1;            // [TE][388]  [Pdk|Pdv|Pf] pre-activations -> their adjoints
+    float* Ss = dyn_smem;                 // [TE][264]  g_Spre (A operand of g_m), later g_q | g_wdot per-edge tiles
+    float* Ps = Ss + TE * LEQ;            // [TE][388]  g_P (A operand of g_f)
     EdgeMeta<TE>& meta = *reinterpret_cast<EdgeMeta<TE>*>(Ps + TE * LE3);
     const Workspace& ws = a.ws;
     const int l = a.layer;
     const LayerW& lw = a.mw.layer[l];
     const bool upd = (l < L - 1);
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, col = lane * 4;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, col = lane * 4, hd = lane >> 2;
     const int E = ws.rowptr[ws.N];
-    const float* __restrict__ Fin = ws.F[l];
     const float* __restrict__ QKV = ws.QKV[l];
     const float* __restrict__ VN = ws.VN[l];
     const float* __restrict__ TU = ws.TU[l];
+    const float* __restrict__ P1 = ws.P1[l];
+    const float* __restrict__ SP = ws.SP[l];
+    const float* __restrict__ ATT = ws.ATT[l];
     const int r0 = warp * R;
+    constexpr int QOFF = 0, WOFF = D + LDS_PAD;   // column offsets of the two per-edge tiles inside an Ss row
 
     for (int e0 = blockIdx.x * TE; e0 < E; e0 += gridDim.x * TE) {
         const int nvalid = min(TE, E - e0);
-        load_f_tile<TE, NT>(Fs, Fin, e0, nvalid);
         load_edge_meta<TE, NT>(meta, ws, e0, nvalid);
         __syncthreads();
         float acc[R][4];
-        float areg[R];           // attention pre-activation a_h of this lane's head
         float gdx[R], gdy[R], gdz[R], gC[R];
-        // ---- recompute forward pre-activations ----
-        acc_set_bias<R>(acc, lw.b1, lane);
-        warp_gemm<R, D, LE1>(acc, Fs + r0 * LE1, lw.W1T, 3 * D, lane);
-#pragma unroll
-        for (int r = 0; r < R; r++) {
-            const int row = r0 + r;
-            st4(Ps + row * LE3 + col, arr4(acc[r]));
-            const float4 qi = ld4(QKV + (size_t)meta.dst[row] * 3 * D + col);
-            const float4 kj = ld4(QKV + (size_t)meta.src[row] * 3 * D + D + col);
-            areg[r] = quad_sum(hsum4(qi * kj * silu4(arr4(acc[r]))));
-        }
-        acc_set_bias<R>(acc, lw.b1 + D, lane);
-        warp_gemm<R, D, LE1>(acc, Fs + r0 * LE1, lw.W1T + D, 3 * D, lane);
-#pragma unroll
-        for (int r = 0; r < R; r++) {
-            const int row = r0 + r;
-            st4(Ps + row * LE3 + D + col, arr4(acc[r]));
-            const float4 vj = ld4(QKV + (size_t)meta.src[row] * 3 * D + 2 * D + col);
-            st4(Ms + row * LE1 + col, vj * silu4(arr4(acc[r])) * (silu_(areg[r]) * meta.C[row]));
-        }
-        if (upd) {
-            acc_set_bias<R>(acc, lw.b1 + 2 * D, lane);
-            warp_gemm<R, D, LE1>(acc, Fs + r0 * LE1, lw.W1T + 2 * D, 3 * D, lane);
-#pragma unroll
-            for (int r = 0; r < R; r++) st4(Ps + (r0 + r) * LE3 + 2 * D + col, arr4(acc[r]));
-        }
-        __syncwarp();
-        // s_proj pre-activation: cols 0..127 -> Fs rows (f is dead), cols 128..255 -> Xs rows
-        acc_set_bias<R>(acc, lw.bs, lane);
-        warp_gemm<R, D, LE1>(acc, Ms + r0 * LE1, lw.WsT, 2 * D, lane);
-#pragma unroll
-        for (int r = 0; r < R; r++) st4(Fs + (r0 + r) * LE1 + col, arr4(acc[r]));
-        acc_set_bias<R>(acc, lw.bs + D, lane);
-        warp_gemm<R, D, LE1>(acc, Ms + r0 * LE1, lw.WsT + D, 2 * D, lane);
-#pragma unroll
-        for (int r = 0; r < R; r++) st4(Xs + (r0 + r) * LE1 + col, arr4(acc[r]));
-        // ---- adjoint of M = vn_j*s1 + s2*d  and of silu(s_proj) ----
+        // ---- adjoint of M = vn_j*s1 + s2*d and of silu(s_proj) ----
 #pragma unroll
         for (int r = 0; r < R; r++) {
             const int row = r0 + r;
             const bool ok = row < nvalid;
+            const size_t e = (size_t)(e0 + (ok ? row : 0));
             const size_t i3 = (size_t)meta.dst[row] * 3, j3 = (size_t)meta.src[row] * 3;
             const float4 dd = meta.d[row];
-            const float4 sp1 = ld4(Fs + row * LE1 + col), sp2 = ld4(Xs + row * LE1 + col);
+            const float4 sp1 = ld4(SP + e * 2 * D + col), sp2 = ld4(SP + e * 2 * D + D + col);
             const float4 s1 = silu4(sp1), s2 = silu4(sp2);
             const float4 gM0 = ld4(ws.GVEC + (i3 + 0) * D + col);
             const float4 gM1 = ld4(ws.GVEC + (i3 + 1) * D + col);
@@ -289,8 +274,8 @@ __global__ void __launch_bounds__(NW * 32) edge_bwd_kernel(EdgeArgs a) {
             gdx[r] = warp_sum(hsum4(gM0 * s2));
             gdy[r] = warp_sum(hsum4(gM1 * s2));
             gdz[r] = warp_sum(hsum4(gM2 * s2));
-            st4(Fs + row * LE1 + col, gs1 * dsilu4(sp1));
-            st4(Xs + row * LE1 + col, gs2 * dsilu4(sp2));
+            st4(Ss + row * LEQ + col, ok ? gs1 * dsilu4(sp1) : f4s(0.f));
+            st4(Ss + row * LEQ + D + col, ok ? gs2 * dsilu4(sp2) : f4s(0.f));
         }
         __syncwarp();
         // ---- g_m = g_xa_i + g_Spre Ws ----
@@ -299,32 +284,32 @@ __global__ void __launch_bounds__(NW * 32) edge_bwd_kernel(EdgeArgs a) {
             const float4 t = ld4(ws.GXA + (size_t)meta.dst[r0 + r] * D + col);
             acc[r][0] = t.x; acc[r][1] = t.y; acc[r][2] = t.z; acc[r][3] = t.w;
         }
-        warp_gemm<R, D, LE1>(acc, Fs + r0 * LE1, lw.WsN, D, lane);
-        warp_gemm<R, D, LE1>(acc, Xs + r0 * LE1, lw.WsN + (size_t)D * D, D, lane);
+        warp_gemm<R, 2 * D, LEQ>(acc, Ss + r0 * LEQ, lw.WsN, D, lane);
         __syncwarp();
 #pragma unroll
         for (int r = 0; r < R; r++) {
             const int row = r0 + r;
             const bool ok = row < nvalid;
+            const size_t e = (size_t)(e0 + (ok ? row : 0));
             const size_t i = meta.dst[row], j = meta.src[row];
             const float4 gm = arr4(acc[r]);
             const float Ce = meta.C[row];
-            const float av = areg[r], sa = silu_(av), A = sa * Ce;
+            const float av = ok ? ATT[e * H + hd] : 0.f, sa = silu_(av), A = sa * Ce;
             const float4 vj = ld4(QKV + j * 3 * D + 2 * D + col);
-            const float4 pdv = ld4(Ps + row * LE3 + D + col);
+            const float4 pdv = ld4(P1 + e * 3 * D + D + col);
             const float4 dv = silu4(pdv);
             if (ok) red4(ws.GQKV + j * 3 * D + 2 * D + col, gm * dv * A);
-            st4(Ps + row * LE3 + D + col, gm * vj * A * dsilu4(pdv));
+            st4(Ps + row * LE3 + D + col, ok ? gm * vj * A * dsilu4(pdv) : f4s(0.f));
             const float gA = quad_sum(hsum4(gm * vj * dv));
             const float ga = gA * Ce * dsilu_(av);
             gC[r] = warp_sum((lane & 3) == 0 ? gA * sa : 0.f);
-            const float4 pdk = ld4(Ps + row * LE3 + col);
+            const float4 pdk = ld4(P1 + e * 3 * D + col);
             const float4 dk = silu4(pdk);
             const float4 qi = ld4(QKV + i * 3 * D + col);
             const float4 kj = ld4(QKV + j * 3 * D + D + col);
-            st4(Fs + row * LE1 + col, kj * dk * ga);                    // per-edge g_q contribution
+            st4(Ss + row * LEQ + QOFF + col, kj * dk * ga);              // per-edge g_q contribution
             if (ok) red4(ws.GQKV + j * 3 * D + D + col, qi * dk * ga);   // g_k (source side)
-            st4(Ps + row * LE3 + col, qi * kj * ga * dsilu4(pdk));
+            st4(Ps + row * LE3 + col, ok ? qi * kj * ga * dsilu4(pdk) : f4s(0.f));
         }
         // ---- adjoint of the edge update ----
         if (upd) {
@@ -332,10 +317,11 @@ __global__ void __launch_bounds__(NW * 32) edge_bwd_kernel(EdgeArgs a) {
             for (int r = 0; r < R; r++) {
                 const int row = r0 + r;
                 const bool ok = row < nvalid;
+                const size_t e = (size_t)(e0 + (ok ? row : 0));
                 const size_t i3 = (size_t)meta.dst[row] * 3, j3 = (size_t)meta.src[row] * 3;
                 const float4 dd = meta.d[row];
-                const float4 gfn = ok ? ld4(ws.GF + (size_t)(e0 + row) * D + col) : f4s(0.f);
-                const float4 pf = ld4(Ps + row * LE3 + 2 * D + col);
+                const float4 gfn = ok ? ld4(ws.GF + e * D + col) : f4s(0.f);
+                const float4 pf = ld4(P1 + e * 3 * D + 2 * D + col);
                 const float4 fp = silu4(pf);
                 float4 ti[3], uj[3];
 #pragma unroll
@@ -351,9 +337,8 @@ __global__ void __launch_bounds__(NW * 32) edge_bwd_kernel(EdgeArgs a) {
                 for (int s = 0; s < 3; s++) { w1[s] = ti[s] - a1 * dv3[s]; w2[s] = uj[s] - a2 * dv3[s]; }
                 const float4 wdot = w1[0] * w2[0] + w1[1] * w2[1] + w1[2] * w2[2];
                 const float4 gwd = gfn * fp;
-                st4(Ms + row * LE1 + col, gwd);
+                st4(Ss + row * LEQ + WOFF + col, gwd);
                 st4(Ps + row * LE3 + 2 * D + col, gfn * wdot * dsilu4(pf));
-                // g_w1 = gwd*w2, g_w2 = gwd*w1
                 const float4 c1 = gwd * (w2[0] * dd.x + w2[1] * dd.y + w2[2] * dd.z);
                 const float4 c2 = gwd * (w1[0] * dd.x + w1[1] * dd.y + w1[2] * dd.z);
                 float gdl[3];
@@ -394,11 +379,11 @@ __global__ void __launch_bounds__(NW * 32) edge_bwd_kernel(EdgeArgs a) {
                 const int hi = min(ws.rowptr[i + 1], e0 + nvalid) - e0;
                 float gq = 0.f, gt0 = 0.f, gt1 = 0.f, gt2 = 0.f;
                 for (int e = lo; e < hi; e++) {
-                    gq += Fs[e * LE1 + c];
+                    gq += Ss[e * LEQ + QOFF + c];
                     if (upd) {
                         const size_t j3 = (size_t)meta.src[e] * 3;
                         const float4 dd = meta.d[e];
-                        const float gw = Ms[e * LE1 + c];
+                        const float gw = Ss[e * LEQ + WOFF + c];
                         const float u0 = TU[(j3 + 0) * 2 * D + D + c], u1 = TU[(j3 + 1) * 2 * D + D + c],
                                     u2 = TU[(j3 + 2) * 2 * D + D + c];
                         const float a2 = u0 * dd.x + u1 * dd.y + u2 * dd.z;

@@ -298,6 +298,9 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) edge_fwd_tc_kernel(const __gri
         const float* __restrict__ QKV = ws.QKV[l];
         const float* __restrict__ VN = ws.VN[l];
         const float* __restrict__ TU = ws.TU[l];
+        float* __restrict__ P1 = ws.P1[l];
+        float* __restrict__ SP = ws.SP[l];
+        float* __restrict__ ATT = ws.ATT[l];
         const int r0 = warp * TC2_RPW;
         const int cch = threadIdx.x & (D - 1), grp = threadIdx.x >> 7;      // aggregation role: channel, target parity
         for (int it = 0; it < my_tiles; it++) {
@@ -329,8 +332,13 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) edge_fwd_tc_kernel(const __gri
                     const int row = r0 + r;
                     const float4 qi = ld4(QKV + (size_t)sh.meta.dst[row] * 3 * D + col);
                     const float4 kj = ld4(QKV + (size_t)sh.meta.src[row] * 3 * D + D + col);
-                    const float av = quad_sum(hsum4(qi * kj * silu4(ld4(&sh.tile[row][col]) + bb)));
+                    const float4 P = ld4(&sh.tile[row][col]) + bb;
+                    const float av = quad_sum(hsum4(qi * kj * silu4(P)));
                     Areg[r] = silu_(av) * sh.meta.C[row];
+                    if (row < nvalid) {
+                        st4(P1 + (size_t)(e0 + row) * 3 * D + col, P);
+                        if ((lane & 3) == 0) ATT[(size_t)(e0 + row) * H + (lane >> 2)] = av;
+                    }
                 }
             }
             if (upd) { tc::fence_before_sync(); tc::mbar_arrive(&sh.go[J_F]); }     // D0 is free
@@ -346,7 +354,9 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) edge_fwd_tc_kernel(const __gri
                 for (int r = 0; r < TC2_RPW; r++) {
                     const int row = r0 + r;
                     const float4 vj = ld4(QKV + (size_t)sh.meta.src[row] * 3 * D + 2 * D + col);
-                    st4(&sh.tile[row][col], vj * silu4(ld4(&sh.tile[row][col]) + bb) * Areg[r]);
+                    const float4 P = ld4(&sh.tile[row][col]) + bb;
+                    st4(&sh.tile[row][col], vj * silu4(P) * Areg[r]);
+                    if (row < nvalid) st4(P1 + (size_t)(e0 + row) * 3 * D + D + col, P);
                 }
             }
             csync();
@@ -378,7 +388,9 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) edge_fwd_tc_kernel(const __gri
                     const int row = r0 + r;
                     const size_t i3 = (size_t)sh.meta.dst[row] * 3, j3 = (size_t)sh.meta.src[row] * 3;
                     const float4 dd = sh.meta.d[row];
-                    const float4 fp = silu4(ld4(&sh.tile[row][col]) + bb);
+                    const float4 Pf = ld4(&sh.tile[row][col]) + bb;
+                    const float4 fp = silu4(Pf);
+                    if (row < nvalid) st4(P1 + (size_t)(e0 + row) * 3 * D + 2 * D + col, Pf);
                     float4 ti[3], uj[3];
 #pragma unroll
                     for (int s = 0; s < 3; s++) {
@@ -417,14 +429,18 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) edge_fwd_tc_kernel(const __gri
                         for (int u = 0; u < 4; u++) {
                             const size_t j3 = (size_t)sh.meta.src[r + u] * 3;
                             g[u][0] = VN[(j3 + 0) * D + cch]; g[u][1] = VN[(j3 + 1) * D + cch]; g[u][2] = VN[(j3 + 2) * D + cch];
-                            s1[u] = silu_(sh.tile[r + u][cch] + b);
+                            const float sp = sh.tile[r + u][cch] + b;
+                            SP[(size_t)(e0 + r + u) * 2 * D + cch] = sp;
+                            s1[u] = silu_(sp);
                         }
 #pragma unroll
                         for (int u = 0; u < 4; u++) { v0 += g[u][0] * s1[u]; v1 += g[u][1] * s1[u]; v2 += g[u][2] * s1[u]; }
                     }
                     for (; r < hi; r++) {
                         const size_t j3 = (size_t)sh.meta.src[r] * 3;
-                        const float s1 = silu_(sh.tile[r][cch] + b);
+                        const float sp = sh.tile[r][cch] + b;
+                        SP[(size_t)(e0 + r) * 2 * D + cch] = sp;
+                        const float s1 = silu_(sp);
                         v0 += VN[(j3 + 0) * D + cch] * s1;
                         v1 += VN[(j3 + 1) * D + cch] * s1;
                         v2 += VN[(j3 + 2) * D + cch] * s1;
@@ -456,7 +472,9 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) edge_fwd_tc_kernel(const __gri
                     float v0 = 0.f, v1 = 0.f, v2 = 0.f;
                     for (int r = lo; r < hi; r++) {
                         const float4 de = sh.meta.d[r];
-                        const float s2 = silu_(sh.tile[r][cch] + b);
+                        const float sp = sh.tile[r][cch] + b;
+                        SP[(size_t)(e0 + r) * 2 * D + D + cch] = sp;
+                        const float s2 = silu_(sp);
                         v0 += s2 * de.x; v1 += s2 * de.y; v2 += s2 * de.z;
                     }
                     if (q0 >= e0 && q1 <= e0 + nvalid) {
@@ -482,24 +500,19 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) edge_fwd_tc_kernel(const __gri
 namespace vb {
 
 // ---------------------------------------------------------------------------------------------
-// adjoint (math and reference lines: see edge_bwd_kernel in k_edge.cuh)
-// jobs (upd):  0 dk->D0  1 dv->D1  2 f->D0  3 s1->D1  4 s2->D0  5 g3a->D1  6 g3b->D1(+)  7 g4dv->D0  8 g4dk->D0(+)  9 g4f->D0(+)
-// last layer:  0 dk->D0  1 dv->D1           2 s1->D1  3 s2->D0  4 g3a->D1  5 g3b->D1(+)  6 g4dv->D0  7 g4dk->D0(+)
-// scr = per-CTA global scratch [3][128][128] holding the pre-activations Pdk, Pdv, Pf (L2 resident), later
-// overwritten in place by their adjoints before those are staged as A operands.
+// adjoint on tensor cores (math and reference lines: see edge_bwd_kernel in k_edge.cuh).  Pre-activations come
+// from the forward stage (P1, SP, ATT), so the tile runs only the two adjoint contractions:
+// jobs (upd):  0 g3a -> D1   1 g3b -> D1(+)   2 g4dv -> D0   3 g4dk -> D0(+)   4 g4f -> D0(+)
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(TC2_THREADS, 1) edge_bwd_tc_kernel(const __grid_constant__ EdgeTcArgs a, float* __restrict__ scratch) {
+__global__ void __launch_bounds__(TC2_THREADS, 1) edge_bwd_tc_kernel(const __grid_constant__ EdgeTcArgs a) {
     extern __shared__ __align__(1024) uint8_t dyn_raw[];
     TcShared& sh = *tc_shared_base(dyn_raw);
     const Workspace& ws = a.ws;
     const int l = a.layer;
-    const LayerW& lw = a.mw.layer[l];
     const bool upd = (l < L - 1);
-    const int o = upd ? 1 : 0;
-    const int J_DK = 0, J_DV = 1, J_F = 2, J_S1 = 2 + o, J_S2 = 3 + o, J_G3A = 4 + o, J_G3B = 5 + o, J_G4DV = 6 + o,
-              J_G4DK = 7 + o, J_G4F = 9;
+    const int J_G3A = 0, J_G3B = 1, J_G4DV = 2, J_G4DK = 3, J_G4F = 4;
     const int J_LAST = upd ? J_G4F : J_G4DK;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, col = lane * 4;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, col = lane * 4, hd = lane >> 2;
     const int E = ws.rowptr[ws.N];
     const int ntiles_total = (E + TC_TE - 1) / TC_TE;
     const int my_tiles = ((int)blockIdx.x < ntiles_total) ? (ntiles_total - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
@@ -510,164 +523,120 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) edge_bwd_tc_kernel(const __gri
     } else if (warp == TC2_CWARPS + 1) {
         if (lane == 0) tc_mma_issuer(sh, a.jobs, a.njobs, my_tiles, tmem);
     } else {
-        const float* __restrict__ Fin = ws.F[l];
         const float* __restrict__ QKV = ws.QKV[l];
         const float* __restrict__ VN = ws.VN[l];
         const float* __restrict__ TU = ws.TU[l];
-        float* scr0 = scratch + (size_t)blockIdx.x * 3 * TC_TE * D;
-        float* scr1 = scr0 + TC_TE * D;
-        float* scr2 = scr1 + TC_TE * D;
+        const float* __restrict__ P1 = ws.P1[l];
+        const float* __restrict__ SP = ws.SP[l];
+        const float* __restrict__ ATT = ws.ATT[l];
         const int r0 = warp * TC2_RPW;
         const int cch = threadIdx.x & (D - 1), grp = threadIdx.x >> 7;
         auto wait_done = [&](int j, uint32_t tpar) { tc::mbar_wait(&sh.done[j], tpar); tc::fence_after_sync(); };
-        auto stage_d = [&](uint32_t d_col) {           // accumulator -> tile, bracketed by CTA barriers
-            csync();
-            tc2_d_to_tile(sh, tmem, d_col, warp, lane);
-            tc::fence_before_sync();
-            csync();
-        };
         for (int it = 0; it < my_tiles; it++) {
             const uint32_t tpar = (uint32_t)(it & 1);
             const int e0 = ((int)blockIdx.x + it * (int)gridDim.x) * TC_TE;
             const int nvalid = min(TC_TE, E - e0);
-            for (int idx = threadIdx.x; idx < TC_TE * 32; idx += TC2_CTHREADS) {
-                const int row = idx >> 5, c4 = (idx & 31) * 4;
-                st4(&sh.tile[row][c4], row < nvalid ? ld4(Fin + (size_t)(e0 + row) * D + c4) : f4s(0.f));
-            }
             load_edge_meta<TC_TE, TC2_CTHREADS>(sh.meta, ws, e0, nvalid);
             csync();
-            tc2_tile_to_a(sh, tmem, warp, lane);
-            tc2_go(sh, J_DK);
-            tc2_go(sh, J_DV);
-            const int hd = lane >> 2;                           // head owned by this lane's 4 channels
-            // ---- recompute Pdk, attention pre-activation ----
-            wait_done(J_DK, tpar);
-            stage_d(TC_COL_D0);
-            {
-                const float4 bb = ldg4(lw.b1 + col);
-#pragma unroll
-                for (int r = 0; r < TC2_RPW; r++) {
-                    const int row = r0 + r;
-                    const float4 P = ld4(&sh.tile[row][col]) + bb;
-                    st4(scr0 + row * D + col, P);
-                    const float4 qi = ld4(QKV + (size_t)sh.meta.dst[row] * 3 * D + col);
-                    const float4 kj = ld4(QKV + (size_t)sh.meta.src[row] * 3 * D + D + col);
-                    const float av = quad_sum(hsum4(qi * kj * silu4(P)));
-                    if ((lane & 3) == 0) sh.attn[row][hd] = av;
-                }
-            }
-            if (upd) { tc::fence_before_sync(); tc::mbar_arrive(&sh.go[J_F]); }
-            // ---- recompute Pdv, message m ----
-            wait_done(J_DV, tpar);
-            stage_d(TC_COL_D1);
-            {
-                const float4 bb = ldg4(lw.b1 + D + col);
-#pragma unroll
-                for (int r = 0; r < TC2_RPW; r++) {
-                    const int row = r0 + r;
-                    const float4 P = ld4(&sh.tile[row][col]) + bb;
-                    st4(scr1 + row * D + col, P);
-                    const float4 vj = ld4(QKV + (size_t)sh.meta.src[row] * 3 * D + 2 * D + col);
-                    st4(&sh.tile[row][col], vj * silu4(P) * (silu_(sh.attn[row][hd]) * sh.meta.C[row]));
-                }
-            }
-            csync();
-            if (upd) wait_done(J_F, tpar);
-            tc2_tile_to_a(sh, tmem, warp, lane);               // A = m
-            tc2_go(sh, J_S1);
-            if (upd) {
-                stage_d(TC_COL_D0);
-                const float4 bb = ldg4(lw.b1 + 2 * D + col);
-#pragma unroll
-                for (int r = 0; r < TC2_RPW; r++) st4(scr2 + (r0 + r) * D + col, ld4(&sh.tile[r0 + r][col]) + bb);
-            }
-            tc::fence_before_sync();
-            tc::mbar_arrive(&sh.go[J_S2]);
-            // ---- s1 half: adjoint of M = vn_j*s1 (+ s2*d) ----
-            wait_done(J_S1, tpar);
-            stage_d(TC_COL_D1);
-            {
-                const float4 bb = ldg4(lw.bs + col);
-#pragma unroll 4
-                for (int r = 0; r < TC2_RPW; r++) {
-                    const int row = r0 + r;
-                    const size_t i3 = (size_t)sh.meta.dst[row] * 3, j3 = (size_t)sh.meta.src[row] * 3;
-                    const float4 sp = ld4(&sh.tile[row][col]) + bb;
-                    const float4 s1 = silu4(sp);
-                    const float4 gM0 = ld4(ws.GVEC + (i3 + 0) * D + col), gM1 = ld4(ws.GVEC + (i3 + 1) * D + col),
-                                 gM2 = ld4(ws.GVEC + (i3 + 2) * D + col);
-                    const float4 gs1 = gM0 * ld4(VN + (j3 + 0) * D + col) + gM1 * ld4(VN + (j3 + 1) * D + col) +
-                                       gM2 * ld4(VN + (j3 + 2) * D + col);
-                    if (row < nvalid) {
-                        red4(ws.GVNMSG + (j3 + 0) * D + col, gM0 * s1);
-                        red4(ws.GVNMSG + (j3 + 1) * D + col, gM1 * s1);
-                        red4(ws.GVNMSG + (j3 + 2) * D + col, gM2 * s1);
-                    }
-                    st4(&sh.tile[row][col], gs1 * dsilu4(sp));
-                }
-            }
-            csync();
-            wait_done(J_S2, tpar);                               // the s2 GEMM no longer reads A = m
-            tc2_tile_to_a(sh, tmem, warp, lane);               // A = g_Spre[:, 0:128]
-            tc2_go(sh, J_G3A);
-            // ---- s2 half ----
-            stage_d(TC_COL_D0);
-            {
-                const float4 bb = ldg4(lw.bs + D + col);
-#pragma unroll 4
-                for (int r = 0; r < TC2_RPW; r++) {
-                    const int row = r0 + r;
-                    const size_t i3 = (size_t)sh.meta.dst[row] * 3;
-                    const float4 dd = sh.meta.d[row];
-                    const float4 sp = ld4(&sh.tile[row][col]) + bb;
-                    const float4 s2 = silu4(sp);
-                    const float4 gM0 = ld4(ws.GVEC + (i3 + 0) * D + col), gM1 = ld4(ws.GVEC + (i3 + 1) * D + col),
-                                 gM2 = ld4(ws.GVEC + (i3 + 2) * D + col);
-                    const float gx_ = warp_sum(hsum4(gM0 * s2)), gy_ = warp_sum(hsum4(gM1 * s2)), gz_ = warp_sum(hsum4(gM2 * s2));
-                    if (lane == 0) { sh.eacc[row][1] = gx_; sh.eacc[row][2] = gy_; sh.eacc[row][3] = gz_; }
-                    st4(&sh.tile[row][col], (gM0 * dd.x + gM1 * dd.y + gM2 * dd.z) * dsilu4(sp));
-                }
-            }
-            csync();
-            wait_done(J_G3A, tpar);
-            tc2_tile_to_a(sh, tmem, warp, lane);               // A = g_Spre[:, 128:256]
-            tc2_go(sh, J_G3B);
-            // ---- g_m = g_xa_i + g_Spre Ws ; adjoint of m = v_j dv A ----
-            wait_done(J_G3B, tpar);
-            stage_d(TC_COL_D1);
+            // ---- s1 half: g_Spre[:, 0:128] -> tile -> A ; source-side g_vn ----
 #pragma unroll 4
             for (int r = 0; r < TC2_RPW; r++) {
                 const int row = r0 + r;
+                const bool ok = row < nvalid;
+                const size_t e = (size_t)(e0 + (ok ? row : 0));
+                const size_t i3 = (size_t)sh.meta.dst[row] * 3, j3 = (size_t)sh.meta.src[row] * 3;
+                const float4 sp = ld4(SP + e * 2 * D + col);
+                const float4 s1 = silu4(sp);
+                const float4 gM0 = ld4(ws.GVEC + (i3 + 0) * D + col), gM1 = ld4(ws.GVEC + (i3 + 1) * D + col),
+                             gM2 = ld4(ws.GVEC + (i3 + 2) * D + col);
+                const float4 gs1 = gM0 * ld4(VN + (j3 + 0) * D + col) + gM1 * ld4(VN + (j3 + 1) * D + col) +
+                                   gM2 * ld4(VN + (j3 + 2) * D + col);
+                if (ok) {
+                    red4(ws.GVNMSG + (j3 + 0) * D + col, gM0 * s1);
+                    red4(ws.GVNMSG + (j3 + 1) * D + col, gM1 * s1);
+                    red4(ws.GVNMSG + (j3 + 2) * D + col, gM2 * s1);
+                }
+                st4(&sh.tile[row][col], ok ? gs1 * dsilu4(sp) : f4s(0.f));
+            }
+            csync();
+            tc2_tile_to_a(sh, tmem, warp, lane);
+            tc2_go(sh, J_G3A);
+            csync();
+            // ---- s2 half ----
+#pragma unroll 4
+            for (int r = 0; r < TC2_RPW; r++) {
+                const int row = r0 + r;
+                const bool ok = row < nvalid;
+                const size_t e = (size_t)(e0 + (ok ? row : 0));
+                const size_t i3 = (size_t)sh.meta.dst[row] * 3;
+                const float4 dd = sh.meta.d[row];
+                const float4 sp = ld4(SP + e * 2 * D + D + col);
+                const float4 s2 = silu4(sp);
+                const float4 gM0 = ld4(ws.GVEC + (i3 + 0) * D + col), gM1 = ld4(ws.GVEC + (i3 + 1) * D + col),
+                             gM2 = ld4(ws.GVEC + (i3 + 2) * D + col);
+                const float gx_ = warp_sum(hsum4(gM0 * s2)), gy_ = warp_sum(hsum4(gM1 * s2)), gz_ = warp_sum(hsum4(gM2 * s2));
+                if (lane == 0) { sh.eacc[row][1] = gx_; sh.eacc[row][2] = gy_; sh.eacc[row][3] = gz_; }
+                st4(&sh.tile[row][col], ok ? (gM0 * dd.x + gM1 * dd.y + gM2 * dd.z) * dsilu4(sp) : f4s(0.f));
+            }
+            csync();
+            wait_done(J_G3A, tpar);
+            tc2_tile_to_a(sh, tmem, warp, lane);
+            tc2_go(sh, J_G3B);
+            // ---- g_m = g_xa_i + g_Spre Ws ; adjoint of m = v_j dv A ----
+            wait_done(J_G3B, tpar);
+            csync();
+            tc2_d_to_tile(sh, tmem, TC_COL_D1, warp, lane);
+            tc::fence_before_sync();
+            csync();
+#pragma unroll 4
+            for (int r = 0; r < TC2_RPW; r++) {
+                const int row = r0 + r;
+                const bool ok = row < nvalid;
+                const size_t e = (size_t)(e0 + (ok ? row : 0));
                 const size_t i = sh.meta.dst[row], j = sh.meta.src[row];
                 const float Ce = sh.meta.C[row];
-                const float av = sh.attn[row][hd], sa = silu_(av), A = sa * Ce;
+                const float av = ok ? ATT[e * H + hd] : 0.f, sa = silu_(av), A = sa * Ce;
                 const float4 gm = ld4(&sh.tile[row][col]) + ld4(ws.GXA + i * D + col);
                 const float4 vj = ld4(QKV + j * 3 * D + 2 * D + col);
-                const float4 pdv = ld4(scr1 + row * D + col);
+                const float4 pdv = ld4(P1 + e * 3 * D + D + col);
                 const float4 dv = silu4(pdv);
-                if (row < nvalid) red4(ws.GQKV + j * 3 * D + 2 * D + col, gm * dv * A);
-                st4(&sh.tile[row][col], gm * vj * A * dsilu4(pdv));      // g_Pdv
+                if (ok) red4(ws.GQKV + j * 3 * D + 2 * D + col, gm * dv * A);
+                st4(&sh.tile[row][col], ok ? gm * vj * A * dsilu4(pdv) : f4s(0.f));      // g_Pdv
                 const float gA = quad_sum(hsum4(gm * vj * dv));
                 if ((lane & 3) == 0) sh.gattn[row][hd] = gA * Ce * dsilu_(av);
                 const float gc = warp_sum((lane & 3) == 0 ? gA * sa : 0.f);
                 if (lane == 0) sh.eacc[row][0] = gc;
             }
             csync();
-            tc2_tile_to_a(sh, tmem, warp, lane);               // A = g_Pdv  (A free: g3b done)
+            tc2_tile_to_a(sh, tmem, warp, lane);               // A = g_Pdv (A planes free: g3b done)
             tc2_go(sh, J_G4DV);
             csync();
-            // ---- adjoint of a_h = sum q_i k_j dk ----
+            // ---- adjoint of a_h = sum q_i k_j dk : first g_Pdk (next A operand), then the g_q tile ----
 #pragma unroll 4
             for (int r = 0; r < TC2_RPW; r++) {
                 const int row = r0 + r;
+                const bool ok = row < nvalid;
+                const size_t e = (size_t)(e0 + (ok ? row : 0));
                 const size_t i = sh.meta.dst[row], j = sh.meta.src[row];
-                const float4 pdk = ld4(scr0 + row * D + col);
+                const float4 pdk = ld4(P1 + e * 3 * D + col);
                 const float4 dk = silu4(pdk);
                 const float4 qi = ld4(QKV + i * 3 * D + col), kj = ld4(QKV + j * 3 * D + D + col);
                 const float gav = sh.gattn[row][hd];
-                st4(&sh.tile[row][col], kj * dk * gav);                   // per-edge g_q contribution
-                if (row < nvalid) red4(ws.GQKV + j * 3 * D + D + col, qi * dk * gav);
-                st4(scr0 + row * D + col, qi * kj * gav * dsilu4(pdk));    // g_Pdk
+                if (ok) red4(ws.GQKV + j * 3 * D + D + col, qi * dk * gav);
+                st4(&sh.tile[row][col], ok ? qi * kj * gav * dsilu4(pdk) : f4s(0.f));   // g_Pdk
+            }
+            csync();
+            wait_done(J_G4DV, tpar);
+            tc2_tile_to_a(sh, tmem, warp, lane);               // A = g_Pdk
+            tc2_go(sh, J_G4DK);
+            csync();
+#pragma unroll 4
+            for (int r = 0; r < TC2_RPW; r++) {
+                const int row = r0 + r;
+                const size_t e = (size_t)(e0 + (row < nvalid ? row : 0));
+                const float4 dk = silu4(ld4(P1 + e * 3 * D + col));
+                const float4 kj = ld4(QKV + (size_t)sh.meta.src[row] * 3 * D + D + col);
+                st4(&sh.tile[row][col], kj * dk * sh.gattn[row][hd]);                    // per-edge g_q contribution
             }
             csync();
             {
@@ -681,26 +650,18 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) edge_bwd_tc_kernel(const __gri
                     else atomicAdd(ws.GQKV + (size_t)i * 3 * D + cch, gq);
                 }
             }
-            csync();
-            for (int idx = threadIdx.x; idx < TC_TE * 32; idx += TC2_CTHREADS) {
-                const int row = idx >> 5, c4 = (idx & 31) * 4;
-                st4(&sh.tile[row][c4], ld4(scr0 + row * D + c4));
-            }
-            csync();
-            wait_done(J_G4DV, tpar);
-            tc2_tile_to_a(sh, tmem, warp, lane);               // A = g_Pdk
-            tc2_go(sh, J_G4DK);
-            // ---- adjoint of the edge update ----
+            // ---- adjoint of the edge update: first g_Pf (A operand), then the g_wdot tile ----
             if (upd) {
                 csync();
 #pragma unroll 2
                 for (int r = 0; r < TC2_RPW; r++) {
                     const int row = r0 + r;
                     const bool ok = row < nvalid;
+                    const size_t e = (size_t)(e0 + (ok ? row : 0));
                     const size_t i3 = (size_t)sh.meta.dst[row] * 3, j3 = (size_t)sh.meta.src[row] * 3;
                     const float4 dd = sh.meta.d[row];
-                    const float4 gfn = ok ? ld4(ws.GF + (size_t)(e0 + row) * D + col) : f4s(0.f);
-                    const float4 pf = ld4(scr2 + row * D + col);
+                    const float4 gfn = ok ? ld4(ws.GF + e * D + col) : f4s(0.f);
+                    const float4 pf = ld4(P1 + e * 3 * D + 2 * D + col);
                     const float4 fp = silu4(pf);
                     float4 ti[3], uj[3];
 #pragma unroll
@@ -716,8 +677,7 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) edge_bwd_tc_kernel(const __gri
                     for (int s = 0; s < 3; s++) { w1[s] = ti[s] - a1 * dv3[s]; w2[s] = uj[s] - a2 * dv3[s]; }
                     const float4 wdot = w1[0] * w2[0] + w1[1] * w2[1] + w1[2] * w2[2];
                     const float4 gwd = gfn * fp;
-                    st4(&sh.tile[row][col], gwd);
-                    st4(scr2 + row * D + col, gfn * wdot * dsilu4(pf));       // g_Pf
+                    st4(&sh.tile[row][col], gfn * wdot * dsilu4(pf));                    // g_Pf
                     const float4 c1 = gwd * (w2[0] * dd.x + w2[1] * dd.y + w2[2] * dd.z);
                     const float4 c2 = gwd * (w1[0] * dd.x + w1[1] * dd.y + w1[2] * dd.z);
                     float gdl[3];
@@ -728,6 +688,19 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) edge_bwd_tc_kernel(const __gri
                         gdl[s] = warp_sum(hsum4(ti[s] * c1 + a1 * gw1 + uj[s] * c2 + a2 * gw2));
                     }
                     if (lane == 0) { sh.eacc[row][1] -= gdl[0]; sh.eacc[row][2] -= gdl[1]; sh.eacc[row][3] -= gdl[2]; }
+                }
+                csync();
+                wait_done(J_G4DK, tpar);
+                tc2_tile_to_a(sh, tmem, warp, lane);           // A = g_Pf
+                tc2_go(sh, J_G4F);
+                csync();
+#pragma unroll 4
+                for (int r = 0; r < TC2_RPW; r++) {
+                    const int row = r0 + r;
+                    const bool ok = row < nvalid;
+                    const size_t e = (size_t)(e0 + (ok ? row : 0));
+                    const float4 gfn = ok ? ld4(ws.GF + e * D + col) : f4s(0.f);
+                    st4(&sh.tile[row][col], gfn * silu4(ld4(P1 + e * 3 * D + 2 * D + col)));   // g_wdot
                 }
                 csync();
                 {
@@ -760,19 +733,13 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) edge_bwd_tc_kernel(const __gri
                         }
                     }
                 }
-                csync();
-                for (int idx = threadIdx.x; idx < TC_TE * 32; idx += TC2_CTHREADS) {
-                    const int row = idx >> 5, c4 = (idx & 31) * 4;
-                    st4(&sh.tile[row][c4], ld4(scr2 + row * D + c4));
-                }
-                csync();
-                wait_done(J_G4DK, tpar);
-                tc2_tile_to_a(sh, tmem, warp, lane);           // A = g_Pf
-                tc2_go(sh, J_G4F);
             }
             // ---- g_f = g_f_next + [g_Pdk|g_Pdv|g_Pf] W1 ----
             wait_done(J_LAST, tpar);
-            stage_d(TC_COL_D0);
+            csync();
+            tc2_d_to_tile(sh, tmem, TC_COL_D0, warp, lane);
+            tc::fence_before_sync();
+            csync();
 #pragma unroll 4
             for (int r = 0; r < TC2_RPW; r++) {
                 const int row = r0 + r;

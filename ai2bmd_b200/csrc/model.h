@@ -84,6 +84,10 @@ struct Workspace {
     float* VDOT[L];         // [N][128]
     float* TU[L];           // [N][3][256]  [w_trg vn | w_src vn]   (unused for the last layer)
     float* O[L];            // [N][384]     o_proj output
+    // per-layer edge pre-activations written by the forward edge stage, read by its adjoint (no recompute)
+    float* P1[L];           // [Ecap][384]  f W1^T + b1 = [Pdk | Pdv | Pf]
+    float* SP[L];           // [Ecap][256]  m Ws^T + bs
+    float* ATT[L];          // [Ecap][8]    attention pre-activation a_h
     // transient aggregates
     float* XA;              // [N][128]
     float* VA;              // [N][3][128]
