@@ -53,7 +53,7 @@ template <int TE, int NT>
 __device__ __forceinline__ void load_f_tile(float* Fs, const float* __restrict__ Fin, int e0, int nvalid) {
     for (int idx = threadIdx.x; idx < TE * 32; idx += NT) {
         const int row = idx >> 5, c4 = (idx & 31) * 4;
-        st4(Fs + row * LE1 + c4, row < nvalid ? ld4(Fin + (size_t)(e0 + row) * D + c4) : f4s(0.f));
+        st4(Fs + row * LE1 + c4, row < nvalid ? ldg4(Fin + (size_t)(e0 + row) * D + c4) : f4s(0.f));
     }
 }
 
@@ -108,8 +108,8 @@ __global__ void __launch_bounds__(NW * 32) edge_fwd_kernel(EdgeArgs a) {
                 float4 ti[3], uj[3];
 #pragma unroll
                 for (int s = 0; s < 3; s++) {
-                    ti[s] = ld4(TU + ((size_t)i * 3 + s) * 2 * D + col);
-                    uj[s] = ld4(TU + ((size_t)j * 3 + s) * 2 * D + D + col);
+                    ti[s] = ldg4(TU + ((size_t)i * 3 + s) * 2 * D + col);
+                    uj[s] = ldg4(TU + ((size_t)j * 3 + s) * 2 * D + D + col);
                 }
                 const float4 a1 = ti[0] * dd.x + ti[1] * dd.y + ti[2] * dd.z;
                 const float4 a2 = uj[0] * dd.x + uj[1] * dd.y + uj[2] * dd.z;
@@ -128,8 +128,8 @@ __global__ void __launch_bounds__(NW * 32) edge_fwd_kernel(EdgeArgs a) {
 #pragma unroll
         for (int r = 0; r < R; r++) {
             const int row = r0 + r;
-            const float4 qi = ld4(QKV + (size_t)meta.dst[row] * 3 * D + col);
-            const float4 kj = ld4(QKV + (size_t)meta.src[row] * 3 * D + D + col);
+            const float4 qi = ldg4(QKV + (size_t)meta.dst[row] * 3 * D + col);
+            const float4 kj = ldg4(QKV + (size_t)meta.src[row] * 3 * D + D + col);
             const float av = quad_sum(hsum4(qi * kj * silu4(arr4(acc[r]))));
             Areg[r] = silu_(av) * meta.C[row];
             if (row < nvalid) {
@@ -144,7 +144,7 @@ __global__ void __launch_bounds__(NW * 32) edge_fwd_kernel(EdgeArgs a) {
 #pragma unroll
         for (int r = 0; r < R; r++) {
             const int row = r0 + r;
-            const float4 vj = ld4(QKV + (size_t)meta.src[row] * 3 * D + 2 * D + col);
+            const float4 vj = ldg4(QKV + (size_t)meta.src[row] * 3 * D + 2 * D + col);
             st4(Fs + row * LE1 + col, vj * silu4(arr4(acc[r])) * Areg[r]);
             if (row < nvalid) st4(P1 + (size_t)(e0 + row) * 3 * D + D + col, arr4(acc[r]));
         }
@@ -175,7 +175,7 @@ __global__ void __launch_bounds__(NW * 32) edge_fwd_kernel(EdgeArgs a) {
 #pragma unroll
                     for (int u = 0; u < 4; u++) {
                         const size_t j3 = (size_t)meta.src[e + u] * 3;
-                        g[u][0] = VN[(j3 + 0) * D + c]; g[u][1] = VN[(j3 + 1) * D + c]; g[u][2] = VN[(j3 + 2) * D + c];
+                        g[u][0] = __ldg(VN + (j3 + 0) * D + c); g[u][1] = __ldg(VN + (j3 + 1) * D + c); g[u][2] = __ldg(VN + (j3 + 2) * D + c);
                     }
 #pragma unroll
                     for (int u = 0; u < 4; u++) {
@@ -192,9 +192,9 @@ __global__ void __launch_bounds__(NW * 32) edge_fwd_kernel(EdgeArgs a) {
                     const float4 dd = meta.d[e];
                     const float s1 = Ss[e * LE2 + c], s2 = Ss[e * LE2 + D + c];
                     xa += Fs[e * LE1 + c];
-                    va0 += VN[(j3 + 0) * D + c] * s1 + s2 * dd.x;
-                    va1 += VN[(j3 + 1) * D + c] * s1 + s2 * dd.y;
-                    va2 += VN[(j3 + 2) * D + c] * s1 + s2 * dd.z;
+                    va0 += __ldg(VN + (j3 + 0) * D + c) * s1 + s2 * dd.x;
+                    va1 += __ldg(VN + (j3 + 1) * D + c) * s1 + s2 * dd.y;
+                    va2 += __ldg(VN + (j3 + 2) * D + c) * s1 + s2 * dd.z;
                 }
                 atomicAdd(ws.XA + (size_t)i * D + c, xa);
                 atomicAdd(ws.VA + ((size_t)i * 3 + 0) * D + c, va0);
@@ -251,65 +251,87 @@ __global__ void __launch_bounds__(NW * 32) edge_bwd_kernel(EdgeArgs a) {
         float acc[R][4];
         float gdx[R], gdy[R], gdz[R], gC[R];
         // ---- adjoint of M = vn_j*s1 + s2*d and of silu(s_proj) ----
+        // (all loads of a batch are issued before the first atomic: atomics are compiler barriers for load hoisting)
+        constexpr int RBB = (R < 2) ? R : 2;
 #pragma unroll
-        for (int r = 0; r < R; r++) {
-            const int row = r0 + r;
-            const bool ok = row < nvalid;
-            const size_t e = (size_t)(e0 + (ok ? row : 0));
-            const size_t i3 = (size_t)meta.dst[row] * 3, j3 = (size_t)meta.src[row] * 3;
-            const float4 dd = meta.d[row];
-            const float4 sp1 = ld4(SP + e * 2 * D + col), sp2 = ld4(SP + e * 2 * D + D + col);
-            const float4 s1 = silu4(sp1), s2 = silu4(sp2);
-            const float4 gM0 = ld4(ws.GVEC + (i3 + 0) * D + col);
-            const float4 gM1 = ld4(ws.GVEC + (i3 + 1) * D + col);
-            const float4 gM2 = ld4(ws.GVEC + (i3 + 2) * D + col);
-            const float4 gs1 = gM0 * ld4(VN + (j3 + 0) * D + col) + gM1 * ld4(VN + (j3 + 1) * D + col) +
-                               gM2 * ld4(VN + (j3 + 2) * D + col);
-            const float4 gs2 = gM0 * dd.x + gM1 * dd.y + gM2 * dd.z;
-            if (ok) {
-                red4(ws.GVNMSG + (j3 + 0) * D + col, gM0 * s1);
-                red4(ws.GVNMSG + (j3 + 1) * D + col, gM1 * s1);
-                red4(ws.GVNMSG + (j3 + 2) * D + col, gM2 * s1);
+        for (int rb = 0; rb < R; rb += RBB) {
+            float4 sp1r[RBB], sp2r[RBB], gMr[RBB][3], vnr[RBB][3];
+#pragma unroll
+            for (int u = 0; u < RBB; u++) {
+                const int row = r0 + rb + u;
+                const size_t e = (size_t)(e0 + (row < nvalid ? row : 0));
+                const size_t i3 = (size_t)meta.dst[row] * 3, j3 = (size_t)meta.src[row] * 3;
+                sp1r[u] = ldg4(SP + e * 2 * D + col);
+                sp2r[u] = ldg4(SP + e * 2 * D + D + col);
+#pragma unroll
+                for (int s = 0; s < 3; s++) { gMr[u][s] = ldg4(ws.GVEC + (i3 + s) * D + col); vnr[u][s] = ldg4(VN + (j3 + s) * D + col); }
             }
-            gdx[r] = warp_sum(hsum4(gM0 * s2));
-            gdy[r] = warp_sum(hsum4(gM1 * s2));
-            gdz[r] = warp_sum(hsum4(gM2 * s2));
-            st4(Ss + row * LEQ + col, ok ? gs1 * dsilu4(sp1) : f4s(0.f));
-            st4(Ss + row * LEQ + D + col, ok ? gs2 * dsilu4(sp2) : f4s(0.f));
+#pragma unroll
+            for (int u = 0; u < RBB; u++) {
+                const int r = rb + u, row = r0 + r;
+                const bool ok = row < nvalid;
+                const size_t j3 = (size_t)meta.src[row] * 3;
+                const float4 dd = meta.d[row];
+                const float4 s1 = silu4(sp1r[u]), s2 = silu4(sp2r[u]);
+                const float4 gs1 = gMr[u][0] * vnr[u][0] + gMr[u][1] * vnr[u][1] + gMr[u][2] * vnr[u][2];
+                const float4 gs2 = gMr[u][0] * dd.x + gMr[u][1] * dd.y + gMr[u][2] * dd.z;
+                gdx[r] = warp_sum(hsum4(gMr[u][0] * s2));
+                gdy[r] = warp_sum(hsum4(gMr[u][1] * s2));
+                gdz[r] = warp_sum(hsum4(gMr[u][2] * s2));
+                st4(Ss + row * LEQ + col, ok ? gs1 * dsilu4(sp1r[u]) : f4s(0.f));
+                st4(Ss + row * LEQ + D + col, ok ? gs2 * dsilu4(sp2r[u]) : f4s(0.f));
+                if (ok) {
+                    red4(ws.GVNMSG + (j3 + 0) * D + col, gMr[u][0] * s1);
+                    red4(ws.GVNMSG + (j3 + 1) * D + col, gMr[u][1] * s1);
+                    red4(ws.GVNMSG + (j3 + 2) * D + col, gMr[u][2] * s1);
+                }
+            }
         }
         __syncwarp();
         // ---- g_m = g_xa_i + g_Spre Ws ----
 #pragma unroll
         for (int r = 0; r < R; r++) {
-            const float4 t = ld4(ws.GXA + (size_t)meta.dst[r0 + r] * D + col);
+            const float4 t = ldg4(ws.GXA + (size_t)meta.dst[r0 + r] * D + col);
             acc[r][0] = t.x; acc[r][1] = t.y; acc[r][2] = t.z; acc[r][3] = t.w;
         }
         warp_gemm<R, 2 * D, LEQ>(acc, Ss + r0 * LEQ, lw.WsN, D, lane);
         __syncwarp();
 #pragma unroll
-        for (int r = 0; r < R; r++) {
-            const int row = r0 + r;
-            const bool ok = row < nvalid;
-            const size_t e = (size_t)(e0 + (ok ? row : 0));
-            const size_t i = meta.dst[row], j = meta.src[row];
-            const float4 gm = arr4(acc[r]);
-            const float Ce = meta.C[row];
-            const float av = ok ? ATT[e * H + hd] : 0.f, sa = silu_(av), A = sa * Ce;
-            const float4 vj = ld4(QKV + j * 3 * D + 2 * D + col);
-            const float4 pdv = ld4(P1 + e * 3 * D + D + col);
-            const float4 dv = silu4(pdv);
-            if (ok) red4(ws.GQKV + j * 3 * D + 2 * D + col, gm * dv * A);
-            st4(Ps + row * LE3 + D + col, ok ? gm * vj * A * dsilu4(pdv) : f4s(0.f));
-            const float gA = quad_sum(hsum4(gm * vj * dv));
-            const float ga = gA * Ce * dsilu_(av);
-            gC[r] = warp_sum((lane & 3) == 0 ? gA * sa : 0.f);
-            const float4 pdk = ld4(P1 + e * 3 * D + col);
-            const float4 dk = silu4(pdk);
-            const float4 qi = ld4(QKV + i * 3 * D + col);
-            const float4 kj = ld4(QKV + j * 3 * D + D + col);
-            st4(Ss + row * LEQ + QOFF + col, kj * dk * ga);              // per-edge g_q contribution
-            if (ok) red4(ws.GQKV + j * 3 * D + D + col, qi * dk * ga);   // g_k (source side)
-            st4(Ps + row * LE3 + col, ok ? qi * kj * ga * dsilu4(pdk) : f4s(0.f));
+        for (int rb = 0; rb < R; rb += RBB) {
+            float4 vjr[RBB], pdvr[RBB], pdkr[RBB], qir[RBB], kjr[RBB];
+            float avr[RBB];
+#pragma unroll
+            for (int u = 0; u < RBB; u++) {
+                const int row = r0 + rb + u;
+                const size_t e = (size_t)(e0 + (row < nvalid ? row : 0));
+                const size_t i = meta.dst[row], j = meta.src[row];
+                vjr[u] = ldg4(QKV + j * 3 * D + 2 * D + col);
+                pdvr[u] = ldg4(P1 + e * 3 * D + D + col);
+                pdkr[u] = ldg4(P1 + e * 3 * D + col);
+                qir[u] = ldg4(QKV + i * 3 * D + col);
+                kjr[u] = ldg4(QKV + j * 3 * D + D + col);
+                avr[u] = row < nvalid ? __ldg(ATT + e * H + hd) : 0.f;
+            }
+#pragma unroll
+            for (int u = 0; u < RBB; u++) {
+                const int r = rb + u, row = r0 + r;
+                const bool ok = row < nvalid;
+                const size_t j = meta.src[row];
+                const float4 gm = arr4(acc[r]);
+                const float Ce = meta.C[row];
+                const float av = avr[u], sa = silu_(av), A = sa * Ce;
+                const float4 dv = silu4(pdvr[u]), dk = silu4(pdkr[u]);
+                st4(Ps + row * LE3 + D + col, ok ? gm * vjr[u] * A * dsilu4(pdvr[u]) : f4s(0.f));
+                const float gA = quad_sum(hsum4(gm * vjr[u] * dv));
+                const float ga = gA * Ce * dsilu_(av);
+                gC[r] = warp_sum((lane & 3) == 0 ? gA * sa : 0.f);
+                st4(Ss + row * LEQ + QOFF + col, kjr[u] * dk * ga);                        // per-edge g_q contribution
+                st4(Ps + row * LE3 + col, ok ? qir[u] * kjr[u] * ga * dsilu4(pdkr[u]) : f4s(0.f));
+                if (ok) {
+                    red4(ws.GQKV + j * 3 * D + 2 * D + col, gm * dv * A);
+                    red4(ws.GQKV + j * 3 * D + D + col, qir[u] * dk * ga);                  // g_k (source side)
+                }
+            }
         }
         // ---- adjoint of the edge update ----
         if (upd) {
@@ -321,13 +343,13 @@ __global__ void __launch_bounds__(NW * 32) edge_bwd_kernel(EdgeArgs a) {
                 const size_t i3 = (size_t)meta.dst[row] * 3, j3 = (size_t)meta.src[row] * 3;
                 const float4 dd = meta.d[row];
                 const float4 gfn = ok ? ld4(ws.GF + e * D + col) : f4s(0.f);
-                const float4 pf = ld4(P1 + e * 3 * D + 2 * D + col);
+                const float4 pf = ldg4(P1 + e * 3 * D + 2 * D + col);
                 const float4 fp = silu4(pf);
                 float4 ti[3], uj[3];
 #pragma unroll
                 for (int s = 0; s < 3; s++) {
-                    ti[s] = ld4(TU + (i3 + s) * 2 * D + col);
-                    uj[s] = ld4(TU + (j3 + s) * 2 * D + D + col);
+                    ti[s] = ldg4(TU + (i3 + s) * 2 * D + col);
+                    uj[s] = ldg4(TU + (j3 + s) * 2 * D + D + col);
                 }
                 const float dv3[3] = {dd.x, dd.y, dd.z};
                 const float4 a1 = ti[0] * dd.x + ti[1] * dd.y + ti[2] * dd.z;
@@ -384,8 +406,8 @@ __global__ void __launch_bounds__(NW * 32) edge_bwd_kernel(EdgeArgs a) {
                         const size_t j3 = (size_t)meta.src[e] * 3;
                         const float4 dd = meta.d[e];
                         const float gw = Ss[e * LEQ + WOFF + c];
-                        const float u0 = TU[(j3 + 0) * 2 * D + D + c], u1 = TU[(j3 + 1) * 2 * D + D + c],
-                                    u2 = TU[(j3 + 2) * 2 * D + D + c];
+                        const float u0 = __ldg(TU + (j3 + 0) * 2 * D + D + c), u1 = __ldg(TU + (j3 + 1) * 2 * D + D + c),
+                                    u2 = __ldg(TU + (j3 + 2) * 2 * D + D + c);
                         const float a2 = u0 * dd.x + u1 * dd.y + u2 * dd.z;
                         const float w20 = u0 - a2 * dd.x, w21 = u1 - a2 * dd.y, w22 = u2 - a2 * dd.z;
                         const float wd = w20 * dd.x + w21 * dd.y + w22 * dd.z;

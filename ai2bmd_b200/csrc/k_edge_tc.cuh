@@ -310,7 +310,7 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) edge_fwd_tc_kernel(const __gri
             // ---- load f tile + meta (coalesced) ----
             for (int idx = threadIdx.x; idx < TC_TE * 32; idx += TC2_CTHREADS) {
                 const int row = idx >> 5, c4 = (idx & 31) * 4;
-                st4(&sh.tile[row][c4], row < nvalid ? ld4(Fin + (size_t)(e0 + row) * D + c4) : f4s(0.f));
+                st4(&sh.tile[row][c4], row < nvalid ? ldg4(Fin + (size_t)(e0 + row) * D + c4) : f4s(0.f));
             }
             load_edge_meta<TC_TE, TC2_CTHREADS>(sh.meta, ws, e0, nvalid);
             csync();
@@ -330,8 +330,8 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) edge_fwd_tc_kernel(const __gri
 #pragma unroll
                 for (int r = 0; r < TC2_RPW; r++) {
                     const int row = r0 + r;
-                    const float4 qi = ld4(QKV + (size_t)sh.meta.dst[row] * 3 * D + col);
-                    const float4 kj = ld4(QKV + (size_t)sh.meta.src[row] * 3 * D + D + col);
+                    const float4 qi = ldg4(QKV + (size_t)sh.meta.dst[row] * 3 * D + col);
+                    const float4 kj = ldg4(QKV + (size_t)sh.meta.src[row] * 3 * D + D + col);
                     const float4 P = ld4(&sh.tile[row][col]) + bb;
                     const float av = quad_sum(hsum4(qi * kj * silu4(P)));
                     Areg[r] = silu_(av) * sh.meta.C[row];
@@ -353,7 +353,7 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) edge_fwd_tc_kernel(const __gri
 #pragma unroll
                 for (int r = 0; r < TC2_RPW; r++) {
                     const int row = r0 + r;
-                    const float4 vj = ld4(QKV + (size_t)sh.meta.src[row] * 3 * D + 2 * D + col);
+                    const float4 vj = ldg4(QKV + (size_t)sh.meta.src[row] * 3 * D + 2 * D + col);
                     const float4 P = ld4(&sh.tile[row][col]) + bb;
                     st4(&sh.tile[row][col], vj * silu4(P) * Areg[r]);
                     if (row < nvalid) st4(P1 + (size_t)(e0 + row) * 3 * D + D + col, P);
@@ -394,15 +394,15 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) edge_fwd_tc_kernel(const __gri
                     float4 ti[3], uj[3];
 #pragma unroll
                     for (int s = 0; s < 3; s++) {
-                        ti[s] = ld4(TU + (i3 + s) * 2 * D + col);
-                        uj[s] = ld4(TU + (j3 + s) * 2 * D + D + col);
+                        ti[s] = ldg4(TU + (i3 + s) * 2 * D + col);
+                        uj[s] = ldg4(TU + (j3 + s) * 2 * D + D + col);
                     }
                     const float4 a1 = ti[0] * dd.x + ti[1] * dd.y + ti[2] * dd.z;
                     const float4 a2 = uj[0] * dd.x + uj[1] * dd.y + uj[2] * dd.z;
                     const float4 wdot = (ti[0] - a1 * dd.x) * (uj[0] - a2 * dd.x) + (ti[1] - a1 * dd.y) * (uj[1] - a2 * dd.y) +
                                         (ti[2] - a1 * dd.z) * (uj[2] - a2 * dd.z);
                     if (row < nvalid)
-                        st4(Fout + (size_t)(e0 + row) * D + col, ld4(Fin + (size_t)(e0 + row) * D + col) + fp * wdot);
+                        st4(Fout + (size_t)(e0 + row) * D + col, ldg4(Fin + (size_t)(e0 + row) * D + col) + fp * wdot);
                 }
             }
             tc::fence_before_sync();
@@ -428,7 +428,7 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) edge_fwd_tc_kernel(const __gri
 #pragma unroll
                         for (int u = 0; u < 4; u++) {
                             const size_t j3 = (size_t)sh.meta.src[r + u] * 3;
-                            g[u][0] = VN[(j3 + 0) * D + cch]; g[u][1] = VN[(j3 + 1) * D + cch]; g[u][2] = VN[(j3 + 2) * D + cch];
+                            g[u][0] = __ldg(VN + (j3 + 0) * D + cch); g[u][1] = __ldg(VN + (j3 + 1) * D + cch); g[u][2] = __ldg(VN + (j3 + 2) * D + cch);
                             const float sp = sh.tile[r + u][cch] + b;
                             SP[(size_t)(e0 + r + u) * 2 * D + cch] = sp;
                             s1[u] = silu_(sp);
@@ -441,9 +441,9 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) edge_fwd_tc_kernel(const __gri
                         const float sp = sh.tile[r][cch] + b;
                         SP[(size_t)(e0 + r) * 2 * D + cch] = sp;
                         const float s1 = silu_(sp);
-                        v0 += VN[(j3 + 0) * D + cch] * s1;
-                        v1 += VN[(j3 + 1) * D + cch] * s1;
-                        v2 += VN[(j3 + 2) * D + cch] * s1;
+                        v0 += __ldg(VN + (j3 + 0) * D + cch) * s1;
+                        v1 += __ldg(VN + (j3 + 1) * D + cch) * s1;
+                        v2 += __ldg(VN + (j3 + 2) * D + cch) * s1;
                     }
                     if (q0 >= e0 && q1 <= e0 + nvalid) {
                         ws.VA[((size_t)i * 3 + 0) * D + cch] = v0;
@@ -539,24 +539,33 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) edge_bwd_tc_kernel(const __gri
             load_edge_meta<TC_TE, TC2_CTHREADS>(sh.meta, ws, e0, nvalid);
             csync();
             // ---- s1 half: g_Spre[:, 0:128] -> tile -> A ; source-side g_vn ----
-#pragma unroll 4
-            for (int r = 0; r < TC2_RPW; r++) {
-                const int row = r0 + r;
-                const bool ok = row < nvalid;
-                const size_t e = (size_t)(e0 + (ok ? row : 0));
-                const size_t i3 = (size_t)sh.meta.dst[row] * 3, j3 = (size_t)sh.meta.src[row] * 3;
-                const float4 sp = ld4(SP + e * 2 * D + col);
-                const float4 s1 = silu4(sp);
-                const float4 gM0 = ld4(ws.GVEC + (i3 + 0) * D + col), gM1 = ld4(ws.GVEC + (i3 + 1) * D + col),
-                             gM2 = ld4(ws.GVEC + (i3 + 2) * D + col);
-                const float4 gs1 = gM0 * ld4(VN + (j3 + 0) * D + col) + gM1 * ld4(VN + (j3 + 1) * D + col) +
-                                   gM2 * ld4(VN + (j3 + 2) * D + col);
-                if (ok) {
-                    red4(ws.GVNMSG + (j3 + 0) * D + col, gM0 * s1);
-                    red4(ws.GVNMSG + (j3 + 1) * D + col, gM1 * s1);
-                    red4(ws.GVNMSG + (j3 + 2) * D + col, gM2 * s1);
+            // (loads of 4 rows are issued together: the atomics below are compiler barriers for load hoisting)
+#pragma unroll 1
+            for (int rb = 0; rb < TC2_RPW; rb += 4) {
+                float4 sp[4], gM[4][3], vn[4][3];
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    const int row = r0 + rb + u;
+                    const size_t e = (size_t)(e0 + (row < nvalid ? row : 0));
+                    const size_t i3 = (size_t)sh.meta.dst[row] * 3, j3 = (size_t)sh.meta.src[row] * 3;
+                    sp[u] = ldg4(SP + e * 2 * D + col);
+#pragma unroll
+                    for (int s = 0; s < 3; s++) { gM[u][s] = ldg4(ws.GVEC + (i3 + s) * D + col); vn[u][s] = ldg4(VN + (j3 + s) * D + col); }
                 }
-                st4(&sh.tile[row][col], ok ? gs1 * dsilu4(sp) : f4s(0.f));
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    const int row = r0 + rb + u;
+                    const bool ok = row < nvalid;
+                    const size_t j3 = (size_t)sh.meta.src[row] * 3;
+                    const float4 s1 = silu4(sp[u]);
+                    const float4 gs1 = gM[u][0] * vn[u][0] + gM[u][1] * vn[u][1] + gM[u][2] * vn[u][2];
+                    st4(&sh.tile[row][col], ok ? gs1 * dsilu4(sp[u]) : f4s(0.f));
+                    if (ok) {
+                        red4(ws.GVNMSG + (j3 + 0) * D + col, gM[u][0] * s1);
+                        red4(ws.GVNMSG + (j3 + 1) * D + col, gM[u][1] * s1);
+                        red4(ws.GVNMSG + (j3 + 2) * D + col, gM[u][2] * s1);
+                    }
+                }
             }
             csync();
             tc2_tile_to_a(sh, tmem, warp, lane);
@@ -570,10 +579,10 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) edge_bwd_tc_kernel(const __gri
                 const size_t e = (size_t)(e0 + (ok ? row : 0));
                 const size_t i3 = (size_t)sh.meta.dst[row] * 3;
                 const float4 dd = sh.meta.d[row];
-                const float4 sp = ld4(SP + e * 2 * D + D + col);
+                const float4 sp = ldg4(SP + e * 2 * D + D + col);
                 const float4 s2 = silu4(sp);
-                const float4 gM0 = ld4(ws.GVEC + (i3 + 0) * D + col), gM1 = ld4(ws.GVEC + (i3 + 1) * D + col),
-                             gM2 = ld4(ws.GVEC + (i3 + 2) * D + col);
+                const float4 gM0 = ldg4(ws.GVEC + (i3 + 0) * D + col), gM1 = ldg4(ws.GVEC + (i3 + 1) * D + col),
+                             gM2 = ldg4(ws.GVEC + (i3 + 2) * D + col);
                 const float gx_ = warp_sum(hsum4(gM0 * s2)), gy_ = warp_sum(hsum4(gM1 * s2)), gz_ = warp_sum(hsum4(gM2 * s2));
                 if (lane == 0) { sh.eacc[row][1] = gx_; sh.eacc[row][2] = gy_; sh.eacc[row][3] = gz_; }
                 st4(&sh.tile[row][col], ok ? (gM0 * dd.x + gM1 * dd.y + gM2 * dd.z) * dsilu4(sp) : f4s(0.f));
@@ -588,42 +597,62 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) edge_bwd_tc_kernel(const __gri
             tc2_d_to_tile(sh, tmem, TC_COL_D1, warp, lane);
             tc::fence_before_sync();
             csync();
-#pragma unroll 4
-            for (int r = 0; r < TC2_RPW; r++) {
-                const int row = r0 + r;
-                const bool ok = row < nvalid;
-                const size_t e = (size_t)(e0 + (ok ? row : 0));
-                const size_t i = sh.meta.dst[row], j = sh.meta.src[row];
-                const float Ce = sh.meta.C[row];
-                const float av = ok ? ATT[e * H + hd] : 0.f, sa = silu_(av), A = sa * Ce;
-                const float4 gm = ld4(&sh.tile[row][col]) + ld4(ws.GXA + i * D + col);
-                const float4 vj = ld4(QKV + j * 3 * D + 2 * D + col);
-                const float4 pdv = ld4(P1 + e * 3 * D + D + col);
-                const float4 dv = silu4(pdv);
-                if (ok) red4(ws.GQKV + j * 3 * D + 2 * D + col, gm * dv * A);
-                st4(&sh.tile[row][col], ok ? gm * vj * A * dsilu4(pdv) : f4s(0.f));      // g_Pdv
-                const float gA = quad_sum(hsum4(gm * vj * dv));
-                if ((lane & 3) == 0) sh.gattn[row][hd] = gA * Ce * dsilu_(av);
-                const float gc = warp_sum((lane & 3) == 0 ? gA * sa : 0.f);
-                if (lane == 0) sh.eacc[row][0] = gc;
+#pragma unroll 1
+            for (int rb = 0; rb < TC2_RPW; rb += 4) {
+                float4 gxa[4], vjr[4], pdvr[4];
+                float avr[4];
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    const int row = r0 + rb + u;
+                    const size_t e = (size_t)(e0 + (row < nvalid ? row : 0));
+                    gxa[u] = ldg4(ws.GXA + (size_t)sh.meta.dst[row] * D + col);
+                    vjr[u] = ldg4(QKV + (size_t)sh.meta.src[row] * 3 * D + 2 * D + col);
+                    pdvr[u] = ldg4(P1 + e * 3 * D + D + col);
+                    avr[u] = row < nvalid ? __ldg(ATT + e * H + hd) : 0.f;
+                }
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    const int row = r0 + rb + u;
+                    const bool ok = row < nvalid;
+                    const size_t j = sh.meta.src[row];
+                    const float Ce = sh.meta.C[row];
+                    const float av = avr[u], sa = silu_(av), A = sa * Ce;
+                    const float4 gm = ld4(&sh.tile[row][col]) + gxa[u];
+                    const float4 dv = silu4(pdvr[u]);
+                    st4(&sh.tile[row][col], ok ? gm * vjr[u] * A * dsilu4(pdvr[u]) : f4s(0.f));      // g_Pdv
+                    const float gA = quad_sum(hsum4(gm * vjr[u] * dv));
+                    if ((lane & 3) == 0) sh.gattn[row][hd] = gA * Ce * dsilu_(av);
+                    const float gc = warp_sum((lane & 3) == 0 ? gA * sa : 0.f);
+                    if (lane == 0) sh.eacc[row][0] = gc;
+                    if (ok) red4(ws.GQKV + j * 3 * D + 2 * D + col, gm * dv * A);
+                }
             }
             csync();
             tc2_tile_to_a(sh, tmem, warp, lane);               // A = g_Pdv (A planes free: g3b done)
             tc2_go(sh, J_G4DV);
             csync();
             // ---- adjoint of a_h = sum q_i k_j dk : first g_Pdk (next A operand), then the g_q tile ----
-#pragma unroll 4
-            for (int r = 0; r < TC2_RPW; r++) {
-                const int row = r0 + r;
-                const bool ok = row < nvalid;
-                const size_t e = (size_t)(e0 + (ok ? row : 0));
-                const size_t i = sh.meta.dst[row], j = sh.meta.src[row];
-                const float4 pdk = ld4(P1 + e * 3 * D + col);
-                const float4 dk = silu4(pdk);
-                const float4 qi = ld4(QKV + i * 3 * D + col), kj = ld4(QKV + j * 3 * D + D + col);
-                const float gav = sh.gattn[row][hd];
-                if (ok) red4(ws.GQKV + j * 3 * D + D + col, qi * dk * gav);
-                st4(&sh.tile[row][col], ok ? qi * kj * gav * dsilu4(pdk) : f4s(0.f));   // g_Pdk
+#pragma unroll 1
+            for (int rb = 0; rb < TC2_RPW; rb += 4) {
+                float4 pdkr[4], qir[4], kjr[4];
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    const int row = r0 + rb + u;
+                    const size_t e = (size_t)(e0 + (row < nvalid ? row : 0));
+                    pdkr[u] = ldg4(P1 + e * 3 * D + col);
+                    qir[u] = ldg4(QKV + (size_t)sh.meta.dst[row] * 3 * D + col);
+                    kjr[u] = ldg4(QKV + (size_t)sh.meta.src[row] * 3 * D + D + col);
+                }
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    const int row = r0 + rb + u;
+                    const bool ok = row < nvalid;
+                    const size_t j = sh.meta.src[row];
+                    const float4 dk = silu4(pdkr[u]);
+                    const float gav = sh.gattn[row][hd];
+                    st4(&sh.tile[row][col], ok ? qir[u] * kjr[u] * gav * dsilu4(pdkr[u]) : f4s(0.f));   // g_Pdk
+                    if (ok) red4(ws.GQKV + j * 3 * D + D + col, qir[u] * dk * gav);
+                }
             }
             csync();
             wait_done(J_G4DV, tpar);
@@ -634,8 +663,8 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) edge_bwd_tc_kernel(const __gri
             for (int r = 0; r < TC2_RPW; r++) {
                 const int row = r0 + r;
                 const size_t e = (size_t)(e0 + (row < nvalid ? row : 0));
-                const float4 dk = silu4(ld4(P1 + e * 3 * D + col));
-                const float4 kj = ld4(QKV + (size_t)sh.meta.src[row] * 3 * D + D + col);
+                const float4 dk = silu4(ldg4(P1 + e * 3 * D + col));
+                const float4 kj = ldg4(QKV + (size_t)sh.meta.src[row] * 3 * D + D + col);
                 st4(&sh.tile[row][col], kj * dk * sh.gattn[row][hd]);                    // per-edge g_q contribution
             }
             csync();
@@ -653,41 +682,59 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) edge_bwd_tc_kernel(const __gri
             // ---- adjoint of the edge update: first g_Pf (A operand), then the g_wdot tile ----
             if (upd) {
                 csync();
-#pragma unroll 2
-                for (int r = 0; r < TC2_RPW; r++) {
-                    const int row = r0 + r;
-                    const bool ok = row < nvalid;
-                    const size_t e = (size_t)(e0 + (ok ? row : 0));
-                    const size_t i3 = (size_t)sh.meta.dst[row] * 3, j3 = (size_t)sh.meta.src[row] * 3;
-                    const float4 dd = sh.meta.d[row];
-                    const float4 gfn = ok ? ld4(ws.GF + e * D + col) : f4s(0.f);
-                    const float4 pf = ld4(P1 + e * 3 * D + 2 * D + col);
-                    const float4 fp = silu4(pf);
-                    float4 ti[3], uj[3];
+#pragma unroll 1
+                for (int rb = 0; rb < TC2_RPW; rb += 2) {
+                    float4 gfr[2], pfr[2], tir[2][3], ujr[2][3];
 #pragma unroll
-                    for (int s = 0; s < 3; s++) {
-                        ti[s] = ld4(TU + (i3 + s) * 2 * D + col);
-                        uj[s] = ld4(TU + (j3 + s) * 2 * D + D + col);
+                    for (int u = 0; u < 2; u++) {
+                        const int row = r0 + rb + u;
+                        const bool ok = row < nvalid;
+                        const size_t e = (size_t)(e0 + (ok ? row : 0));
+                        const size_t i3 = (size_t)sh.meta.dst[row] * 3, j3 = (size_t)sh.meta.src[row] * 3;
+                        gfr[u] = ok ? ld4(ws.GF + e * D + col) : f4s(0.f);
+                        pfr[u] = ldg4(P1 + e * 3 * D + 2 * D + col);
+#pragma unroll
+                        for (int s = 0; s < 3; s++) {
+                            tir[u][s] = ldg4(TU + (i3 + s) * 2 * D + col);
+                            ujr[u][s] = ldg4(TU + (j3 + s) * 2 * D + D + col);
+                        }
                     }
-                    const float dv3[3] = {dd.x, dd.y, dd.z};
-                    const float4 a1 = ti[0] * dd.x + ti[1] * dd.y + ti[2] * dd.z;
-                    const float4 a2 = uj[0] * dd.x + uj[1] * dd.y + uj[2] * dd.z;
-                    float4 w1[3], w2[3];
 #pragma unroll
-                    for (int s = 0; s < 3; s++) { w1[s] = ti[s] - a1 * dv3[s]; w2[s] = uj[s] - a2 * dv3[s]; }
-                    const float4 wdot = w1[0] * w2[0] + w1[1] * w2[1] + w1[2] * w2[2];
-                    const float4 gwd = gfn * fp;
-                    st4(&sh.tile[row][col], gfn * wdot * dsilu4(pf));                    // g_Pf
-                    const float4 c1 = gwd * (w2[0] * dd.x + w2[1] * dd.y + w2[2] * dd.z);
-                    const float4 c2 = gwd * (w1[0] * dd.x + w1[1] * dd.y + w1[2] * dd.z);
-                    float gdl[3];
+                    for (int u = 0; u < 2; u++) {
+                        const int row = r0 + rb + u;
+                        const bool ok = row < nvalid;
+                        const size_t e = (size_t)(e0 + (ok ? row : 0));
+                        const size_t j3 = (size_t)sh.meta.src[row] * 3;
+                        const float4 dd = sh.meta.d[row];
+                        const float4 gfn = gfr[u], pf = pfr[u];
+                        const float4 fp = silu4(pf);
+                        const float dv3[3] = {dd.x, dd.y, dd.z};
+                        const float4 a1 = tir[u][0] * dd.x + tir[u][1] * dd.y + tir[u][2] * dd.z;
+                        const float4 a2 = ujr[u][0] * dd.x + ujr[u][1] * dd.y + ujr[u][2] * dd.z;
+                        float4 w1[3], w2[3];
 #pragma unroll
-                    for (int s = 0; s < 3; s++) {
-                        const float4 gw1 = gwd * w2[s], gw2 = gwd * w1[s];
-                        if (ok) red4(ws.GTU + (j3 + s) * 2 * D + D + col, gw2 - c2 * dv3[s]);
-                        gdl[s] = warp_sum(hsum4(ti[s] * c1 + a1 * gw1 + uj[s] * c2 + a2 * gw2));
+                        for (int s = 0; s < 3; s++) { w1[s] = tir[u][s] - a1 * dv3[s]; w2[s] = ujr[u][s] - a2 * dv3[s]; }
+                        const float4 wdot = w1[0] * w2[0] + w1[1] * w2[1] + w1[2] * w2[2];
+                        const float4 gwd = gfn * fp;
+                        st4(&sh.tile[row][col], gfn * wdot * dsilu4(pf));                    // g_Pf
+                        const float4 c1 = gwd * (w2[0] * dd.x + w2[1] * dd.y + w2[2] * dd.z);
+                        const float4 c2 = gwd * (w1[0] * dd.x + w1[1] * dd.y + w1[2] * dd.z);
+                        float gdl[3];
+                        float4 gu[3];
+#pragma unroll
+                        for (int s = 0; s < 3; s++) {
+                            const float4 gw1 = gwd * w2[s], gw2 = gwd * w1[s];
+                            gu[s] = gw2 - c2 * dv3[s];
+                            gdl[s] = warp_sum(hsum4(tir[u][s] * c1 + a1 * gw1 + ujr[u][s] * c2 + a2 * gw2));
+                        }
+                        if (lane == 0) { sh.eacc[row][1] -= gdl[0]; sh.eacc[row][2] -= gdl[1]; sh.eacc[row][3] -= gdl[2]; }
+                        if (ok) {
+                            red4(ws.GTU + (j3 + 0) * 2 * D + D + col, gu[0]);
+                            red4(ws.GTU + (j3 + 1) * 2 * D + D + col, gu[1]);
+                            red4(ws.GTU + (j3 + 2) * 2 * D + D + col, gu[2]);
+                        }
+                        (void)e;
                     }
-                    if (lane == 0) { sh.eacc[row][1] -= gdl[0]; sh.eacc[row][2] -= gdl[1]; sh.eacc[row][3] -= gdl[2]; }
                 }
                 csync();
                 wait_done(J_G4DK, tpar);
@@ -700,7 +747,7 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) edge_bwd_tc_kernel(const __gri
                     const bool ok = row < nvalid;
                     const size_t e = (size_t)(e0 + (ok ? row : 0));
                     const float4 gfn = ok ? ld4(ws.GF + e * D + col) : f4s(0.f);
-                    st4(&sh.tile[row][col], gfn * silu4(ld4(P1 + e * 3 * D + 2 * D + col)));   // g_wdot
+                    st4(&sh.tile[row][col], gfn * silu4(ldg4(P1 + e * 3 * D + 2 * D + col)));   // g_wdot
                 }
                 csync();
                 {
@@ -713,8 +760,8 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) edge_bwd_tc_kernel(const __gri
                             const size_t j3 = (size_t)sh.meta.src[r] * 3;
                             const float4 dd = sh.meta.d[r];
                             const float gw = sh.tile[r][cch];
-                            const float u0 = TU[(j3 + 0) * 2 * D + D + cch], u1 = TU[(j3 + 1) * 2 * D + D + cch],
-                                        u2 = TU[(j3 + 2) * 2 * D + D + cch];
+                            const float u0 = __ldg(TU + (j3 + 0) * 2 * D + D + cch), u1 = __ldg(TU + (j3 + 1) * 2 * D + D + cch),
+                                        u2 = __ldg(TU + (j3 + 2) * 2 * D + D + cch);
                             const float a2 = u0 * dd.x + u1 * dd.y + u2 * dd.z;
                             const float w20 = u0 - a2 * dd.x, w21 = u1 - a2 * dd.y, w22 = u2 - a2 * dd.z;
                             const float wd = w20 * dd.x + w21 * dd.y + w22 * dd.z;

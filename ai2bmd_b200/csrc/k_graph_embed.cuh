@@ -118,11 +118,22 @@ __global__ void __launch_bounds__(128) edge_geom_kernel(int N, const float* __re
 //   agg_i[c] = sum_{e->i, j!=i} (rbf_e . Wd[c,:] + bd[c]) * C_e * nb_emb[z_j][c]
 //   x_i = [emb[z_i] | agg_i] Wc^T + bc
 // ---------------------------------------------------------------------------------------------
-constexpr int EMB_NB = 8;
+constexpr int EMB_NB = 1;      // one node per 128-thread block: the per-edge loop is a serial latency chain
 __global__ void __launch_bounds__(128) embed_node_kernel(ModelW mw, Workspace ws) {
-    __shared__ float cat[EMB_NB][2 * D];
+    __shared__ float cat[2 * D];
+    __shared__ int sj[KNB];
+    __shared__ int sz[KNB];
+    __shared__ float sC[KNB];
     const int c = threadIdx.x;
-    const int n0 = blockIdx.x * EMB_NB;
+    const int i = blockIdx.x;
+    if (i >= ws.N) return;
+    const int e0 = ws.rowptr[i], dg = ws.rowptr[i + 1] - e0;
+    if (c < dg) {                                   // edge metadata first: breaks the esrc -> z -> embedding load chain
+        const int j = ws.esrc[e0 + c];
+        sj[c] = j;
+        sz[c] = ws.z[j];
+        sC[c] = ws.geom[(size_t)(e0 + c) * 8 + 1];
+    }
     float wd[NR];
 #pragma unroll
     for (int k = 0; k < NR; k += 4) {
@@ -130,43 +141,34 @@ __global__ void __launch_bounds__(128) embed_node_kernel(ModelW mw, Workspace ws
         wd[k] = w.x; wd[k + 1] = w.y; wd[k + 2] = w.z; wd[k + 3] = w.w;
     }
     const float bd = __ldg(mw.bd + c);
-    for (int nd = 0; nd < EMB_NB; nd++) {
-        const int i = n0 + nd;
-        float acc = 0.f, x0 = 0.f;
-        if (i < ws.N) {
-            x0 = __ldg(mw.emb + ws.z[i] * D + c);
-            const int e1 = ws.rowptr[i + 1];
-            for (int e = ws.rowptr[i]; e < e1; e++) {
-                const int j = ws.esrc[e];
-                if (j == i) continue;
-                float dp = bd;
-#pragma unroll
-                for (int k = 0; k < NR; k += 4) {
-                    const float4 rb = ld4(ws.rbf + (size_t)e * NR + k);
-                    dp = fmaf(rb.x, wd[k], dp); dp = fmaf(rb.y, wd[k + 1], dp);
-                    dp = fmaf(rb.z, wd[k + 2], dp); dp = fmaf(rb.w, wd[k + 3], dp);
-                }
-                const float Ce = ws.geom[(size_t)e * 8 + 1];
-                acc = fmaf(dp * Ce, __ldg(mw.nb_emb + ws.z[j] * D + c), acc);
-            }
-        }
-        cat[nd][c] = x0;
-        cat[nd][D + c] = acc;
-    }
+    const float x0 = __ldg(mw.emb + ws.z[i] * D + c);
     __syncthreads();
-    float out[EMB_NB];
-    const float bc = __ldg(mw.bc + c);
+    float acc = 0.f;
+#pragma unroll 2
+    for (int k2 = 0; k2 < dg; k2++) {
+        if (sj[k2] == i) continue;
+        const float nb = __ldg(mw.nb_emb + sz[k2] * D + c);
+        float dp = bd;
 #pragma unroll
-    for (int nd = 0; nd < EMB_NB; nd++) out[nd] = bc;
-#pragma unroll 8
-    for (int k = 0; k < 2 * D; k++) {
-        const float w = __ldg(mw.WcT + k * D + c);
-#pragma unroll
-        for (int nd = 0; nd < EMB_NB; nd++) out[nd] = fmaf(cat[nd][k], w, out[nd]);
+        for (int k = 0; k < NR; k += 4) {
+            const float4 rb = ldg4(ws.rbf + (size_t)(e0 + k2) * NR + k);
+            dp = fmaf(rb.x, wd[k], dp); dp = fmaf(rb.y, wd[k + 1], dp);
+            dp = fmaf(rb.z, wd[k + 2], dp); dp = fmaf(rb.w, wd[k + 3], dp);
+        }
+        acc = fmaf(dp * sC[k2], nb, acc);
     }
-#pragma unroll
-    for (int nd = 0; nd < EMB_NB; nd++)
-        if (n0 + nd < ws.N) ws.X[0][(size_t)(n0 + nd) * D + c] = out[nd];
+    cat[c] = x0;
+    cat[D + c] = acc;
+    __syncthreads();
+    float o0 = __ldg(mw.bc + c), o1 = 0.f, o2 = 0.f, o3 = 0.f;      // 4 independent chains over k
+#pragma unroll 4
+    for (int k = 0; k < 2 * D; k += 4) {
+        o0 = fmaf(cat[k], __ldg(mw.WcT + (k + 0) * D + c), o0);
+        o1 = fmaf(cat[k + 1], __ldg(mw.WcT + (k + 1) * D + c), o1);
+        o2 = fmaf(cat[k + 2], __ldg(mw.WcT + (k + 2) * D + c), o2);
+        o3 = fmaf(cat[k + 3], __ldg(mw.WcT + (k + 3) * D + c), o3);
+    }
+    ws.X[0][(size_t)i * D + c] = (o0 + o1) + (o2 + o3);
 }
 
 // K5: edge embedding  f0_e[c] = (x_i[c] + x_j[c]) * (rbf_e . We[c,:] + be[c]).   thread = channel.
