@@ -95,12 +95,12 @@ __device__ __forceinline__ void warp_gemm_loadw(float4 (&w)[4], const float* __r
 
 // Software-pipelined: the weight rows of the next k-groups are in flight while the current group is
 // multiplied (register ring of NBUF groups; NBUF = 4 for small R where the math does not cover L2 latency).
-template <int R, int K, int LDA>
+template <int R, int K, int LDA, int NBUF = (R <= 4 ? 4 : 2)>
 __device__ __forceinline__ void warp_gemm(float (&acc)[R][4], const float* __restrict__ As,
                                           const float* __restrict__ W, int ldw, int lane) {
     static_assert(K % 16 == 0, "K must be a multiple of 16");
     const float* Wp = W + lane * 4;
-    if constexpr (R <= 4) {
+    if constexpr (NBUF == 4) {
         float4 w0[4], w1[4], w2[4], w3[4];
         warp_gemm_loadw(w0, Wp, ldw, 0);
         warp_gemm_loadw(w1, Wp, ldw, 4);

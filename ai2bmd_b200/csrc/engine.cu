@@ -453,7 +453,10 @@ void choose_defaults(vb_handle* h) {
     if (h->npw == 0) h->npw = (N > 4096) ? 2 : 1;
     if (h->te_fwd == 0) h->te_fwd = ((long long)N * 17 / 64 >= 2LL * h->sm_count) ? 64 : 32;
     // tensor-core edge kernels own a whole SM per 128-edge tile: worth it once every SM gets several tiles
-    if (h->edge_tc < 0) h->edge_tc = ((long long)N * 17 / TC_TE >= 2LL * h->sm_count) ? 3 : 0;
+    if (h->edge_tc < 0) {
+        const long long tiles = (long long)N * 17 / TC_TE;      // estimated 128-edge tiles
+        h->edge_tc = (tiles >= 32 ? 1 : 0) | (tiles >= 2LL * h->sm_count ? 2 : 0);   // measured cross-over points
+    }
 }
 
 }  // namespace

@@ -336,42 +336,58 @@ __global__ void __launch_bounds__(NW * 32) edge_bwd_kernel(EdgeArgs a) {
         // ---- adjoint of the edge update ----
         if (upd) {
 #pragma unroll
-            for (int r = 0; r < R; r++) {
-                const int row = r0 + r;
-                const bool ok = row < nvalid;
-                const size_t e = (size_t)(e0 + (ok ? row : 0));
-                const size_t i3 = (size_t)meta.dst[row] * 3, j3 = (size_t)meta.src[row] * 3;
-                const float4 dd = meta.d[row];
-                const float4 gfn = ok ? ld4(ws.GF + e * D + col) : f4s(0.f);
-                const float4 pf = ldg4(P1 + e * 3 * D + 2 * D + col);
-                const float4 fp = silu4(pf);
-                float4 ti[3], uj[3];
+            for (int rb = 0; rb < R; rb += RBB) {
+                float4 gfr[RBB], pfr[RBB], tir[RBB][3], ujr[RBB][3];
 #pragma unroll
-                for (int s = 0; s < 3; s++) {
-                    ti[s] = ldg4(TU + (i3 + s) * 2 * D + col);
-                    uj[s] = ldg4(TU + (j3 + s) * 2 * D + D + col);
+                for (int u = 0; u < RBB; u++) {
+                    const int row = r0 + rb + u;
+                    const bool ok = row < nvalid;
+                    const size_t e = (size_t)(e0 + (ok ? row : 0));
+                    const size_t i3 = (size_t)meta.dst[row] * 3, j3 = (size_t)meta.src[row] * 3;
+                    gfr[u] = ok ? ld4(ws.GF + e * D + col) : f4s(0.f);
+                    pfr[u] = ldg4(P1 + e * 3 * D + 2 * D + col);
+#pragma unroll
+                    for (int s = 0; s < 3; s++) {
+                        tir[u][s] = ldg4(TU + (i3 + s) * 2 * D + col);
+                        ujr[u][s] = ldg4(TU + (j3 + s) * 2 * D + D + col);
+                    }
                 }
-                const float dv3[3] = {dd.x, dd.y, dd.z};
-                const float4 a1 = ti[0] * dd.x + ti[1] * dd.y + ti[2] * dd.z;
-                const float4 a2 = uj[0] * dd.x + uj[1] * dd.y + uj[2] * dd.z;
-                float4 w1[3], w2[3];
 #pragma unroll
-                for (int s = 0; s < 3; s++) { w1[s] = ti[s] - a1 * dv3[s]; w2[s] = uj[s] - a2 * dv3[s]; }
-                const float4 wdot = w1[0] * w2[0] + w1[1] * w2[1] + w1[2] * w2[2];
-                const float4 gwd = gfn * fp;
-                st4(Ss + row * LEQ + WOFF + col, gwd);
-                st4(Ps + row * LE3 + 2 * D + col, gfn * wdot * dsilu4(pf));
-                const float4 c1 = gwd * (w2[0] * dd.x + w2[1] * dd.y + w2[2] * dd.z);
-                const float4 c2 = gwd * (w1[0] * dd.x + w1[1] * dd.y + w1[2] * dd.z);
-                float gdl[3];
+                for (int u = 0; u < RBB; u++) {
+                    const int r = rb + u, row = r0 + r;
+                    const bool ok = row < nvalid;
+                    const size_t j3 = (size_t)meta.src[row] * 3;
+                    const float4 dd = meta.d[row];
+                    const float4 gfn = gfr[u], pf = pfr[u];
+                    const float4 fp = silu4(pf);
+                    const float dv3[3] = {dd.x, dd.y, dd.z};
+                    const float4 a1 = tir[u][0] * dd.x + tir[u][1] * dd.y + tir[u][2] * dd.z;
+                    const float4 a2 = ujr[u][0] * dd.x + ujr[u][1] * dd.y + ujr[u][2] * dd.z;
+                    float4 w1[3], w2[3];
 #pragma unroll
-                for (int s = 0; s < 3; s++) {
-                    const float4 gw1 = gwd * w2[s], gw2 = gwd * w1[s];
-                    if (ok) red4(ws.GTU + (j3 + s) * 2 * D + D + col, gw2 - c2 * dv3[s]);   // g_u (source side)
-                    gdl[s] = warp_sum(hsum4(ti[s] * c1 + a1 * gw1 + uj[s] * c2 + a2 * gw2));
+                    for (int s = 0; s < 3; s++) { w1[s] = tir[u][s] - a1 * dv3[s]; w2[s] = ujr[u][s] - a2 * dv3[s]; }
+                    const float4 wdot = w1[0] * w2[0] + w1[1] * w2[1] + w1[2] * w2[2];
+                    const float4 gwd = gfn * fp;
+                    st4(Ss + row * LEQ + WOFF + col, gwd);
+                    st4(Ps + row * LE3 + 2 * D + col, gfn * wdot * dsilu4(pf));
+                    const float4 c1 = gwd * (w2[0] * dd.x + w2[1] * dd.y + w2[2] * dd.z);
+                    const float4 c2 = gwd * (w1[0] * dd.x + w1[1] * dd.y + w1[2] * dd.z);
+                    float gdl[3];
+                    float4 gu[3];
+#pragma unroll
+                    for (int s = 0; s < 3; s++) {
+                        const float4 gw1 = gwd * w2[s], gw2 = gwd * w1[s];
+                        gu[s] = gw2 - c2 * dv3[s];
+                        gdl[s] = warp_sum(hsum4(tir[u][s] * c1 + a1 * gw1 + ujr[u][s] * c2 + a2 * gw2));
+                    }
+                    gdx[r] -= gdl[0]; gdy[r] -= gdl[1]; gdz[r] -= gdl[2];
+                    acc[r][0] = gfn.x; acc[r][1] = gfn.y; acc[r][2] = gfn.z; acc[r][3] = gfn.w;
+                    if (ok) {
+                        red4(ws.GTU + (j3 + 0) * 2 * D + D + col, gu[0]);   // g_u (source side)
+                        red4(ws.GTU + (j3 + 1) * 2 * D + D + col, gu[1]);
+                        red4(ws.GTU + (j3 + 2) * 2 * D + D + col, gu[2]);
+                    }
                 }
-                gdx[r] -= gdl[0]; gdy[r] -= gdl[1]; gdz[r] -= gdl[2];
-                acc[r][0] = gfn.x; acc[r][1] = gfn.y; acc[r][2] = gfn.z; acc[r][3] = gfn.w;
             }
         } else {
             acc_zero<R>(acc);

@@ -383,26 +383,35 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) edge_fwd_tc_kernel(const __gri
                 tc::fence_before_sync();
                 csync();
                 const float4 bb = ldg4(lw.b1 + 2 * D + col);
-#pragma unroll 4
-                for (int r = 0; r < TC2_RPW; r++) {
-                    const int row = r0 + r;
-                    const size_t i3 = (size_t)sh.meta.dst[row] * 3, j3 = (size_t)sh.meta.src[row] * 3;
-                    const float4 dd = sh.meta.d[row];
-                    const float4 Pf = ld4(&sh.tile[row][col]) + bb;
-                    const float4 fp = silu4(Pf);
-                    if (row < nvalid) st4(P1 + (size_t)(e0 + row) * 3 * D + 2 * D + col, Pf);
-                    float4 ti[3], uj[3];
+#pragma unroll 1
+                for (int rb = 0; rb < TC2_RPW; rb += 2) {       // gathers of 2 rows in flight before the first global store
+                    float4 tir[2][3], ujr[2][3], fin[2];
 #pragma unroll
-                    for (int s = 0; s < 3; s++) {
-                        ti[s] = ldg4(TU + (i3 + s) * 2 * D + col);
-                        uj[s] = ldg4(TU + (j3 + s) * 2 * D + D + col);
+                    for (int u = 0; u < 2; u++) {
+                        const int row = r0 + rb + u;
+                        const size_t i3 = (size_t)sh.meta.dst[row] * 3, j3 = (size_t)sh.meta.src[row] * 3;
+                        fin[u] = row < nvalid ? ldg4(Fin + (size_t)(e0 + row) * D + col) : f4s(0.f);
+#pragma unroll
+                        for (int s = 0; s < 3; s++) {
+                            tir[u][s] = ldg4(TU + (i3 + s) * 2 * D + col);
+                            ujr[u][s] = ldg4(TU + (j3 + s) * 2 * D + D + col);
+                        }
                     }
-                    const float4 a1 = ti[0] * dd.x + ti[1] * dd.y + ti[2] * dd.z;
-                    const float4 a2 = uj[0] * dd.x + uj[1] * dd.y + uj[2] * dd.z;
-                    const float4 wdot = (ti[0] - a1 * dd.x) * (uj[0] - a2 * dd.x) + (ti[1] - a1 * dd.y) * (uj[1] - a2 * dd.y) +
-                                        (ti[2] - a1 * dd.z) * (uj[2] - a2 * dd.z);
-                    if (row < nvalid)
-                        st4(Fout + (size_t)(e0 + row) * D + col, ldg4(Fin + (size_t)(e0 + row) * D + col) + fp * wdot);
+#pragma unroll
+                    for (int u = 0; u < 2; u++) {
+                        const int row = r0 + rb + u;
+                        const float4 dd = sh.meta.d[row];
+                        const float4 Pf = ld4(&sh.tile[row][col]) + bb;
+                        const float4 fp = silu4(Pf);
+                        const float4 a1 = tir[u][0] * dd.x + tir[u][1] * dd.y + tir[u][2] * dd.z;
+                        const float4 a2 = ujr[u][0] * dd.x + ujr[u][1] * dd.y + ujr[u][2] * dd.z;
+                        const float4 wdot = (tir[u][0] - a1 * dd.x) * (ujr[u][0] - a2 * dd.x) + (tir[u][1] - a1 * dd.y) * (ujr[u][1] - a2 * dd.y) +
+                                            (tir[u][2] - a1 * dd.z) * (ujr[u][2] - a2 * dd.z);
+                        if (row < nvalid) {
+                            st4(P1 + (size_t)(e0 + row) * 3 * D + 2 * D + col, Pf);
+                            st4(Fout + (size_t)(e0 + row) * D + col, fin[u] + fp * wdot);
+                        }
+                    }
                 }
             }
             tc::fence_before_sync();

@@ -47,7 +47,7 @@ __global__ void __launch_bounds__(N2_THREADS) node_fwd2_kernel(NodeArgs a) {
             const int ch = u % 3, rb = u / 3;
             float acc[N2_RB][4];
             acc_set_bias<N2_RB>(acc, lw.bo + ch * D, lane);
-            warp_gemm<N2_RB, D, LDA>(acc, &sm.xs[rb * N2_RB][0], lw.WoT + ch * D, 3 * D, lane);
+            warp_gemm<N2_RB, D, LDA, (NB <= 8 ? 4 : 2)>(acc, &sm.xs[rb * N2_RB][0], lw.WoT + ch * D, 3 * D, lane);
 #pragma unroll
             for (int r = 0; r < N2_RB; r++) st4(&sm.os[rb * N2_RB + r][ch * D + col], arr4(acc[r]));
         }
@@ -104,7 +104,7 @@ __global__ void __launch_bounds__(N2_THREADS) node_fwd2_kernel(NodeArgs a) {
         if (u < UQ) {
             const int ch = u % 3, rb = u / 3;
             acc_set_bias<N2_RB>(acc, lw.bqkv + ch * D, lane);
-            warp_gemm<N2_RB, D, LDA>(acc, &sm.xs[rb * N2_RB][0], lw.WqkvT + ch * D, 3 * D, lane);
+            warp_gemm<N2_RB, D, LDA, (NB <= 8 ? 4 : 2)>(acc, &sm.xs[rb * N2_RB][0], lw.WqkvT + ch * D, 3 * D, lane);
 #pragma unroll
             for (int r = 0; r < N2_RB; r++) {
                 const int nd = rb * N2_RB + r;
@@ -113,7 +113,7 @@ __global__ void __launch_bounds__(N2_THREADS) node_fwd2_kernel(NodeArgs a) {
         } else if (u < UQ + UV) {
             const int v = u - UQ, ch = v % 3, rb = v / 3;
             acc_zero<N2_RB>(acc);
-            warp_gemm<N2_RB, D, LDA>(acc, &sm.vs[rb * N2_RB][0], lw.WvecT + ch * D, 3 * D, lane);
+            warp_gemm<N2_RB, D, LDA, (NB <= 8 ? 4 : 2)>(acc, &sm.vs[rb * N2_RB][0], lw.WvecT + ch * D, 3 * D, lane);
 #pragma unroll
             for (int r = 0; r < N2_RB; r++) {
                 const int row = rb * N2_RB + r;                  // = nd*3 + s
@@ -122,7 +122,7 @@ __global__ void __launch_bounds__(N2_THREADS) node_fwd2_kernel(NodeArgs a) {
         } else {
             const int v = u - UQ - UV, ch = v % 2, rb = v / 2;
             acc_zero<N2_RB>(acc);
-            warp_gemm<N2_RB, D, LDA>(acc, &sm.vs[rb * N2_RB][0], lw.WtuT + ch * D, 2 * D, lane);
+            warp_gemm<N2_RB, D, LDA, (NB <= 8 ? 4 : 2)>(acc, &sm.vs[rb * N2_RB][0], lw.WtuT + ch * D, 2 * D, lane);
 #pragma unroll
             for (int r = 0; r < N2_RB; r++) {
                 const int row = rb * N2_RB + r;
@@ -212,13 +212,13 @@ __global__ void __launch_bounds__(N2_THREADS) node_bwd2_kernel(NodeArgs a) {
             acc_zero<N2_RB>(acc);
             if (u < UX) {
                 const int kc = u % 3, rb = u / 3;
-                warp_gemm<N2_RB, D, LD3>(acc, &sm.gq[rb * N2_RB][kc * D], lw.WqkvN + (size_t)kc * D * D, D, lane);
+                warp_gemm<N2_RB, D, LD3, 4>(acc, &sm.gq[rb * N2_RB][kc * D], lw.WqkvN + (size_t)kc * D * D, D, lane);
 #pragma unroll
                 for (int r = 0; r < N2_RB; r++) st4(&sm.part_x[kc][rb * N2_RB + r][col], arr4(acc[r]));
             } else {
                 const int v = u - UX, kc = v % kv, rb = v / kv;
-                if (kc < 3) warp_gemm<N2_RB, D, LD3>(acc, &sm.gvp[rb * N2_RB][kc * D], lw.WvecN + (size_t)kc * D * D, D, lane);
-                else        warp_gemm<N2_RB, D, LD2>(acc, &sm.gtu[rb * N2_RB][(kc - 3) * D], lw.WtuN + (size_t)(kc - 3) * D * D, D, lane);
+                if (kc < 3) warp_gemm<N2_RB, D, LD3, 4>(acc, &sm.gvp[rb * N2_RB][kc * D], lw.WvecN + (size_t)kc * D * D, D, lane);
+                else        warp_gemm<N2_RB, D, LD2, 4>(acc, &sm.gtu[rb * N2_RB][(kc - 3) * D], lw.WtuN + (size_t)(kc - 3) * D * D, D, lane);
 #pragma unroll
                 for (int r = 0; r < N2_RB; r++) st4(&sm.part_v[kc][rb * N2_RB + r][col], arr4(acc[r]));
             }
@@ -282,7 +282,7 @@ __global__ void __launch_bounds__(N2_THREADS) node_bwd2_kernel(NodeArgs a) {
             const int kc = u % 3, rb = u / 3;
             float acc[N2_RB][4];
             acc_zero<N2_RB>(acc);
-            warp_gemm<N2_RB, D, LD3>(acc, &sm.gq[rb * N2_RB][kc * D], lw.WoN + (size_t)kc * D * D, D, lane);
+            warp_gemm<N2_RB, D, LD3, 4>(acc, &sm.gq[rb * N2_RB][kc * D], lw.WoN + (size_t)kc * D * D, D, lane);
 #pragma unroll
             for (int r = 0; r < N2_RB; r++) st4(&sm.part_x[kc][rb * N2_RB + r][col], arr4(acc[r]));
         }
