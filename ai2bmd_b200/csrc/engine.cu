@@ -278,18 +278,24 @@ void launch_node_fwd2(Launcher& Lc, int k) {
     node_fwd2_kernel<NB><<<(h->ws.N + NB - 1) / NB, N2_THREADS, sizeof(NodeFwd2Smem<NB>), Lc.st>>>(a);
     Lc.check();
 }
+template <int NB>
 void launch_node_bwd2(Launcher& Lc, int k) {
     vb_handle* h = Lc.h;
     NodeArgs a{k, h->mw, h->ws};
-    node_bwd2_kernel<8><<<(h->ws.N + 7) / 8, N2_THREADS, sizeof(NodeBwd2Smem<8>), Lc.st>>>(a);
+    node_bwd2_kernel<NB><<<(h->ws.N + NB - 1) / NB, N2_THREADS, sizeof(NodeBwd2Smem<NB>), Lc.st>>>(a);
     Lc.check();
 }
 void node_fwd(Launcher& Lc, int k) {
-    if (Lc.h->node_impl == 1) { Lc.h->npw == 2 ? launch_node_fwd2<16>(Lc, k) : launch_node_fwd2<8>(Lc, k); return; }
+    if (Lc.h->node_impl == 1) {
+        if (Lc.h->npw == 2) launch_node_fwd2<16>(Lc, k);
+        else if (Lc.h->ws.N <= 1024) launch_node_fwd2<4>(Lc, k);     // small systems: more, smaller CTAs
+        else launch_node_fwd2<8>(Lc, k);
+        return;
+    }
     Lc.h->npw == 2 ? launch_node_fwd<2>(Lc, k) : launch_node_fwd<1>(Lc, k);
 }
 void node_bwd(Launcher& Lc, int k) {
-    if (Lc.h->node_impl == 1) { launch_node_bwd2(Lc, k); return; }
+    if (Lc.h->node_impl == 1) { Lc.h->ws.N <= 1024 ? launch_node_bwd2<4>(Lc, k) : launch_node_bwd2<8>(Lc, k); return; }
     Lc.h->npw == 2 ? launch_node_bwd<2>(Lc, k) : launch_node_bwd<1>(Lc, k);
 }
 void head(Launcher& Lc) { Lc.h->npw == 2 ? launch_head<2>(Lc) : launch_head<1>(Lc); }
@@ -402,6 +408,8 @@ int configure_kernels(vb_handle* h) {
     CUDA_TRY(h, opt_in_smem(edge_fwd_tc_kernel, TC_SMEM_BYTES));
     CUDA_TRY(h, opt_in_smem(edge_bwd_tc_kernel, TC_SMEM_BYTES));
 
+    CUDA_TRY(h, opt_in_smem(node_fwd2_kernel<4>, sizeof(NodeFwd2Smem<4>)));
+    CUDA_TRY(h, opt_in_smem(node_bwd2_kernel<4>, sizeof(NodeBwd2Smem<4>)));
     CUDA_TRY(h, opt_in_smem(node_fwd2_kernel<8>, sizeof(NodeFwd2Smem<8>)));
     CUDA_TRY(h, opt_in_smem(node_fwd2_kernel<16>, sizeof(NodeFwd2Smem<16>)));
     CUDA_TRY(h, opt_in_smem(node_bwd2_kernel<8>, sizeof(NodeBwd2Smem<8>)));

@@ -9,7 +9,7 @@ namespace vb {
 
 constexpr int N2_WARPS = 8;
 constexpr int N2_THREADS = N2_WARPS * 32;
-constexpr int N2_RB = 8;                         // rows per GEMM unit
+template <int NB> struct N2Rows { static constexpr int RB = (NB < 8) ? NB : 8; };   // rows per GEMM unit
 
 template <int NB>
 struct NodeFwd2Smem {
@@ -27,6 +27,7 @@ template <int NB>
 __global__ void __launch_bounds__(N2_THREADS) node_fwd2_kernel(NodeArgs a) {
     using S = NodeFwd2Smem<NB>;
     constexpr int LDA = S::LDA;
+    constexpr int N2_RB = N2Rows<NB>::RB;
     extern __shared__ __align__(16) float dyn_smem[];
     S& sm = *reinterpret_cast<S*>(dyn_smem);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, col = lane * 4;
@@ -149,8 +150,8 @@ template <int NB>
 struct NodeBwd2Smem {
     static constexpr int LD3 = 3 * D + LDS_PAD;   // 388
     static constexpr int LD2 = 2 * D + LDS_PAD;   // 260
-    static constexpr int NVB = 3 * NB / N2_RB;    // vector row blocks
-    static constexpr int NXB = NB / N2_RB;        // scalar row blocks
+    static constexpr int NVB = 3 * NB / N2Rows<NB>::RB;    // vector row blocks
+    static constexpr int NXB = NB / N2Rows<NB>::RB;        // scalar row blocks
     float gq[NB][LD3];                            // g_qkv rows -> later g_o rows
     float gvp[3 * NB][LD3];                       // [g_vdot*v2 | g_vdot*v1 | gvec*o1] rows
     float gtu[3 * NB][LD2];                       // [g_t | g_u] rows
@@ -162,6 +163,7 @@ template <int NB>
 __global__ void __launch_bounds__(N2_THREADS) node_bwd2_kernel(NodeArgs a) {
     using S = NodeBwd2Smem<NB>;
     constexpr int LD3 = S::LD3, LD2 = S::LD2;
+    constexpr int N2_RB = N2Rows<NB>::RB;
     extern __shared__ __align__(16) float dyn_smem[];
     S& sm = *reinterpret_cast<S*>(dyn_smem);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, col = lane * 4;
