@@ -298,7 +298,15 @@ void node_bwd(Launcher& Lc, int k) {
     if (Lc.h->node_impl == 1) { Lc.h->ws.N <= 1024 ? launch_node_bwd2<4>(Lc, k) : launch_node_bwd2<8>(Lc, k); return; }
     Lc.h->npw == 2 ? launch_node_bwd<2>(Lc, k) : launch_node_bwd<1>(Lc, k);
 }
-void head(Launcher& Lc) { Lc.h->npw == 2 ? launch_head<2>(Lc) : launch_head<1>(Lc); }
+void head(Launcher& Lc) {
+    vb_handle* h = Lc.h;
+    if (h->ws.N <= 4096) {            // small systems: K-split head, one node per CTA
+        head2_kernel<<<h->ws.N, 128, 0, Lc.st>>>(h->mw, h->ws);
+        Lc.check();
+        return;
+    }
+    h->npw == 2 ? launch_head<2>(Lc) : launch_head<1>(Lc);
+}
 void launch_edge_fwd_tc(Launcher& Lc, int l) {
     vb_handle* h = Lc.h;
     EdgeTcArgs a{};
