@@ -68,13 +68,37 @@ class ProteinMap:
     frag_sign: np.ndarray   # float32 [G] (+1 dipeptide, -1 ACE-NME)
 
 
+@dataclass
+class FragmentRecipe:
+    """How every packed fragment atom follows the protein coordinates (``distancefrag.py:34-54``): real atoms
+    copy ``P[real]``; an added cap hydrogen sits at ``P[acc] + unit(P[rem] - P[acc]) * blen``."""
+    real: np.ndarray        # int32 [N] protein index, -1 for an added hydrogen
+    acc: np.ndarray         # int32 [N] acceptor protein index (added hydrogens only, else 0)
+    rem: np.ndarray         # int32 [N] removed-atom protein index (added hydrogens only, else 0)
+    blen: np.ndarray        # float32 [N] bond length
+
+    def positions(self, prot_pos: np.ndarray) -> np.ndarray:
+        p = np.asarray(prot_pos, dtype=np.float64)
+        out = p[np.maximum(self.real, 0)]
+        cap = self.real < 0
+        if cap.any():
+            d = p[self.rem[cap]] - p[self.acc[cap]]
+            d /= np.linalg.norm(d, axis=1, keepdims=True)
+            out[cap] = p[self.acc[cap]] + d * self.blen[cap, None]
+        return out.astype(np.float32)
+
+
+class _Cap:
+    """Marker for an added hydrogen: (acceptor, removed atom, bond length)."""
+    def __init__(self, acc, rem, blen):
+        self.acc, self.rem, self.blen = acc, rem, blen
+
+
 def _cap_h(pos, acceptor, removed, acc_elem):
-    d = pos[removed] - pos[acceptor]
-    d = d / np.linalg.norm(d)
-    return pos[acceptor] + d * (_RCOV[acc_elem] + _RCOV["H"])
+    return _Cap(acceptor, removed, _RCOV[acc_elem] + _RCOV["H"])
 
 
-def fragment_protein(prot: CappedProtein) -> Tuple[FragmentData, ProteinMap]:
+def fragment_protein(prot: CappedProtein, with_recipe: bool = False):
     R = int(prot.resnums.max())
     assert len(set(prot.resnums.tolist())) == R, "residue numbers are not continuous"
     nd, na = R - 2, R - 3
@@ -128,28 +152,34 @@ def fragment_protein(prot: CappedProtein) -> Tuple[FragmentData, ProteinMap]:
             # ACE-NME k: leading group of dipeptide k+1 (from residue k+2) + trailing group of dipeptide k (k+3)
             frags.append((-1.0, lead_group(centre) + trail_group(centre + 1)))
 
-    z, pos, batch, start, end = [], [], [], [], []
+    z, batch, start, end = [], [], [], []
     src, dst, sgn, fsgn = [], [], [], []
+    r_real, r_acc, r_rem, r_len = [], [], [], []
     off = 0
     for g, (s, atoms) in enumerate(frags):
         start.append(off)
         for (pi, el, xyz) in atoms:
             z.append(_Z[el])
-            pos.append(xyz)
             batch.append(g)
             if pi is not None:
                 src.append(off)
                 dst.append(pi)
                 sgn.append(s)
+                r_real.append(pi); r_acc.append(0); r_rem.append(0); r_len.append(0.0)
+            else:
+                r_real.append(-1); r_acc.append(xyz.acc); r_rem.append(xyz.rem); r_len.append(xyz.blen)
             off += 1
         end.append(off)
         fsgn.append(s)
+    recipe = FragmentRecipe(np.asarray(r_real, dtype=np.int32), np.asarray(r_acc, dtype=np.int32),
+                            np.asarray(r_rem, dtype=np.int32), np.asarray(r_len, dtype=np.float32))
+    pos = recipe.positions(P)
     fd = FragmentData(np.asarray(z, dtype=np.int64), np.asarray(pos, dtype=np.float32),
                       np.asarray(start, dtype=np.int64), np.asarray(end, dtype=np.int64),
                       np.asarray(batch, dtype=np.int64))
     pm = ProteinMap(len(prot), np.asarray(src, dtype=np.int32), np.asarray(dst, dtype=np.int32),
                     np.asarray(sgn, dtype=np.float32), np.asarray(fsgn, dtype=np.float32))
-    return fd, pm
+    return (fd, pm, recipe) if with_recipe else (fd, pm)
 
 
 def single_graph(z, pos) -> FragmentData:

@@ -61,11 +61,15 @@ def main():
 
     frs = {}
     for name in ("chig", "trpcage", "ww", "abd"):
-        fd, pm = fragment_protein(read_pdb(f"{REF}/examples/{name}.pdb"))
+        prot = read_pdb(f"{REF}/examples/{name}.pdb")
+        fd, pm, rc = fragment_protein(prot, with_recipe=True)
         frs[name] = (fd, pm)
+        zmap = {"H": 1, "C": 6, "N": 7, "O": 8, "S": 16}
         np.savez_compressed(os.path.join(HERE, f"fragments_{name}.npz"), z=fd.z, pos=fd.pos, start=fd.start,
                             end=fd.end, batch=fd.batch, n_protein=pm.n_protein, src_atom=pm.src_atom,
-                            dst_atom=pm.dst_atom, sign=pm.sign, frag_sign=pm.frag_sign)
+                            dst_atom=pm.dst_atom, sign=pm.sign, frag_sign=pm.frag_sign,
+                            prot_pos=prot.positions, prot_z=np.array([zmap[e] for e in prot.elements]),
+                            rc_real=rc.real, rc_acc=rc.acc, rc_rem=rc.rem, rc_blen=rc.blen)
 
     model = load_reference_model()
     o64 = O.OracleViSNet(sd, torch.float64)
