@@ -275,27 +275,27 @@ template <int NB>
 void launch_node_fwd2(Launcher& Lc, int k) {
     vb_handle* h = Lc.h;
     NodeArgs a{k, h->mw, h->ws};
-    node_fwd2_kernel<NB><<<(h->ws.N + NB - 1) / NB, N2_THREADS, sizeof(NodeFwd2Smem<NB>), Lc.st>>>(a);
+    node_fwd2_kernel<NB><<<(h->ws.N + NB - 1) / NB, N2Cfg<NB>::THREADS, sizeof(NodeFwd2Smem<NB>), Lc.st>>>(a);
     Lc.check();
 }
 template <int NB>
 void launch_node_bwd2(Launcher& Lc, int k) {
     vb_handle* h = Lc.h;
     NodeArgs a{k, h->mw, h->ws};
-    node_bwd2_kernel<NB><<<(h->ws.N + NB - 1) / NB, N2_THREADS, sizeof(NodeBwd2Smem<NB>), Lc.st>>>(a);
+    node_bwd2_kernel<NB><<<(h->ws.N + NB - 1) / NB, N2Cfg<NB>::THREADS, sizeof(NodeBwd2Smem<NB>), Lc.st>>>(a);
     Lc.check();
 }
 void node_fwd(Launcher& Lc, int k) {
     if (Lc.h->node_impl == 1) {
         if (Lc.h->npw == 2) launch_node_fwd2<16>(Lc, k);
-        else if (Lc.h->ws.N <= 1024) launch_node_fwd2<4>(Lc, k);     // small systems: more, smaller CTAs
+        else if ((Lc.h->ws.N + 3) / 4 <= Lc.h->sm_count) launch_node_fwd2<4>(Lc, k);   // one wave of 4-node, 16-warp CTAs
         else launch_node_fwd2<8>(Lc, k);
         return;
     }
     Lc.h->npw == 2 ? launch_node_fwd<2>(Lc, k) : launch_node_fwd<1>(Lc, k);
 }
 void node_bwd(Launcher& Lc, int k) {
-    if (Lc.h->node_impl == 1) { Lc.h->ws.N <= 1024 ? launch_node_bwd2<4>(Lc, k) : launch_node_bwd2<8>(Lc, k); return; }
+    if (Lc.h->node_impl == 1) { (Lc.h->ws.N + 3) / 4 <= Lc.h->sm_count ? launch_node_bwd2<4>(Lc, k) : launch_node_bwd2<8>(Lc, k); return; }
     Lc.h->npw == 2 ? launch_node_bwd<2>(Lc, k) : launch_node_bwd<1>(Lc, k);
 }
 void head(Launcher& Lc) {

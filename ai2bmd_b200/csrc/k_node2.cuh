@@ -7,8 +7,8 @@
 
 namespace vb {
 
-constexpr int N2_WARPS = 8;
-constexpr int N2_THREADS = N2_WARPS * 32;
+// warps per CTA: 16 for the 4-node variant (small systems: more units in flight per node), 8 otherwise
+template <int NB> struct N2Cfg { static constexpr int WARPS = (NB <= 4) ? 16 : 8; static constexpr int THREADS = WARPS * 32; };
 template <int NB> struct N2Rows { static constexpr int RB = (NB < 8) ? NB : 8; };   // rows per GEMM unit
 
 template <int NB>
@@ -18,13 +18,15 @@ struct NodeFwd2Smem {
     float xs[NB][LDA];                            // xa rows, later LayerNorm(x) rows
     float vs[3 * NB][LDA];                        // VecLayerNorm(vec) rows
     float os[NB][LDO];                            // o_proj output rows
+    float osp[(NB <= 4) ? 3 : 1][NB][LDO];        // 4-node variant: K-quarter partials 1..3 of the o_proj rows
 };
 
 // ---------------------------------------------------------------------------------------------
 // forward node stage k (same contract as node_fwd_kernel)
 // ---------------------------------------------------------------------------------------------
 template <int NB>
-__global__ void __launch_bounds__(N2_THREADS) node_fwd2_kernel(NodeArgs a) {
+__global__ void __launch_bounds__(N2Cfg<NB>::THREADS) node_fwd2_kernel(NodeArgs a) {
+    constexpr int N2_WARPS = N2Cfg<NB>::WARPS, N2_THREADS = N2Cfg<NB>::THREADS;
     using S = NodeFwd2Smem<NB>;
     constexpr int LDA = S::LDA;
     constexpr int N2_RB = N2Rows<NB>::RB;
@@ -43,14 +45,34 @@ __global__ void __launch_bounds__(N2_THREADS) node_fwd2_kernel(NodeArgs a) {
             st4(&sm.xs[nd][c4], nd < nn ? ld4(ws.XA + (size_t)(n0 + nd) * D + c4) : f4s(0.f));
         }
         __syncthreads();
-        // o = xa Wo^T + bo : units = 3 chunks x NB/8 row blocks
-        for (int u = warp; u < 3 * (NB / N2_RB); u += N2_WARPS) {
-            const int ch = u % 3, rb = u / 3;
-            float acc[N2_RB][4];
-            acc_set_bias<N2_RB>(acc, lw.bo + ch * D, lane);
-            warp_gemm<N2_RB, D, LDA, (NB <= 8 ? 4 : 2)>(acc, &sm.xs[rb * N2_RB][0], lw.WoT + ch * D, 3 * D, lane);
+        // o = xa Wo^T + bo : units = 3 chunks x NB/8 row blocks (x 4 K-quarters in the 16-warp variant)
+        if constexpr (NB <= 4) {
+            for (int u = warp; u < 12; u += N2_WARPS) {
+                const int ch = u % 3, kq = u / 3;
+                float acc[N2_RB][4];
+                if (kq == 0) acc_set_bias<N2_RB>(acc, lw.bo + ch * D, lane);
+                else acc_zero<N2_RB>(acc);
+                warp_gemm<N2_RB, D / 4, LDA, 4>(acc, &sm.xs[0][kq * (D / 4)], lw.WoT + (size_t)kq * (D / 4) * 3 * D + ch * D, 3 * D, lane);
 #pragma unroll
-            for (int r = 0; r < N2_RB; r++) st4(&sm.os[rb * N2_RB + r][ch * D + col], arr4(acc[r]));
+                for (int r = 0; r < N2_RB; r++) {
+                    if (kq == 0) st4(&sm.os[r][ch * D + col], arr4(acc[r]));
+                    else st4(&sm.osp[kq - 1][r][ch * D + col], arr4(acc[r]));
+                }
+            }
+            __syncthreads();
+            for (int idx = threadIdx.x; idx < NB * 96; idx += N2_THREADS) {      // fixed-order sum of the K-quarters
+                const int r = idx / 96, c4 = (idx % 96) * 4;
+                st4(&sm.os[r][c4], (ld4(&sm.os[r][c4]) + ld4(&sm.osp[0][r][c4])) + (ld4(&sm.osp[1][r][c4]) + ld4(&sm.osp[2][r][c4])));
+            }
+        } else {
+            for (int u = warp; u < 3 * (NB / N2_RB); u += N2_WARPS) {
+                const int ch = u % 3, rb = u / 3;
+                float acc[N2_RB][4];
+                acc_set_bias<N2_RB>(acc, lw.bo + ch * D, lane);
+                warp_gemm<N2_RB, D, LDA, (NB <= 8 ? 4 : 2)>(acc, &sm.xs[rb * N2_RB][0], lw.WoT + ch * D, 3 * D, lane);
+#pragma unroll
+                for (int r = 0; r < N2_RB; r++) st4(&sm.os[rb * N2_RB + r][ch * D + col], arr4(acc[r]));
+            }
         }
         __syncthreads();
     }
@@ -160,7 +182,8 @@ struct NodeBwd2Smem {
 };
 
 template <int NB>
-__global__ void __launch_bounds__(N2_THREADS) node_bwd2_kernel(NodeArgs a) {
+__global__ void __launch_bounds__(N2Cfg<NB>::THREADS) node_bwd2_kernel(NodeArgs a) {
+    constexpr int N2_WARPS = N2Cfg<NB>::WARPS;
     using S = NodeBwd2Smem<NB>;
     constexpr int LD3 = S::LD3, LD2 = S::LD2;
     constexpr int N2_RB = N2Rows<NB>::RB;
