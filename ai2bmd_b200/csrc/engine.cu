@@ -471,7 +471,7 @@ void choose_defaults(vb_handle* h) {
     // tensor-core edge kernels own a whole SM per 128-edge tile: worth it once every SM gets several tiles
     if (h->edge_tc < 0) {
         const long long tiles = (long long)N * 17 / TC_TE;      // estimated 128-edge tiles
-        h->edge_tc = (tiles >= 32 ? 1 : 0) | (tiles >= 2LL * h->sm_count ? 2 : 0);   // measured cross-over points
+        h->edge_tc = (tiles >= 32 ? 1 : 0) | (tiles >= 80 ? 2 : 0);   // measured cross-over points (profiles/README.md)
     }
 }
 

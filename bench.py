@@ -45,11 +45,12 @@ def parse():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="chig", choices=["chig", "trpcage", "ww", "abd", "c4", "c4_20k", "c5"])
     ap.add_argument("--no-flush", action="store_true", help="keep L2 warm between timed steps (diagnostic)")
+    ap.add_argument("--fragments", type=int, default=512, help="fragment count of the synthetic c4 batch")
     ap.add_argument("--skip-cpu-baseline", action="store_true")
     return ap.parse_args()
 
 
-def load_workload(name):
+def load_workload(name, n_fragments=512):
     from ai2bmd_b200.fixtures import load_fragments
     from ai2bmd_b200.synth import conformer_batch, synthetic_batch, synthetic_protein_map
     if name in ("chig", "trpcage", "ww", "abd"):
@@ -57,8 +58,8 @@ def load_workload(name):
         desc = {"chig": "Chignolin (chig.pdb) full fragmentation", "trpcage": "Trp-cage full fragmentation",
                 "ww": "WW domain full fragmentation", "abd": "ABD full fragmentation"}[name]
     elif name == "c4":
-        fd = synthetic_batch(512, seed=0)
-        pm, desc = synthetic_protein_map(fd), "synthetic 512-fragment batch (seed 0)"
+        fd = synthetic_batch(n_fragments, seed=0)
+        pm, desc = synthetic_protein_map(fd), f"synthetic {n_fragments}-fragment batch (seed 0)"
     elif name == "c4_20k":
         fd = synthetic_batch(512, seed=0, min_atoms=20000)
         pm, desc = synthetic_protein_map(fd), "synthetic >=20k-atom batch (seed 0)"
@@ -165,7 +166,7 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    fd, pm, desc = load_workload(args.workload)
+    fd, pm, desc = load_workload(args.workload, args.fragments)
     sd = load_weights()
     calib = fd if len(fd) <= 8 else fd[0:8]
     model, threads, avail = make_cpu_model(sd, calib)
@@ -213,7 +214,7 @@ def run_ours(args):
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    fd, pm, desc = load_workload(args.workload)
+    fd, pm, desc = load_workload(args.workload, args.fragments)
     sd = load_weights()
     n_atoms, n_frag = len(fd.z), len(fd)
 
@@ -323,10 +324,14 @@ def run_ours(args):
     ab = sum(algorithmic_bytes(n, loc_atoms, n_edges) or 0 for n, _ in launches)
     t_fam = fam_ms[top_fam] * 1e-3
     achieved = (ab / t_fam / 1e9) if ab else None
+    traffic = None      # dram__bytes_read.sum + dram__bytes_write.sum per launch, from the committed ncu --set full capture
+    tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if os.path.exists(tpath) and world == 1:
+        traffic = json.load(open(tpath)).get(f"{args.workload}:{top_fam}")
     roofline = {"bound": "hbm", "kernel": top_fam, "launches_per_step": len(launches),
                 "kernel_ms": fam_ms[top_fam] / len(launches), "algorithmic_bytes": ab / len(launches) if ab else None,
                 "achieved": achieved, "peak": peak, "peak_kind": peak_kind, "unit": "GB/s",
-                "frac": (achieved / peak) if achieved else None, "traffic": None,
+                "frac": (achieved / peak) if achieved else None, "traffic": traffic,
                 "note": "algorithmic bytes = SURVEY 8d fused lower bound per launch; this stage is contraction/latency bound, "
                         "not HBM bound (DESIGN.md section 5); workloads below ~2k atoms are L2 resident",
                 "share_of_step": fam_ms[top_fam] / total_ms,
