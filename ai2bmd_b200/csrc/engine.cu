@@ -365,7 +365,7 @@ void enqueue_all(Launcher& Lc) {
     char name[64];
     if (Lc.next("nbr_build")) {
         nbr_build_kernel<<<(N + 127) / 128, 128, 0, Lc.st>>>(N, h->d_pos, ws.frag_of, ws.frag_start, h->mw.cutoff,
-                                                           ws.slots, ws.deg);
+                                                           ws.slots, ws.deg, h->d_forces);
         Lc.check();
     }
     if (Lc.next("rowptr_scan")) { rowptr_scan_kernel<<<1, 1024, 0, Lc.st>>>(N, ws.deg, ws.rowptr); Lc.check(); }
@@ -392,9 +392,10 @@ void enqueue_all(Launcher& Lc) {
         if (Lc.next(name)) edge_bwd(Lc, l);
     }
     if (Lc.next("node_bwd0")) node_bwd(Lc, 0);
-    if (Lc.next("embed_edge_bwd")) { embed_edge_bwd_kernel<<<eblocks, 128, 0, Lc.st>>>(h->mw, ws); Lc.check(); }
-    if (Lc.next("forces_zero")) {
-        if (Lc.status == cudaSuccess) Lc.status = cudaMemsetAsync(h->d_forces, 0, sizeof(float) * 3 * N, Lc.st);
+    if (Lc.next("embed_edge_bwd")) {
+        const int bb = std::max(1, std::min((ws.Ecap + EEB_WARPS - 1) / EEB_WARPS, h->sm_count * 4));
+        embed_edge_bwd_kernel<<<bb, EEB_WARPS * 32, 0, Lc.st>>>(h->mw, ws);
+        Lc.check();
     }
     if (Lc.next("embed_node_bwd")) { embed_node_bwd_kernel<<<N, 128, 0, Lc.st>>>(h->mw, ws, h->d_forces); Lc.check(); }
 }

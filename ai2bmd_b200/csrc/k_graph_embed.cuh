@@ -14,9 +14,11 @@ namespace vb {
 __global__ void __launch_bounds__(128) nbr_build_kernel(int N, const float* __restrict__ pos,
                                                         const int* __restrict__ frag_of,
                                                         const int* __restrict__ frag_start, float rc,
-                                                        int* __restrict__ slots, int* __restrict__ deg) {
+                                                        int* __restrict__ slots, int* __restrict__ deg,
+                                                        float* __restrict__ forces) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= N) return;
+    forces[3 * i] = 0.f; forces[3 * i + 1] = 0.f; forces[3 * i + 2] = 0.f;   // accumulated by the last kernel of the sweep
     const int g = frag_of[i];
     const int j0 = frag_start[g], j1 = frag_start[g + 1];
     const float xi = pos[3 * i], yi = pos[3 * i + 1], zi = pos[3 * i + 2];
@@ -197,143 +199,124 @@ __global__ void __launch_bounds__(128) embed_edge_kernel(ModelW mw, Workspace ws
 }
 
 // ---------------------------------------------------------------------------------------------
-// K14: adjoint of the edge embedding.  gf = dE/df0 (in ws.GF).
-//   gx_i += gf*ep, gx_j += gf*ep ; g_rbf[e][k] = sum_c gf*(x_i+x_j) * We[c][k]
+// K14: adjoint of the edge embedding.  gf = dE/df0 (in ws.GF).  One warp per edge, no block barriers:
+//   phase A (lane = 4 channels): ep = rbf.We^T + be ; gx_i += gf*ep, gx_j += gf*ep ; g_ep = gf*(x_i+x_j) -> smem
+//   phase B (lane = rbf index k): g_rbf[e][k] = sum_c g_ep[c] * We[c][k]
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) embed_edge_bwd_kernel(ModelW mw, Workspace ws) {
-    __shared__ float gep_s[D];
-    __shared__ float part[4][NR];
-    const int c = threadIdx.x;
-    float we[NR];
-#pragma unroll
-    for (int k = 0; k < NR; k += 4) {
-        const float4 w = ldg4(mw.WeN + c * NR + k);
-        we[k] = w.x; we[k + 1] = w.y; we[k + 2] = w.z; we[k + 3] = w.w;
+constexpr int EEB_WARPS = 8;
+__global__ void __launch_bounds__(EEB_WARPS * 32) embed_edge_bwd_kernel(ModelW mw, Workspace ws) {
+    __shared__ __align__(16) float WeT_s[NR][D];          // [k][c]
+    __shared__ float WeN_s[D][NR + 1];                    // [c][k] (+1: conflict-free column walks)
+    __shared__ __align__(16) float gep_s[EEB_WARPS][D];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, col = lane * 4;
+    for (int idx = threadIdx.x; idx < D * NR; idx += blockDim.x) {
+        const int c = idx / NR, k = idx % NR;
+        const float w = __ldg(mw.WeN + idx);
+        WeT_s[k][c] = w;
+        WeN_s[c][k] = w;
     }
-    const float be = __ldg(mw.be + c);
+    __syncthreads();
+    const float4 be = ldg4(mw.be + col);
     const int E = ws.rowptr[ws.N];
     const float* __restrict__ X = ws.X[0];
-    const int kk = c & 31, pp = c >> 5;   // reduction role: output k, channel quarter pp
-    for (int e = blockIdx.x; e < E; e += gridDim.x) {
-        float ep = be;
-#pragma unroll
-        for (int k = 0; k < NR; k += 4) {
-            const float4 rb = ld4(ws.rbf + (size_t)e * NR + k);
-            ep = fmaf(rb.x, we[k], ep); ep = fmaf(rb.y, we[k + 1], ep);
-            ep = fmaf(rb.z, we[k + 2], ep); ep = fmaf(rb.w, we[k + 3], ep);
-        }
+    for (int e = blockIdx.x * EEB_WARPS + warp; e < E; e += gridDim.x * EEB_WARPS) {
         const int i = ws.edst[e], j = ws.esrc[e];
-        const float gf = ws.GF[(size_t)e * D + c];
-        const float gfe = gf * ep;
-        atomicAdd(ws.GX + (size_t)i * D + c, gfe);
-        atomicAdd(ws.GX + (size_t)j * D + c, gfe);
-        __syncthreads();
-        gep_s[c] = gf * (X[(size_t)i * D + c] + X[(size_t)j * D + c]);
-        __syncthreads();
-        float s = 0.f;
+        const float rk = __ldg(ws.rbf + (size_t)e * NR + lane);
+        const float4 gf = ld4(ws.GF + (size_t)e * D + col);
+        const float4 xs = ldg4(X + (size_t)i * D + col) + ldg4(X + (size_t)j * D + col);
+        float4 ep = be;
+#pragma unroll
+        for (int k = 0; k < NR; k++) ep = ep + ld4(&WeT_s[k][col]) * __shfl_sync(0xffffffffu, rk, k);
+        const float4 gfe = gf * ep;
+        red4(ws.GX + (size_t)i * D + col, gfe);
+        red4(ws.GX + (size_t)j * D + col, gfe);
+        __syncwarp();
+        st4(&gep_s[warp][col], gf * xs);
+        __syncwarp();
+        float g = 0.f;
 #pragma unroll 8
-        for (int q = 0; q < 32; q++) {
-            const int cc = pp * 32 + q;
-            s = fmaf(gep_s[cc], __ldg(mw.WeN + cc * NR + kk), s);
-        }
-        part[pp][kk] = s;
-        __syncthreads();
-        if (c < NR) ws.grbf[(size_t)e * NR + c] = (part[0][c] + part[1][c]) + (part[2][c] + part[3][c]);
+        for (int c = 0; c < D; c++) g = fmaf(gep_s[warp][c], WeN_s[c][lane], g);
+        ws.grbf[(size_t)e * NR + lane] = g;
     }
 }
 
 // ---------------------------------------------------------------------------------------------
-// K15: adjoint of the neighbour embedding + geometry adjoint + force accumulation.
-// One block (128 threads) per target node i; needs the complete gx (all scatter-adds done).
+// K15: adjoint of the neighbour embedding + geometry adjoint + force accumulation.  One block (4 warps) per target
+// node i (needs the complete gx); each warp takes every 4th edge of the node, no block barriers in the edge loop:
 //   g_agg = (gx_i Wc)[128:256]
-//   per edge e->i (j != i): g_We = g_agg * nb[z_j]; gC += sum_c g_We*dp ; g_rbf[k] += sum_c g_We*C*Wd[c][k]
-//   g_r = gC*C'(r) + sum_k g_rbf[k]*drbf_k/dr ; g_ev = g_r d + (g_d - (g_d.d) d)/r
-//   dE/dpos_j += g_ev, dE/dpos_i -= g_ev ; forces = -dE/dpos
+//   phase A (lane = 4 channels): dp = rbf.Wd^T + bd ; g_We = g_agg * nb[z_j] ; gC += sum_c g_We*dp ; g_We*C -> smem
+//   phase B (lane = rbf index k): g_rbf[k] += sum_c g_We[c]*C*Wd[c][k] ; g_r = gC*C'(r) + sum_k g_rbf[k]*drbf_k/dr
+//   g_ev = g_r d + (g_d - (g_d.d) d)/r ; dE/dpos_j += g_ev, dE/dpos_i -= g_ev ; forces = -dE/dpos
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128) embed_node_bwd_kernel(ModelW mw, Workspace ws,
                                                              float* __restrict__ forces) {
-    __shared__ float gx_s[D];
-    __shared__ float gwe_s[D];
-    __shared__ float part[4][NR];
-    __shared__ float red_s[4];
-    const int c = threadIdx.x, lane = c & 31, warp = c >> 5;
+    __shared__ __align__(16) float WdT_s[NR][D];
+    __shared__ float WdN_s[D][NR + 1];
+    __shared__ __align__(16) float gx_s[D];
+    __shared__ __align__(16) float gwe_s[4][D];
+    __shared__ float fi_s[4][3];
+    const int c = threadIdx.x, lane = c & 31, warp = c >> 5, col = lane * 4;
     const int i = blockIdx.x;
     if (i >= ws.N) return;
     gx_s[c] = ws.GX[(size_t)i * D + c];
-    float wd[NR];
-#pragma unroll
-    for (int k = 0; k < NR; k += 4) {
-        const float4 w = ldg4(mw.WdN + c * NR + k);
-        wd[k] = w.x; wd[k + 1] = w.y; wd[k + 2] = w.z; wd[k + 3] = w.w;
+    for (int idx = threadIdx.x; idx < D * NR; idx += 128) {
+        const int cc = idx / NR, k = idx % NR;
+        const float w = __ldg(mw.WdN + idx);
+        WdT_s[k][cc] = w;
+        WdN_s[cc][k] = w;
     }
-    const float bd = __ldg(mw.bd + c);
     __syncthreads();
-    float g_agg = 0.f;
-#pragma unroll 8
-    for (int k = 0; k < D; k++) g_agg = fmaf(gx_s[k], __ldg(mw.WcN + (size_t)k * 2 * D + D + c), g_agg);
+    // g_agg for this lane's 4 channels (every warp computes the same values; 4 independent chains over k)
+    float4 g_agg = f4s(0.f);
+#pragma unroll 4
+    for (int k = 0; k < D; k++) g_agg = g_agg + ldg4(mw.WcN + (size_t)k * 2 * D + D + col) * gx_s[k];
+    const float4 bd = ldg4(mw.bd + col);
     const float alpha = 5.0f / mw.cutoff;
-    float fix = 0.f, fiy = 0.f, fiz = 0.f;   // accumulated -dE/dpos_i contributions (thread 0)
+    const float mu = __ldg(mw.rbf_means + lane), beta = __ldg(mw.rbf_betas + lane);
+    float fix = 0.f, fiy = 0.f, fiz = 0.f;
     const int e1 = ws.rowptr[i + 1];
-    for (int e = ws.rowptr[i]; e < e1; e++) {
+    for (int e = ws.rowptr[i] + warp; e < e1; e += 4) {
         const int j = ws.esrc[e];
         if (j == i) continue;     // self-loops carry no geometry and are masked out of the neighbour embedding
         const float4 g0 = ld4(ws.geom + (size_t)e * 8);
         const float4 g1 = ld4(ws.geom + (size_t)e * 8 + 4);
         const float r = g0.x, Ce = g0.y, dx = g0.z, dy = g0.w, dz = g1.x, inv_r = g1.y;
-        float dp = bd;
+        const float rk = __ldg(ws.rbf + (size_t)e * NR + lane);
+        float4 dp = bd;
 #pragma unroll
-        for (int k = 0; k < NR; k += 4) {
-            const float4 rb = ld4(ws.rbf + (size_t)e * NR + k);
-            dp = fmaf(rb.x, wd[k], dp); dp = fmaf(rb.y, wd[k + 1], dp);
-            dp = fmaf(rb.z, wd[k + 2], dp); dp = fmaf(rb.w, wd[k + 3], dp);
-        }
-        const float gwe = g_agg * __ldg(mw.nb_emb + ws.z[j] * D + c);
-        float gc = warp_sum(gwe * dp);
-        __syncthreads();                 // previous iteration finished reading gwe_s / part / red_s
-        gwe_s[c] = gwe * Ce;
-        if (lane == 0) red_s[warp] = gc;
-        __syncthreads();
-        {
-            const int kk = lane, pp = warp;
-            float s = 0.f;
+        for (int k = 0; k < NR; k++) dp = dp + ld4(&WdT_s[k][col]) * __shfl_sync(0xffffffffu, rk, k);
+        const float4 gwe = g_agg * ldg4(mw.nb_emb + ws.z[j] * D + col);
+        const float gc = warp_sum(hsum4(gwe * dp));
+        __syncwarp();
+        st4(&gwe_s[warp][col], gwe * Ce);
+        __syncwarp();
+        float g = 0.f;
 #pragma unroll 8
-            for (int q = 0; q < 32; q++) {
-                const int cc = pp * 32 + q;
-                s = fmaf(gwe_s[cc], __ldg(mw.WdN + cc * NR + kk), s);
-            }
-            part[pp][kk] = s;
-        }
-        __syncthreads();
-        if (warp == 0) {
-            const float4 ea = ld4(ws.eacc + (size_t)e * 4);
-            const float gC = ea.x + ((red_s[0] + red_s[1]) + (red_s[2] + red_s[3]));
-            const float grbf = ws.grbf[(size_t)e * NR + lane] +
-                               ((part[0][lane] + part[1][lane]) + (part[2][lane] + part[3][lane]));
-            const float mu = __ldg(mw.rbf_means + lane), beta = __ldg(mw.rbf_betas + lane);
-            const float ex = expf(-alpha * r);
-            const float t = ex - mu;
-            const float gk = expf(-beta * t * t);
-            const float dC = cutoff_dfn(r, mw.cutoff);
-            const float drbf = dC * gk + Ce * gk * (2.0f * beta * alpha) * t * ex;
-            const float g_r = gC * dC + warp_sum(grbf * drbf);
-            if (lane == 0) {
-                const float gdd = ea.y * dx + ea.z * dy + ea.w * dz;
-                const float gx_ = g_r * dx + (ea.y - gdd * dx) * inv_r;
-                const float gy_ = g_r * dy + (ea.z - gdd * dy) * inv_r;
-                const float gz_ = g_r * dz + (ea.w - gdd * dz) * inv_r;
-                // dE/dpos_j += g_ev  -> F_j -= g_ev ; dE/dpos_i -= g_ev -> F_i += g_ev
-                atomicAdd(forces + 3 * j, -gx_);
-                atomicAdd(forces + 3 * j + 1, -gy_);
-                atomicAdd(forces + 3 * j + 2, -gz_);
-                fix += gx_; fiy += gy_; fiz += gz_;
-            }
+        for (int cc = 0; cc < D; cc++) g = fmaf(gwe_s[warp][cc], WdN_s[cc][lane], g);
+        const float4 ea = ld4(ws.eacc + (size_t)e * 4);
+        const float gC = ea.x + gc;
+        const float grbf = ws.grbf[(size_t)e * NR + lane] + g;
+        const float ex = __expf(-alpha * r);
+        const float t = ex - mu;
+        const float gk = __expf(-beta * t * t);
+        const float dC = cutoff_dfn(r, mw.cutoff);
+        const float drbf = dC * gk + Ce * gk * (2.0f * beta * alpha) * t * ex;
+        const float g_r = gC * dC + warp_sum(grbf * drbf);
+        if (lane == 0) {
+            const float gdd = ea.y * dx + ea.z * dy + ea.w * dz;
+            const float gx_ = g_r * dx + (ea.y - gdd * dx) * inv_r;
+            const float gy_ = g_r * dy + (ea.z - gdd * dy) * inv_r;
+            const float gz_ = g_r * dz + (ea.w - gdd * dz) * inv_r;
+            // dE/dpos_j += g_ev  -> F_j -= g_ev ; dE/dpos_i -= g_ev -> F_i += g_ev
+            atomicAdd(forces + 3 * j, -gx_);
+            atomicAdd(forces + 3 * j + 1, -gy_);
+            atomicAdd(forces + 3 * j + 2, -gz_);
+            fix += gx_; fiy += gy_; fiz += gz_;
         }
     }
-    if (c == 0) {
-        atomicAdd(forces + 3 * i, fix);
-        atomicAdd(forces + 3 * i + 1, fiy);
-        atomicAdd(forces + 3 * i + 2, fiz);
-    }
+    if (lane == 0) { fi_s[warp][0] = fix; fi_s[warp][1] = fiy; fi_s[warp][2] = fiz; }
+    __syncthreads();
+    if (c < 3) atomicAdd(forces + 3 * i + c, (fi_s[0][c] + fi_s[1][c]) + (fi_s[2][c] + fi_s[3][c]));
 }
 
 // per-fragment energy: E_g = sum_a e_atom[a] + mean   (one warp per fragment; visnet.py:146-149).
