@@ -469,10 +469,11 @@ void choose_defaults(vb_handle* h) {
     h->npw = h->npw_opt; h->te_fwd = h->te_fwd_opt; h->edge_tc = h->edge_tc_opt;
     if (h->npw == 0) h->npw = (N > 4096) ? 2 : 1;
     if (h->te_fwd == 0) h->te_fwd = ((long long)N * 17 / 64 >= 2LL * h->sm_count) ? 64 : 32;
-    // tensor-core edge kernels own a whole SM per 128-edge tile: worth it once every SM gets several tiles
+    // tcgen05 edge kernels (one 128-edge tile per CTA, 16 compute warps): the forward stage wins at every size
+    // measured, the adjoint stage from ~32 tiles (tools/tc_crossover.py, profiles/README.md)
     if (h->edge_tc < 0) {
         const long long tiles = (long long)N * 17 / TC_TE;      // estimated 128-edge tiles
-        h->edge_tc = (tiles >= 32 ? 1 : 0) | (tiles >= 80 ? 2 : 0);   // measured cross-over points (profiles/README.md)
+        h->edge_tc = 1 | (tiles >= 32 ? 2 : 0);
     }
 }
 

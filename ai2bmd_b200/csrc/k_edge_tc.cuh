@@ -199,10 +199,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_selftest_kernel(const float*
 // =====================================================================================================
 namespace vb {
 
-constexpr int TC2_CWARPS = 8;                       // compute warps
-constexpr int TC2_CTHREADS = TC2_CWARPS * 32;       // 256
+constexpr int TC2_CWARPS = 16;                      // compute warps
+constexpr int TC2_CTHREADS = TC2_CWARPS * 32;       // 512
 constexpr int TC2_THREADS = TC2_CTHREADS + 64;      // + producer warp + MMA warp
-constexpr int TC2_RPW = TC_TE / TC2_CWARPS;         // rows per compute warp in the coalesced phases (16)
+constexpr int TC2_CBLK = D / (TC2_CWARPS / 4);         // columns each warp moves between the staging tile and TMEM
+constexpr int TC2_NGRP = TC2_CTHREADS / D;             // channel groups in the per-target aggregation phases
+constexpr int TC2_RPW = TC_TE / TC2_CWARPS;         // rows per compute warp in the coalesced phases (8)
 
 struct EdgeTcArgs {
     int layer;
@@ -212,7 +214,7 @@ struct EdgeTcArgs {
     int njobs;
 };
 
-__device__ __forceinline__ void csync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+__device__ __forceinline__ void csync() { asm volatile("bar.sync 1, %0;" ::"n"(TC2_CTHREADS) : "memory"); }
 
 __device__ __forceinline__ uint32_t tc2_setup(TcShared& sh, int njobs) {
     const int warp = threadIdx.x >> 5;
@@ -236,10 +238,10 @@ __device__ __forceinline__ void tc2_teardown(uint32_t tmem_base) {
 // staging tile (fp32, row-major, padded) -> A operand planes in TMEM.  Compute warp w serves TMEM lane quarter
 // w&3 (rows 32*(w&3)..+31) and column half w>>2.
 __device__ __forceinline__ void tc2_tile_to_a(TcShared& sh, uint32_t tmem, int warp, int lane) {
-    const int row = (warp & 3) * 32 + lane, ch = (warp >> 2) * 64;
+    const int row = (warp & 3) * 32 + lane, ch = (warp >> 2) * TC2_CBLK;
     const uint32_t tl = tmem + ((uint32_t)((warp & 3) * 32) << 16);
 #pragma unroll
-    for (int c0 = 0; c0 < 64; c0 += 16) {
+    for (int c0 = 0; c0 < TC2_CBLK; c0 += 16) {
         float v[16];
 #pragma unroll
         for (int q = 0; q < 16; q += 4) {
@@ -251,14 +253,15 @@ __device__ __forceinline__ void tc2_tile_to_a(TcShared& sh, uint32_t tmem, int w
 }
 // accumulator (TMEM) -> staging tile
 __device__ __forceinline__ void tc2_d_to_tile(TcShared& sh, uint32_t tmem, uint32_t d_col, int warp, int lane) {
-    const int row = (warp & 3) * 32 + lane, ch = (warp >> 2) * 64;
+    const int row = (warp & 3) * 32 + lane, ch = (warp >> 2) * TC2_CBLK;
     const uint32_t tl = tmem + ((uint32_t)((warp & 3) * 32) << 16) + d_col;
-    uint32_t r[4][16];
+    constexpr int NB16 = TC2_CBLK / 16;
+    uint32_t r[NB16][16];
 #pragma unroll
-    for (int b = 0; b < 4; b++) tc::tmem_ld16_nowait(tl + ch + b * 16, r[b]);
+    for (int b = 0; b < NB16; b++) tc::tmem_ld16_nowait(tl + ch + b * 16, r[b]);
     tc::wait_ld();
 #pragma unroll
-    for (int b = 0; b < 4; b++)
+    for (int b = 0; b < NB16; b++)
 #pragma unroll
         for (int q = 0; q < 16; q += 4)
             st4(&sh.tile[row][ch + b * 16 + q], f4(__uint_as_float(r[b][q]), __uint_as_float(r[b][q + 1]),
@@ -363,7 +366,7 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) edge_fwd_tc_kernel(const __gri
             // ---- xa_i = sum_e m_e ----
             {
                 const int i_first = sh.meta.dst[0], i_last = sh.meta.dst[nvalid - 1];
-                for (int i = i_first + grp; i <= i_last; i += 2) {
+                for (int i = i_first + grp; i <= i_last; i += TC2_NGRP) {
                     const int q0 = ws.rowptr[i], q1 = ws.rowptr[i + 1];
                     const int lo = max(q0, e0) - e0, hi = min(q1, e0 + nvalid) - e0;
                     float xa = 0.f;
@@ -427,7 +430,7 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) edge_fwd_tc_kernel(const __gri
                 const float b = __ldg(lw.bs + cch);
                 const int i_first = sh.meta.dst[0], i_last = sh.meta.dst[nvalid - 1];
                 int nb = 0;
-                for (int i = i_first + grp; i <= i_last; i += 2) {
+                for (int i = i_first + grp; i <= i_last; i += TC2_NGRP) {
                     const int q0 = ws.rowptr[i], q1 = ws.rowptr[i + 1];
                     const int lo = max(q0, e0) - e0, hi = min(q1, e0 + nvalid) - e0;
                     float v0 = 0.f, v1 = 0.f, v2 = 0.f;
@@ -475,7 +478,7 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) edge_fwd_tc_kernel(const __gri
                 const float b = __ldg(lw.bs + D + cch);
                 const int i_first = sh.meta.dst[0], i_last = sh.meta.dst[nvalid - 1];
                 int nb = 0;
-                for (int i = i_first + grp; i <= i_last; i += 2) {
+                for (int i = i_first + grp; i <= i_last; i += TC2_NGRP) {
                     const int q0 = ws.rowptr[i], q1 = ws.rowptr[i + 1];
                     const int lo = max(q0, e0) - e0, hi = min(q1, e0 + nvalid) - e0;
                     float v0 = 0.f, v1 = 0.f, v2 = 0.f;
@@ -679,7 +682,7 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) edge_bwd_tc_kernel(const __gri
             csync();
             {
                 const int i_first = sh.meta.dst[0], i_last = sh.meta.dst[nvalid - 1];
-                for (int i = i_first + grp; i <= i_last; i += 2) {
+                for (int i = i_first + grp; i <= i_last; i += TC2_NGRP) {
                     const int q0 = ws.rowptr[i], q1 = ws.rowptr[i + 1];
                     const int lo = max(q0, e0) - e0, hi = min(q1, e0 + nvalid) - e0;
                     float gq = 0.f;
@@ -761,7 +764,7 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) edge_bwd_tc_kernel(const __gri
                 csync();
                 {
                     const int i_first = sh.meta.dst[0], i_last = sh.meta.dst[nvalid - 1];
-                    for (int i = i_first + grp; i <= i_last; i += 2) {
+                    for (int i = i_first + grp; i <= i_last; i += TC2_NGRP) {
                         const int q0 = ws.rowptr[i], q1 = ws.rowptr[i + 1];
                         const int lo = max(q0, e0) - e0, hi = min(q1, e0 + nvalid) - e0;
                         float gt0 = 0.f, gt1 = 0.f, gt2 = 0.f;
