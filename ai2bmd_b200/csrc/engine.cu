@@ -72,6 +72,8 @@ struct vb_handle {
     size_t arena_bytes = 0;
     float* d_pos = nullptr;      // [N][3]
     float* d_energy = nullptr;   // [G]
+    unsigned long long* d_tl = nullptr;   // optional in-kernel timeline of the tcgen05 edge kernels [2L][TC_TL_SLOTS]
+    int timeline = 0;
     float* d_forces = nullptr;   // [N][3]
     float *h_pos = nullptr, *h_energy = nullptr, *h_forces = nullptr;   // pinned staging
     cudaStream_t own_stream = nullptr;
@@ -82,6 +84,7 @@ struct vb_handle {
     // options
     int use_graph = 1, npw = 0, te_fwd = 0, te_bwd = 32;
     int npw_opt = 0, te_fwd_opt = 0, edge_tc_opt = -1;   // user choices (0 / -1 = choose by problem size)
+    int tc_rows_opt = 0, tc_rows = 128;                  // edges per tcgen05 tile (64 / 96 / 128; MMA M stays 128)
     int node_impl = 1; // 0: warp-per-node kernels (k_node.cuh), 1: CTA-cooperative kernels (k_node2.cuh)
     int edge_tc = -1;  // bit 0: forward edge stage on tcgen05, bit 1: adjoint edge stage on tcgen05; -1 = by size
     // graph cache
@@ -320,9 +323,13 @@ void launch_edge_fwd_tc(Launcher& Lc, int l) {
     a.jobs[n++] = TcJob{lw.tcWs, (int)TC_COL_D1, 0};                       // s1
     a.jobs[n++] = TcJob{lw.tcWs + chunk, (int)TC_COL_D0, 0};               // s2
     a.njobs = n;
-    const int tiles = (h->ws.Ecap + TC_TE - 1) / TC_TE;
+    a.tl = h->timeline ? h->d_tl + (size_t)l * TC_TL_SLOTS : nullptr;
+    const int rows = h->tc_rows;
+    const int tiles = (h->ws.Ecap + rows - 1) / rows;
     const int blocks = std::max(1, std::min(tiles, h->sm_count));
-    edge_fwd_tc_kernel<<<blocks, TC2_THREADS, TC_SMEM_BYTES, Lc.st>>>(a);
+    if (rows == 64) edge_fwd_tc_kernel<64><<<blocks, TC2_THREADS, TC_SMEM_BYTES, Lc.st>>>(a);
+    else if (rows == 96) edge_fwd_tc_kernel<96><<<blocks, TC2_THREADS, TC_SMEM_BYTES, Lc.st>>>(a);
+    else edge_fwd_tc_kernel<128><<<blocks, TC2_THREADS, TC_SMEM_BYTES, Lc.st>>>(a);
     Lc.check();
 }
 
@@ -345,9 +352,13 @@ void launch_edge_bwd_tc(Launcher& Lc, int l) {
     a.jobs[n++] = TcJob{lw.tcW1N, (int)TC_COL_D0, 1};                        //      + g_Pdk Wdk
     if (upd) a.jobs[n++] = TcJob{lw.tcW1N + 2 * chunk, (int)TC_COL_D0, 1};   //      + g_Pf  Wf
     a.njobs = n;
-    const int tiles = (h->ws.Ecap + TC_TE - 1) / TC_TE;
+    a.tl = h->timeline ? h->d_tl + (size_t)(L + l) * TC_TL_SLOTS : nullptr;
+    const int rows = h->tc_rows;
+    const int tiles = (h->ws.Ecap + rows - 1) / rows;
     const int blocks = std::max(1, std::min(tiles, h->sm_count));
-    edge_bwd_tc_kernel<<<blocks, TC2_THREADS, TC_SMEM_BYTES, Lc.st>>>(a);
+    if (rows == 64) edge_bwd_tc_kernel<64><<<blocks, TC2_THREADS, TC_SMEM_BYTES, Lc.st>>>(a);
+    else if (rows == 96) edge_bwd_tc_kernel<96><<<blocks, TC2_THREADS, TC_SMEM_BYTES, Lc.st>>>(a);
+    else edge_bwd_tc_kernel<128><<<blocks, TC2_THREADS, TC_SMEM_BYTES, Lc.st>>>(a);
     Lc.check();
 }
 
@@ -414,8 +425,12 @@ int configure_kernels(vb_handle* h) {
     CUDA_TRY(h, opt_in_smem(node_bwd_kernel<2>, node_bwd_smem_bytes<2>()));
     CUDA_TRY(h, opt_in_smem(head_kernel<1>, HeadSmem<1>::BYTES));
     CUDA_TRY(h, opt_in_smem(head_kernel<2>, HeadSmem<2>::BYTES));
-    CUDA_TRY(h, opt_in_smem(edge_fwd_tc_kernel, TC_SMEM_BYTES));
-    CUDA_TRY(h, opt_in_smem(edge_bwd_tc_kernel, TC_SMEM_BYTES));
+    CUDA_TRY(h, opt_in_smem(edge_fwd_tc_kernel<64>, TC_SMEM_BYTES));
+    CUDA_TRY(h, opt_in_smem(edge_fwd_tc_kernel<96>, TC_SMEM_BYTES));
+    CUDA_TRY(h, opt_in_smem(edge_fwd_tc_kernel<128>, TC_SMEM_BYTES));
+    CUDA_TRY(h, opt_in_smem(edge_bwd_tc_kernel<64>, TC_SMEM_BYTES));
+    CUDA_TRY(h, opt_in_smem(edge_bwd_tc_kernel<96>, TC_SMEM_BYTES));
+    CUDA_TRY(h, opt_in_smem(edge_bwd_tc_kernel<128>, TC_SMEM_BYTES));
 
     CUDA_TRY(h, opt_in_smem(node_fwd2_kernel<4>, sizeof(NodeFwd2Smem<4>)));
     CUDA_TRY(h, opt_in_smem(node_bwd2_kernel<4>, sizeof(NodeBwd2Smem<4>)));
@@ -474,6 +489,17 @@ void choose_defaults(vb_handle* h) {
     if (h->edge_tc < 0) {
         const long long tiles = (long long)N * 17 / TC_TE;      // estimated 128-edge tiles
         h->edge_tc = 1 | (tiles >= 32 ? 2 : 0);
+    }
+    // short tiles spread a small system over more SMs (the per-tile latency is mostly the per-row SIMT phases):
+    // the longest tile that still fits the estimated edge count into one wave of CTAs
+    h->tc_rows = h->tc_rows_opt;
+    if (h->tc_rows == 0) {
+        const long long est_edges = (long long)N * 17;
+        h->tc_rows = 128;
+        if ((est_edges + 127) / 128 < h->sm_count) {
+            if ((est_edges + 95) / 96 <= h->sm_count) h->tc_rows = 96;
+            if ((est_edges + 63) / 64 <= h->sm_count) h->tc_rows = 64;
+        }
     }
 }
 
@@ -537,6 +563,7 @@ int vb_create(const float* weights_host, size_t n_floats, const vb_hparams* hp, 
     if (const char* s = getenv("VB_TE_FWD")) h->te_fwd_opt = atoi(s);
     if (const char* s = getenv("VB_TE_BWD")) h->te_bwd = atoi(s);
     if (const char* s = getenv("VB_EDGE_TC")) h->edge_tc_opt = atoi(s);
+    if (const char* s = getenv("VB_TC_ROWS")) { const int v = atoi(s); if (v == 64 || v == 96 || v == 128) h->tc_rows_opt = v; }
     if (const char* s = getenv("VB_NODE_IMPL")) h->node_impl = atoi(s);
     *out = h;
     return VB_OK;
@@ -549,6 +576,7 @@ void vb_destroy(vb_handle* h) {
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
     cudaFree(h->d_weights);
     cudaFree(h->d_tc_scratch);
+    cudaFree(h->d_tl);
     cudaFree(h->arena);
     cudaFree(h->d_map_src); cudaFree(h->d_map_dst); cudaFree(h->d_map_sign); cudaFree(h->d_frag_sign);
     cudaFreeHost(h->h_pos); cudaFreeHost(h->h_energy); cudaFreeHost(h->h_forces);
@@ -727,7 +755,17 @@ int vb_set_option(vb_handle* h, const char* key, int64_t value) {
     else if (k == "te_fwd" && (value == 32 || value == 64)) h->te_fwd = h->te_fwd_opt = (int)value;
     else if (k == "te_bwd" && (value == 32 || value == 64)) h->te_bwd = (int)value;
     else if (k == "edge_tc" && value >= 0 && value <= 3) h->edge_tc = h->edge_tc_opt = (int)value;
+    else if (k == "tc_rows" && (value == 64 || value == 96 || value == 128)) h->tc_rows = h->tc_rows_opt = (int)value;
     else if (k == "node_impl" && (value == 0 || value == 1)) h->node_impl = (int)value;
+    else if (k == "timeline" && (value == 0 || value == 1)) {
+        if (value && !h->d_tl) {
+            if (cudaSetDevice(h->device) != cudaSuccess || cudaMalloc(&h->d_tl, sizeof(unsigned long long) * 2 * L * TC_TL_SLOTS) != cudaSuccess) {
+                h->set_error("vb_set_option: timeline buffer allocation failed"); return VB_ERR_CUDA;
+            }
+            cudaMemset(h->d_tl, 0, sizeof(unsigned long long) * 2 * L * TC_TL_SLOTS);
+        }
+        h->timeline = (int)value;
+    }
     else { h->set_error("vb_set_option: unknown key or bad value: %s", key); return VB_ERR_ARG; }
     h->drop_graph();
     return VB_OK;
@@ -742,6 +780,8 @@ int64_t vb_get_option(const vb_handle* h, const char* key) {
     if (k == "te_bwd") return h->te_bwd;
     if (k == "edge_tc") return h->edge_tc;
     if (k == "node_impl") return h->node_impl;
+    if (k == "timeline") return h->timeline;
+    if (k == "tc_rows") return h->tc_rows;
     if (k == "n_edges_capacity") return h->ws.Ecap;
     return VB_ERR_ARG;
 }
@@ -849,6 +889,7 @@ int64_t vb_debug_read(vb_handle* h, const char* name, int layer, void* host_dst,
     else if (k == "P1" && lay(L)) { src = ws.P1[layer]; bytes = E * 3 * D * 4; }
     else if (k == "SP" && lay(L)) { src = ws.SP[layer]; bytes = E * 2 * D * 4; }
     else if (k == "ATT" && lay(L)) { src = ws.ATT[layer]; bytes = E * H * 4; }
+    else if (k == "TL" && lay(2 * L) && h->d_tl) { src = h->d_tl + (size_t)layer * TC_TL_SLOTS; bytes = TC_TL_SLOTS * 8; }
     else BUF("XA", ws.XA, N * D, 4)
     else BUF("VA", ws.VA, N * 3 * D, 4)
     else BUF("GX", ws.GX, N * D, 4)

@@ -93,7 +93,8 @@ __device__ __forceinline__ void tc_producer(TcShared& sh, const TcJob* jobs, int
 }
 
 // MMA issuer: one thread
-__device__ __forceinline__ void tc_mma_issuer(TcShared& sh, const TcJob* jobs, int njobs, int ntiles, uint32_t tmem_base) {
+__device__ __forceinline__ void tc_mma_issuer(TcShared& sh, const TcJob* jobs, int njobs, int ntiles, uint32_t tmem_base,
+                                              unsigned long long* tl = nullptr) {
     constexpr uint32_t idesc = tc::idesc_tf32(128, 128);
     int stage = 0;
     uint32_t phase = 0;
@@ -102,6 +103,7 @@ __device__ __forceinline__ void tc_mma_issuer(TcShared& sh, const TcJob* jobs, i
         for (int j = 0; j < njobs; j++) {
             tc::mbar_wait(&sh.go[j], tpar);
             tc::fence_after_sync();
+            if (tl != nullptr && t == 0) tl[32 + 2 * j] = (unsigned long long)clock64();
             const uint32_t d_addr = tmem_base + (uint32_t)jobs[j].d_col;
             uint32_t acc = (uint32_t)jobs[j].accumulate;
 #pragma unroll 1
@@ -124,6 +126,7 @@ __device__ __forceinline__ void tc_mma_issuer(TcShared& sh, const TcJob* jobs, i
                 if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
             }
             tc::mma_commit(&sh.done[j]);
+            if (tl != nullptr && t == 0) tl[33 + 2 * j] = (unsigned long long)clock64();
         }
     }
 }
@@ -204,7 +207,6 @@ constexpr int TC2_CTHREADS = TC2_CWARPS * 32;       // 512
 constexpr int TC2_THREADS = TC2_CTHREADS + 64;      // + producer warp + MMA warp
 constexpr int TC2_CBLK = D / (TC2_CWARPS / 4);         // columns each warp moves between the staging tile and TMEM
 constexpr int TC2_NGRP = TC2_CTHREADS / D;             // channel groups in the per-target aggregation phases
-constexpr int TC2_RPW = TC_TE / TC2_CWARPS;         // rows per compute warp in the coalesced phases (8)
 
 struct EdgeTcArgs {
     int layer;
@@ -212,7 +214,10 @@ struct EdgeTcArgs {
     Workspace ws;
     TcJob jobs[TC_MAXJOBS];
     int njobs;
+    unsigned long long* tl;     // optional timeline (SM clock stamps of CTA 0, first tile); nullptr = off
 };
+constexpr int TC_TL_SLOTS = 64;  // [0,32): compute thread 0 phase stamps ; [32,48): MMA issuer (go seen / MMAs issued per job)
+#define TC_TL(k) do { if (a.tl != nullptr && blockIdx.x == 0 && it == 0 && threadIdx.x == 0) a.tl[k] = (unsigned long long)clock64(); } while (0)
 
 __device__ __forceinline__ void csync() { asm volatile("bar.sync 1, %0;" ::"n"(TC2_CTHREADS) : "memory"); }
 
@@ -237,7 +242,9 @@ __device__ __forceinline__ void tc2_teardown(uint32_t tmem_base) {
 
 // staging tile (fp32, row-major, padded) -> A operand planes in TMEM.  Compute warp w serves TMEM lane quarter
 // w&3 (rows 32*(w&3)..+31) and column half w>>2.
+template <int ROWS>
 __device__ __forceinline__ void tc2_tile_to_a(TcShared& sh, uint32_t tmem, int warp, int lane) {
+    if ((warp & 3) * 32 >= ROWS) return;          // short tiles: TMEM lanes >= ROWS stay stale (their D rows are never read)
     const int row = (warp & 3) * 32 + lane, ch = (warp >> 2) * TC2_CBLK;
     const uint32_t tl = tmem + ((uint32_t)((warp & 3) * 32) << 16);
 #pragma unroll
@@ -252,7 +259,9 @@ __device__ __forceinline__ void tc2_tile_to_a(TcShared& sh, uint32_t tmem, int w
     }
 }
 // accumulator (TMEM) -> staging tile
+template <int ROWS>
 __device__ __forceinline__ void tc2_d_to_tile(TcShared& sh, uint32_t tmem, uint32_t d_col, int warp, int lane) {
+    if ((warp & 3) * 32 >= ROWS) return;
     const int row = (warp & 3) * 32 + lane, ch = (warp >> 2) * TC2_CBLK;
     const uint32_t tl = tmem + ((uint32_t)((warp & 3) * 32) << 16) + d_col;
     constexpr int NB16 = TC2_CBLK / 16;
@@ -277,6 +286,7 @@ __device__ __forceinline__ void tc2_go(TcShared& sh, int j) {      // every comp
 // forward (math and reference lines: see edge_fwd_kernel in k_edge.cuh)
 // job order: dk -> D0, dv -> D1, [f -> D0], s1 -> D1, s2 -> D0
 // ---------------------------------------------------------------------------------------------
+template <int ROWS>
 __global__ void __launch_bounds__(TC2_THREADS, 1) edge_fwd_tc_kernel(const __grid_constant__ EdgeTcArgs a) {
     extern __shared__ __align__(1024) uint8_t dyn_raw[];
     TcShared& sh = *tc_shared_base(dyn_raw);
@@ -285,16 +295,19 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) edge_fwd_tc_kernel(const __gri
     const LayerW& lw = a.mw.layer[l];
     const bool upd = (l < L - 1);
     const int J_DK = 0, J_DV = 1, J_F = 2, J_S1 = upd ? 3 : 2, J_S2 = upd ? 4 : 3;
+    constexpr int RPW = ROWS / TC2_CWARPS;      // rows per compute warp in the coalesced phases
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, col = lane * 4;
     const int E = ws.rowptr[ws.N];
-    const int ntiles_total = (E + TC_TE - 1) / TC_TE;
+    const int ntiles_total = (E + ROWS - 1) / ROWS;
     const int my_tiles = ((int)blockIdx.x < ntiles_total) ? (ntiles_total - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+    if (a.tl != nullptr && blockIdx.x == 0 && threadIdx.x == 0) a.tl[0] = (unsigned long long)clock64();
     const uint32_t tmem = tc2_setup(sh, a.njobs);
+    if (a.tl != nullptr && blockIdx.x == 0 && threadIdx.x == 0) a.tl[1] = (unsigned long long)clock64();
 
     if (warp == TC2_CWARPS) {
         if (lane == 0) tc_producer(sh, a.jobs, a.njobs, my_tiles);
     } else if (warp == TC2_CWARPS + 1) {
-        if (lane == 0) tc_mma_issuer(sh, a.jobs, a.njobs, my_tiles, tmem);
+        if (lane == 0) tc_mma_issuer(sh, a.jobs, a.njobs, my_tiles, tmem, blockIdx.x == 0 ? a.tl : nullptr);
     } else {
         const float* __restrict__ Fin = ws.F[l];
         float* __restrict__ Fout = upd ? ws.F[l + 1] : nullptr;
@@ -304,34 +317,38 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) edge_fwd_tc_kernel(const __gri
         float* __restrict__ P1 = ws.P1[l];
         float* __restrict__ SP = ws.SP[l];
         float* __restrict__ ATT = ws.ATT[l];
-        const int r0 = warp * TC2_RPW;
+        const int r0 = warp * RPW;
         const int cch = threadIdx.x & (D - 1), grp = threadIdx.x >> 7;      // aggregation role: channel, target parity
         for (int it = 0; it < my_tiles; it++) {
             const uint32_t tpar = (uint32_t)(it & 1);
-            const int e0 = ((int)blockIdx.x + it * (int)gridDim.x) * TC_TE;
-            const int nvalid = min(TC_TE, E - e0);
+            const int e0 = ((int)blockIdx.x + it * (int)gridDim.x) * ROWS;
+            const int nvalid = min(ROWS, E - e0);
             // ---- load f tile + meta (coalesced) ----
-            for (int idx = threadIdx.x; idx < TC_TE * 32; idx += TC2_CTHREADS) {
+            for (int idx = threadIdx.x; idx < ROWS * 32; idx += TC2_CTHREADS) {
                 const int row = idx >> 5, c4 = (idx & 31) * 4;
                 st4(&sh.tile[row][c4], row < nvalid ? ldg4(Fin + (size_t)(e0 + row) * D + c4) : f4s(0.f));
             }
             load_edge_meta<TC_TE, TC2_CTHREADS>(sh.meta, ws, e0, nvalid);
             csync();
-            tc2_tile_to_a(sh, tmem, warp, lane);
+            TC_TL(2);
+            tc2_tile_to_a<ROWS>(sh, tmem, warp, lane);
             tc2_go(sh, J_DK);
             tc2_go(sh, J_DV);
+            TC_TL(3);
             // ---- dk -> attention weights ----
-            float Areg[TC2_RPW];
+            float Areg[RPW];
             tc::mbar_wait(&sh.done[J_DK], tpar);
             tc::fence_after_sync();
+            TC_TL(4);
             csync();                                              // everyone finished reading f from the tile
-            tc2_d_to_tile(sh, tmem, TC_COL_D0, warp, lane);
+            tc2_d_to_tile<ROWS>(sh, tmem, TC_COL_D0, warp, lane);
             tc::fence_before_sync();
             csync();
             {
+                TC_TL(5);
                 const float4 bb = ldg4(lw.b1 + col);
 #pragma unroll
-                for (int r = 0; r < TC2_RPW; r++) {
+                for (int r = 0; r < RPW; r++) {
                     const int row = r0 + r;
                     const float4 qi = ldg4(QKV + (size_t)sh.meta.dst[row] * 3 * D + col);
                     const float4 kj = ldg4(QKV + (size_t)sh.meta.src[row] * 3 * D + D + col);
@@ -344,17 +361,20 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) edge_fwd_tc_kernel(const __gri
                     }
                 }
             }
+            TC_TL(6);
             if (upd) { tc::fence_before_sync(); tc::mbar_arrive(&sh.go[J_F]); }     // D0 is free
             // ---- dv -> message m (in place in the tile) ----
             tc::mbar_wait(&sh.done[J_DV], tpar);
             tc::fence_after_sync();
+            TC_TL(7);
             csync();
-            tc2_d_to_tile(sh, tmem, TC_COL_D1, warp, lane);
+            tc2_d_to_tile<ROWS>(sh, tmem, TC_COL_D1, warp, lane);
             csync();
             {
+                TC_TL(8);
                 const float4 bb = ldg4(lw.b1 + D + col);
 #pragma unroll
-                for (int r = 0; r < TC2_RPW; r++) {
+                for (int r = 0; r < RPW; r++) {
                     const int row = r0 + r;
                     const float4 vj = ldg4(QKV + (size_t)sh.meta.src[row] * 3 * D + 2 * D + col);
                     const float4 P = ld4(&sh.tile[row][col]) + bb;
@@ -363,6 +383,7 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) edge_fwd_tc_kernel(const __gri
                 }
             }
             csync();
+            TC_TL(9);
             // ---- xa_i = sum_e m_e ----
             {
                 const int i_first = sh.meta.dst[0], i_last = sh.meta.dst[nvalid - 1];
@@ -375,19 +396,21 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) edge_fwd_tc_kernel(const __gri
                     else atomicAdd(ws.XA + (size_t)i * D + cch, xa);
                 }
             }
+            TC_TL(10);
             // ---- A = m, start s1 (-> D1) ----
             if (upd) { tc::mbar_wait(&sh.done[J_F], tpar); tc::fence_after_sync(); }   // A planes no longer read
-            tc2_tile_to_a(sh, tmem, warp, lane);
+            tc2_tile_to_a<ROWS>(sh, tmem, warp, lane);
             tc2_go(sh, J_S1);
+            TC_TL(11);
             // ---- edge update from the f chunk (D0) ----
             if (upd) {
                 csync();                                          // m tile fully consumed (xa + A copy)
-                tc2_d_to_tile(sh, tmem, TC_COL_D0, warp, lane);
+                tc2_d_to_tile<ROWS>(sh, tmem, TC_COL_D0, warp, lane);
                 tc::fence_before_sync();
                 csync();
                 const float4 bb = ldg4(lw.b1 + 2 * D + col);
 #pragma unroll 1
-                for (int rb = 0; rb < TC2_RPW; rb += 2) {       // gathers of 2 rows in flight before the first global store
+                for (int rb = 0; rb < RPW; rb += 2) {       // gathers of 2 rows in flight before the first global store
                     float4 tir[2][3], ujr[2][3], fin[2];
 #pragma unroll
                     for (int u = 0; u < 2; u++) {
@@ -417,16 +440,19 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) edge_fwd_tc_kernel(const __gri
                     }
                 }
             }
+            TC_TL(12);
             tc::fence_before_sync();
             tc::mbar_arrive(&sh.go[J_S2]);                        // D0 is free (A = m already published by go[J_S1])
             // ---- s1 (D1): va_i += sum_e vn_j * s1 ----
             float bnd[2][3] = {{0.f, 0.f, 0.f}, {0.f, 0.f, 0.f}};
             tc::mbar_wait(&sh.done[J_S1], tpar);
             tc::fence_after_sync();
+            TC_TL(13);
             csync();
-            tc2_d_to_tile(sh, tmem, TC_COL_D1, warp, lane);
+            tc2_d_to_tile<ROWS>(sh, tmem, TC_COL_D1, warp, lane);
             csync();
             {
+                TC_TL(14);
                 const float b = __ldg(lw.bs + cch);
                 const int i_first = sh.meta.dst[0], i_last = sh.meta.dst[nvalid - 1];
                 int nb = 0;
@@ -467,14 +493,17 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) edge_fwd_tc_kernel(const __gri
                     }
                 }
             }
+            TC_TL(15);
             // ---- s2 (D0): va_i += sum_e s2 * d ----
             tc::mbar_wait(&sh.done[J_S2], tpar);
             tc::fence_after_sync();
+            TC_TL(16);
             csync();
-            tc2_d_to_tile(sh, tmem, TC_COL_D0, warp, lane);
+            tc2_d_to_tile<ROWS>(sh, tmem, TC_COL_D0, warp, lane);
             tc::fence_before_sync();
             csync();
             {
+                TC_TL(17);
                 const float b = __ldg(lw.bs + D + cch);
                 const int i_first = sh.meta.dst[0], i_last = sh.meta.dst[nvalid - 1];
                 int nb = 0;
@@ -501,10 +530,12 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) edge_fwd_tc_kernel(const __gri
                     }
                 }
             }
+            TC_TL(18);
             csync();                                              // tile / meta free for the next tile
         }
     }
     tc2_teardown(tmem);
+    if (a.tl != nullptr && blockIdx.x == 0 && threadIdx.x == 0) a.tl[31] = (unsigned long long)clock64();
 }
 
 }  // namespace vb
@@ -516,6 +547,7 @@ namespace vb {
 // from the forward stage (P1, SP, ATT), so the tile runs only the two adjoint contractions:
 // jobs (upd):  0 g3a -> D1   1 g3b -> D1(+)   2 g4dv -> D0   3 g4dk -> D0(+)   4 g4f -> D0(+)
 // ---------------------------------------------------------------------------------------------
+template <int ROWS>
 __global__ void __launch_bounds__(TC2_THREADS, 1) edge_bwd_tc_kernel(const __grid_constant__ EdgeTcArgs a) {
     extern __shared__ __align__(1024) uint8_t dyn_raw[];
     TcShared& sh = *tc_shared_base(dyn_raw);
@@ -524,16 +556,20 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) edge_bwd_tc_kernel(const __gri
     const bool upd = (l < L - 1);
     const int J_G3A = 0, J_G3B = 1, J_G4DV = 2, J_G4DK = 3, J_G4F = 4;
     const int J_LAST = upd ? J_G4F : J_G4DK;
+    constexpr int RPW = ROWS / TC2_CWARPS;
+    constexpr int RB4 = (RPW % 4 == 0) ? 4 : 2;     // rows whose loads are issued together
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, col = lane * 4, hd = lane >> 2;
     const int E = ws.rowptr[ws.N];
-    const int ntiles_total = (E + TC_TE - 1) / TC_TE;
+    const int ntiles_total = (E + ROWS - 1) / ROWS;
     const int my_tiles = ((int)blockIdx.x < ntiles_total) ? (ntiles_total - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+    if (a.tl != nullptr && blockIdx.x == 0 && threadIdx.x == 0) a.tl[0] = (unsigned long long)clock64();
     const uint32_t tmem = tc2_setup(sh, a.njobs);
+    if (a.tl != nullptr && blockIdx.x == 0 && threadIdx.x == 0) a.tl[1] = (unsigned long long)clock64();
 
     if (warp == TC2_CWARPS) {
         if (lane == 0) tc_producer(sh, a.jobs, a.njobs, my_tiles);
     } else if (warp == TC2_CWARPS + 1) {
-        if (lane == 0) tc_mma_issuer(sh, a.jobs, a.njobs, my_tiles, tmem);
+        if (lane == 0) tc_mma_issuer(sh, a.jobs, a.njobs, my_tiles, tmem, blockIdx.x == 0 ? a.tl : nullptr);
     } else {
         const float* __restrict__ QKV = ws.QKV[l];
         const float* __restrict__ VN = ws.VN[l];
@@ -541,22 +577,23 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) edge_bwd_tc_kernel(const __gri
         const float* __restrict__ P1 = ws.P1[l];
         const float* __restrict__ SP = ws.SP[l];
         const float* __restrict__ ATT = ws.ATT[l];
-        const int r0 = warp * TC2_RPW;
+        const int r0 = warp * RPW;
         const int cch = threadIdx.x & (D - 1), grp = threadIdx.x >> 7;
         auto wait_done = [&](int j, uint32_t tpar) { tc::mbar_wait(&sh.done[j], tpar); tc::fence_after_sync(); };
         for (int it = 0; it < my_tiles; it++) {
             const uint32_t tpar = (uint32_t)(it & 1);
-            const int e0 = ((int)blockIdx.x + it * (int)gridDim.x) * TC_TE;
-            const int nvalid = min(TC_TE, E - e0);
+            const int e0 = ((int)blockIdx.x + it * (int)gridDim.x) * ROWS;
+            const int nvalid = min(ROWS, E - e0);
             load_edge_meta<TC_TE, TC2_CTHREADS>(sh.meta, ws, e0, nvalid);
             csync();
+            TC_TL(2);
             // ---- s1 half: g_Spre[:, 0:128] -> tile -> A ; source-side g_vn ----
             // (loads of 4 rows are issued together: the atomics below are compiler barriers for load hoisting)
 #pragma unroll 1
-            for (int rb = 0; rb < TC2_RPW; rb += 4) {
-                float4 sp[4], gM[4][3], vn[4][3];
+            for (int rb = 0; rb < RPW; rb += RB4) {
+                float4 sp[RB4], gM[RB4][3], vn[RB4][3];
 #pragma unroll
-                for (int u = 0; u < 4; u++) {
+                for (int u = 0; u < RB4; u++) {
                     const int row = r0 + rb + u;
                     const size_t e = (size_t)(e0 + (row < nvalid ? row : 0));
                     const size_t i3 = (size_t)sh.meta.dst[row] * 3, j3 = (size_t)sh.meta.src[row] * 3;
@@ -565,7 +602,7 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) edge_bwd_tc_kernel(const __gri
                     for (int s = 0; s < 3; s++) { gM[u][s] = ldg4(ws.GVEC + (i3 + s) * D + col); vn[u][s] = ldg4(VN + (j3 + s) * D + col); }
                 }
 #pragma unroll
-                for (int u = 0; u < 4; u++) {
+                for (int u = 0; u < RB4; u++) {
                     const int row = r0 + rb + u;
                     const bool ok = row < nvalid;
                     const size_t j3 = (size_t)sh.meta.src[row] * 3;
@@ -579,13 +616,15 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) edge_bwd_tc_kernel(const __gri
                     }
                 }
             }
+            TC_TL(3);
             csync();
-            tc2_tile_to_a(sh, tmem, warp, lane);
+            tc2_tile_to_a<ROWS>(sh, tmem, warp, lane);
             tc2_go(sh, J_G3A);
+            TC_TL(4);
             csync();
             // ---- s2 half ----
 #pragma unroll 4
-            for (int r = 0; r < TC2_RPW; r++) {
+            for (int r = 0; r < RPW; r++) {
                 const int row = r0 + r;
                 const bool ok = row < nvalid;
                 const size_t e = (size_t)(e0 + (ok ? row : 0));
@@ -599,22 +638,27 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) edge_bwd_tc_kernel(const __gri
                 if (lane == 0) { sh.eacc[row][1] = gx_; sh.eacc[row][2] = gy_; sh.eacc[row][3] = gz_; }
                 st4(&sh.tile[row][col], ok ? (gM0 * dd.x + gM1 * dd.y + gM2 * dd.z) * dsilu4(sp) : f4s(0.f));
             }
+            TC_TL(5);
             csync();
             wait_done(J_G3A, tpar);
-            tc2_tile_to_a(sh, tmem, warp, lane);
+            TC_TL(6);
+            tc2_tile_to_a<ROWS>(sh, tmem, warp, lane);
             tc2_go(sh, J_G3B);
+            TC_TL(7);
             // ---- g_m = g_xa_i + g_Spre Ws ; adjoint of m = v_j dv A ----
             wait_done(J_G3B, tpar);
+            TC_TL(8);
             csync();
-            tc2_d_to_tile(sh, tmem, TC_COL_D1, warp, lane);
+            tc2_d_to_tile<ROWS>(sh, tmem, TC_COL_D1, warp, lane);
             tc::fence_before_sync();
             csync();
+            TC_TL(9);
 #pragma unroll 1
-            for (int rb = 0; rb < TC2_RPW; rb += 4) {
-                float4 gxa[4], vjr[4], pdvr[4];
-                float avr[4];
+            for (int rb = 0; rb < RPW; rb += RB4) {
+                float4 gxa[RB4], vjr[RB4], pdvr[RB4];
+                float avr[RB4];
 #pragma unroll
-                for (int u = 0; u < 4; u++) {
+                for (int u = 0; u < RB4; u++) {
                     const int row = r0 + rb + u;
                     const size_t e = (size_t)(e0 + (row < nvalid ? row : 0));
                     gxa[u] = ldg4(ws.GXA + (size_t)sh.meta.dst[row] * D + col);
@@ -623,7 +667,7 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) edge_bwd_tc_kernel(const __gri
                     avr[u] = row < nvalid ? __ldg(ATT + e * H + hd) : 0.f;
                 }
 #pragma unroll
-                for (int u = 0; u < 4; u++) {
+                for (int u = 0; u < RB4; u++) {
                     const int row = r0 + rb + u;
                     const bool ok = row < nvalid;
                     const size_t j = sh.meta.src[row];
@@ -639,16 +683,18 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) edge_bwd_tc_kernel(const __gri
                     if (ok) red4(ws.GQKV + j * 3 * D + 2 * D + col, gm * dv * A);
                 }
             }
+            TC_TL(10);
             csync();
-            tc2_tile_to_a(sh, tmem, warp, lane);               // A = g_Pdv (A planes free: g3b done)
+            tc2_tile_to_a<ROWS>(sh, tmem, warp, lane);               // A = g_Pdv (A planes free: g3b done)
             tc2_go(sh, J_G4DV);
+            TC_TL(11);
             csync();
             // ---- adjoint of a_h = sum q_i k_j dk : first g_Pdk (next A operand), then the g_q tile ----
 #pragma unroll 1
-            for (int rb = 0; rb < TC2_RPW; rb += 4) {
-                float4 pdkr[4], qir[4], kjr[4];
+            for (int rb = 0; rb < RPW; rb += RB4) {
+                float4 pdkr[RB4], qir[RB4], kjr[RB4];
 #pragma unroll
-                for (int u = 0; u < 4; u++) {
+                for (int u = 0; u < RB4; u++) {
                     const int row = r0 + rb + u;
                     const size_t e = (size_t)(e0 + (row < nvalid ? row : 0));
                     pdkr[u] = ldg4(P1 + e * 3 * D + col);
@@ -656,7 +702,7 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) edge_bwd_tc_kernel(const __gri
                     kjr[u] = ldg4(QKV + (size_t)sh.meta.src[row] * 3 * D + D + col);
                 }
 #pragma unroll
-                for (int u = 0; u < 4; u++) {
+                for (int u = 0; u < RB4; u++) {
                     const int row = r0 + rb + u;
                     const bool ok = row < nvalid;
                     const size_t j = sh.meta.src[row];
@@ -666,13 +712,16 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) edge_bwd_tc_kernel(const __gri
                     if (ok) red4(ws.GQKV + j * 3 * D + D + col, qir[u] * dk * gav);
                 }
             }
+            TC_TL(12);
             csync();
             wait_done(J_G4DV, tpar);
-            tc2_tile_to_a(sh, tmem, warp, lane);               // A = g_Pdk
+            TC_TL(13);
+            tc2_tile_to_a<ROWS>(sh, tmem, warp, lane);               // A = g_Pdk
             tc2_go(sh, J_G4DK);
+            TC_TL(14);
             csync();
 #pragma unroll 4
-            for (int r = 0; r < TC2_RPW; r++) {
+            for (int r = 0; r < RPW; r++) {
                 const int row = r0 + r;
                 const size_t e = (size_t)(e0 + (row < nvalid ? row : 0));
                 const float4 dk = silu4(ldg4(P1 + e * 3 * D + col));
@@ -691,11 +740,12 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) edge_bwd_tc_kernel(const __gri
                     else atomicAdd(ws.GQKV + (size_t)i * 3 * D + cch, gq);
                 }
             }
+            TC_TL(15);
             // ---- adjoint of the edge update: first g_Pf (A operand), then the g_wdot tile ----
             if (upd) {
                 csync();
 #pragma unroll 1
-                for (int rb = 0; rb < TC2_RPW; rb += 2) {
+                for (int rb = 0; rb < RPW; rb += 2) {
                     float4 gfr[2], pfr[2], tir[2][3], ujr[2][3];
 #pragma unroll
                     for (int u = 0; u < 2; u++) {
@@ -748,13 +798,16 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) edge_bwd_tc_kernel(const __gri
                         (void)e;
                     }
                 }
+                TC_TL(16);
                 csync();
                 wait_done(J_G4DK, tpar);
-                tc2_tile_to_a(sh, tmem, warp, lane);           // A = g_Pf
+                TC_TL(17);
+                tc2_tile_to_a<ROWS>(sh, tmem, warp, lane);           // A = g_Pf
                 tc2_go(sh, J_G4F);
+                TC_TL(18);
                 csync();
 #pragma unroll 4
-                for (int r = 0; r < TC2_RPW; r++) {
+                for (int r = 0; r < RPW; r++) {
                     const int row = r0 + r;
                     const bool ok = row < nvalid;
                     const size_t e = (size_t)(e0 + (ok ? row : 0));
@@ -793,14 +846,17 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) edge_bwd_tc_kernel(const __gri
                     }
                 }
             }
+            TC_TL(19);
             // ---- g_f = g_f_next + [g_Pdk|g_Pdv|g_Pf] W1 ----
             wait_done(J_LAST, tpar);
+            TC_TL(20);
             csync();
-            tc2_d_to_tile(sh, tmem, TC_COL_D0, warp, lane);
+            tc2_d_to_tile<ROWS>(sh, tmem, TC_COL_D0, warp, lane);
             tc::fence_before_sync();
             csync();
+            TC_TL(21);
 #pragma unroll 4
-            for (int r = 0; r < TC2_RPW; r++) {
+            for (int r = 0; r < RPW; r++) {
                 const int row = r0 + r;
                 if (row < nvalid) {
                     float* g = ws.GF + (size_t)(e0 + row) * D + col;
@@ -813,10 +869,12 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) edge_bwd_tc_kernel(const __gri
                 float* ea = ws.eacc + (size_t)(e0 + threadIdx.x) * 4;
                 st4(ea, ld4(ea) + ld4(&sh.eacc[threadIdx.x][0]));
             }
+            TC_TL(22);
             csync();
         }
     }
     tc2_teardown(tmem);
+    if (a.tl != nullptr && blockIdx.x == 0 && threadIdx.x == 0) a.tl[31] = (unsigned long long)clock64();
 }
 
 }  // namespace vb

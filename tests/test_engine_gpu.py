@@ -83,6 +83,24 @@ def test_parity_dense_fragment(model, reference_outputs):
     assert np.abs(e - r["dense44_e64"]).max() <= 2e-6 * np.abs(r["dense44_e64"]).max() + 4e-3
 
 
+@pytest.mark.parametrize("edge_tc,tc_rows", [(0, 128), (1, 64), (3, 64), (3, 96), (3, 128)])
+@pytest.mark.parametrize("key", ["chig", "dense44"])
+def test_parity_every_edge_kernel_variant(real_weights, reference_outputs, key, edge_tc, tc_rows):
+    """SIMT and tcgen05 (3xTF32) edge stages, every tile length, against the fp64 anchor (same bar as the default)."""
+    r = reference_outputs
+    fd = _case(r, key)
+    eng = Engine(real_weights, 0)
+    eng.set_option("edge_tc", edge_tc)
+    eng.set_option("tc_rows", tc_rows)
+    eng.set_topology(fd.z, fd.batch, n_graphs=len(fd))
+    assert eng.get_option("edge_tc") == edge_tc and eng.get_option("tc_rows") == tc_rows
+    e, f = eng.forward_host(fd.pos)
+    e64, f64 = r[f"{key}_e64"], r[f"{key}_f64"]
+    assert np.abs(f - f64).max() <= 2e-5 * np.abs(f64).max() + 5e-5
+    tol = e_tol(e64) if key == "chig" else 2e-6 * np.abs(e64).max() + 4e-3      # same bars as the default-path tests
+    assert (np.abs(e.reshape(e64.shape) - e64) <= tol).all()
+
+
 @pytest.mark.parametrize("seed", [0, 7])
 def test_parity_random_weights(seed, chig):
     fd, _ = chig
