@@ -16,6 +16,7 @@
 #include "k_edge_tc.cuh"
 #include "k_graph_embed.cuh"
 #include "k_head.cuh"
+#include "k_md.cuh"
 #include "k_node.cuh"
 #include "k_node2.cuh"
 
@@ -92,6 +93,16 @@ struct vb_handle {
     cudaGraphExec_t graph_exec = nullptr;
     int launches = 0;
     std::vector<std::string> stage_names;
+    // device-resident MD state (k_md.cuh)
+    bool md_ready = false;
+    MdParams md{};
+    double *d_mx = nullptr, *d_mv = nullptr, *d_mmass = nullptr, *d_ehist = nullptr;
+    int *d_real = nullptr, *d_acc = nullptr, *d_rem = nullptr;
+    float* d_blen = nullptr;
+    long long* d_step = nullptr;
+    long long ehist_cap = 1 << 16;
+    float* md_ef = nullptr;              // caller-owned [3*n_protein + 1]
+    cudaGraphExec_t md_graph = nullptr;  // one whole MD step
 
     void set_error(const char* fmt, ...) {
         char buf[1024];
@@ -103,6 +114,13 @@ struct vb_handle {
     }
     void drop_graph() {
         if (graph_exec) { cudaGraphExecDestroy(graph_exec); graph_exec = nullptr; }
+        if (md_graph) { cudaGraphExecDestroy(md_graph); md_graph = nullptr; }
+    }
+    void free_md() {
+        cudaFree(d_mx); cudaFree(d_mv); cudaFree(d_mmass); cudaFree(d_ehist);
+        cudaFree(d_real); cudaFree(d_acc); cudaFree(d_rem); cudaFree(d_blen); cudaFree(d_step);
+        d_mx = d_mv = d_mmass = d_ehist = nullptr; d_real = d_acc = d_rem = nullptr; d_blen = nullptr; d_step = nullptr;
+        md_ready = false;
     }
 };
 
@@ -577,6 +595,7 @@ void vb_destroy(vb_handle* h) {
     cudaFree(h->d_weights);
     cudaFree(h->d_tc_scratch);
     cudaFree(h->d_tl);
+    h->free_md();
     cudaFree(h->arena);
     cudaFree(h->d_map_src); cudaFree(h->d_map_dst); cudaFree(h->d_map_sign); cudaFree(h->d_frag_sign);
     cudaFreeHost(h->h_pos); cudaFreeHost(h->h_energy); cudaFreeHost(h->h_forces);
@@ -606,6 +625,7 @@ int vb_set_topology(vb_handle* h, int64_t n_atoms, int64_t n_graphs, const int64
     for (int64_t g = 0; g < n_graphs; g++) frag_start[g + 1] += frag_start[g];
     CUDA_TRY(h, cudaSetDevice(h->device));
     h->drop_graph();
+    h->free_md();                 // the MD recipe indexes the fragment atoms of the old topology
     h->has_topology = false;
     cudaFree(h->arena); h->arena = nullptr;
     cudaFreeHost(h->h_pos); cudaFreeHost(h->h_energy); cudaFreeHost(h->h_forces);
@@ -732,6 +752,203 @@ int vb_forward_protein(vb_handle* h, const float* pos_dev, float* ef_prot_dev, v
     CUDA_TRY(h, cudaGetLastError());
     return VB_OK;
 }
+
+// ---- device-resident MD (k_md.cuh) ---------------------------------------------------------------------
+namespace {
+// fragment placement -> core evaluation -> signed whole-protein reduction, all on st (inline launches: usable under capture)
+int md_eval_enqueue(vb_handle* h, cudaStream_t st, bool inline_core) {
+    const int N = h->ws.N;
+    md_place_kernel<<<(N + 255) / 256, 256, 0, st>>>(N, h->d_real, h->d_acc, h->d_rem, h->d_blen, h->d_mx, h->d_pos);
+    if (inline_core) {
+        Launcher Lc{h, st, -1, 0, false};
+        enqueue_all(Lc);
+        if (Lc.status != cudaSuccess) { h->set_error("kernel launch failed: %s", cudaGetErrorString(Lc.status)); return VB_ERR_CUDA; }
+    } else {
+        int rc = run_core(h, st);
+        if (rc != VB_OK) return rc;
+    }
+    CUDA_TRY(h, cudaMemsetAsync(h->md_ef, 0, sizeof(float) * (3 * (size_t)h->n_protein + 1), st));
+    if (h->n_map > 0)
+        protein_scatter_kernel<<<(h->n_map + 255) / 256, 256, 0, st>>>(h->n_map, h->d_map_src, h->d_map_dst, h->d_map_sign,
+                                                                      h->d_forces, h->md_ef);
+    protein_energy_kernel<<<1, 32, 0, st>>>(h->ws.G, h->d_frag_sign, h->d_energy, h->md_ef + 3 * (size_t)h->n_protein);
+    CUDA_TRY(h, cudaGetLastError());
+    return VB_OK;
+}
+void md_kick1_enqueue(vb_handle* h, cudaStream_t st) {
+    const int n3 = 3 * h->n_protein;
+    md_kick1_kernel<<<(n3 + 255) / 256, 256, 0, st>>>(h->md, h->d_step, h->d_mmass, h->md_ef, h->d_mx, h->d_mv);
+}
+void md_kick2_enqueue(vb_handle* h, cudaStream_t st) {
+    md_kick2_kernel<<<1, MD_K2_THREADS, 0, st>>>(h->md, h->d_step, h->d_mmass, h->md_ef, h->d_mv, h->d_ehist, h->ehist_cap);
+}
+int md_check(vb_handle* h, const char* who) {
+    if (!h->md_ready) { h->set_error("%s: call vb_md_setup first", who); return VB_ERR_STATE; }
+    return VB_OK;
+}
+}  // namespace
+
+int vb_md_setup(vb_handle* h, int64_t n_protein_atoms, const double* masses_host, const int32_t* real_host,
+                const int32_t* acc_host, const int32_t* rem_host, const float* blen_host, double dt, double kT,
+                double friction, uint64_t seed, float* ef_prot_dev) {
+    if (!h) return VB_ERR_ARG;
+    std::lock_guard<std::mutex> lk(h->mu);
+    if (!h->has_topology || h->n_protein <= 0) { h->set_error("vb_md_setup: topology / protein map not set"); return VB_ERR_STATE; }
+    if (n_protein_atoms != h->n_protein || !masses_host || !real_host || !acc_host || !rem_host || !blen_host || !ef_prot_dev ||
+        !(dt > 0.0) || kT < 0.0 || friction < 0.0) {
+        h->set_error("vb_md_setup: bad arguments (n_protein must equal the protein map's)");
+        return VB_ERR_ARG;
+    }
+    const int N = h->ws.N, P = h->n_protein;
+    for (int a = 0; a < N; a++) {
+        const bool cap = real_host[a] < 0;
+        if ((!cap && real_host[a] >= P) || (cap && (acc_host[a] < 0 || acc_host[a] >= P || rem_host[a] < 0 || rem_host[a] >= P ||
+                                                     acc_host[a] == rem_host[a]))) {
+            h->set_error("vb_md_setup: recipe index out of range at fragment atom %d", a);
+            return VB_ERR_ARG;
+        }
+    }
+    for (int i = 0; i < P; i++)
+        if (!(masses_host[i] > 0.0)) { h->set_error("vb_md_setup: non-positive mass at atom %d", i); return VB_ERR_ARG; }
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    h->drop_graph();
+    h->free_md();
+    CUDA_TRY(h, cudaMalloc(&h->d_mx, sizeof(double) * 3 * P));
+    CUDA_TRY(h, cudaMalloc(&h->d_mv, sizeof(double) * 3 * P));
+    CUDA_TRY(h, cudaMalloc(&h->d_mmass, sizeof(double) * P));
+    CUDA_TRY(h, cudaMalloc(&h->d_ehist, sizeof(double) * h->ehist_cap));
+    CUDA_TRY(h, cudaMalloc(&h->d_real, sizeof(int) * N));
+    CUDA_TRY(h, cudaMalloc(&h->d_acc, sizeof(int) * N));
+    CUDA_TRY(h, cudaMalloc(&h->d_rem, sizeof(int) * N));
+    CUDA_TRY(h, cudaMalloc(&h->d_blen, sizeof(float) * N));
+    CUDA_TRY(h, cudaMalloc(&h->d_step, sizeof(long long)));
+    CUDA_TRY(h, cudaMemcpy(h->d_mmass, masses_host, sizeof(double) * P, cudaMemcpyHostToDevice));
+    CUDA_TRY(h, cudaMemcpy(h->d_real, real_host, sizeof(int) * N, cudaMemcpyHostToDevice));
+    CUDA_TRY(h, cudaMemcpy(h->d_acc, acc_host, sizeof(int) * N, cudaMemcpyHostToDevice));
+    CUDA_TRY(h, cudaMemcpy(h->d_rem, rem_host, sizeof(int) * N, cudaMemcpyHostToDevice));
+    CUDA_TRY(h, cudaMemcpy(h->d_blen, blen_host, sizeof(float) * N, cudaMemcpyHostToDevice));
+    CUDA_TRY(h, cudaMemset(h->d_mx, 0, sizeof(double) * 3 * P));
+    CUDA_TRY(h, cudaMemset(h->d_mv, 0, sizeof(double) * 3 * P));
+    CUDA_TRY(h, cudaMemset(h->d_ehist, 0, sizeof(double) * h->ehist_cap));
+    CUDA_TRY(h, cudaMemset(h->d_step, 0, sizeof(long long)));
+    h->md = MdParams{P, dt, kT, friction, (unsigned long long)seed, nullptr, 0};
+    h->md_ef = ef_prot_dev;
+    h->md_ready = true;
+    return VB_OK;
+}
+
+int vb_md_set_normals(vb_handle* h, const double* pool_dev, int64_t pool_steps) {
+    if (!h) return VB_ERR_ARG;
+    std::lock_guard<std::mutex> lk(h->mu);
+    if (int rc = md_check(h, "vb_md_set_normals")) return rc;
+    if ((pool_dev == nullptr) != (pool_steps == 0) || pool_steps < 0) { h->set_error("vb_md_set_normals: bad arguments"); return VB_ERR_ARG; }
+    h->md.pool = pool_dev;
+    h->md.pool_steps = pool_steps;
+    h->drop_graph();              // kernel arguments are baked into the captured step
+    return VB_OK;
+}
+
+int vb_md_set_state(vb_handle* h, const double* x_host, const double* v_host, int64_t step) {
+    if (!h) return VB_ERR_ARG;
+    std::lock_guard<std::mutex> lk(h->mu);
+    if (int rc = md_check(h, "vb_md_set_state")) return rc;
+    if (!x_host || !v_host || step < 0) { h->set_error("vb_md_set_state: bad arguments"); return VB_ERR_ARG; }
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    CUDA_TRY(h, cudaDeviceSynchronize());
+    const long long s = step;
+    CUDA_TRY(h, cudaMemcpy(h->d_mx, x_host, sizeof(double) * 3 * h->n_protein, cudaMemcpyHostToDevice));
+    CUDA_TRY(h, cudaMemcpy(h->d_mv, v_host, sizeof(double) * 3 * h->n_protein, cudaMemcpyHostToDevice));
+    CUDA_TRY(h, cudaMemcpy(h->d_step, &s, sizeof(long long), cudaMemcpyHostToDevice));
+    return VB_OK;
+}
+
+int vb_md_eval(vb_handle* h, void* stream) {
+    if (!h) return VB_ERR_ARG;
+    std::lock_guard<std::mutex> lk(h->mu);
+    if (int rc = md_check(h, "vb_md_eval")) return rc;
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    return md_eval_enqueue(h, (cudaStream_t)stream, false);
+}
+
+int vb_md_kick1(vb_handle* h, void* stream) {
+    if (!h) return VB_ERR_ARG;
+    std::lock_guard<std::mutex> lk(h->mu);
+    if (int rc = md_check(h, "vb_md_kick1")) return rc;
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    md_kick1_enqueue(h, (cudaStream_t)stream);
+    CUDA_TRY(h, cudaGetLastError());
+    return VB_OK;
+}
+
+int vb_md_kick2(vb_handle* h, void* stream) {
+    if (!h) return VB_ERR_ARG;
+    std::lock_guard<std::mutex> lk(h->mu);
+    if (int rc = md_check(h, "vb_md_kick2")) return rc;
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    md_kick2_enqueue(h, (cudaStream_t)stream);
+    CUDA_TRY(h, cudaGetLastError());
+    return VB_OK;
+}
+
+int vb_md_run(vb_handle* h, int64_t n_steps, void* stream) {
+    if (!h) return VB_ERR_ARG;
+    std::lock_guard<std::mutex> lk(h->mu);
+    if (int rc = md_check(h, "vb_md_run")) return rc;
+    if (n_steps < 0) { h->set_error("vb_md_run: negative step count"); return VB_ERR_ARG; }
+    cudaStream_t st = (cudaStream_t)stream;
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    if (h->use_graph && !h->md_graph) {
+        cudaGraph_t graph = nullptr;
+        CUDA_TRY(h, cudaStreamBeginCapture(h->own_stream, cudaStreamCaptureModeThreadLocal));
+        md_kick1_enqueue(h, h->own_stream);
+        int rc = md_eval_enqueue(h, h->own_stream, true);
+        md_kick2_enqueue(h, h->own_stream);
+        cudaError_t e_end = cudaStreamEndCapture(h->own_stream, &graph);
+        if (rc != VB_OK || e_end != cudaSuccess) {
+            if (rc == VB_OK) h->set_error("MD graph capture failed: %s", cudaGetErrorString(e_end));
+            if (graph) cudaGraphDestroy(graph);
+            return VB_ERR_CUDA;
+        }
+        cudaError_t e_inst = cudaGraphInstantiate(&h->md_graph, graph, 0);
+        cudaGraphDestroy(graph);
+        if (e_inst != cudaSuccess) { h->md_graph = nullptr; h->set_error("cudaGraphInstantiate (MD) failed: %s", cudaGetErrorString(e_inst)); return VB_ERR_CUDA; }
+    }
+    for (int64_t s = 0; s < n_steps; s++) {
+        if (h->use_graph) {
+            CUDA_TRY(h, cudaGraphLaunch(h->md_graph, st));
+        } else {
+            md_kick1_enqueue(h, st);
+            if (int rc = md_eval_enqueue(h, st, true)) return rc;
+            md_kick2_enqueue(h, st);
+            CUDA_TRY(h, cudaGetLastError());
+        }
+    }
+    return VB_OK;
+}
+
+int vb_md_get_state(vb_handle* h, double* x_host, double* v_host, int64_t* step_out, double* epot_hist_host, int64_t n_hist) {
+    if (!h) return VB_ERR_ARG;
+    std::lock_guard<std::mutex> lk(h->mu);
+    if (int rc = md_check(h, "vb_md_get_state")) return rc;
+    if (n_hist < 0 || n_hist > h->ehist_cap || (n_hist > 0 && !epot_hist_host)) { h->set_error("vb_md_get_state: bad history request"); return VB_ERR_ARG; }
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    CUDA_TRY(h, cudaDeviceSynchronize());
+    long long step = 0;
+    CUDA_TRY(h, cudaMemcpy(&step, h->d_step, sizeof(long long), cudaMemcpyDeviceToHost));
+    if (x_host) CUDA_TRY(h, cudaMemcpy(x_host, h->d_mx, sizeof(double) * 3 * h->n_protein, cudaMemcpyDeviceToHost));
+    if (v_host) CUDA_TRY(h, cudaMemcpy(v_host, h->d_mv, sizeof(double) * 3 * h->n_protein, cudaMemcpyDeviceToHost));
+    if (step_out) *step_out = step;
+    if (n_hist > 0) {       // potential energies recorded at the end of the last n_hist steps, oldest first
+        std::vector<double> ring(h->ehist_cap);
+        CUDA_TRY(h, cudaMemcpy(ring.data(), h->d_ehist, sizeof(double) * h->ehist_cap, cudaMemcpyDeviceToHost));
+        for (int64_t i = 0; i < n_hist; i++) {
+            const long long sidx = step - n_hist + i;
+            epot_hist_host[i] = sidx >= 0 ? ring[sidx % h->ehist_cap] : 0.0;
+        }
+    }
+    return VB_OK;
+}
+
 
 int vb_get_edges(vb_handle* h, int32_t* slots_host, int32_t* deg_host) {
     if (!h) return VB_ERR_ARG;

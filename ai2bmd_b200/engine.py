@@ -28,6 +28,7 @@ EXPORTED_SYMBOLS = [
     "vb_weight_manifest", "vb_create", "vb_destroy", "vb_last_error", "vb_set_topology", "vb_forward",
     "vb_forward_host", "vb_set_protein_map", "vb_forward_protein", "vb_get_edges", "vb_launches_per_forward",
     "vb_set_option", "vb_get_option", "vb_num_stages", "vb_stage_name", "vb_debug_run", "vb_debug_read", "vb_profile_stages", "vb_tc_selftest",
+    "vb_md_setup", "vb_md_set_normals", "vb_md_set_state", "vb_md_kick1", "vb_md_eval", "vb_md_kick2", "vb_md_run", "vb_md_get_state",
 ]
 
 
@@ -80,6 +81,19 @@ def load_library(path: Optional[str] = None):
     lib.vb_tc_selftest.argtypes = [C.c_int, vp, vp, vp, C.c_int, vp]
     lib.vb_debug_read.restype = i64
     lib.vb_debug_read.argtypes = [vp, C.c_char_p, C.c_int, vp, i64]
+    lib.vb_md_setup.restype = C.c_int
+    lib.vb_md_setup.argtypes = [vp, i64, vp, vp, vp, vp, vp, C.c_double, C.c_double, C.c_double, C.c_uint64, vp]
+    lib.vb_md_set_normals.restype = C.c_int
+    lib.vb_md_set_normals.argtypes = [vp, vp, i64]
+    lib.vb_md_set_state.restype = C.c_int
+    lib.vb_md_set_state.argtypes = [vp, vp, vp, i64]
+    for name in ("vb_md_kick1", "vb_md_eval", "vb_md_kick2"):
+        getattr(lib, name).restype = C.c_int
+        getattr(lib, name).argtypes = [vp, vp]
+    lib.vb_md_run.restype = C.c_int
+    lib.vb_md_run.argtypes = [vp, i64, vp]
+    lib.vb_md_get_state.restype = C.c_int
+    lib.vb_md_get_state.argtypes = [vp, vp, vp, vp, vp, i64]
     if path == _build.LIB_PATH:
         _lib = lib
     return lib
@@ -169,6 +183,51 @@ class Engine:
 
     def forward_protein_device(self, pos_ptr: int, ef_ptr: int, stream_ptr: int = 0):
         self._check(self.lib.vb_forward_protein(self.h, pos_ptr, ef_ptr, stream_ptr), "vb_forward_protein")
+
+    # ---- device-resident MD (include/visnet_b200.h: vb_md_*) ----
+    def md_setup(self, masses, real, acc, rem, blen, dt, kT, friction, seed, ef_ptr: int):
+        self._md_keep = [np.ascontiguousarray(masses, dtype=np.float64), np.ascontiguousarray(real, dtype=np.int32),
+                         np.ascontiguousarray(acc, dtype=np.int32), np.ascontiguousarray(rem, dtype=np.int32),
+                         np.ascontiguousarray(blen, dtype=np.float32)]
+        m, r, a, q, b = self._md_keep
+        if not (len(r) == len(a) == len(q) == len(b)):
+            raise ValueError("recipe arrays must have one entry per fragment atom")
+        self._check(self.lib.vb_md_setup(self.h, len(m), m.ctypes.data, r.ctypes.data, a.ctypes.data, q.ctypes.data,
+                                         b.ctypes.data, float(dt), float(kT), float(friction), int(seed), ef_ptr),
+                    "vb_md_setup")
+        self._md_n = len(m)
+
+    def md_set_normals(self, pool_ptr: int, pool_steps: int):
+        self._check(self.lib.vb_md_set_normals(self.h, pool_ptr, int(pool_steps)), "vb_md_set_normals")
+
+    def md_set_state(self, x, v, step: int = 0):
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        v = np.ascontiguousarray(v, dtype=np.float64)
+        if x.size != 3 * self._md_n or v.size != 3 * self._md_n:
+            raise ValueError("state arrays must be [n_protein, 3]")
+        self._check(self.lib.vb_md_set_state(self.h, x.ctypes.data, v.ctypes.data, int(step)), "vb_md_set_state")
+
+    def md_kick1(self, stream_ptr: int = 0):
+        self._check(self.lib.vb_md_kick1(self.h, stream_ptr), "vb_md_kick1")
+
+    def md_eval(self, stream_ptr: int = 0):
+        self._check(self.lib.vb_md_eval(self.h, stream_ptr), "vb_md_eval")
+
+    def md_kick2(self, stream_ptr: int = 0):
+        self._check(self.lib.vb_md_kick2(self.h, stream_ptr), "vb_md_kick2")
+
+    def md_run(self, n_steps: int, stream_ptr: int = 0):
+        self._check(self.lib.vb_md_run(self.h, int(n_steps), stream_ptr), "vb_md_run")
+
+    def md_get_state(self, n_hist: int = 0):
+        """(x [n,3], v [n,3], step, epot history of the last n_hist steps) -- synchronises the device."""
+        x = np.empty((self._md_n, 3), dtype=np.float64)
+        v = np.empty((self._md_n, 3), dtype=np.float64)
+        step = C.c_int64(0)
+        hist = np.zeros(max(n_hist, 1), dtype=np.float64)
+        self._check(self.lib.vb_md_get_state(self.h, x.ctypes.data, v.ctypes.data, C.byref(step), hist.ctypes.data,
+                                             int(n_hist)), "vb_md_get_state")
+        return x, v, int(step.value), hist[:n_hist]
 
     def get_edges(self) -> Tuple[np.ndarray, np.ndarray]:
         slots = np.empty((self.n_atoms, 32), dtype=np.int32)

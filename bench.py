@@ -209,6 +209,9 @@ def run_ours(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    if os.environ.get("BENCH_FAULT_AFTER"):       # debugging aid: dump every thread's stack and exit after N seconds
+        import faulthandler
+        faulthandler.dump_traceback_later(int(os.environ["BENCH_FAULT_AFTER"]), exit=True)
     if not torch.cuda.is_available():
         raise RuntimeError("bench.py needs a CUDA device; the engine has no CPU path")
     torch.cuda.set_device(local)
@@ -301,6 +304,39 @@ def run_ours(args):
     g_loc = len(local_frags) if local_frags is not None else 0
     e2e = {"value": args.steps / float(t_e2e.item()), "unit": "steps/s", "h2d_bytes_per_step": 12 * n_loc,
            "d2h_bytes_per_step": 12 * n_loc + 4 * g_loc, "api": "ViSNetModel.dl_potential_loader(FragmentData) (host numpy in/out)"}
+
+    # ---- the same loop with the integrator on the device (vb_md_*): state never leaves the GPU ----
+    md_device = None
+    if args.workload in ("chig", "trpcage", "ww", "abd"):
+        from ai2bmd_b200.fixtures import load_protein
+        from ai2bmd_b200.md import DeviceLangevin
+        from ai2bmd_b200.pdbfrag import FragmentRecipe
+        have = torch.tensor([1 if shard.engine is not None else 0], device="cuda")
+        if world > 1:
+            dist.all_reduce(have, op=dist.ReduceOp.MIN)
+        if int(have.item()) == 1:
+            prot_pos, prot_z, recipe = load_protein(args.workload)
+            lo, hi = (shard.plan.atom_lo, shard.plan.atom_hi) if world > 1 else (0, n_atoms)
+            local_recipe = FragmentRecipe(recipe.real[lo:hi], recipe.acc[lo:hi], recipe.rem[lo:hi], recipe.blen[lo:hi])
+            dmd = DeviceLangevin(None, None, pm, local_recipe, prot_pos, prot_z, dt_fs=1.0, temperature_K=300.0,
+                                 friction_per_fs=0.001, seed=0, device=local, group=dist.group.WORLD if world > 1 else None,
+                                 engine=shard.engine)
+            dmd.run(10)
+            barrier()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(stream)
+            dmd.run(args.steps)
+            b.record(stream)
+            barrier()
+            t_md = torch.tensor([a.elapsed_time(b) / 1e3], dtype=torch.float64, device="cuda")
+            if world > 1:
+                dist.all_reduce(t_md, op=dist.ReduceOp.MAX)
+            md_device = {"value": args.steps / float(t_md.item()), "unit": "steps/s", "temperature_K": dmd.temperature(),
+                         "launches_per_step": shard.engine.launches_per_forward + 6,
+                         "what": "Langevin (dt 1 fs, 300 K, friction 0.001/fs) entirely on the device: half-kick + drift, "
+                                 "cap-H placement, engine, signed reduction" + (", NCCL all-reduce" if world > 1 else "") +
+                                 ", half-kick; " + ("one CUDA graph replay per step" if world == 1 else "phases enqueued by the host around the engine's graph") +
+                                 ", no host synchronisation, L2 in the loop's steady state"}
 
     if rank != 0:
         if world > 1:
@@ -396,6 +432,7 @@ def run_ours(args):
         "roofline": roofline,
         "cpu_baseline": cpu,
         "md_loop": md_loop,
+        "md_device": md_device,
         "checksum": {"E_prot_eV": float(ef[-1].item()), "F_abs_sum": float(ef[:-1].abs().sum().item())},
     }
     print(json.dumps(line))

@@ -80,6 +80,40 @@ int vb_set_protein_map(vb_handle* h, int64_t n_protein_atoms, int64_t n_map, con
  * the caller all-reduces ef_prot_dev (NCCL sum).  Replaces: DLBondedCalculator.__call__, bonded.py:102-123. */
 int vb_forward_protein(vb_handle* h, const float* pos_dev, float* ef_prot_dev, void* stream);
 
+/* ---- Device-resident MD step (SURVEY section 8f, rank 3 and the first half of rank 1) ------------------------
+ * State (protein positions / velocities, fp64) stays on the GPU; one step is
+ *   kick1 (half-kick + drift) -> eval (place fragment atoms, ViSNet, signed reduction into ef) -> kick2.
+ * Replaces: the ASE Langevin loop the reference runs (src/AIMD/simulator.py:96-137: Langevin(dt = 1 fs, 300 K,
+ *           friction 0.001/fs), MaxwellBoltzmannDistribution start; ASE 3.22 ase/md/langevin.py step()) and the
+ *           per-step fragment coordinate rebuild with cap hydrogens on the acceptor->removed ray
+ *           (src/Fragmentation/distancefrag.py:34-54), without the Amber-term LBFGS refinement.
+ * Units as ASE: eV, Angstrom, amu; dt in Angstrom*sqrt(amu/eV), friction in 1/that; kT in eV.  friction = 0 is
+ * velocity Verlet (no random numbers, no centre-of-mass correction).  Normals come from Philox4x32-10 keyed by
+ * (seed; step, component): every rank of a sharded run draws the same numbers.
+ *
+ * vb_md_setup: recipe per FRAGMENT atom a (arrays of length N): real[a] = protein index, or -1 for an added
+ * hydrogen placed at P[acc[a]] + unit(P[rem[a]] - P[acc[a]]) * blen[a].  ef_prot_dev[3*n_protein + 1] is the
+ * caller-owned force/energy buffer (must hold forces of the current positions before the first kick1: call
+ * vb_md_eval after vb_md_set_state).  Requires vb_set_protein_map with the same n_protein_atoms. */
+int vb_md_setup(vb_handle* h, int64_t n_protein_atoms, const double* masses_host, const int32_t* real_host,
+                const int32_t* acc_host, const int32_t* rem_host, const float* blen_host, double dt, double kT,
+                double friction, uint64_t seed, float* ef_prot_dev);
+/* Optional externally supplied normals, device array [pool_steps][2][3*n_protein] (xi, eta), step s reads row
+ * s % pool_steps; (NULL, 0) returns to Philox.  For parity tests against a host integrator. */
+int vb_md_set_normals(vb_handle* h, const double* pool_dev, int64_t pool_steps);
+int vb_md_set_state(vb_handle* h, const double* x_host, const double* v_host, int64_t step);
+/* The three phases, asynchronous on `stream`.  With several GPUs every rank holds the whole-protein state and its
+ * own shard of fragments: kick1; eval; all-reduce ef_prot_dev (NCCL sum, by the caller); kick2. */
+int vb_md_kick1(vb_handle* h, void* stream);
+int vb_md_eval(vb_handle* h, void* stream);
+int vb_md_kick2(vb_handle* h, void* stream);
+/* Single GPU: n_steps whole steps, each one replay of a captured CUDA graph, no host synchronisation. */
+int vb_md_run(vb_handle* h, int64_t n_steps, void* stream);
+/* Synchronises; any of x_host / v_host / step_out may be NULL.  epot_hist_host[n_hist] receives the potential
+ * energies recorded at the end of the last n_hist steps (oldest first). */
+int vb_md_get_state(vb_handle* h, double* x_host, double* v_host, int64_t* step_out, double* epot_hist_host,
+                    int64_t n_hist);
+
 /* Copy the current neighbour list to the host: slots[N*32] (source index or -1), deg[N].
  * Replaces: the edge_index returned by torch_cluster.radius_graph at src/ViSNet/model/utils.py:260-266. */
 int vb_get_edges(vb_handle* h, int32_t* slots_host, int32_t* deg_host);
@@ -87,7 +121,8 @@ int vb_get_edges(vb_handle* h, int32_t* slots_host, int32_t* deg_host);
 /* Number of kernel launches of one vb_forward(), and whether it replays a captured CUDA graph. */
 int vb_launches_per_forward(const vb_handle* h);
 /* Tuning knobs: "use_graph" 0/1, "npw" 1/2, "te_fwd" 32/64, "te_bwd" 32/64, "node_impl" 0/1,
- * "edge_tc" bit0 = forward / bit1 = adjoint edge stage on tcgen05 (default: chosen by problem size). */
+ * "edge_tc" bit0 = forward / bit1 = adjoint edge stage on tcgen05, "tc_rows" 64/96/128 edges per tcgen05 tile
+ * (defaults: chosen by problem size), "timeline" 0/1 in-kernel phase stamps of the tcgen05 edge kernels. */
 int vb_set_option(vb_handle* h, const char* key, int64_t value);
 int64_t vb_get_option(const vb_handle* h, const char* key);   /* resolved value (after vb_set_topology) */
 

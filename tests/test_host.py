@@ -24,7 +24,7 @@ def lib():
 def test_library_exports_every_declared_symbol(lib):
     header = open(os.path.join(ROOT, "include", "visnet_b200.h")).read()
     import re
-    declared = set(re.findall(r"\b(vb_[a-z_]+)\s*\(", header))
+    declared = set(re.findall(r"\b(vb_[a-z_0-9]+)\s*\(", header))
     assert declared == set(vengine.EXPORTED_SYMBOLS)
     for sym in declared:
         assert hasattr(lib, sym), sym
@@ -135,3 +135,49 @@ def test_partition_is_contiguous_balanced_cover(chig, trpcage, n_parts):
         # shard maps partition the full map
         total = sum(len(shard_protein_map(pm, fd, lo, hi).src_atom) for lo, hi in parts)
         assert total == len(pm.src_atom)
+
+
+def test_philox_known_answers_and_normals():
+    """Random123 known-answer vectors for Philox4x32-10 pin the host restatement of the device RNG (k_md.cuh)."""
+    from ai2bmd_b200.md import philox4x32_10, philox_normals
+    kat = [((0, 0, 0, 0), (0, 0), (0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8)),
+           ((0xffffffff,) * 4, (0xffffffff,) * 2, (0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd)),
+           ((0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344), (0xa4093822, 0x299f31d0), (0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1))]
+    for ctr, key, want in kat:
+        got = tuple(int(w[0]) for w in philox4x32_10(*ctr, *key))
+        assert got == want
+    xi, eta = philox_normals(7, 3, 200000)
+    for a in (xi, eta):
+        assert abs(a.mean()) < 0.01 and abs(a.std() - 1.0) < 0.01 and np.isfinite(a).all()
+    assert abs(np.corrcoef(xi, eta)[0, 1]) < 0.01
+    xi2, _ = philox_normals(7, 4, 200000)
+    assert abs(np.corrcoef(xi, xi2)[0, 1]) < 0.01                 # steps are independent streams
+    assert np.array_equal(philox_normals(7, 3, 16)[0], xi[:16])     # component i does not depend on the array length
+
+
+def test_host_langevin_with_normal_source_and_verlet_limit():
+    """The host integrator (checker of the device one): harmonic forces, friction 0 conserves energy; a supplied
+    normal source is used step by step."""
+    from ai2bmd_b200.md import Langevin, philox_normals
+    rng = np.random.default_rng(0)
+    x0 = rng.standard_normal((12, 3))
+    z = np.array([1, 6, 7, 8] * 3)
+
+    def force_fn(x):
+        return 0.5 * float((x * x).sum()), -x
+
+    md = Langevin(x0, z, force_fn, dt_fs=0.5, friction_per_fs=0.0, seed=1)
+    e0 = md.energy + md.kinetic_energy()
+    md.run(200)
+    assert abs(md.energy + md.kinetic_energy() - e0) < 1e-3 * abs(e0) and md.nsteps == 200
+    calls = []
+
+    def src(step):
+        calls.append(step)
+        xi, eta = philox_normals(9, step, 36)
+        return xi.reshape(12, 3), eta.reshape(12, 3)
+
+    md2 = Langevin(x0, z, force_fn, friction_per_fs=0.01, seed=1, normal_source=src)
+    md2.run(5)
+    assert calls == [0, 1, 2, 3, 4] and np.isfinite(md2.x).all()
+    assert np.abs((md2.m * md2.v).sum(0)).max() < 1e-12
