@@ -17,6 +17,7 @@
 #include "k_graph_embed.cuh"
 #include "k_head.cuh"
 #include "k_md.cuh"
+#include "k_nonbonded.cuh"
 #include "k_node.cuh"
 #include "k_node2.cuh"
 
@@ -102,6 +103,12 @@ struct vb_handle {
     long long* d_step = nullptr;
     long long ehist_cap = 1 << 16;
     float* md_ef = nullptr;              // caller-owned [3*n_protein + 1]
+    // non-bonded MM term (k_nonbonded.cuh)
+    bool nb_ready = false;
+    NbParams nb{};
+    float *d_nb_q = nullptr, *d_nb_sigma = nullptr, *d_nb_eps = nullptr;
+    int *d_nb_rowptr = nullptr, *d_nb_col = nullptr;
+    double* d_nb_eatom = nullptr;
     cudaGraphExec_t md_graph = nullptr;  // one whole MD step
 
     void set_error(const char* fmt, ...) {
@@ -115,6 +122,11 @@ struct vb_handle {
     void drop_graph() {
         if (graph_exec) { cudaGraphExecDestroy(graph_exec); graph_exec = nullptr; }
         if (md_graph) { cudaGraphExecDestroy(md_graph); md_graph = nullptr; }
+    }
+    void free_nb() {
+        cudaFree(d_nb_q); cudaFree(d_nb_sigma); cudaFree(d_nb_eps); cudaFree(d_nb_rowptr); cudaFree(d_nb_col); cudaFree(d_nb_eatom);
+        d_nb_q = d_nb_sigma = d_nb_eps = nullptr; d_nb_rowptr = d_nb_col = nullptr; d_nb_eatom = nullptr;
+        nb_ready = false;
     }
     void free_md() {
         cudaFree(d_mx); cudaFree(d_mv); cudaFree(d_mmass); cudaFree(d_ehist);
@@ -596,6 +608,7 @@ void vb_destroy(vb_handle* h) {
     cudaFree(h->d_tc_scratch);
     cudaFree(h->d_tl);
     h->free_md();
+    h->free_nb();
     cudaFree(h->arena);
     cudaFree(h->d_map_src); cudaFree(h->d_map_dst); cudaFree(h->d_map_sign); cudaFree(h->d_frag_sign);
     cudaFreeHost(h->h_pos); cudaFreeHost(h->h_energy); cudaFreeHost(h->h_forces);
@@ -772,6 +785,10 @@ int md_eval_enqueue(vb_handle* h, cudaStream_t st, bool inline_core) {
         protein_scatter_kernel<<<(h->n_map + 255) / 256, 256, 0, st>>>(h->n_map, h->d_map_src, h->d_map_dst, h->d_map_sign,
                                                                       h->d_forces, h->md_ef);
     protein_energy_kernel<<<1, 32, 0, st>>>(h->ws.G, h->d_frag_sign, h->d_energy, h->md_ef + 3 * (size_t)h->n_protein);
+    if (h->nb_ready && h->nb.hi > h->nb.lo) {      // non-bonded MM term on the same protein coordinates
+        nonbonded_kernel<double><<<(h->nb.hi - h->nb.lo + 7) / 8, 256, 0, st>>>(h->nb, h->d_mx, h->md_ef, h->d_nb_eatom);
+        nonbonded_energy_kernel<<<1, 256, 0, st>>>(h->nb, h->d_nb_eatom, h->md_ef);
+    }
     CUDA_TRY(h, cudaGetLastError());
     return VB_OK;
 }
@@ -946,6 +963,75 @@ int vb_md_get_state(vb_handle* h, double* x_host, double* v_host, int64_t* step_
             epot_hist_host[i] = sidx >= 0 ? ring[sidx % h->ehist_cap] : 0.0;
         }
     }
+    return VB_OK;
+}
+
+
+// ---- non-bonded MM term (k_nonbonded.cuh) ----------------------------------------------------------------
+int vb_set_nonbonded(vb_handle* h, int64_t n_protein_atoms, const float* charges_host, const float* sigmas_nm_host,
+                     const float* epsilons_kj_host, const int32_t* excl_rowptr_host, const int32_t* excl_col_host,
+                     int64_t atom_lo, int64_t atom_hi) {
+    if (!h) return VB_ERR_ARG;
+    std::lock_guard<std::mutex> lk(h->mu);
+    if (n_protein_atoms <= 0 || !charges_host || !sigmas_nm_host || !epsilons_kj_host || !excl_rowptr_host ||
+        atom_lo < 0 || atom_hi < atom_lo || atom_hi > n_protein_atoms) {
+        h->set_error("vb_set_nonbonded: bad arguments");
+        return VB_ERR_ARG;
+    }
+    if (h->n_protein > 0 && h->n_protein != n_protein_atoms) {
+        h->set_error("vb_set_nonbonded: n_protein_atoms differs from the protein map's");
+        return VB_ERR_ARG;
+    }
+    const int P = (int)n_protein_atoms;
+    const int64_t nx = excl_rowptr_host[P];
+    if (excl_rowptr_host[0] != 0 || nx < 0 || (nx > 0 && !excl_col_host)) { h->set_error("vb_set_nonbonded: bad exclusion table"); return VB_ERR_ARG; }
+    for (int i = 0; i < P; i++) {
+        if (excl_rowptr_host[i + 1] < excl_rowptr_host[i]) { h->set_error("vb_set_nonbonded: exclusion row pointer not monotone"); return VB_ERR_ARG; }
+        for (int k = excl_rowptr_host[i]; k < excl_rowptr_host[i + 1]; k++) {
+            const int c = excl_col_host[k];
+            if (c < 0 || c >= P || (k > excl_rowptr_host[i] && c <= excl_col_host[k - 1])) {
+                h->set_error("vb_set_nonbonded: exclusion row %d must be strictly ascending atom indices", i);
+                return VB_ERR_ARG;
+            }
+        }
+    }
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    h->drop_graph();
+    h->free_nb();
+    CUDA_TRY(h, cudaMalloc(&h->d_nb_q, sizeof(float) * P));
+    CUDA_TRY(h, cudaMalloc(&h->d_nb_sigma, sizeof(float) * P));
+    CUDA_TRY(h, cudaMalloc(&h->d_nb_eps, sizeof(float) * P));
+    CUDA_TRY(h, cudaMalloc(&h->d_nb_rowptr, sizeof(int) * (P + 1)));
+    CUDA_TRY(h, cudaMalloc(&h->d_nb_col, sizeof(int) * std::max<int64_t>(nx, 1)));
+    CUDA_TRY(h, cudaMalloc(&h->d_nb_eatom, sizeof(double) * P));
+    CUDA_TRY(h, cudaMemcpy(h->d_nb_q, charges_host, sizeof(float) * P, cudaMemcpyHostToDevice));
+    CUDA_TRY(h, cudaMemcpy(h->d_nb_sigma, sigmas_nm_host, sizeof(float) * P, cudaMemcpyHostToDevice));
+    CUDA_TRY(h, cudaMemcpy(h->d_nb_eps, epsilons_kj_host, sizeof(float) * P, cudaMemcpyHostToDevice));
+    CUDA_TRY(h, cudaMemcpy(h->d_nb_rowptr, excl_rowptr_host, sizeof(int) * (P + 1), cudaMemcpyHostToDevice));
+    if (nx > 0) CUDA_TRY(h, cudaMemcpy(h->d_nb_col, excl_col_host, sizeof(int) * nx, cudaMemcpyHostToDevice));
+    CUDA_TRY(h, cudaMemset(h->d_nb_eatom, 0, sizeof(double) * P));
+    // ASE 3.22 unit system (CODATA 2014): nonbonded.py:18 k = 1/(4 pi eps0) * 10e6 * mol * C^-2 ; kJ/mol in eV
+    const double c = 299792458.0, mu0 = 4.0e-7 * 3.14159265358979323846, eps0 = 1.0 / mu0 / (c * c);
+    const double e_ch = 1.6021766208e-19, nav = 6.022140857e23, coul = 1.0 / e_ch, kj = 1000.0 / e_ch;
+    const double k = 1.0 / (4.0 * 3.14159265358979323846 * eps0) * 10e6 * nav / (coul * coul);
+    h->nb = NbParams{P, (int)atom_lo, (int)atom_hi, h->d_nb_q, h->d_nb_sigma, h->d_nb_eps, h->d_nb_rowptr, h->d_nb_col,
+                     (float)k, (float)(kj / nav)};
+    h->nb_ready = true;
+    return VB_OK;
+}
+
+int vb_nonbonded(vb_handle* h, const float* prot_pos_dev, float* ef_prot_dev, void* stream) {
+    if (!h) return VB_ERR_ARG;
+    std::lock_guard<std::mutex> lk(h->mu);
+    if (!h->nb_ready) { h->set_error("vb_nonbonded: call vb_set_nonbonded first"); return VB_ERR_STATE; }
+    if (!prot_pos_dev || !ef_prot_dev) { h->set_error("vb_nonbonded: null buffer"); return VB_ERR_ARG; }
+    cudaStream_t st = (cudaStream_t)stream;
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    if (h->nb.hi > h->nb.lo) {
+        nonbonded_kernel<float><<<(h->nb.hi - h->nb.lo + 7) / 8, 256, 0, st>>>(h->nb, prot_pos_dev, ef_prot_dev, h->d_nb_eatom);
+        nonbonded_energy_kernel<<<1, 256, 0, st>>>(h->nb, h->d_nb_eatom, ef_prot_dev);
+    }
+    CUDA_TRY(h, cudaGetLastError());
     return VB_OK;
 }
 

@@ -29,6 +29,7 @@ EXPORTED_SYMBOLS = [
     "vb_forward_host", "vb_set_protein_map", "vb_forward_protein", "vb_get_edges", "vb_launches_per_forward",
     "vb_set_option", "vb_get_option", "vb_num_stages", "vb_stage_name", "vb_debug_run", "vb_debug_read", "vb_profile_stages", "vb_tc_selftest",
     "vb_md_setup", "vb_md_set_normals", "vb_md_set_state", "vb_md_kick1", "vb_md_eval", "vb_md_kick2", "vb_md_run", "vb_md_get_state",
+    "vb_set_nonbonded", "vb_nonbonded",
 ]
 
 
@@ -92,6 +93,10 @@ def load_library(path: Optional[str] = None):
         getattr(lib, name).argtypes = [vp, vp]
     lib.vb_md_run.restype = C.c_int
     lib.vb_md_run.argtypes = [vp, i64, vp]
+    lib.vb_set_nonbonded.restype = C.c_int
+    lib.vb_set_nonbonded.argtypes = [vp, i64, vp, vp, vp, vp, vp, i64, i64]
+    lib.vb_nonbonded.restype = C.c_int
+    lib.vb_nonbonded.argtypes = [vp, vp, vp, vp]
     lib.vb_md_get_state.restype = C.c_int
     lib.vb_md_get_state.argtypes = [vp, vp, vp, vp, vp, i64]
     if path == _build.LIB_PATH:
@@ -183,6 +188,23 @@ class Engine:
 
     def forward_protein_device(self, pos_ptr: int, ef_ptr: int, stream_ptr: int = 0):
         self._check(self.lib.vb_forward_protein(self.h, pos_ptr, ef_ptr, stream_ptr), "vb_forward_protein")
+
+    # ---- non-bonded MM term ----
+    def set_nonbonded(self, charges, sigmas_nm, epsilons_kj, excl_rowptr, excl_col, atom_lo: int = 0, atom_hi: int = -1):
+        q = np.ascontiguousarray(charges, dtype=np.float32)
+        sg = np.ascontiguousarray(sigmas_nm, dtype=np.float32)
+        ep = np.ascontiguousarray(epsilons_kj, dtype=np.float32)
+        rp = np.ascontiguousarray(excl_rowptr, dtype=np.int32)
+        cl = np.ascontiguousarray(excl_col, dtype=np.int32)
+        n = len(q)
+        if not (len(sg) == len(ep) == n and len(rp) == n + 1 and int(rp[-1]) == len(cl)):
+            raise ValueError("non-bonded parameter arrays / exclusion table have inconsistent lengths")
+        self._check(self.lib.vb_set_nonbonded(self.h, n, q.ctypes.data, sg.ctypes.data, ep.ctypes.data, rp.ctypes.data,
+                                              cl.ctypes.data if len(cl) else None, int(atom_lo),
+                                              int(n if atom_hi < 0 else atom_hi)), "vb_set_nonbonded")
+
+    def nonbonded_device(self, prot_pos_ptr: int, ef_ptr: int, stream_ptr: int = 0):
+        self._check(self.lib.vb_nonbonded(self.h, prot_pos_ptr, ef_ptr, stream_ptr), "vb_nonbonded")
 
     # ---- device-resident MD (include/visnet_b200.h: vb_md_*) ----
     def md_setup(self, masses, real, acc, rem, blen, dt, kT, friction, seed, ef_ptr: int):
