@@ -411,7 +411,7 @@ void enqueue_all(Launcher& Lc) {
     }
     if (Lc.next("rowptr_scan")) { rowptr_scan_kernel<<<1, 1024, 0, Lc.st>>>(N, ws.deg, ws.rowptr); Lc.check(); }
     if (Lc.next("edge_geom")) { edge_geom_kernel<<<(N + 3) / 4, 128, 0, Lc.st>>>(N, h->d_pos, h->mw, ws); Lc.check(); }
-    if (Lc.next("embed_node")) { embed_node_kernel<<<(N + EMB_NB - 1) / EMB_NB, 128, 0, Lc.st>>>(h->mw, ws); Lc.check(); }
+    if (Lc.next("embed_node")) { embed_node_kernel<<<N, EMB_THREADS, 0, Lc.st>>>(h->mw, ws); Lc.check(); }
     const int eblocks = std::max(1, std::min(ws.Ecap, h->sm_count * 16));
     if (Lc.next("embed_edge")) { embed_edge_kernel<<<eblocks, 128, 0, Lc.st>>>(h->mw, ws); Lc.check(); }
     for (int l = 0; l < L; l++) {
@@ -438,7 +438,7 @@ void enqueue_all(Launcher& Lc) {
         embed_edge_bwd_kernel<<<bb, EEB_WARPS * 32, 0, Lc.st>>>(h->mw, ws);
         Lc.check();
     }
-    if (Lc.next("embed_node_bwd")) { embed_node_bwd_kernel<<<N, 128, 0, Lc.st>>>(h->mw, ws, h->d_forces); Lc.check(); }
+    if (Lc.next("embed_node_bwd")) { embed_node_bwd_kernel<<<N, ENB_WARPS * 32, 0, Lc.st>>>(h->mw, ws, h->d_forces); Lc.check(); }
 }
 
 template <typename K>

@@ -120,21 +120,24 @@ __global__ void __launch_bounds__(128) edge_geom_kernel(int N, const float* __re
 //   agg_i[c] = sum_{e->i, j!=i} (rbf_e . Wd[c,:] + bd[c]) * C_e * nb_emb[z_j][c]
 //   x_i = [emb[z_i] | agg_i] Wc^T + bc
 // ---------------------------------------------------------------------------------------------
-constexpr int EMB_NB = 1;      // one node per 128-thread block: the per-edge loop is a serial latency chain
-__global__ void __launch_bounds__(128) embed_node_kernel(ModelW mw, Workspace ws) {
+// One node per 256-thread block (thread = channel x K-half): the per-edge loop and the final K = 256 product are serial
+// latency chains, so both are split in two and the halves summed in a fixed order through shared memory.
+constexpr int EMB_THREADS = 2 * D;
+__global__ void __launch_bounds__(EMB_THREADS) embed_node_kernel(ModelW mw, Workspace ws) {
     __shared__ float cat[2 * D];
+    __shared__ float part[D];
     __shared__ int sj[KNB];
     __shared__ int sz[KNB];
     __shared__ float sC[KNB];
-    const int c = threadIdx.x;
+    const int c = threadIdx.x & (D - 1), half = threadIdx.x >> 7;
     const int i = blockIdx.x;
     if (i >= ws.N) return;
     const int e0 = ws.rowptr[i], dg = ws.rowptr[i + 1] - e0;
-    if (c < dg) {                                   // edge metadata first: breaks the esrc -> z -> embedding load chain
-        const int j = ws.esrc[e0 + c];
-        sj[c] = j;
-        sz[c] = ws.z[j];
-        sC[c] = ws.geom[(size_t)(e0 + c) * 8 + 1];
+    if (threadIdx.x < dg) {                         // edge metadata first: breaks the esrc -> z -> embedding load chain
+        const int j = ws.esrc[e0 + threadIdx.x];
+        sj[threadIdx.x] = j;
+        sz[threadIdx.x] = ws.z[j];
+        sC[threadIdx.x] = ws.geom[(size_t)(e0 + threadIdx.x) * 8 + 1];
     }
     float wd[NR];
 #pragma unroll
@@ -147,7 +150,7 @@ __global__ void __launch_bounds__(128) embed_node_kernel(ModelW mw, Workspace ws
     __syncthreads();
     float acc = 0.f;
 #pragma unroll 2
-    for (int k2 = 0; k2 < dg; k2++) {
+    for (int k2 = half; k2 < dg; k2 += 2) {         // even edges on one half, odd edges on the other
         if (sj[k2] == i) continue;
         const float nb = __ldg(mw.nb_emb + sz[k2] * D + c);
         float dp = bd;
@@ -159,18 +162,24 @@ __global__ void __launch_bounds__(128) embed_node_kernel(ModelW mw, Workspace ws
         }
         acc = fmaf(dp * sC[k2], nb, acc);
     }
-    cat[c] = x0;
-    cat[D + c] = acc;
+    if (half == 1) part[c] = acc;
     __syncthreads();
-    float o0 = __ldg(mw.bc + c), o1 = 0.f, o2 = 0.f, o3 = 0.f;      // 4 independent chains over k
-#pragma unroll 4
-    for (int k = 0; k < 2 * D; k += 4) {
-        o0 = fmaf(cat[k], __ldg(mw.WcT + (k + 0) * D + c), o0);
-        o1 = fmaf(cat[k + 1], __ldg(mw.WcT + (k + 1) * D + c), o1);
-        o2 = fmaf(cat[k + 2], __ldg(mw.WcT + (k + 2) * D + c), o2);
-        o3 = fmaf(cat[k + 3], __ldg(mw.WcT + (k + 3) * D + c), o3);
+    if (half == 0) { cat[c] = x0; cat[D + c] = acc + part[c]; }
+    __syncthreads();
+    // x_i = [emb | agg] Wc^T + bc : each half takes 128 of the 256 k's, 8 independent chains
+    float o[8];
+#pragma unroll
+    for (int u = 0; u < 8; u++) o[u] = 0.f;
+    const int kb = half * D;
+#pragma unroll 2
+    for (int k = 0; k < D; k += 8) {
+#pragma unroll
+        for (int u = 0; u < 8; u++) o[u] = fmaf(cat[kb + k + u], __ldg(mw.WcT + (size_t)(kb + k + u) * D + c), o[u]);
     }
-    ws.X[0][(size_t)i * D + c] = (o0 + o1) + (o2 + o3);
+    const float sum = ((o[0] + o[1]) + (o[2] + o[3])) + ((o[4] + o[5]) + (o[6] + o[7]));
+    if (half == 1) part[c] = sum;
+    __syncthreads();
+    if (half == 0) ws.X[0][(size_t)i * D + c] = (__ldg(mw.bc + c) + sum) + part[c];
 }
 
 // K5: edge embedding  f0_e[c] = (x_i[c] + x_j[c]) * (rbf_e . We[c,:] + be[c]).   thread = channel.
@@ -248,44 +257,58 @@ __global__ void __launch_bounds__(EEB_WARPS * 32) embed_edge_bwd_kernel(ModelW m
 //   phase B (lane = rbf index k): g_rbf[k] += sum_c g_We[c]*C*Wd[c][k] ; g_r = gC*C'(r) + sum_k g_rbf[k]*drbf_k/dr
 //   g_ev = g_r d + (g_d - (g_d.d) d)/r ; dE/dpos_j += g_ev, dE/dpos_i -= g_ev ; forces = -dE/dpos
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) embed_node_bwd_kernel(ModelW mw, Workspace ws,
-                                                             float* __restrict__ forces) {
+constexpr int ENB_WARPS = 8;
+__global__ void __launch_bounds__(ENB_WARPS * 32) embed_node_bwd_kernel(ModelW mw, Workspace ws,
+                                                                        float* __restrict__ forces) {
     __shared__ __align__(16) float WdT_s[NR][D];
     __shared__ float WdN_s[D][NR + 1];
     __shared__ __align__(16) float gx_s[D];
-    __shared__ __align__(16) float gwe_s[4][D];
-    __shared__ float fi_s[4][3];
-    const int c = threadIdx.x, lane = c & 31, warp = c >> 5, col = lane * 4;
+    __shared__ __align__(16) float gagg_s[ENB_WARPS][D];
+    __shared__ __align__(16) float gwe_s[ENB_WARPS][D];
+    __shared__ float fi_s[ENB_WARPS][3];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, col = lane * 4;
     const int i = blockIdx.x;
     if (i >= ws.N) return;
-    gx_s[c] = ws.GX[(size_t)i * D + c];
-    for (int idx = threadIdx.x; idx < D * NR; idx += 128) {
+    if (threadIdx.x < D) gx_s[threadIdx.x] = ws.GX[(size_t)i * D + threadIdx.x];
+    for (int idx = threadIdx.x; idx < D * NR; idx += ENB_WARPS * 32) {
         const int cc = idx / NR, k = idx % NR;
         const float w = __ldg(mw.WdN + idx);
         WdT_s[k][cc] = w;
         WdN_s[cc][k] = w;
     }
     __syncthreads();
-    // g_agg for this lane's 4 channels (every warp computes the same values; 4 independent chains over k)
+    // g_agg = (gx_i Wc)[128:256]: K split over the warps (16 k's each, all loads in flight), fixed-order sum
+    {
+        constexpr int KW = D / ENB_WARPS;
+        float4 part = f4s(0.f);
+#pragma unroll
+        for (int k = 0; k < KW; k++)
+            part = part + ldg4(mw.WcN + (size_t)(warp * KW + k) * 2 * D + D + col) * gx_s[warp * KW + k];
+        st4(&gagg_s[warp][col], part);
+    }
+    __syncthreads();
     float4 g_agg = f4s(0.f);
-#pragma unroll 4
-    for (int k = 0; k < D; k++) g_agg = g_agg + ldg4(mw.WcN + (size_t)k * 2 * D + D + col) * gx_s[k];
+#pragma unroll
+    for (int w = 0; w < ENB_WARPS; w++) g_agg = g_agg + ld4(&gagg_s[w][col]);
     const float4 bd = ldg4(mw.bd + col);
     const float alpha = 5.0f / mw.cutoff;
     const float mu = __ldg(mw.rbf_means + lane), beta = __ldg(mw.rbf_betas + lane);
     float fix = 0.f, fiy = 0.f, fiz = 0.f;
     const int e1 = ws.rowptr[i + 1];
-    for (int e = ws.rowptr[i] + warp; e < e1; e += 4) {
+    for (int e = ws.rowptr[i] + warp; e < e1; e += ENB_WARPS) {
         const int j = ws.esrc[e];
         if (j == i) continue;     // self-loops carry no geometry and are masked out of the neighbour embedding
         const float4 g0 = ld4(ws.geom + (size_t)e * 8);
         const float4 g1 = ld4(ws.geom + (size_t)e * 8 + 4);
         const float r = g0.x, Ce = g0.y, dx = g0.z, dy = g0.w, dz = g1.x, inv_r = g1.y;
         const float rk = __ldg(ws.rbf + (size_t)e * NR + lane);
+        const float4 nbj = ldg4(mw.nb_emb + ws.z[j] * D + col);
+        const float4 ea = ld4(ws.eacc + (size_t)e * 4);
+        const float grbf0 = ws.grbf[(size_t)e * NR + lane];
         float4 dp = bd;
 #pragma unroll
         for (int k = 0; k < NR; k++) dp = dp + ld4(&WdT_s[k][col]) * __shfl_sync(0xffffffffu, rk, k);
-        const float4 gwe = g_agg * ldg4(mw.nb_emb + ws.z[j] * D + col);
+        const float4 gwe = g_agg * nbj;
         const float gc = warp_sum(hsum4(gwe * dp));
         __syncwarp();
         st4(&gwe_s[warp][col], gwe * Ce);
@@ -293,9 +316,8 @@ __global__ void __launch_bounds__(128) embed_node_bwd_kernel(ModelW mw, Workspac
         float g = 0.f;
 #pragma unroll 8
         for (int cc = 0; cc < D; cc++) g = fmaf(gwe_s[warp][cc], WdN_s[cc][lane], g);
-        const float4 ea = ld4(ws.eacc + (size_t)e * 4);
         const float gC = ea.x + gc;
-        const float grbf = ws.grbf[(size_t)e * NR + lane] + g;
+        const float grbf = grbf0 + g;
         const float ex = __expf(-alpha * r);
         const float t = ex - mu;
         const float gk = __expf(-beta * t * t);
@@ -316,7 +338,12 @@ __global__ void __launch_bounds__(128) embed_node_bwd_kernel(ModelW mw, Workspac
     }
     if (lane == 0) { fi_s[warp][0] = fix; fi_s[warp][1] = fiy; fi_s[warp][2] = fiz; }
     __syncthreads();
-    if (c < 3) atomicAdd(forces + 3 * i + c, (fi_s[0][c] + fi_s[1][c]) + (fi_s[2][c] + fi_s[3][c]));
+    if (threadIdx.x < 3) {
+        float t = 0.f;
+#pragma unroll
+        for (int w = 0; w < ENB_WARPS; w++) t += fi_s[w][threadIdx.x];
+        atomicAdd(forces + 3 * i + threadIdx.x, t);
+    }
 }
 
 // per-fragment energy: E_g = sum_a e_atom[a] + mean   (one warp per fragment; visnet.py:146-149).
