@@ -86,7 +86,7 @@ struct vb_handle {
     // options
     int use_graph = 1, npw = 0, te_fwd = 0, te_bwd = 32;
     int npw_opt = 0, te_fwd_opt = 0, edge_tc_opt = -1;   // user choices (0 / -1 = choose by problem size)
-    int tc_rows_opt = 0, tc_rows = 128;                  // edges per tcgen05 tile (64 / 96 / 128; MMA M stays 128)
+    int tc_rows_opt = 0, tc_rows = 128;                  // edges per tcgen05 tile (32 / 64 / 96 / 128; MMA M stays 128)
     int node_impl = 1; // 0: warp-per-node kernels (k_node.cuh), 1: CTA-cooperative kernels (k_node2.cuh)
     int edge_tc = -1;  // bit 0: forward edge stage on tcgen05, bit 1: adjoint edge stage on tcgen05; -1 = by size
     // graph cache
@@ -357,7 +357,8 @@ void launch_edge_fwd_tc(Launcher& Lc, int l) {
     const int rows = h->tc_rows;
     const int tiles = (h->ws.Ecap + rows - 1) / rows;
     const int blocks = std::max(1, std::min(tiles, h->sm_count));
-    if (rows == 64) edge_fwd_tc_kernel<64><<<blocks, TC2_THREADS, TC_SMEM_BYTES, Lc.st>>>(a);
+    if (rows == 32) edge_fwd_tc_kernel<32><<<blocks, TC2_THREADS, TC_SMEM_BYTES, Lc.st>>>(a);
+    else if (rows == 64) edge_fwd_tc_kernel<64><<<blocks, TC2_THREADS, TC_SMEM_BYTES, Lc.st>>>(a);
     else if (rows == 96) edge_fwd_tc_kernel<96><<<blocks, TC2_THREADS, TC_SMEM_BYTES, Lc.st>>>(a);
     else edge_fwd_tc_kernel<128><<<blocks, TC2_THREADS, TC_SMEM_BYTES, Lc.st>>>(a);
     Lc.check();
@@ -386,7 +387,8 @@ void launch_edge_bwd_tc(Launcher& Lc, int l) {
     const int rows = h->tc_rows;
     const int tiles = (h->ws.Ecap + rows - 1) / rows;
     const int blocks = std::max(1, std::min(tiles, h->sm_count));
-    if (rows == 64) edge_bwd_tc_kernel<64><<<blocks, TC2_THREADS, TC_SMEM_BYTES, Lc.st>>>(a);
+    if (rows == 32) edge_bwd_tc_kernel<32><<<blocks, TC2_THREADS, TC_SMEM_BYTES, Lc.st>>>(a);
+    else if (rows == 64) edge_bwd_tc_kernel<64><<<blocks, TC2_THREADS, TC_SMEM_BYTES, Lc.st>>>(a);
     else if (rows == 96) edge_bwd_tc_kernel<96><<<blocks, TC2_THREADS, TC_SMEM_BYTES, Lc.st>>>(a);
     else edge_bwd_tc_kernel<128><<<blocks, TC2_THREADS, TC_SMEM_BYTES, Lc.st>>>(a);
     Lc.check();
@@ -455,9 +457,11 @@ int configure_kernels(vb_handle* h) {
     CUDA_TRY(h, opt_in_smem(node_bwd_kernel<2>, node_bwd_smem_bytes<2>()));
     CUDA_TRY(h, opt_in_smem(head_kernel<1>, HeadSmem<1>::BYTES));
     CUDA_TRY(h, opt_in_smem(head_kernel<2>, HeadSmem<2>::BYTES));
+    CUDA_TRY(h, opt_in_smem(edge_fwd_tc_kernel<32>, TC_SMEM_BYTES));
     CUDA_TRY(h, opt_in_smem(edge_fwd_tc_kernel<64>, TC_SMEM_BYTES));
     CUDA_TRY(h, opt_in_smem(edge_fwd_tc_kernel<96>, TC_SMEM_BYTES));
     CUDA_TRY(h, opt_in_smem(edge_fwd_tc_kernel<128>, TC_SMEM_BYTES));
+    CUDA_TRY(h, opt_in_smem(edge_bwd_tc_kernel<32>, TC_SMEM_BYTES));
     CUDA_TRY(h, opt_in_smem(edge_bwd_tc_kernel<64>, TC_SMEM_BYTES));
     CUDA_TRY(h, opt_in_smem(edge_bwd_tc_kernel<96>, TC_SMEM_BYTES));
     CUDA_TRY(h, opt_in_smem(edge_bwd_tc_kernel<128>, TC_SMEM_BYTES));
@@ -514,12 +518,10 @@ void choose_defaults(vb_handle* h) {
     h->npw = h->npw_opt; h->te_fwd = h->te_fwd_opt; h->edge_tc = h->edge_tc_opt;
     if (h->npw == 0) h->npw = (N > 4096) ? 2 : 1;
     if (h->te_fwd == 0) h->te_fwd = ((long long)N * 17 / 64 >= 2LL * h->sm_count) ? 64 : 32;
-    // tcgen05 edge kernels (one 128-edge tile per CTA, 16 compute warps): the forward stage wins at every size
-    // measured, the adjoint stage from ~32 tiles (tools/tc_crossover.py, profiles/README.md)
-    if (h->edge_tc < 0) {
-        const long long tiles = (long long)N * 17 / TC_TE;      // estimated 128-edge tiles
-        h->edge_tc = 1 | (tiles >= 32 ? 2 : 0);
-    }
+    // tcgen05 edge kernels (one tile per CTA, 16 compute warps): with the tile length chosen below both stages beat
+    // the fp32 SIMT kernels at every size measured, down to a single 26-atom fragment (tools/tc_crossover.py,
+    // profiles/README.md); the SIMT kernels stay selectable ("edge_tc" 0..2) as the independent implementation
+    if (h->edge_tc < 0) h->edge_tc = 3;
     // short tiles spread a small system over more SMs (the per-tile latency is mostly the per-row SIMT phases):
     // the longest tile that still fits the estimated edge count into one wave of CTAs
     h->tc_rows = h->tc_rows_opt;
@@ -529,6 +531,7 @@ void choose_defaults(vb_handle* h) {
         if ((est_edges + 127) / 128 < h->sm_count) {
             if ((est_edges + 95) / 96 <= h->sm_count) h->tc_rows = 96;
             if ((est_edges + 63) / 64 <= h->sm_count) h->tc_rows = 64;
+            if ((est_edges + 31) / 32 <= h->sm_count) h->tc_rows = 32;
         }
     }
 }
@@ -593,7 +596,7 @@ int vb_create(const float* weights_host, size_t n_floats, const vb_hparams* hp, 
     if (const char* s = getenv("VB_TE_FWD")) h->te_fwd_opt = atoi(s);
     if (const char* s = getenv("VB_TE_BWD")) h->te_bwd = atoi(s);
     if (const char* s = getenv("VB_EDGE_TC")) h->edge_tc_opt = atoi(s);
-    if (const char* s = getenv("VB_TC_ROWS")) { const int v = atoi(s); if (v == 64 || v == 96 || v == 128) h->tc_rows_opt = v; }
+    if (const char* s = getenv("VB_TC_ROWS")) { const int v = atoi(s); if (v == 32 || v == 64 || v == 96 || v == 128) h->tc_rows_opt = v; }
     if (const char* s = getenv("VB_NODE_IMPL")) h->node_impl = atoi(s);
     *out = h;
     return VB_OK;
@@ -1058,7 +1061,7 @@ int vb_set_option(vb_handle* h, const char* key, int64_t value) {
     else if (k == "te_fwd" && (value == 32 || value == 64)) h->te_fwd = h->te_fwd_opt = (int)value;
     else if (k == "te_bwd" && (value == 32 || value == 64)) h->te_bwd = (int)value;
     else if (k == "edge_tc" && value >= 0 && value <= 3) h->edge_tc = h->edge_tc_opt = (int)value;
-    else if (k == "tc_rows" && (value == 64 || value == 96 || value == 128)) h->tc_rows = h->tc_rows_opt = (int)value;
+    else if (k == "tc_rows" && (value == 32 || value == 64 || value == 96 || value == 128)) h->tc_rows = h->tc_rows_opt = (int)value;
     else if (k == "node_impl" && (value == 0 || value == 1)) h->node_impl = (int)value;
     else if (k == "timeline" && (value == 0 || value == 1)) {
         if (value && !h->d_tl) {

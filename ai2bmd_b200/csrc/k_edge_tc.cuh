@@ -821,18 +821,33 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) edge_bwd_tc_kernel(const __gri
                         const int q0 = ws.rowptr[i], q1 = ws.rowptr[i + 1];
                         const int lo = max(q0, e0) - e0, hi = min(q1, e0 + nvalid) - e0;
                         float gt0 = 0.f, gt1 = 0.f, gt2 = 0.f;
-                        for (int r = lo; r < hi; r++) {
-                            const size_t j3 = (size_t)sh.meta.src[r] * 3;
+                        auto term = [&](int r, float u0, float u1, float u2) {
                             const float4 dd = sh.meta.d[r];
                             const float gw = sh.tile[r][cch];
-                            const float u0 = __ldg(TU + (j3 + 0) * 2 * D + D + cch), u1 = __ldg(TU + (j3 + 1) * 2 * D + D + cch),
-                                        u2 = __ldg(TU + (j3 + 2) * 2 * D + D + cch);
                             const float a2 = u0 * dd.x + u1 * dd.y + u2 * dd.z;
                             const float w20 = u0 - a2 * dd.x, w21 = u1 - a2 * dd.y, w22 = u2 - a2 * dd.z;
                             const float wd = w20 * dd.x + w21 * dd.y + w22 * dd.z;
                             gt0 += gw * (w20 - wd * dd.x);
                             gt1 += gw * (w21 - wd * dd.y);
                             gt2 += gw * (w22 - wd * dd.z);
+                        };
+                        int r = lo;
+                        for (; r + 4 <= hi; r += 4) {              // 12 independent gathers in flight
+                            float u[4][3];
+#pragma unroll
+                            for (int q = 0; q < 4; q++) {
+                                const size_t j3 = (size_t)sh.meta.src[r + q] * 3;
+                                u[q][0] = __ldg(TU + (j3 + 0) * 2 * D + D + cch);
+                                u[q][1] = __ldg(TU + (j3 + 1) * 2 * D + D + cch);
+                                u[q][2] = __ldg(TU + (j3 + 2) * 2 * D + D + cch);
+                            }
+#pragma unroll
+                            for (int q = 0; q < 4; q++) term(r + q, u[q][0], u[q][1], u[q][2]);
+                        }
+                        for (; r < hi; r++) {
+                            const size_t j3 = (size_t)sh.meta.src[r] * 3;
+                            term(r, __ldg(TU + (j3 + 0) * 2 * D + D + cch), __ldg(TU + (j3 + 1) * 2 * D + D + cch),
+                                 __ldg(TU + (j3 + 2) * 2 * D + D + cch));
                         }
                         if (q0 >= e0 && q1 <= e0 + nvalid) {
                             ws.GTU[((size_t)i * 3 + 0) * 2 * D + cch] = gt0;

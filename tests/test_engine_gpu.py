@@ -83,7 +83,7 @@ def test_parity_dense_fragment(model, reference_outputs):
     assert np.abs(e - r["dense44_e64"]).max() <= 2e-6 * np.abs(r["dense44_e64"]).max() + 4e-3
 
 
-@pytest.mark.parametrize("edge_tc,tc_rows", [(0, 128), (1, 64), (3, 64), (3, 96), (3, 128)])
+@pytest.mark.parametrize("edge_tc,tc_rows", [(0, 128), (1, 64), (3, 32), (3, 64), (3, 96), (3, 128)])
 @pytest.mark.parametrize("key", ["chig", "dense44"])
 def test_parity_every_edge_kernel_variant(real_weights, reference_outputs, key, edge_tc, tc_rows):
     """SIMT and tcgen05 (3xTF32) edge stages, every tile length, against the fp64 anchor (same bar as the default)."""

@@ -1,6 +1,7 @@
 #!/usr/bin/env python
 """Where do the tcgen05 edge kernels start to pay?  Sweep the fragment count of the synthetic batch and time one
-evaluation (CUDA events, L2 flushed) with edge_tc = 0 (SIMT), 1 (TC forward), 3 (TC forward + adjoint).
+evaluation (CUDA events, L2 flushed) with edge_tc = 0 (SIMT), 1 (TC forward), 3 (TC forward + adjoint) at every tile
+length, and with the engine's automatic choice.
 
     python tools/tc_crossover.py [--fragments 1,2,4,8,12,19,32] [--steps 40]
 
@@ -55,20 +56,23 @@ def main():
         print(f"{'sum':<24} {sum(m for _, m in prof) * 1e3:8.1f} us  ({len(prof)} launches, edge_tc={eng.get_option('edge_tc')})")
         return
     flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device="cuda")
-    print(f"{'frags':>6} {'atoms':>6} {'tiles':>6} {'simt':>8} {'tc_fwd':>8} {'tc_both':>8}   ms per evaluation")
+    print(f"{'frags':>6} {'atoms':>6} {'tiles':>6} {'simt':>8} {'tc_fwd':>8} {'tc r32':>8} {'tc r64':>8} {'tc r96':>8} {'tc r128':>8} {'auto':>8}   ms per evaluation")
     for g in [int(x) for x in args.fragments.split(",")]:
         fd = synthetic_batch(g, seed=0)
         pos = torch.from_numpy(np.ascontiguousarray(fd.pos, dtype=np.float32)).cuda()
         e = torch.empty(len(fd), dtype=torch.float32, device="cuda")
         f = torch.empty((len(fd.z), 3), dtype=torch.float32, device="cuda")
         row = []
-        for tc in (0, 1, 3):
+        for tc, rows in ((0, 0), (1, 0), (3, 32), (3, 64), (3, 96), (3, 128), (-1, 0)):
             eng = Engine(sd, 0)
-            eng.set_option("edge_tc", tc)
+            if tc >= 0:
+                eng.set_option("edge_tc", tc)
+            if rows:
+                eng.set_option("tc_rows", rows)
             eng.set_topology(fd.z, fd.batch, n_graphs=len(fd))
             row.append(time_eval(eng, pos, e, f, flush, args.steps))
             eng.close()
-        print(f"{g:>6} {len(fd.z):>6} {len(fd.z) * 17 // 128:>6} {row[0]:>8.3f} {row[1]:>8.3f} {row[2]:>8.3f}")
+        print(f"{g:>6} {len(fd.z):>6} {len(fd.z) * 17 // 128:>6} " + " ".join(f"{t:>8.3f}" for t in row))
 
 
 if __name__ == "__main__":
