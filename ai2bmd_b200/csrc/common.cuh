@@ -163,6 +163,14 @@ __device__ __forceinline__ void acc_zero(float (&acc)[R][4]) {
     for (int r = 0; r < R; r++) { acc[r][0] = 0.f; acc[r][1] = 0.f; acc[r][2] = 0.f; acc[r][3] = 0.f; }
 }
 
+// Programmatic dependent launch (engine.cu Launcher::launch): let the next kernel of the stream start launching, then
+// wait until the previous one has completed and its writes are visible.  Nothing before this call may touch data
+// produced by another kernel.  Both instructions are no-ops for a kernel launched without the attribute.
+__device__ __forceinline__ void pdl_entry() {
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+
 // cosine cutoff and its derivative (utils.py:16-19), cutoff passed in
 __device__ __forceinline__ float cutoff_fn(float r, float rc) {
     return (r < rc) ? 0.5f * (cosf(r * (3.14159265358979323846f / rc)) + 1.0f) : 0.0f;

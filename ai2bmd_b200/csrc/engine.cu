@@ -85,6 +85,7 @@ struct vb_handle {
     float *d_map_sign = nullptr, *d_frag_sign = nullptr;
     // options
     int use_graph = 1, npw = 0, te_fwd = 0, te_bwd = 32;
+    int use_pdl = 0;   // programmatic dependent launch between the stages: measured slower with the trigger at kernel entry
     int npw_opt = 0, te_fwd_opt = 0, edge_tc_opt = -1;   // user choices (0 / -1 = choose by problem size)
     int tc_rows_opt = 0, tc_rows = 128;                  // edges per tcgen05 tile (32 / 64 / 96 / 128; MMA M stays 128)
     int node_impl = 1; // 0: warp-per-node kernels (k_node.cuh), 1: CTA-cooperative kernels (k_node2.cuh)
@@ -260,6 +261,21 @@ struct Launcher {
     void check() {
         if (status == cudaSuccess) status = cudaGetLastError();
     }
+    // Optionally ("use_pdl") launch with programmatic dependent launch: the next kernel's CTAs may become resident while
+    // this one drains and park at griddepcontrol.wait (pdl_entry() at the top of every kernel).  Off by default: with
+    // the trigger at kernel entry the parked CTAs cost more than the hidden launch gaps (Chignolin 0.796 -> 0.833 ms).
+    template <typename... KArgs, typename... Args>
+    void launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, Args&&... args) {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = h->use_pdl ? 1 : 0;
+        cudaError_t e = cudaLaunchKernelEx(&cfg, kernel, KArgs(std::forward<Args>(args))...);
+        if (status == cudaSuccess && e != cudaSuccess) status = e;
+    }
 };
 
 template <int NPW>
@@ -267,7 +283,7 @@ void launch_node_fwd(Launcher& Lc, int k) {
     vb_handle* h = Lc.h;
     NodeArgs a{k, h->mw, h->ws};
     const int blocks = (h->ws.N + NODE_WARPS * NPW - 1) / (NODE_WARPS * NPW);
-    node_fwd_kernel<NPW><<<blocks, NODE_WARPS * 32, 0, Lc.st>>>(a);
+    Lc.launch(node_fwd_kernel<NPW>, dim3(blocks), dim3(NODE_WARPS * 32), 0, a);
     Lc.check();
 }
 template <int NPW>
@@ -275,14 +291,14 @@ void launch_node_bwd(Launcher& Lc, int k) {
     vb_handle* h = Lc.h;
     NodeArgs a{k, h->mw, h->ws};
     const int blocks = (h->ws.N + NODE_WARPS * NPW - 1) / (NODE_WARPS * NPW);
-    node_bwd_kernel<NPW><<<blocks, NODE_WARPS * 32, node_bwd_smem_bytes<NPW>(), Lc.st>>>(a);
+    Lc.launch(node_bwd_kernel<NPW>, dim3(blocks), dim3(NODE_WARPS * 32), node_bwd_smem_bytes<NPW>(), a);
     Lc.check();
 }
 template <int NPW>
 void launch_head(Launcher& Lc) {
     vb_handle* h = Lc.h;
     const int blocks = (h->ws.N + NODE_WARPS * NPW - 1) / (NODE_WARPS * NPW);
-    head_kernel<NPW><<<blocks, NODE_WARPS * 32, HeadSmem<NPW>::BYTES, Lc.st>>>(h->mw, h->ws);
+    Lc.launch(head_kernel<NPW>, dim3(blocks), dim3(NODE_WARPS * 32), HeadSmem<NPW>::BYTES, h->mw, h->ws);
     Lc.check();
 }
 template <int TE, int NW>
@@ -291,7 +307,7 @@ void launch_edge_fwd(Launcher& Lc, int l, int occ) {
     EdgeArgs a{l, h->mw, h->ws};
     const int tiles = (h->ws.Ecap + TE - 1) / TE;
     const int blocks = std::max(1, std::min(tiles, h->sm_count * occ));
-    edge_fwd_kernel<TE, NW><<<blocks, NW * 32, edge_fwd_smem_bytes<TE>(), Lc.st>>>(a);
+    Lc.launch(edge_fwd_kernel<TE, NW>, dim3(blocks), dim3(NW * 32), edge_fwd_smem_bytes<TE>(), a);
     Lc.check();
 }
 template <int TE, int NW>
@@ -300,7 +316,7 @@ void launch_edge_bwd(Launcher& Lc, int l, int occ) {
     EdgeArgs a{l, h->mw, h->ws};
     const int tiles = (h->ws.Ecap + TE - 1) / TE;
     const int blocks = std::max(1, std::min(tiles, h->sm_count * occ));
-    edge_bwd_kernel<TE, NW><<<blocks, NW * 32, edge_bwd_smem_bytes<TE>(), Lc.st>>>(a);
+    Lc.launch(edge_bwd_kernel<TE, NW>, dim3(blocks), dim3(NW * 32), edge_bwd_smem_bytes<TE>(), a);
     Lc.check();
 }
 
@@ -308,14 +324,14 @@ template <int NB>
 void launch_node_fwd2(Launcher& Lc, int k) {
     vb_handle* h = Lc.h;
     NodeArgs a{k, h->mw, h->ws};
-    node_fwd2_kernel<NB><<<(h->ws.N + NB - 1) / NB, N2Cfg<NB>::THREADS, sizeof(NodeFwd2Smem<NB>), Lc.st>>>(a);
+    Lc.launch(node_fwd2_kernel<NB>, dim3((h->ws.N + NB - 1) / NB), dim3(N2Cfg<NB>::THREADS), sizeof(NodeFwd2Smem<NB>), a);
     Lc.check();
 }
 template <int NB>
 void launch_node_bwd2(Launcher& Lc, int k) {
     vb_handle* h = Lc.h;
     NodeArgs a{k, h->mw, h->ws};
-    node_bwd2_kernel<NB><<<(h->ws.N + NB - 1) / NB, N2Cfg<NB>::THREADS, sizeof(NodeBwd2Smem<NB>), Lc.st>>>(a);
+    Lc.launch(node_bwd2_kernel<NB>, dim3((h->ws.N + NB - 1) / NB), dim3(N2Cfg<NB>::THREADS), sizeof(NodeBwd2Smem<NB>), a);
     Lc.check();
 }
 void node_fwd(Launcher& Lc, int k) {
@@ -334,7 +350,7 @@ void node_bwd(Launcher& Lc, int k) {
 void head(Launcher& Lc) {
     vb_handle* h = Lc.h;
     if (h->ws.N <= 4096) {            // small systems: K-split head, one node per CTA
-        head2_kernel<<<h->ws.N, 128, 0, Lc.st>>>(h->mw, h->ws);
+        Lc.launch(head2_kernel, dim3(h->ws.N), dim3(128), 0, h->mw, h->ws);
         Lc.check();
         return;
     }
@@ -357,10 +373,10 @@ void launch_edge_fwd_tc(Launcher& Lc, int l) {
     const int rows = h->tc_rows;
     const int tiles = (h->ws.Ecap + rows - 1) / rows;
     const int blocks = std::max(1, std::min(tiles, h->sm_count));
-    if (rows == 32) edge_fwd_tc_kernel<32><<<blocks, TC2_THREADS, TC_SMEM_BYTES, Lc.st>>>(a);
-    else if (rows == 64) edge_fwd_tc_kernel<64><<<blocks, TC2_THREADS, TC_SMEM_BYTES, Lc.st>>>(a);
-    else if (rows == 96) edge_fwd_tc_kernel<96><<<blocks, TC2_THREADS, TC_SMEM_BYTES, Lc.st>>>(a);
-    else edge_fwd_tc_kernel<128><<<blocks, TC2_THREADS, TC_SMEM_BYTES, Lc.st>>>(a);
+    if (rows == 32) Lc.launch(edge_fwd_tc_kernel<32>, dim3(blocks), dim3(TC2_THREADS), TC_SMEM_BYTES, a);
+    else if (rows == 64) Lc.launch(edge_fwd_tc_kernel<64>, dim3(blocks), dim3(TC2_THREADS), TC_SMEM_BYTES, a);
+    else if (rows == 96) Lc.launch(edge_fwd_tc_kernel<96>, dim3(blocks), dim3(TC2_THREADS), TC_SMEM_BYTES, a);
+    else Lc.launch(edge_fwd_tc_kernel<128>, dim3(blocks), dim3(TC2_THREADS), TC_SMEM_BYTES, a);
     Lc.check();
 }
 
@@ -387,10 +403,10 @@ void launch_edge_bwd_tc(Launcher& Lc, int l) {
     const int rows = h->tc_rows;
     const int tiles = (h->ws.Ecap + rows - 1) / rows;
     const int blocks = std::max(1, std::min(tiles, h->sm_count));
-    if (rows == 32) edge_bwd_tc_kernel<32><<<blocks, TC2_THREADS, TC_SMEM_BYTES, Lc.st>>>(a);
-    else if (rows == 64) edge_bwd_tc_kernel<64><<<blocks, TC2_THREADS, TC_SMEM_BYTES, Lc.st>>>(a);
-    else if (rows == 96) edge_bwd_tc_kernel<96><<<blocks, TC2_THREADS, TC_SMEM_BYTES, Lc.st>>>(a);
-    else edge_bwd_tc_kernel<128><<<blocks, TC2_THREADS, TC_SMEM_BYTES, Lc.st>>>(a);
+    if (rows == 32) Lc.launch(edge_bwd_tc_kernel<32>, dim3(blocks), dim3(TC2_THREADS), TC_SMEM_BYTES, a);
+    else if (rows == 64) Lc.launch(edge_bwd_tc_kernel<64>, dim3(blocks), dim3(TC2_THREADS), TC_SMEM_BYTES, a);
+    else if (rows == 96) Lc.launch(edge_bwd_tc_kernel<96>, dim3(blocks), dim3(TC2_THREADS), TC_SMEM_BYTES, a);
+    else Lc.launch(edge_bwd_tc_kernel<128>, dim3(blocks), dim3(TC2_THREADS), TC_SMEM_BYTES, a);
     Lc.check();
 }
 
@@ -411,11 +427,11 @@ void enqueue_all(Launcher& Lc) {
                                                            ws.slots, ws.deg, h->d_forces);
         Lc.check();
     }
-    if (Lc.next("rowptr_scan")) { rowptr_scan_kernel<<<1, 1024, 0, Lc.st>>>(N, ws.deg, ws.rowptr); Lc.check(); }
-    if (Lc.next("edge_geom")) { edge_geom_kernel<<<(N + 3) / 4, 128, 0, Lc.st>>>(N, h->d_pos, h->mw, ws); Lc.check(); }
-    if (Lc.next("embed_node")) { embed_node_kernel<<<N, EMB_THREADS, 0, Lc.st>>>(h->mw, ws); Lc.check(); }
+    if (Lc.next("rowptr_scan")) { Lc.launch(rowptr_scan_kernel, dim3(1), dim3(1024), 0, N, ws.deg, ws.rowptr); Lc.check(); }
+    if (Lc.next("edge_geom")) { Lc.launch(edge_geom_kernel, dim3((N + 3) / 4), dim3(128), 0, N, h->d_pos, h->mw, ws); Lc.check(); }
+    if (Lc.next("embed_node")) { Lc.launch(embed_node_kernel, dim3(N), dim3(EMB_THREADS), 0, h->mw, ws); Lc.check(); }
     const int eblocks = std::max(1, std::min(ws.Ecap, h->sm_count * 16));
-    if (Lc.next("embed_edge")) { embed_edge_kernel<<<eblocks, 128, 0, Lc.st>>>(h->mw, ws); Lc.check(); }
+    if (Lc.next("embed_edge")) { Lc.launch(embed_edge_kernel, dim3(eblocks), dim3(128), 0, h->mw, ws); Lc.check(); }
     for (int l = 0; l < L; l++) {
         snprintf(name, sizeof(name), "node_fwd%d", l);
         if (Lc.next(name)) node_fwd(Lc, l);
@@ -425,7 +441,7 @@ void enqueue_all(Launcher& Lc) {
     if (Lc.next("node_fwd6")) node_fwd(Lc, L);
     if (Lc.next("head")) head(Lc);
     if (Lc.next("energy_reduce")) {
-        energy_reduce_kernel<<<(ws.G + 3) / 4, 128, 0, Lc.st>>>(ws, h->mw.scalars, h->d_energy);
+        Lc.launch(energy_reduce_kernel, dim3((ws.G + 3) / 4), dim3(128), 0, ws, h->mw.scalars, h->d_energy);
         Lc.check();
     }
     for (int l = L - 1; l >= 0; l--) {
@@ -437,10 +453,10 @@ void enqueue_all(Launcher& Lc) {
     if (Lc.next("node_bwd0")) node_bwd(Lc, 0);
     if (Lc.next("embed_edge_bwd")) {
         const int bb = std::max(1, std::min((ws.Ecap + EEB_WARPS - 1) / EEB_WARPS, h->sm_count * 4));
-        embed_edge_bwd_kernel<<<bb, EEB_WARPS * 32, 0, Lc.st>>>(h->mw, ws);
+        Lc.launch(embed_edge_bwd_kernel, dim3(bb), dim3(EEB_WARPS * 32), 0, h->mw, ws);
         Lc.check();
     }
-    if (Lc.next("embed_node_bwd")) { embed_node_bwd_kernel<<<N, ENB_WARPS * 32, 0, Lc.st>>>(h->mw, ws, h->d_forces); Lc.check(); }
+    if (Lc.next("embed_node_bwd")) { Lc.launch(embed_node_bwd_kernel, dim3(N), dim3(ENB_WARPS * 32), 0, h->mw, ws, h->d_forces); Lc.check(); }
 }
 
 template <typename K>
@@ -474,7 +490,7 @@ int configure_kernels(vb_handle* h) {
     return VB_OK;
 }
 
-int ensure_graph(vb_handle* h) {
+int ensure_graph_once(vb_handle* h) {
     if (h->graph_exec) return VB_OK;
     cudaGraph_t graph = nullptr;
     CUDA_TRY(h, cudaStreamBeginCapture(h->own_stream, cudaStreamCaptureModeThreadLocal));
@@ -494,6 +510,18 @@ int ensure_graph(vb_handle* h) {
         return VB_ERR_CUDA;
     }
     return VB_OK;
+}
+
+// Programmatic-dependent-launch edges inside a captured graph need a recent driver: if capture or instantiation fails
+// with them, fall back to plain launches once and remember the choice.
+int ensure_graph(vb_handle* h) {
+    int rc = ensure_graph_once(h);
+    if (rc != VB_OK && h->use_pdl) {
+        h->use_pdl = 0;
+        (void)cudaGetLastError();
+        rc = ensure_graph_once(h);
+    }
+    return rc;
 }
 
 // core evaluation on internal buffers, asynchronous on st
@@ -596,6 +624,7 @@ int vb_create(const float* weights_host, size_t n_floats, const vb_hparams* hp, 
     if (const char* s = getenv("VB_TE_FWD")) h->te_fwd_opt = atoi(s);
     if (const char* s = getenv("VB_TE_BWD")) h->te_bwd = atoi(s);
     if (const char* s = getenv("VB_EDGE_TC")) h->edge_tc_opt = atoi(s);
+    if (const char* s = getenv("VB_USE_PDL")) h->use_pdl = atoi(s) ? 1 : 0;
     if (const char* s = getenv("VB_TC_ROWS")) { const int v = atoi(s); if (v == 32 || v == 64 || v == 96 || v == 128) h->tc_rows_opt = v; }
     if (const char* s = getenv("VB_NODE_IMPL")) h->node_impl = atoi(s);
     *out = h;
@@ -918,20 +947,26 @@ int vb_md_run(vb_handle* h, int64_t n_steps, void* stream) {
     cudaStream_t st = (cudaStream_t)stream;
     CUDA_TRY(h, cudaSetDevice(h->device));
     if (h->use_graph && !h->md_graph) {
-        cudaGraph_t graph = nullptr;
-        CUDA_TRY(h, cudaStreamBeginCapture(h->own_stream, cudaStreamCaptureModeThreadLocal));
-        md_kick1_enqueue(h, h->own_stream);
-        int rc = md_eval_enqueue(h, h->own_stream, true);
-        md_kick2_enqueue(h, h->own_stream);
-        cudaError_t e_end = cudaStreamEndCapture(h->own_stream, &graph);
-        if (rc != VB_OK || e_end != cudaSuccess) {
-            if (rc == VB_OK) h->set_error("MD graph capture failed: %s", cudaGetErrorString(e_end));
+        for (int attempt = 0; attempt < 2 && !h->md_graph; attempt++) {
+            cudaGraph_t graph = nullptr;
+            CUDA_TRY(h, cudaStreamBeginCapture(h->own_stream, cudaStreamCaptureModeThreadLocal));
+            md_kick1_enqueue(h, h->own_stream);
+            int rc = md_eval_enqueue(h, h->own_stream, true);
+            md_kick2_enqueue(h, h->own_stream);
+            cudaError_t e_end = cudaStreamEndCapture(h->own_stream, &graph);
+            cudaError_t e_inst = cudaSuccess;
+            if (rc == VB_OK && e_end == cudaSuccess) e_inst = cudaGraphInstantiate(&h->md_graph, graph, 0);
             if (graph) cudaGraphDestroy(graph);
+            if (rc == VB_OK && e_end == cudaSuccess && e_inst == cudaSuccess) break;
+            h->md_graph = nullptr;
+            if (h->use_pdl && attempt == 0) {          // retry once without programmatic launch edges
+                h->use_pdl = 0;
+                (void)cudaGetLastError();
+                continue;
+            }
+            if (rc == VB_OK) h->set_error("MD graph capture failed: %s / %s", cudaGetErrorString(e_end), cudaGetErrorString(e_inst));
             return VB_ERR_CUDA;
         }
-        cudaError_t e_inst = cudaGraphInstantiate(&h->md_graph, graph, 0);
-        cudaGraphDestroy(graph);
-        if (e_inst != cudaSuccess) { h->md_graph = nullptr; h->set_error("cudaGraphInstantiate (MD) failed: %s", cudaGetErrorString(e_inst)); return VB_ERR_CUDA; }
     }
     for (int64_t s = 0; s < n_steps; s++) {
         if (h->use_graph) {
@@ -1057,6 +1092,7 @@ int vb_set_option(vb_handle* h, const char* key, int64_t value) {
     std::lock_guard<std::mutex> lk(h->mu);
     const std::string k(key);
     if (k == "use_graph") h->use_graph = (int)value;
+    else if (k == "use_pdl" && (value == 0 || value == 1)) h->use_pdl = (int)value;
     else if (k == "npw" && (value == 1 || value == 2)) h->npw = h->npw_opt = (int)value;
     else if (k == "te_fwd" && (value == 32 || value == 64)) h->te_fwd = h->te_fwd_opt = (int)value;
     else if (k == "te_bwd" && (value == 32 || value == 64)) h->te_bwd = (int)value;
@@ -1081,6 +1117,7 @@ int64_t vb_get_option(const vb_handle* h, const char* key) {
     if (!h || !key) return VB_ERR_ARG;
     const std::string k(key);
     if (k == "use_graph") return h->use_graph;
+    if (k == "use_pdl") return h->use_pdl;
     if (k == "npw") return h->npw;
     if (k == "te_fwd") return h->te_fwd;
     if (k == "te_bwd") return h->te_bwd;

@@ -67,6 +67,7 @@ constexpr size_t edge_fwd_smem_bytes() {
 // ---------------------------------------------------------------------------------------------
 template <int TE, int NW>
 __global__ void __launch_bounds__(NW * 32) edge_fwd_kernel(EdgeArgs a) {
+    pdl_entry();
     constexpr int R = TE / NW, NT = NW * 32;
     static_assert(TE % NW == 0 && NT % D == 0, "tile shape");
     extern __shared__ __align__(16) float dyn_smem[];
@@ -223,6 +224,7 @@ constexpr size_t edge_bwd_smem_bytes() {
 
 template <int TE, int NW>
 __global__ void __launch_bounds__(NW * 32) edge_bwd_kernel(EdgeArgs a) {
+    pdl_entry();
     constexpr int R = TE / NW, NT = NW * 32;
     static_assert(TE % NW == 0 && NT % D == 0, "tile shape");
     extern __shared__ __align__(16) float dyn_smem[];

@@ -288,6 +288,7 @@ __device__ __forceinline__ void tc2_go(TcShared& sh, int j) {      // every comp
 // ---------------------------------------------------------------------------------------------
 template <int ROWS>
 __global__ void __launch_bounds__(TC2_THREADS, 1) edge_fwd_tc_kernel(const __grid_constant__ EdgeTcArgs a) {
+    pdl_entry();
     extern __shared__ __align__(1024) uint8_t dyn_raw[];
     TcShared& sh = *tc_shared_base(dyn_raw);
     const Workspace& ws = a.ws;
@@ -549,6 +550,7 @@ namespace vb {
 // ---------------------------------------------------------------------------------------------
 template <int ROWS>
 __global__ void __launch_bounds__(TC2_THREADS, 1) edge_bwd_tc_kernel(const __grid_constant__ EdgeTcArgs a) {
+    pdl_entry();
     extern __shared__ __align__(1024) uint8_t dyn_raw[];
     TcShared& sh = *tc_shared_base(dyn_raw);
     const Workspace& ws = a.ws;

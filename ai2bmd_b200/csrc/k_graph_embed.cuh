@@ -16,6 +16,7 @@ __global__ void __launch_bounds__(128) nbr_build_kernel(int N, const float* __re
                                                         const int* __restrict__ frag_start, float rc,
                                                         int* __restrict__ slots, int* __restrict__ deg,
                                                         float* __restrict__ forces) {
+    pdl_entry();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= N) return;
     forces[3 * i] = 0.f; forces[3 * i + 1] = 0.f; forces[3 * i + 2] = 0.f;   // accumulated by the last kernel of the sweep
@@ -40,6 +41,7 @@ __global__ void __launch_bounds__(128) nbr_build_kernel(int N, const float* __re
 // K2: exclusive scan of deg -> rowptr (single block; N is small enough that this is latency only).
 __global__ void __launch_bounds__(1024) rowptr_scan_kernel(int N, const int* __restrict__ deg,
                                                            int* __restrict__ rowptr) {
+    pdl_entry();
     __shared__ int wsum[32];
     __shared__ int carry_s;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -79,6 +81,7 @@ __global__ void __launch_bounds__(1024) rowptr_scan_kernel(int N, const int* __r
 // K3: per-edge geometry + RBF.  One warp per target atom, lane k = neighbour slot k.
 __global__ void __launch_bounds__(128) edge_geom_kernel(int N, const float* __restrict__ pos, ModelW mw,
                                                         Workspace ws) {
+    pdl_entry();
     const int lane = threadIdx.x & 31;
     const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (i >= N) return;
@@ -124,6 +127,7 @@ __global__ void __launch_bounds__(128) edge_geom_kernel(int N, const float* __re
 // latency chains, so both are split in two and the halves summed in a fixed order through shared memory.
 constexpr int EMB_THREADS = 2 * D;
 __global__ void __launch_bounds__(EMB_THREADS) embed_node_kernel(ModelW mw, Workspace ws) {
+    pdl_entry();
     __shared__ float cat[2 * D];
     __shared__ float part[D];
     __shared__ int sj[KNB];
@@ -184,6 +188,7 @@ __global__ void __launch_bounds__(EMB_THREADS) embed_node_kernel(ModelW mw, Work
 
 // K5: edge embedding  f0_e[c] = (x_i[c] + x_j[c]) * (rbf_e . We[c,:] + be[c]).   thread = channel.
 __global__ void __launch_bounds__(128) embed_edge_kernel(ModelW mw, Workspace ws) {
+    pdl_entry();
     const int c = threadIdx.x;
     float we[NR];
 #pragma unroll
@@ -214,6 +219,7 @@ __global__ void __launch_bounds__(128) embed_edge_kernel(ModelW mw, Workspace ws
 // ---------------------------------------------------------------------------------------------
 constexpr int EEB_WARPS = 8;
 __global__ void __launch_bounds__(EEB_WARPS * 32) embed_edge_bwd_kernel(ModelW mw, Workspace ws) {
+    pdl_entry();
     __shared__ __align__(16) float WeT_s[NR][D];          // [k][c]
     __shared__ float WeN_s[D][NR + 1];                    // [c][k] (+1: conflict-free column walks)
     __shared__ __align__(16) float gep_s[EEB_WARPS][D];
@@ -260,6 +266,7 @@ __global__ void __launch_bounds__(EEB_WARPS * 32) embed_edge_bwd_kernel(ModelW m
 constexpr int ENB_WARPS = 8;
 __global__ void __launch_bounds__(ENB_WARPS * 32) embed_node_bwd_kernel(ModelW mw, Workspace ws,
                                                                         float* __restrict__ forces) {
+    pdl_entry();
     __shared__ __align__(16) float WdT_s[NR][D];
     __shared__ float WdN_s[D][NR + 1];
     __shared__ __align__(16) float gx_s[D];
@@ -350,6 +357,7 @@ __global__ void __launch_bounds__(ENB_WARPS * 32) embed_node_bwd_kernel(ModelW m
 // The <= 44 per-atom terms are summed in double and rounded once, so the result does not depend on order.
 __global__ void __launch_bounds__(128) energy_reduce_kernel(Workspace ws, const float* __restrict__ scalars,
                                                             float* __restrict__ energy) {
+    pdl_entry();
     const int lane = threadIdx.x & 31;
     const int g = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (g >= ws.G) return;

@@ -25,6 +25,7 @@ struct HeadSmem {
 
 template <int NPW>
 __global__ void __launch_bounds__(NODE_WARPS * 32) head_kernel(ModelW mw, Workspace ws) {
+    pdl_entry();
     using S = HeadSmem<NPW>;
     constexpr int L128 = S::L128, L256 = S::L256, L64 = S::L64;
     extern __shared__ __align__(16) float dyn_smem[];
@@ -282,6 +283,7 @@ __device__ __forceinline__ void ksplit_gemm2(float (&acc)[R][2], const float* As
 }
 
 __global__ void __launch_bounds__(128) head2_kernel(ModelW mw, Workspace ws) {
+    pdl_entry();
     constexpr int L128 = Head2Smem::L128, L256 = Head2Smem::L256, L64 = Head2Smem::L64;
     __shared__ __align__(16) Head2Smem sm;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;

@@ -156,6 +156,7 @@ __device__ __forceinline__ void vecln_backward(const float4 (&v)[3], const float
 // ---------------------------------------------------------------------------------------------
 template <int NPW>
 __global__ void __launch_bounds__(NODE_WARPS * 32) node_fwd_kernel(NodeArgs a) {
+    pdl_entry();
     constexpr int LDA = D + LDS_PAD;
     __shared__ __align__(16) float smem[NODE_WARPS][4 * NPW][LDA];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -303,6 +304,7 @@ __global__ void __launch_bounds__(NODE_WARPS * 32) node_fwd_kernel(NodeArgs a) {
 // ---------------------------------------------------------------------------------------------
 template <int NPW>
 __global__ void __launch_bounds__(NODE_WARPS * 32) node_bwd_kernel(NodeArgs a) {
+    pdl_entry();
     constexpr int LD3 = 3 * D + LDS_PAD;   // 388
     constexpr int LD2 = 2 * D + LDS_PAD;   // 260
     extern __shared__ __align__(16) float dyn_smem[];

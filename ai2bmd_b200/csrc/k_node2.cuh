@@ -26,6 +26,7 @@ struct NodeFwd2Smem {
 // ---------------------------------------------------------------------------------------------
 template <int NB>
 __global__ void __launch_bounds__(N2Cfg<NB>::THREADS) node_fwd2_kernel(NodeArgs a) {
+    pdl_entry();
     constexpr int N2_WARPS = N2Cfg<NB>::WARPS, N2_THREADS = N2Cfg<NB>::THREADS;
     using S = NodeFwd2Smem<NB>;
     constexpr int LDA = S::LDA;
@@ -183,6 +184,7 @@ struct NodeBwd2Smem {
 
 template <int NB>
 __global__ void __launch_bounds__(N2Cfg<NB>::THREADS) node_bwd2_kernel(NodeArgs a) {
+    pdl_entry();
     constexpr int N2_WARPS = N2Cfg<NB>::WARPS;
     using S = NodeBwd2Smem<NB>;
     constexpr int LD3 = S::LD3, LD2 = S::LD2;

@@ -137,7 +137,7 @@ int vb_get_edges(vb_handle* h, int32_t* slots_host, int32_t* deg_host);
 
 /* Number of kernel launches of one vb_forward(), and whether it replays a captured CUDA graph. */
 int vb_launches_per_forward(const vb_handle* h);
-/* Tuning knobs: "use_graph" 0/1, "npw" 1/2, "te_fwd" 32/64, "te_bwd" 32/64, "node_impl" 0/1,
+/* Tuning knobs: "use_graph" 0/1, "use_pdl" 0/1 (programmatic dependent launch between the stages, default off), "npw" 1/2, "te_fwd" 32/64, "te_bwd" 32/64, "node_impl" 0/1,
  * "edge_tc" bit0 = forward / bit1 = adjoint edge stage on tcgen05, "tc_rows" 32/64/96/128 edges per tcgen05 tile
  * (defaults: chosen by problem size), "timeline" 0/1 in-kernel phase stamps of the tcgen05 edge kernels. */
 int vb_set_option(vb_handle* h, const char* key, int64_t value);
