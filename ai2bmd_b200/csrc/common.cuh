@@ -163,11 +163,12 @@ __device__ __forceinline__ void acc_zero(float (&acc)[R][4]) {
     for (int r = 0; r < R; r++) { acc[r][0] = 0.f; acc[r][1] = 0.f; acc[r][2] = 0.f; acc[r][3] = 0.f; }
 }
 
-// Programmatic dependent launch (engine.cu Launcher::launch): let the next kernel of the stream start launching, then
-// wait until the previous one has completed and its writes are visible.  Nothing before this call may touch data
-// produced by another kernel.  Both instructions are no-ops for a kernel launched without the attribute.
+// Programmatic dependent launch (engine.cu Launcher::launch, option "use_pdl"): wait until the previous kernel of the
+// stream has completed and its writes are visible.  No kernel triggers its dependents early (an entry-time
+// griddepcontrol.launch_dependents parked the next kernels' CTAs on the SMs and cost more than it hid), so with the
+// attribute the next grid starts launching when the last CTA of this one exits, overlapping only the completion
+// latency.  Nothing before this call may touch data produced by another kernel.  A no-op without the attribute.
 __device__ __forceinline__ void pdl_entry() {
-    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     asm volatile("griddepcontrol.wait;" ::: "memory");
 }
 

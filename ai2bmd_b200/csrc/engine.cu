@@ -85,7 +85,7 @@ struct vb_handle {
     float *d_map_sign = nullptr, *d_frag_sign = nullptr;
     // options
     int use_graph = 1, npw = 0, te_fwd = 0, te_bwd = 32;
-    int use_pdl = 0;   // programmatic dependent launch between the stages: measured slower with the trigger at kernel entry
+    int use_pdl = 0;   // programmatic dependent launch between the stages: measured neutral to slower
     int npw_opt = 0, te_fwd_opt = 0, edge_tc_opt = -1;   // user choices (0 / -1 = choose by problem size)
     int tc_rows_opt = 0, tc_rows = 128;                  // edges per tcgen05 tile (32 / 64 / 96 / 128; MMA M stays 128)
     int node_impl = 1; // 0: warp-per-node kernels (k_node.cuh), 1: CTA-cooperative kernels (k_node2.cuh)
@@ -261,9 +261,9 @@ struct Launcher {
     void check() {
         if (status == cudaSuccess) status = cudaGetLastError();
     }
-    // Optionally ("use_pdl") launch with programmatic dependent launch: the next kernel's CTAs may become resident while
-    // this one drains and park at griddepcontrol.wait (pdl_entry() at the top of every kernel).  Off by default: with
-    // the trigger at kernel entry the parked CTAs cost more than the hidden launch gaps (Chignolin 0.796 -> 0.833 ms).
+    // Optionally ("use_pdl") launch with the programmatic-dependent-launch attribute: the next grid may start launching
+    // as soon as the last CTA of this one exits and waits at griddepcontrol.wait (pdl_entry() at the top of every
+    // kernel) for its completion.  Off by default: measured neutral (exit-time trigger) to slower (entry-time trigger).
     template <typename... KArgs, typename... Args>
     void launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, Args&&... args) {
         cudaLaunchConfig_t cfg = {};
