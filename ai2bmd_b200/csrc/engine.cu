@@ -91,7 +91,6 @@ struct vb_handle {
     int node_impl = 1; // 0: warp-per-node kernels (k_node.cuh), 1: CTA-cooperative kernels (k_node2.cuh)
     int edge_tc = -1;  // bit 0: forward edge stage on tcgen05, bit 1: adjoint edge stage on tcgen05; -1 = by size
     // graph cache
-    float* d_tc_scratch = nullptr;   // per-CTA scratch of the tensor-core adjoint edge kernel
     cudaGraphExec_t graph_exec = nullptr;
     int launches = 0;
     std::vector<std::string> stage_names;
@@ -637,7 +636,6 @@ void vb_destroy(vb_handle* h) {
     h->drop_graph();
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
     cudaFree(h->d_weights);
-    cudaFree(h->d_tc_scratch);
     cudaFree(h->d_tl);
     h->free_md();
     h->free_nb();
@@ -740,6 +738,14 @@ int vb_forward_host(vb_handle* h, const float* pos_host, float* energy_host, flo
     CUDA_TRY(h, cudaMemcpyAsync(h->h_energy, h->d_energy, sizeof(float) * G, cudaMemcpyDeviceToHost, st));
     CUDA_TRY(h, cudaMemcpyAsync(h->h_forces, h->d_forces, sizeof(float) * 3 * N, cudaMemcpyDeviceToHost, st));
     CUDA_TRY(h, cudaStreamSynchronize(st));
+    if ((int64_t)h->ws.Ecap < (int64_t)N * KNB) {      // caller-trimmed edge capacity is a promise: verify it on this synchronous path
+        int n_edges = 0;
+        CUDA_TRY(h, cudaMemcpy(&n_edges, h->ws.rowptr + N, sizeof(int), cudaMemcpyDeviceToHost));
+        if (n_edges > h->ws.Ecap) {
+            h->set_error("vb_forward_host: %d edges exceed the max_edges = %d given to vb_set_topology (results invalid)", n_edges, h->ws.Ecap);
+            return VB_ERR_STATE;
+        }
+    }
     memcpy(energy_host, h->h_energy, sizeof(float) * G);
     memcpy(forces_host, h->h_forces, sizeof(float) * 3 * N);
     return VB_OK;

@@ -194,11 +194,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_selftest_kernel(const float*
 
 // =====================================================================================================
 // Tensor-core edge stage, hybrid layout.
-//   * 8 compute warps keep the coalesced "lane owns 4 channels" layout of k_edge.cuh for every global
+//   * 16 compute warps keep the coalesced "lane owns 4 channels" layout of k_edge.cuh for every global
 //     gather / scatter / elementwise step (one 512 B request per node row per warp);
 //   * the five 128x128x128 contractions per tile run on tcgen05: the A operand is moved from the padded
 //     shared staging tile into TMEM (thread-per-row, 3xTF32 planes), the accumulator comes back the same way;
-//   * warp 8 lane 0 = TMA weight producer, warp 9 lane 0 = MMA issuer (tc_producer / tc_mma_issuer).
+//   * warp 16 lane 0 = TMA weight producer, warp 17 lane 0 = MMA issuer (tc_producer / tc_mma_issuer);
+//   * a tile holds ROWS = 32 / 64 / 96 / 128 edges (template parameter): MMA M stays 128, TMEM lanes >= ROWS are never
+//     written or read, compute warp w owns rows [w*ROWS/16, (w+1)*ROWS/16) in the coalesced phases.
 // =====================================================================================================
 namespace vb {
 

@@ -52,7 +52,9 @@ void vb_destroy(vb_handle* h);
 const char* vb_last_error(const vb_handle* h);   /* h may be NULL: last creation error */
 
 /* Static topology of the packed batch: atomic numbers and graph ids (sorted, contiguous) of N atoms in
- * G fragments -- host pointers, copied.  max_edges <= 0 selects the worst case N*32.
+ * G fragments -- host pointers, copied.  max_edges <= 0 selects the worst case N*32 (always safe); a smaller value
+ * trims the workspace and is a promise by the caller that no step produces more directed edges (incl. self-loops):
+ * vb_forward_host verifies it after the fact and fails, the asynchronous entry points cannot.
  * Replaces: the z / batch members of FragmentData (src/AIMD/fragment.py:7-13) that
  *           ViSNetModel.collate() uploads every step (visnet_calculator.py:47-52). */
 int vb_set_topology(vb_handle* h, int64_t n_atoms, int64_t n_graphs, const int64_t* z_host,

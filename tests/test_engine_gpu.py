@@ -219,6 +219,43 @@ def test_errors_are_loud(real_weights, chig):
         eng.forward_host(fd.pos[:-1])
 
 
+def test_md_and_nonbonded_errors_are_loud(real_weights, chig):
+    from ai2bmd_b200.fixtures import load_protein
+    fd, pm = chig
+    _, _, recipe = load_protein("chig")
+    n = pm.n_protein
+    eng = Engine(real_weights, 0)
+    eng.set_topology(fd.z, fd.batch)
+    ef = torch.zeros(3 * n + 1, device="cuda")
+    masses = np.ones(n)
+    args = (recipe.real, recipe.acc, recipe.rem, recipe.blen, 0.1, 0.025, 0.0, 0, ef.data_ptr())
+    with pytest.raises(RuntimeError, match="protein map"):
+        eng.md_setup(masses, *args)
+    with pytest.raises(RuntimeError, match="vb_md_setup first"):
+        eng.md_run(1)
+    eng.set_protein_map(n, pm.src_atom, pm.dst_atom, pm.sign, pm.frag_sign)
+    bad = recipe.real.copy()
+    bad[0] = n
+    with pytest.raises(RuntimeError, match="recipe index"):
+        eng.md_setup(masses, bad, *args[1:])
+    with pytest.raises(RuntimeError, match="mass"):
+        eng.md_setup(np.zeros(n), *args)
+    with pytest.raises(RuntimeError, match="n_protein"):
+        eng.md_setup(np.ones(n + 1), *args)
+    with pytest.raises(RuntimeError, match="vb_set_nonbonded first"):
+        eng.nonbonded_device(ef.data_ptr(), ef.data_ptr())
+    q = np.zeros(n, np.float32)
+    rowptr = np.zeros(n + 1, np.int32)
+    rowptr[1:] = 2
+    with pytest.raises(RuntimeError, match="ascending"):
+        eng.set_nonbonded(q, q, q, rowptr, np.array([1, 1], np.int32))
+    with pytest.raises(RuntimeError, match="protein map"):
+        eng.set_nonbonded(np.zeros(n + 1, np.float32), np.zeros(n + 1, np.float32), np.zeros(n + 1, np.float32),
+                          np.zeros(n + 2, np.int32), np.zeros(0, np.int32))
+    with pytest.raises(RuntimeError, match="unknown key"):
+        eng.set_option("tc_rows", 48)
+
+
 # ---- full-size properties (config C4: 512 fragments, ~14k atoms): no oracle needed -------------------
 @pytest.fixture(scope="module")
 def c4(real_weights):
