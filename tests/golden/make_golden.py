@@ -9,6 +9,9 @@ Writes, next to this file:
                                 stripped as ``visnet.py:84-86`` does), so GPU-box tests use the real weights
 * ``fragments_<prot>.npz``   -- packed FragmentData + protein force map for chig / trpcage / ww / abd
                                 (``ai2bmd_b200.pdbfrag`` applied to ``/root/reference/examples/<prot>.pdb``)
+* ``fragment_tables.json``   -- the reference's per-residue fragment compositions (``src/utils/reference.py:36-64``,
+                                ``fragment_atomic_numbers``) and the residue sequence of each example protein, so
+                                the fragmentation can be checked against the reference's own tables on any box
 * ``reference_outputs.npz``  -- energies/forces produced by the reference's OWN model source
                                 (``/root/reference/src/ViSNet/model``: ``load_model`` -> ``ViSNet.forward``)
                                 executed here with the third-party stand-ins of ``oracle/ref_shims.py``,
@@ -70,6 +73,22 @@ def main():
                             dst_atom=pm.dst_atom, sign=pm.sign, frag_sign=pm.frag_sign,
                             prot_pos=prot.positions, prot_z=np.array([zmap[e] for e in prot.elements]),
                             rc_real=rc.real, rc_acc=rc.acc, rc_rem=rc.rem, rc_blen=rc.blen)
+
+    # the reference's own fragment composition tables (numpy-only module) + residue sequences of the examples
+    import importlib.util
+    import json
+    spec = importlib.util.spec_from_file_location("ref_reference", f"{REF}/src/utils/reference.py")
+    refmod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(refmod)
+    tables = {"z_by_residue": {k: [int(x) for x in v] for k, v in refmod.fragment_atomic_numbers.items()}, "sequence": {}}
+    for name in ("chig", "trpcage", "ww", "abd"):
+        prot = read_pdb(f"{REF}/examples/{name}.pdb")
+        seq = {}
+        for r, n in zip(prot.resnums, prot.resnames):
+            seq[int(r)] = n
+        tables["sequence"][name] = [seq[r] for r in sorted(seq)]
+    with open(os.path.join(HERE, "fragment_tables.json"), "w") as fh:
+        json.dump(tables, fh, indent=0, sort_keys=True)
 
     model = load_reference_model()
     o64 = O.OracleViSNet(sd, torch.float64)

@@ -181,3 +181,25 @@ def test_host_langevin_with_normal_source_and_verlet_limit():
     md2.run(5)
     assert calls == [0, 1, 2, 3, 4] and np.isfinite(md2.x).all()
     assert np.abs((md2.m * md2.v).sum(0)).max() < 1e-12
+
+
+@pytest.mark.parametrize("name", ["chig", "trpcage", "ww", "abd"])
+def test_fragment_compositions_match_the_reference_tables(golden_dir, name):
+    """Every dipeptide fragment holds exactly the atoms the reference's own table lists for its central residue
+    (``src/utils/reference.py:36-64``), every ACE-NME the 12 atoms of "AN"; fragments alternate dipeptide / ACE-NME
+    (``distancefrag.py:250-284``) and dipeptide k is centred on residue k+2 of the capped chain."""
+    import json
+    from ai2bmd_b200.fixtures import load_fragments
+    tables = json.load(open(os.path.join(golden_dir, "fragment_tables.json")))
+    zref, seq = tables["z_by_residue"], tables["sequence"][name]
+    fd, pm = load_fragments(name)
+    assert seq[0] == "ACE" and seq[-1] == "NME"
+    n_dip = len(seq) - 2
+    assert len(fd) == 2 * n_dip - 1
+    for g in range(len(fd)):
+        z = sorted(int(v) for v in fd.z[fd.start[g]:fd.end[g]])
+        if g % 2 == 0:
+            assert pm.frag_sign[g] > 0
+            assert z == sorted(zref[seq[g // 2 + 1]]), (g, seq[g // 2 + 1])
+        else:
+            assert pm.frag_sign[g] < 0 and z == sorted(zref["AN"])
