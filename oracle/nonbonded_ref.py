@@ -6,9 +6,13 @@ pair list of ``Protein.initial_mm_adjmatrix`` (``src/AIMD/protein.py:133-151``) 
 ``src/Fragmentation/distancefrag.py:355-363``.  ``torch_scatter.scatter_add`` is restated with ``index_add_``; the
 ASE unit constants are ASE 3.22's CODATA-2014 values (recalled: ``ase/units.py``).
 
-Parity status: **unpinned** -- the reference holds no expected non-bonded energies/forces, and its parameter source
-(OpenMM amber14) is not installable here.  Self-checks (tests/test_nonbonded.py): fp64 forces equal the negative
-finite-difference gradient of the fp64 energy; a hand-computed two-atom case.
+Parity status: the formula, the pair list and the scatter are pinned -- ``tests/golden/reference_nonbonded.npz`` holds
+the output of the reference's own ``MMNonBondedCalculator.__call__`` / ``Protein.initial_mm_adjmatrix`` bodies executed
+in the authoring container (tests/golden/make_golden.py) and this restatement reproduces it to fp32 round-off.  Still
+**unpinned**: the six ``ase.units`` constants (ASE is absent; CODATA-2014 values recalled from ``ase/units.py``) and the
+force-field parameters (OpenMM amber14 is not installable; tests use synthetic amber-like values).  Further self-checks
+(tests/test_nonbonded.py): fp64 forces equal the negative finite-difference gradient of the fp64 energy; a
+hand-computed two-atom case with the textbook 1389.35 kJ/mol*A/e^2 Coulomb constant.
 """
 import numpy as np
 import torch

@@ -12,6 +12,19 @@ Writes, next to this file:
 * ``fragment_tables.json``   -- the reference's per-residue fragment compositions (``src/utils/reference.py:36-64``,
                                 ``fragment_atomic_numbers``) and the residue sequence of each example protein, so
                                 the fragmentation can be checked against the reference's own tables on any box
+* ``reference_partitions.json`` -- device blocks computed by the reference's OWN work-partition function
+                                (``src/Calculators/device_strategy.py:83-127``, extracted with ``ast`` because the module
+                                imports ase) for the four proteins at 2/3/4/8 devices
+* ``reference_host_logic.npz`` -- outputs of the reference's OWN host classes on the Chignolin fixture: ``FragmentData``
+                                slicing / ``scalar_split`` / ``vector_split`` (``src/AIMD/fragment.py:7-47``, imported with a
+                                stub for ``ase``) and ``DipeptideBondedCombiner`` (``src/Calculators/combiner.py:11-41``)
+                                on seeded random per-fragment energies / forces
+* ``reference_nonbonded.npz`` -- energy / forces of the reference's OWN ``MMNonBondedCalculator.__call__`` and pair list
+                                ``Protein.initial_mm_adjmatrix`` (``src/Calculators/nonbonded.py:24-63``,
+                                ``src/AIMD/protein.py:133-151``; class / method bodies extracted with ``ast`` because
+                                the modules import ase / openmm) on Chignolin with synthetic amber-like parameters.
+                                The six ``ase.units`` constants are supplied from oracle/nonbonded_ref.py (recalled
+                                CODATA-2014 values): the formula, pair list and scatter are pinned, the constants not.
 * ``reference_outputs.npz``  -- energies/forces produced by the reference's OWN model source
                                 (``/root/reference/src/ViSNet/model``: ``load_model`` -> ``ViSNet.forward``)
                                 executed here with the third-party stand-ins of ``oracle/ref_shims.py``,
@@ -58,6 +71,126 @@ def dense_fragment(seed=0, n=44, box=3.2):
     return single_graph(z, pos)
 
 
+def write_reference_partitions(frs):
+    """Run the reference's own ``DeviceStrategy._set_combined_work_partitions`` (one huge chunk per device, so only
+    the per-device block boundaries remain) on the fragment start/end arrays of the example proteins."""
+    import ast
+    import bisect
+    import json
+    tree = ast.parse(open(f"{REF}/src/Calculators/device_strategy.py").read())
+    fn = [n for n in ast.walk(tree) if isinstance(n, ast.FunctionDef) and n.name == "_set_combined_work_partitions"][0]
+    fn.decorator_list = []
+    ns = {"bisect": bisect}
+    exec(compile(ast.Module(body=[fn], type_ignores=[]), "ref_device_strategy", "exec"), ns)
+
+    class Cls:
+        _chunk_size = 10 ** 9
+        _work_partitions = None
+
+    out = {}
+    for name, (fd, _) in frs.items():
+        start, end = [int(x) for x in fd.start], [int(x) for x in fd.end]
+        for n in (2, 3, 4, 8):
+            ns["_set_combined_work_partitions"](Cls, list(range(n)), start, end)
+            blocks = []
+            for dev in range(n):
+                mine = [(a, b) for d, a, b in Cls._work_partitions if d == dev]
+                blocks.append([min(a for a, _ in mine), max(b for _, b in mine)] if mine else None)
+            out[f"{name}:{n}"] = blocks
+    with open(os.path.join(HERE, "reference_partitions.json"), "w") as fh:
+        json.dump(out, fh, sort_keys=True)
+
+
+def write_reference_host_logic(fd, pm):
+    """Golden outputs of the reference's FragmentData and DipeptideBondedCombiner on the Chignolin fixture."""
+    import importlib.util
+    import types
+    ref_shims.install()
+    if "ase" not in sys.modules:                                   # fragment.py only needs the name
+        ase = types.ModuleType("ase")
+        ase.Atoms = type("Atoms", (), {"__init__": lambda self, **k: None})
+        sys.modules["ase"] = ase
+
+    def load(name, path):
+        spec = importlib.util.spec_from_file_location(name, path)
+        m = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(m)
+        return m
+
+    rf = load("ref_fragment", f"{REF}/src/AIMD/fragment.py")
+    rc = load("ref_combiner", f"{REF}/src/Calculators/combiner.py")
+    out = {}
+    ref_fd = rf.FragmentData(fd.z, fd.pos, fd.start, fd.end, fd.batch)
+    for tag, idx in (("s3_7", slice(3, 7)), ("s0_1", slice(0, 1)), ("i5", 5), ("s10_19", slice(10, 19))):
+        sub = ref_fd[idx]
+        out[f"{tag}_z"], out[f"{tag}_pos"], out[f"{tag}_start"] = sub.z, sub.pos, sub.start
+        out[f"{tag}_end"], out[f"{tag}_batch"] = sub.end, sub.batch
+    out["scalar_dip"], out["scalar_an"] = ref_fd.scalar_split()
+    out["vector_dip"], out["vector_an"] = ref_fd.vector_split()
+    sub = ref_fd[slice(4, 11)]                                     # a chunk that starts on a dipeptide
+    out["sub_scalar_dip"], out["sub_scalar_an"] = sub.scalar_split()
+    out["sub_vector_dip"], out["sub_vector_an"] = sub.vector_split()
+    # combiner: seeded per-fragment energies / per-atom forces, split as DLBondedCalculator.calculate does (bonded.py:91-93)
+    rng = np.random.default_rng(0)
+    e = rng.standard_normal((len(fd), 1)).astype(np.float32) * 100
+    f = rng.standard_normal((len(fd.z), 3)).astype(np.float32)
+    sd_, sa_ = out["scalar_dip"], out["scalar_an"]
+    vd_, va_ = out["vector_dip"], out["vector_an"]
+    order = np.concatenate([np.flatnonzero(vd_), np.flatnonzero(va_)])
+    inv = np.empty_like(order)
+    inv[order] = np.arange(len(order))
+    select, origin = inv[pm.src_atom], pm.dst_atom                 # distancefrag.py:335-353 in this repo's indexing
+    out["comb_e_in"], out["comb_f_in"] = e, f
+    out["comb_select"], out["comb_origin"] = select, origin
+    out["comb_energy"] = rc.DipeptideBondedCombiner.energy_combine(torch.from_numpy(e[sd_]), torch.from_numpy(e[sa_]))
+    out["comb_forces"] = rc.DipeptideBondedCombiner.forces_combine(
+        pm.n_protein, torch.from_numpy(f[vd_]), torch.from_numpy(f[va_]),
+        torch.from_numpy(select.astype(np.int64)), torch.from_numpy(origin.astype(np.int64)))
+    np.savez_compressed(os.path.join(HERE, "reference_host_logic.npz"), **out)
+
+
+def write_reference_nonbonded(fd, pm, prot_pos, prot_z, recipe):
+    import ast
+    from itertools import product
+    from ai2bmd_b200.nonbonded import dipeptide_atom_sets, synthetic_parameters
+    from oracle import nonbonded_ref as NB
+
+    def extract(path, name, kind):
+        tree = ast.parse(open(path).read())
+        node = [n for n in ast.walk(tree) if isinstance(n, kind) and n.name == name][0]
+        return ast.Module(body=[node], type_ignores=[])
+
+    ns = {"np": np, "torch": torch, "scatter_add": lambda src, index, dim=0, dim_size=None: ref_shims._scatter(src, index, dim, None, dim_size),
+          "C": NB.C, "_eps0": NB._eps0, "kJ": NB.kJ, "mol": NB.mol, "nm": NB.nm, "pi": NB.pi, "Protein": object, "product": product}
+    exec(compile(extract(f"{REF}/src/Calculators/nonbonded.py", "MMNonBondedCalculator", ast.ClassDef), "ref_nonbonded", "exec"), ns)
+    exec(compile(extract(f"{REF}/src/AIMD/protein.py", "initial_mm_adjmatrix", ast.FunctionDef), "ref_protein", "exec"), ns)
+
+    q, sg, ep = synthetic_parameters(prot_z, seed=1)
+    groups = dipeptide_atom_sets(fd, recipe, pm)
+
+    class FakeProtein:                       # the attributes the two reference bodies touch
+        def __init__(self):
+            self.positions = np.asarray(prot_pos, dtype=np.float64)
+            self.sigmas, self.epsilons, self.charges = sg, ep, q
+            self.exclude_pair = NB.exclude_pairs_from_groups(groups)      # distancefrag.py:355-361
+        initial_mm_adjmatrix = ns["initial_mm_adjmatrix"]
+
+        def get_positions(self):
+            return self.positions
+
+        def __len__(self):
+            return len(self.positions)
+
+    prot = FakeProtein()
+    calc = ns["MMNonBondedCalculator"](device="cpu")
+    calc.set_parameters(prot)
+    energy, force = calc(prot)
+    np.savez_compressed(os.path.join(HERE, "reference_nonbonded.npz"), charges=q, sigmas=sg, epsilons=ep,
+                        positions=prot.positions, src=calc.src.numpy(), dst=calc.dst.numpy(), energy=np.float64(energy),
+                        forces=force, group_ptr=np.cumsum([0] + [len(g) for g in groups]), group_atoms=np.concatenate(groups))
+    print(f"nonbonded reference: {calc.src.numel()} ordered pairs, E = {energy:.6f} eV, max|F| = {np.abs(force).max():.4f} eV/A")
+
+
 def main():
     sd = O.load_state_dict(CKPT)
     O.save_weights_npz(sd, os.path.join(HERE, "weights_2ef43f29.npz"))
@@ -89,6 +222,11 @@ def main():
         tables["sequence"][name] = [seq[r] for r in sorted(seq)]
     with open(os.path.join(HERE, "fragment_tables.json"), "w") as fh:
         json.dump(tables, fh, indent=0, sort_keys=True)
+
+    write_reference_partitions(frs)
+    write_reference_host_logic(*frs["chig"])
+    from ai2bmd_b200.fixtures import load_protein
+    write_reference_nonbonded(*frs["chig"], *load_protein("chig"))
 
     model = load_reference_model()
     o64 = O.OracleViSNet(sd, torch.float64)

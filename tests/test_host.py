@@ -203,3 +203,43 @@ def test_fragment_compositions_match_the_reference_tables(golden_dir, name):
             assert z == sorted(zref[seq[g // 2 + 1]]), (g, seq[g // 2 + 1])
         else:
             assert pm.frag_sign[g] < 0 and z == sorted(zref["AN"])
+
+
+def test_partition_rule_equals_the_reference_function(golden_dir):
+    """``partition_fragments`` against blocks computed by the reference's own
+    ``DeviceStrategy._set_combined_work_partitions`` (``device_strategy.py:83-127``; generated by make_golden.py)."""
+    import json
+    from ai2bmd_b200.fixtures import load_fragments
+    ref = json.load(open(os.path.join(golden_dir, "reference_partitions.json")))
+    assert len(ref) == 16
+    for key, blocks in ref.items():
+        name, n = key.split(":")
+        fd, _ = load_fragments(name)
+        mine = partition_fragments(fd.start, fd.end, int(n))
+        assert [list(p) for p in mine] == blocks, key
+
+
+def test_host_mirrors_equal_the_reference_classes(golden_dir, chig):
+    """FragmentData slicing / splits, the bonded combiner and the device-epilogue restatement against outputs of the
+    reference's OWN classes (``src/AIMD/fragment.py:7-47``, ``src/Calculators/combiner.py:11-41``) generated by
+    tests/golden/make_golden.py on the Chignolin fixture."""
+    from ai2bmd_b200.calculator import DipeptideBondedCombiner
+    g = np.load(os.path.join(golden_dir, "reference_host_logic.npz"))
+    fd, pm = chig
+    for tag, idx in (("s3_7", slice(3, 7)), ("s0_1", slice(0, 1)), ("i5", 5), ("s10_19", slice(10, 19))):
+        sub = fd[idx]
+        for field in ("z", "pos", "start", "end", "batch"):
+            assert np.array_equal(np.asarray(getattr(sub, field)), g[f"{tag}_{field}"]), (tag, field)
+    sd_, sa_ = fd.scalar_split()
+    vd_, va_ = fd.vector_split()
+    assert np.array_equal(sd_, g["scalar_dip"]) and np.array_equal(sa_, g["scalar_an"])
+    assert np.array_equal(vd_, g["vector_dip"]) and np.array_equal(va_, g["vector_an"])
+    sub = fd[4:11]
+    assert np.array_equal(sub.scalar_split()[0], g["sub_scalar_dip"]) and np.array_equal(sub.vector_split()[1], g["sub_vector_an"])
+    e, f = g["comb_e_in"], g["comb_f_in"]
+    E = DipeptideBondedCombiner.energy_combine(e[sd_], e[sa_])
+    F = DipeptideBondedCombiner.forces_combine(pm.n_protein, f[vd_], f[va_], g["comb_select"], g["comb_origin"])
+    assert abs(float(E) - float(g["comb_energy"])) <= 1e-3          # fp32 sums of 19 terms of O(100)
+    assert np.abs(F - g["comb_forces"]).max() <= 1e-5
+    ef = combine_local(pm, e.reshape(-1), f)                          # what vb_forward_protein computes on the device
+    assert np.abs(ef[:-1].reshape(-1, 3) - g["comb_forces"]).max() <= 1e-5 and abs(ef[-1] - float(g["comb_energy"])) <= 1e-3

@@ -1,4 +1,6 @@
 """Non-bonded MM term: oracle self-checks and host tables on CPU, kernel parity on the GPU."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -57,6 +59,40 @@ def test_oracle_forces_are_the_energy_gradient_and_exclusions_match():
         e2, _ = R.nonbonded(p2, q, sg, ep, src, dst, torch.float64)
         assert abs(-(e1 - e2) / (2 * h) - f[a, c]) <= 1e-6 * max(1.0, abs(f[a, c]))
     assert np.abs(f.sum(0)).max() < 1e-9                           # pairwise forces cancel
+
+
+def _golden(golden_dir):
+    g = np.load(os.path.join(golden_dir, "reference_nonbonded.npz"))
+    groups = [g["group_atoms"][a:b] for a, b in zip(g["group_ptr"][:-1], g["group_ptr"][1:])]
+    return g, groups
+
+
+def test_oracle_equals_the_reference_class_body(golden_dir):
+    """tests/golden/reference_nonbonded.npz holds the output of the reference's own ``MMNonBondedCalculator.__call__``
+    and ``Protein.initial_mm_adjmatrix`` bodies (make_golden.py): same pair list, same fp32 energy and forces."""
+    g, groups = _golden(golden_dir)
+    n = len(g["charges"])
+    src, dst = R.pair_list(n, R.exclude_pairs_from_groups(groups))
+    assert np.array_equal(src.numpy(), g["src"]) and np.array_equal(dst.numpy(), g["dst"])
+    e, f = R.nonbonded(g["positions"], g["charges"], g["sigmas"], g["epsilons"], src, dst, torch.float32)
+    assert abs(e - float(g["energy"])) <= 1e-6 * abs(float(g["energy"])) + 1e-6
+    assert np.abs(f - g["forces"]).max() <= 1e-6 * np.abs(g["forces"]).max()
+    rowptr, col = exclusion_table(n, groups)
+    assert n * (n - 1) - int(rowptr[-1]) == len(g["src"])
+
+
+@pytest.mark.gpu
+def test_kernel_parity_with_the_reference_golden(real_weights, golden_dir):
+    """The CUDA kernel against the reference class body's own output (same tolerance as against the oracle)."""
+    from ai2bmd_b200.engine import Engine
+    from ai2bmd_b200.nonbonded import MMNonBondedCalculator
+    g, groups = _golden(golden_dir)
+    n = len(g["charges"])
+    calc = MMNonBondedCalculator(Engine(real_weights, 0))
+    calc.set_parameters(g["charges"], g["sigmas"], g["epsilons"], *exclusion_table(n, groups))
+    e, f = calc(g["positions"])
+    assert np.abs(f - g["forces"]).max() <= 4e-5 * np.abs(g["forces"]).max() + 2e-6
+    assert abs(e - float(g["energy"])) <= 1e-3 * abs(float(g["energy"])) + 1e-3
 
 
 @pytest.mark.gpu
