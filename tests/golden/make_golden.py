@@ -25,6 +25,9 @@ Writes, next to this file:
                                 the modules import ase / openmm) on Chignolin with synthetic amber-like parameters.
                                 The six ``ase.units`` constants are supplied from oracle/nonbonded_ref.py (recalled
                                 CODATA-2014 values): the formula, pair list and scatter are pinned, the constants not.
+* ``reference_caph.npz``      -- dipeptide coordinates (cap hydrogens placed) from the reference's OWN
+                                ``DistanceFragment.get_dipeptide_positions`` body (``src/Fragmentation/distancefrag.py:34-54``,
+                                extracted with ``ast``) fed with this repo's recipe indices for Chignolin
 * ``reference_outputs.npz``  -- energies/forces produced by the reference's OWN model source
                                 (``/root/reference/src/ViSNet/model``: ``load_model`` -> ``ViSNet.forward``)
                                 executed here with the third-party stand-ins of ``oracle/ref_shims.py``,
@@ -191,6 +194,33 @@ def write_reference_nonbonded(fd, pm, prot_pos, prot_z, recipe):
     print(f"nonbonded reference: {calc.src.numel()} ordered pairs, E = {energy:.6f} eV, max|F| = {np.abs(force).max():.4f} eV/A")
 
 
+def write_reference_caph(fd, pm, prot_pos, prot_z, recipe):
+    import ast
+    tree = ast.parse(open(f"{REF}/src/Fragmentation/distancefrag.py").read())
+    fn = [n for n in ast.walk(tree) if isinstance(n, ast.FunctionDef) and n.name == "get_dipeptide_positions"][0]
+    fn.decorator_list = []
+    ns = {"torch": torch, "Protein": object}
+    exec(compile(ast.Module(body=[fn], type_ignores=[]), "ref_distancefrag", "exec"), ns)
+    dip_atoms = np.concatenate([np.arange(fd.start[g], fd.end[g]) for g in range(len(fd)) if pm.frag_sign[g] > 0])
+    real, acc, rem, blen = recipe.real[dip_atoms], recipe.acc[dip_atoms], recipe.rem[dip_atoms], recipe.blen[dip_atoms]
+    is_real = real >= 0
+    out_idx = np.arange(len(dip_atoms))
+
+    class FakeProtein:
+        arrays = {"positions": np.asarray(prot_pos, dtype=np.float64)}
+        all_dipeptide_index = torch.from_numpy(real[is_real].astype(np.int64))
+        all_hydrogen_index = torch.from_numpy(rem[~is_real].astype(np.int64))
+        all_acceptor_index = torch.from_numpy(acc[~is_real].astype(np.int64))
+        all_hydrogen_radii = torch.from_numpy(blen[~is_real].astype(np.float32))[:, None]
+        scatter_original_index = torch.from_numpy(out_idx[is_real].astype(np.int64))[:, None].expand(-1, 3)
+        scatter_hydrogen_index = torch.from_numpy(out_idx[~is_real].astype(np.int64))[:, None].expand(-1, 3)
+        dipeptides_len = len(dip_atoms)
+
+    pos = ns["get_dipeptide_positions"](FakeProtein, "cpu").numpy()
+    np.savez_compressed(os.path.join(HERE, "reference_caph.npz"), dip_atoms=dip_atoms, positions=pos)
+    print(f"cap-H reference: {len(dip_atoms)} dipeptide atoms, {int((~is_real).sum())} added hydrogens")
+
+
 def main():
     sd = O.load_state_dict(CKPT)
     O.save_weights_npz(sd, os.path.join(HERE, "weights_2ef43f29.npz"))
@@ -227,6 +257,7 @@ def main():
     write_reference_host_logic(*frs["chig"])
     from ai2bmd_b200.fixtures import load_protein
     write_reference_nonbonded(*frs["chig"], *load_protein("chig"))
+    write_reference_caph(*frs["chig"], *load_protein("chig"))
 
     model = load_reference_model()
     o64 = O.OracleViSNet(sd, torch.float64)

@@ -243,3 +243,14 @@ def test_host_mirrors_equal_the_reference_classes(golden_dir, chig):
     assert np.abs(F - g["comb_forces"]).max() <= 1e-5
     ef = combine_local(pm, e.reshape(-1), f)                          # what vb_forward_protein computes on the device
     assert np.abs(ef[:-1].reshape(-1, 3) - g["comb_forces"]).max() <= 1e-5 and abs(ef[-1] - float(g["comb_energy"])) <= 1e-3
+
+
+def test_cap_hydrogen_placement_equals_the_reference_body(golden_dir):
+    """``FragmentRecipe.positions`` (host checker of the device placement kernel) against the output of the reference's own
+    ``DistanceFragment.get_dipeptide_positions`` body (``distancefrag.py:34-54``; fp32 there, fp64-then-cast here)."""
+    from ai2bmd_b200.fixtures import load_protein
+    g = np.load(os.path.join(golden_dir, "reference_caph.npz"))
+    prot_pos, _, recipe = load_protein("chig")
+    mine = recipe.positions(prot_pos)[g["dip_atoms"]]
+    assert mine.dtype == np.float32 and np.abs(mine - g["positions"]).max() <= 4e-6      # <= 4 ulp at 10 A
+    assert int((recipe.real[g["dip_atoms"]] < 0).sum()) == 35
