@@ -1,7 +1,9 @@
-// Per-node stages, CTA-cooperative version: a CTA of 8 warps owns NB consecutive nodes and spreads the
-// (weight chunk x 8-row block) GEMM units over its warps, so the critical path is ~3 units instead of the
-// 11 chunk-GEMMs a single warp walked through in k_node.cuh.  Same math, same buffers, same references
-// (visnet_block.py:237-250, 271-273; utils.py:200-228).
+// Per-node stages, CTA-cooperative version: a CTA of 8 warps (16 in the 4-node variant used for small systems) owns NB
+// consecutive nodes and spreads the (weight chunk x row block) GEMM units over its warps, so the critical path is
+// 1-3 units instead of the 11 chunk-GEMMs a single warp walked through in k_node.cuh; the 4-node variant also splits the
+// o_proj K dimension over warps and sums the partials in a fixed order.  Same math, same buffers, same references
+// (visnet_block.py:237-250, 271-273; utils.py:200-228).  Bound at small sizes by streaming ~720 KB of weights per CTA
+// from L2.
 #pragma once
 #include "k_node.cuh"
 
