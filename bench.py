@@ -121,6 +121,32 @@ def algorithmic_bytes(stage, n_atoms, n_edges):
     return None
 
 
+def tensor_roofline(stages, n_edges, seconds, edge_tc):
+    """Tensor-pipe view of the tcgen05 edge stages (report against the measured bf16 rate, TF32 = 1/2 of it).
+
+    ``stages`` = names of the launches timed in ``seconds``.  Algorithmic MMA work per edge and layer: forward
+    dk, dv, f (3 x 128x128) + s_proj (2 x 128x128), adjoint g_s.Ws (2) + g_P.W1 (3); the last layer has no f chunk.
+    Each product runs as three TF32 MMAs (3xTF32: hi.hi + lo.hi + hi.lo) for fp32 parity, so the executed tensor
+    flops are 3x the fp32-equivalent ones.  Returns None for stages that do not run on tensor cores."""
+    fwd = [s for s in stages if s.startswith("edge_fwd")]
+    bwd = [s for s in stages if s.startswith("edge_bwd")]
+    if not ((fwd and (edge_tc & 1)) or (bwd and (edge_tc & 2))) or seconds <= 0:
+        return None
+    products = 0
+    for s in fwd + bwd:
+        products += 4 if s.endswith(str(L - 1)) else 5
+    fp32_equiv = 2.0 * D * D * n_edges * products
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        bf16, kind = float(json.load(open(p))["bf16_tflops_sustained"]), "measured bf16 sustained / 2"
+    else:
+        bf16, kind = 1590.0, "fallback bf16 / 2"
+    achieved = 3.0 * fp32_equiv / seconds / 1e12
+    return {"bound": "tensor", "achieved": achieved, "peak": bf16 / 2, "peak_kind": kind, "unit": "TFLOP/s",
+            "frac": achieved / (bf16 / 2), "fp32_equivalent_tflops": fp32_equiv / seconds / 1e12,
+            "note": "executed TF32 MMA flops (3xTF32) of the algorithmic products; padded tile rows not counted"}
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -371,6 +397,7 @@ def run_ours(args):
                 "note": "algorithmic bytes = SURVEY 8d fused lower bound per launch; this stage is contraction/latency bound, "
                         "not HBM bound (DESIGN.md section 5); workloads below ~2k atoms are L2 resident",
                 "share_of_step": fam_ms[top_fam] / total_ms,
+                "tensor": tensor_roofline([n for n, _ in launches], n_edges, t_fam, shard.engine.get_option("edge_tc")),
                 "family_ms": {k: round(v, 4) for k, v in sorted(fam_ms.items(), key=lambda x: -x[1])}}
 
     # ---- CPU baseline (bounded sample) ----

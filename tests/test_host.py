@@ -254,3 +254,21 @@ def test_cap_hydrogen_placement_equals_the_reference_body(golden_dir):
     mine = recipe.positions(prot_pos)[g["dip_atoms"]]
     assert mine.dtype == np.float32 and np.abs(mine - g["positions"]).max() <= 4e-6      # <= 4 ulp at 10 A
     assert int((recipe.real[g["dip_atoms"]] < 0).sum()) == 35
+
+
+def test_bench_roofline_arithmetic():
+    """bench.py's algorithmic byte / flop counts -- pure host arithmetic, checked without a GPU."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(ROOT, "bench.py"))
+    b = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(b)
+    assert b.algorithmic_bytes("edge_fwd0", 10, 100) == 100 * 1044 + 10 * 4096
+    assert b.algorithmic_bytes("edge_fwd5", 10, 100) == 100 * 532 + 10 * 4096
+    assert b.algorithmic_bytes("edge_bwd3", 10, 100) == 100 * 1572 + 10 * 8192
+    stages = [f"edge_bwd{l}" for l in range(6)]
+    t = b.tensor_roofline(stages, 1000, 1e-3, 3)
+    products = 5 * 5 + 4
+    assert abs(t["fp32_equivalent_tflops"] - 2 * 128 * 128 * 1000 * products / 1e-3 / 1e12) < 1e-9
+    assert abs(t["achieved"] - 3 * t["fp32_equivalent_tflops"]) < 1e-9 and t["bound"] == "tensor" and 0 < t["frac"] < 1
+    assert b.tensor_roofline(stages, 1000, 1e-3, 1) is None           # adjoint stage on SIMT: no tensor roofline
+    assert b.tensor_roofline(["node_fwd0"], 1000, 1e-3, 3) is None
