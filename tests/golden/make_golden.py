@@ -28,6 +28,11 @@ Writes, next to this file:
 * ``reference_caph.npz``      -- dipeptide coordinates (cap hydrogens placed) from the reference's OWN
                                 ``DistanceFragment.get_dipeptide_positions`` body (``src/Fragmentation/distancefrag.py:34-54``,
                                 extracted with ``ast``) fed with this repo's recipe indices for Chignolin
+* ``reference_caph_lbfgs.npz`` -- the per-step hydrogen refinement on the GLY-centred dipeptide of Chignolin (atoms ordered
+                                like ``GG.prmtop`` by name): tables from the reference's OWN ``CTable.from_prmtop`` and filters
+                                (``hydrogen/ctable.py``), the five energy terms and the relaxed coordinates from its OWN
+                                ``HydrogenOptimizer`` (``hydrogen/energies.py``, decorators stripped with ``ast``; real
+                                ``torch.optim.LBFGS``).  Checker of oracle/caph_ref.py.
 * ``reference_outputs.npz``  -- energies/forces produced by the reference's OWN model source
                                 (``/root/reference/src/ViSNet/model``: ``load_model`` -> ``ViSNet.forward``)
                                 executed here with the third-party stand-ins of ``oracle/ref_shims.py``,
@@ -221,6 +226,97 @@ def write_reference_caph(fd, pm, prot_pos, prot_z, recipe):
     print(f"cap-H reference: {len(dip_atoms)} dipeptide atoms, {int((~is_real).sum())} added hydrogens")
 
 
+def write_reference_caph_lbfgs():
+    import ast
+    import glob
+    import importlib.util
+    import types
+    from oracle import caph_ref as CR
+    spec = importlib.util.spec_from_file_location("ref_ctable", f"{REF}/src/Fragmentation/hydrogen/ctable.py")
+    ctmod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ctmod)
+    # the restated parser equals the reference's on every shipped table
+    fields = ["charge", "atomic_number", "atom_type_idx", "number_excluded_atoms", "nonbonded_parm_index",
+              "bond_force_constant", "bond_equil_value", "angle_force_constant", "angle_equil_value",
+              "dihedral_force_constant", "dihedral_periodicity", "dihedral_phase", "lennard_jones_acoef",
+              "lennard_jones_bcoef", "bonds_inc_hydrogen", "angles_inc_hydrogen", "dihedrals_inc_hydrogen", "excluded_atoms_list"]
+    files = sorted(glob.glob(f"{REF}/src/Fragmentation/prmtop/*.prmtop"))
+    for path in files:
+        ref_t, mine = ctmod.CTable.from_prmtop(path), CR.parse_prmtop(open(path).read())
+        for k in ("natom", "ntypes", "numbnd", "numang", "nptra"):
+            assert getattr(ref_t, k) == mine[k], (path, k)
+        for k in fields:
+            assert np.array_equal(getattr(ref_t, k).numpy(), mine[k]), (path, k)
+    print(f"prmtop parser: {len(files)} tables identical to the reference's CTable")
+
+    # the reference's energy functions and optimiser (jit decorators removed; ProteinData is only a type hint)
+    tree = ast.parse(open(f"{REF}/src/Fragmentation/hydrogen/energies.py").read())
+    body = [n for n in tree.body if isinstance(n, (ast.FunctionDef, ast.ClassDef))]
+    for n in body:
+        n.decorator_list = []
+    ns = {"torch": torch, "F": torch.nn.functional, "ProteinData": object,
+          "scatter_add": lambda src, index, dim=0: ref_shims._scatter(src, index, dim)}
+    exec(compile(ast.Module(body=body, type_ignores=[]), "ref_energies", "exec"), ns)
+
+    # GLY-centred dipeptide of Chignolin (residues 7-8-9 of the capped chain) in GG.prmtop atom order, by name
+    prot = read_pdb(f"{REF}/examples/chig.pdb")
+    P = prot.positions.astype(np.float32)
+
+    def at(res, name):
+        return [i for i in range(len(prot)) if prot.resnums[i] == res and prot.names[i] == name][0]
+
+    def cap(acc, rem, blen=np.float32(0.76 + 0.31)):
+        d = P[rem] - P[acc]
+        return P[acc] + d / np.linalg.norm(d) * blen
+
+    c = 8
+    assert prot.resnames[at(c, "CA")] == "GLY"
+    lead, trail = c - 1, c + 1
+    pos = np.stack([P[at(lead, "HA")], P[at(lead, "CA")], cap(at(lead, "CA"), at(lead, "N")), cap(at(lead, "CA"), at(lead, "CB")),
+                    P[at(lead, "C")], P[at(lead, "O")],
+                    P[at(c, "N")], P[at(c, "H")], P[at(c, "CA")], P[at(c, "HA2")], P[at(c, "HA3")], P[at(c, "C")], P[at(c, "O")],
+                    P[at(trail, "N")], P[at(trail, "H")], P[at(trail, "CA")], P[at(trail, "HA")],
+                    cap(at(trail, "CA"), at(trail, "C")), cap(at(trail, "CA"), at(trail, "CB"))]).astype(np.float32)
+    atom_idx = np.array([2, 3, 17, 18])
+    ct = ctmod.CTable.from_prmtop(f"{REF}/src/Fragmentation/prmtop/GG.prmtop")
+    assert ct.atomic_number.tolist() == [1, 6, 1, 1, 6, 8, 7, 1, 6, 1, 1, 6, 8, 7, 1, 6, 1, 1, 1]
+    aidx = torch.from_numpy(atom_idx)
+    b = types.SimpleNamespace()
+    b.pos = torch.from_numpy(pos.copy())
+    b.atom_idx = aidx
+    b.other_idx = torch.tensor([i for i in range(ct.natom) if i not in atom_idx.tolist()])
+    for k in ("charge", "bond_force_constant", "bond_equil_value", "angle_force_constant", "angle_equil_value",
+              "dihedral_force_constant", "dihedral_periodicity", "dihedral_phase", "lennard_jones_acoef", "lennard_jones_bcoef"):
+        setattr(b, k, getattr(ct, k))
+    b.bonds_atom_idx_src, b.bonds_atom_idx_dst, b.bond_idx = ct.filter_bonds(aidx)
+    b.angles_atom_idx_i, b.angles_atom_idx_j, b.angles_atom_idx_k, b.angle_idx = ct.filter_angles(aidx)
+    (b.dihedrals_atom_idx_i, b.dihedrals_atom_idx_j, b.dihedrals_atom_idx_k, b.dihedrals_atom_idx_l,
+     b.dihedral_idx) = ct.filter_dihedrals(aidx)
+    b.nonbonded_atom_idx_src, b.nonbonded_atom_idx_dst = ct.gen_nonbonded_pair(aidx)
+    b.lj_idx = ct.generate_lj_idx(b.nonbonded_atom_idx_src, b.nonbonded_atom_idx_dst)
+    for k, like in (("bond_batch", b.bond_idx), ("angle_batch", b.angle_idx), ("dihedral_batch", b.dihedral_idx), ("nonbonded_batch", b.lj_idx)):
+        setattr(b, k, torch.zeros_like(like))
+    opt = ns["HydrogenOptimizer"](max_iter=10)                    # DistanceFragment(max_iter=10), distancefrag.py:30-32
+    e0 = opt.cal_potential_energy(b).detach().numpy().reshape(-1)
+    opt.optimize_hydrogen(b)
+    pos1 = b.pos.detach().numpy()
+    e1 = opt.cal_potential_energy(b).detach().numpy().reshape(-1)
+    out = {"prmtop_text_sha": np.frombuffer(__import__("hashlib").sha256(open(f"{REF}/src/Fragmentation/prmtop/GG.prmtop", "rb").read()).digest(), dtype=np.uint8),
+           "atom_idx": atom_idx, "pos0": pos, "pos1": pos1, "energy0": e0, "energy1": e1,
+           "bonds": torch.stack([b.bonds_atom_idx_src, b.bonds_atom_idx_dst, b.bond_idx], 1).numpy(),
+           "angles": torch.stack([b.angles_atom_idx_i, b.angles_atom_idx_j, b.angles_atom_idx_k, b.angle_idx], 1).numpy(),
+           "dihedrals": torch.stack([b.dihedrals_atom_idx_i, b.dihedrals_atom_idx_j, b.dihedrals_atom_idx_k,
+                                     b.dihedrals_atom_idx_l, b.dihedral_idx], 1).numpy(),
+           "pairs": np.array(sorted(zip(b.nonbonded_atom_idx_src.tolist(), b.nonbonded_atom_idx_dst.tolist())))}
+    for k in ("natom", "ntypes", "numbnd", "numang", "nptra"):
+        out["t_" + k] = np.int64(getattr(ct, k))
+    for k in fields:
+        out["t_" + k] = getattr(ct, k).numpy()
+    np.savez_compressed(os.path.join(HERE, "reference_caph_lbfgs.npz"), **out)
+    print(f"cap-H LBFGS reference: E {e0.sum():.4f} -> {e1.sum():.4f} kcal/mol, max shift {np.abs(pos1 - pos).max():.4f} A, "
+          f"{len(out['pairs'])} pairs, {len(out['bonds'])}/{len(out['angles'])}/{len(out['dihedrals'])} bond/angle/dihedral terms")
+
+
 def main():
     sd = O.load_state_dict(CKPT)
     O.save_weights_npz(sd, os.path.join(HERE, "weights_2ef43f29.npz"))
@@ -258,6 +354,7 @@ def main():
     from ai2bmd_b200.fixtures import load_protein
     write_reference_nonbonded(*frs["chig"], *load_protein("chig"))
     write_reference_caph(*frs["chig"], *load_protein("chig"))
+    write_reference_caph_lbfgs()
 
     model = load_reference_model()
     o64 = O.OracleViSNet(sd, torch.float64)

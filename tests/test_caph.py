@@ -1,0 +1,172 @@
+"""Cap-hydrogen refinement oracle (oracle/caph_ref.py): pinned against outputs of the reference's own
+CTable / energy functions / HydrogenOptimizer (tests/golden/reference_caph_lbfgs.npz) and against torch.optim.LBFGS."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import caph_ref as CR
+
+
+@pytest.fixture(scope="module")
+def gold(golden_dir):
+    g = np.load(os.path.join(golden_dir, "reference_caph_lbfgs.npz"))
+    t = {k[2:]: (int(g[k]) if g[k].ndim == 0 else g[k]) for k in g.files if k.startswith("t_")}
+    return g, t
+
+
+def _rows(a):
+    return sorted(map(tuple, np.asarray(a).tolist()))
+
+
+MINI_PRMTOP = """%VERSION  VERSION_STAMP = V0001.000
+%FLAG POINTERS
+%FORMAT(10I8)
+       3       2       2       0       1       0       0       0       0       0
+       3       1       0       0       0       2       1       1       2       0
+%FLAG ATOM_NAME
+%FORMAT(20a4)
+H1  C   H2
+%FLAG CHARGE
+%FORMAT(5E16.8)
+  1.00000000E+00 -2.00000000E+00  1.00000000E+00
+%FLAG ATOMIC_NUMBER
+%FORMAT(10I8)
+       1       6       1
+%FLAG ATOM_TYPE_INDEX
+%FORMAT(10I8)
+       1       2       1
+%FLAG NUMBER_EXCLUDED_ATOMS
+%FORMAT(10I8)
+       2       1       1
+%FLAG NONBONDED_PARM_INDEX
+%FORMAT(10I8)
+       1       2       2       3
+%FLAG BOND_FORCE_CONSTANT
+%FORMAT(5E16.8)
+  3.40000000E+02  3.00000000E+02
+%FLAG BOND_EQUIL_VALUE
+%FORMAT(5E16.8)
+  1.09000000E+00  1.50000000E+00
+%FLAG ANGLE_FORCE_CONSTANT
+%FORMAT(5E16.8)
+  3.50000000E+01
+%FLAG ANGLE_EQUIL_VALUE
+%FORMAT(5E16.8)
+  1.91000000E+00
+%FLAG DIHEDRAL_FORCE_CONSTANT
+%FORMAT(5E16.8)
+  1.50000000E-01
+%FLAG DIHEDRAL_PERIODICITY
+%FORMAT(5E16.8)
+  3.00000000E+00
+%FLAG DIHEDRAL_PHASE
+%FORMAT(5E16.8)
+  0.00000000E+00
+%FLAG SCEE_SCALE_FACTOR
+%FORMAT(5E16.8)
+  1.20000000E+00
+%FLAG SCNB_SCALE_FACTOR
+%FORMAT(5E16.8)
+  2.00000000E+00
+%FLAG LENNARD_JONES_ACOEF
+%FORMAT(5E16.8)
+  1.00000000E+01  2.00000000E+02  3.00000000E+03
+%FLAG LENNARD_JONES_BCOEF
+%FORMAT(5E16.8)
+  1.00000000E+00  2.00000000E+01  3.00000000E+02
+%FLAG BONDS_INC_HYDROGEN
+%FORMAT(10I8)
+       0       3       1       3       6       1
+%FLAG ANGLES_INC_HYDROGEN
+%FORMAT(10I8)
+       0       3       6       1
+%FLAG DIHEDRALS_INC_HYDROGEN
+%FORMAT(10I8)
+
+%FLAG EXCLUDED_ATOMS_LIST
+%FORMAT(10I8)
+       2       3       3       0
+"""
+
+
+def test_prmtop_parser_on_a_hand_written_table():
+    t = CR.parse_prmtop(MINI_PRMTOP)
+    assert (t["natom"], t["ntypes"], t["numbnd"], t["numang"], t["nptra"]) == (3, 2, 2, 1, 1)
+    assert t["charge"].tolist() == [1.0, -2.0, 1.0] and t["atom_type_idx"].tolist() == [0, 1, 0]
+    assert t["nonbonded_parm_index"].tolist() == [0, 1, 1, 2]
+    assert t["bonds_inc_hydrogen"].tolist() == [[0, 1, 0], [1, 2, 0]]         # 3*index -> index, 1-based type -> 0-based
+    assert t["angles_inc_hydrogen"].tolist() == [[0, 1, 2, 0]] and t["dihedrals_inc_hydrogen"].shape == (0, 5)
+    assert t["excluded_atoms_list"].tolist() == [1, 2, 2, -1]
+    terms = CR.hydrogen_terms(t, [0])
+    assert terms["bonds"].tolist() == [[0, 1, 0]] and terms["angles"].tolist() == [[0, 1, 2, 0]]
+    assert terms["pairs"].shape == (0, 2)                                     # both partners of atom 0 are excluded
+
+
+def test_tables_and_terms_equal_the_reference_ctable(gold):
+    g, t = gold
+    assert t["natom"] == 19 and t["atomic_number"].tolist() == [1, 6, 1, 1, 6, 8, 7, 1, 6, 1, 1, 6, 8, 7, 1, 6, 1, 1, 1]
+    terms = CR.hydrogen_terms(t, g["atom_idx"])
+    for key in ("bonds", "angles", "dihedrals", "pairs"):
+        assert _rows(terms[key]) == _rows(g[key]), key
+    assert len(terms["pairs"]) == 44 and (terms["lj_idx"] >= 0).all()
+
+
+def test_energy_terms_equal_the_reference_functions(gold):
+    g, t = gold
+    terms = CR.hydrogen_terms(t, g["atom_idx"])
+    e0 = CR.amber_energy(torch.from_numpy(g["pos0"]), t, terms).numpy()
+    assert np.abs(e0 - g["energy0"]).max() <= 2e-6 * np.abs(g["energy0"]).max()
+    e1 = CR.amber_energy(torch.from_numpy(g["pos1"]), t, terms).numpy()
+    assert np.abs(e1 - g["energy1"]).max() <= 2e-6 * np.abs(g["energy1"]).max()
+    assert e1.sum() < e0.sum()
+
+
+def test_relaxed_hydrogens_equal_the_reference_optimizer(gold):
+    g, t = gold
+    p1 = CR.optimize_hydrogens(g["pos0"], t, g["atom_idx"], max_iter=10)
+    moved = np.abs(g["pos1"] - g["pos0"]).max(axis=1) > 0
+    assert moved.nonzero()[0].tolist() == sorted(g["atom_idx"].tolist())     # only the added hydrogens move
+    assert np.abs(p1 - g["pos1"]).max() <= 2e-6                                # measured: identical in fp32
+    p64 = CR.optimize_hydrogens(g["pos0"], t, g["atom_idx"], max_iter=10, dtype=torch.float64)
+    assert np.abs(p64 - g["pos1"]).max() <= 1e-5                               # fp32 trajectory of the reference vs fp64
+
+
+@pytest.mark.parametrize("scale,max_iter", [(1.0, 10), (5.0, 10), (2.0, 3), (3.0, 25), (0.05, 10), (0.3, 10)])
+def test_lbfgs_restatement_equals_torch_lbfgs(scale, max_iter):
+    """Same iterates and the same number of closure calls as torch.optim.LBFGS (no line search), including the early
+    exits on tolerance_grad / tolerance_change (small scales)."""
+    rng = np.random.default_rng(3)
+    n = 12
+    A = rng.standard_normal((n, n))
+    A = A @ A.T / n + np.eye(n) * 0.5
+    b = rng.standard_normal(n) * scale
+    x0 = rng.standard_normal(n) * scale
+    At, bt = torch.tensor(A), torch.tensor(b)
+
+    def f(x):
+        return 0.5 * x @ At @ x - bt @ x + 0.1 * torch.sin(x).sum()
+
+    p = torch.nn.Parameter(torch.tensor(x0))
+    opt = torch.optim.LBFGS([p], lr=0.1, max_iter=max_iter, tolerance_grad=0.1, tolerance_change=0.01)
+    calls = [0]
+
+    def closure():
+        opt.zero_grad()
+        loss = f(p)
+        loss.backward()
+        calls[0] += 1
+        return loss
+
+    opt.step(closure)
+
+    def fg(x):
+        xt = torch.tensor(x, requires_grad=True)
+        loss = f(xt)
+        (grad,) = torch.autograd.grad(loss, xt)
+        return float(loss.detach()), grad.numpy()
+
+    x, evals = CR.lbfgs_fixed_step(fg, x0, max_iter=max_iter)
+    assert evals == calls[0]
+    assert np.abs(x - p.detach().numpy()).max() <= 1e-12
