@@ -33,6 +33,10 @@ Writes, next to this file:
                                 (``hydrogen/ctable.py``), the five energy terms and the relaxed coordinates from its OWN
                                 ``HydrogenOptimizer`` (``hydrogen/energies.py``, decorators stripped with ``ast``; real
                                 ``torch.optim.LBFGS``).  Checker of oracle/caph_ref.py.
+* ``reference_caph_batch.npz`` -- the same refinement run JOINTLY over the 10 dipeptides of Chignolin (one LBFGS over all 35 added
+                                hydrogens, as ``optimize_hydrogen`` does on a ``ProteinDataBatch``): the reference's own
+                                CTable filters per dipeptide, concatenated with the offsets of ``ProteinData.__inc__``
+                                (``hydrogen/topology.py:108-126``), fed to its own energy functions / optimiser
 * ``reference_outputs.npz``  -- energies/forces produced by the reference's OWN model source
                                 (``/root/reference/src/ViSNet/model``: ``load_model`` -> ``ViSNet.forward``)
                                 executed here with the third-party stand-ins of ``oracle/ref_shims.py``,
@@ -317,6 +321,84 @@ def write_reference_caph_lbfgs():
           f"{len(out['pairs'])} pairs, {len(out['bonds'])}/{len(out['angles'])}/{len(out['dihedrals'])} bond/angle/dihedral terms")
 
 
+def write_reference_caph_batch():
+    import ast
+    import importlib.util
+    import types
+    from oracle import caph_ref as CR
+    spec = importlib.util.spec_from_file_location("ref_ctable", f"{REF}/src/Fragmentation/hydrogen/ctable.py")
+    ctmod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ctmod)
+    tree = ast.parse(open(f"{REF}/src/Fragmentation/hydrogen/energies.py").read())
+    body = [n for n in tree.body if isinstance(n, (ast.FunctionDef, ast.ClassDef))]
+    for n in body:
+        n.decorator_list = []
+    ns = {"torch": torch, "F": torch.nn.functional, "ProteinData": object,
+          "scatter_add": lambda src, index, dim=0: ref_shims._scatter(src, index, dim)}
+    exec(compile(ast.Module(body=body, type_ignores=[]), "ref_energies", "exec"), ns)
+
+    prot = read_pdb(f"{REF}/examples/chig.pdb")
+    resn = {int(r): n for r, n in zip(prot.resnums, prot.resnames)}
+    R = int(prot.resnums.max())
+    cat = {k: [] for k in ("pos", "atom_idx", "other_idx", "charge", "bond_force_constant", "bond_equil_value",
+                           "angle_force_constant", "angle_equil_value", "dihedral_force_constant", "dihedral_periodicity",
+                           "dihedral_phase", "lennard_jones_acoef", "lennard_jones_bcoef", "bonds_atom_idx_src",
+                           "bonds_atom_idx_dst", "bond_idx", "angles_atom_idx_i", "angles_atom_idx_j", "angles_atom_idx_k",
+                           "angle_idx", "dihedrals_atom_idx_i", "dihedrals_atom_idx_j", "dihedrals_atom_idx_k",
+                           "dihedrals_atom_idx_l", "dihedral_idx", "nonbonded_atom_idx_src", "nonbonded_atom_idx_dst",
+                           "lj_idx", "bond_batch", "angle_batch", "dihedral_batch", "nonbonded_batch")}
+    out, stems = {}, []
+    o_atom = o_bnd = o_ang = o_dih = o_lj = 0
+    for g, c in enumerate(range(2, R)):
+        stem = CR.PRMTOP_STEM[resn[c]]
+        stems.append(stem)
+        path = f"{REF}/src/Fragmentation/prmtop/{stem}.prmtop"
+        ct = ctmod.CTable.from_prmtop(path)
+        pos, aidx_np, src = CR.dipeptide_problem(prot, c, CR.prmtop_atom_names(open(path).read()))
+        aidx = torch.from_numpy(aidx_np)
+        bs, bd, bi = ct.filter_bonds(aidx)
+        ai, aj, ak, an = ct.filter_angles(aidx)
+        di, dj, dk, dl, dn = ct.filter_dihedrals(aidx)
+        ps, pd = ct.gen_nonbonded_pair(aidx)
+        lj = ct.generate_lj_idx(ps, pd)
+        other = torch.tensor([i for i in range(ct.natom) if i not in aidx_np.tolist()])
+        cat["pos"].append(torch.from_numpy(pos))
+        for k in ("charge", "bond_force_constant", "bond_equil_value", "angle_force_constant", "angle_equil_value",
+                  "dihedral_force_constant", "dihedral_periodicity", "dihedral_phase", "lennard_jones_acoef", "lennard_jones_bcoef"):
+            cat[k].append(getattr(ct, k))
+        for k, v in (("atom_idx", aidx), ("other_idx", other), ("bonds_atom_idx_src", bs), ("bonds_atom_idx_dst", bd),
+                     ("angles_atom_idx_i", ai), ("angles_atom_idx_j", aj), ("angles_atom_idx_k", ak),
+                     ("dihedrals_atom_idx_i", di), ("dihedrals_atom_idx_j", dj), ("dihedrals_atom_idx_k", dk),
+                     ("dihedrals_atom_idx_l", dl), ("nonbonded_atom_idx_src", ps), ("nonbonded_atom_idx_dst", pd)):
+            cat[k].append(v + o_atom)                               # ProteinData.__inc__: *_atom_idx / other_idx += natom
+        cat["bond_idx"].append(bi + o_bnd)
+        cat["angle_idx"].append(an + o_ang)
+        cat["dihedral_idx"].append(dn + o_dih)
+        cat["lj_idx"].append(lj + o_lj)
+        for k, like in (("bond_batch", bi), ("angle_batch", an), ("dihedral_batch", dn), ("nonbonded_batch", lj)):
+            cat[k].append(torch.full_like(like, g))
+        o_atom += ct.natom; o_bnd += ct.numbnd; o_ang += ct.numang; o_dih += ct.nptra
+        o_lj += ct.ntypes * (ct.ntypes + 1) // 2
+        out[f"g{g}_pos0"], out[f"g{g}_atom_idx"], out[f"g{g}_src"] = pos, aidx_np, src
+        for k in ("natom", "ntypes", "numbnd", "numang", "nptra"):
+            out[f"g{g}_t_{k}"] = np.int64(getattr(ct, k))
+        for k in ("charge", "atomic_number", "atom_type_idx", "number_excluded_atoms", "nonbonded_parm_index",
+                  "bond_force_constant", "bond_equil_value", "angle_force_constant", "angle_equil_value",
+                  "dihedral_force_constant", "dihedral_periodicity", "dihedral_phase", "lennard_jones_acoef",
+                  "lennard_jones_bcoef", "bonds_inc_hydrogen", "angles_inc_hydrogen", "dihedrals_inc_hydrogen", "excluded_atoms_list"):
+            out[f"g{g}_t_{k}"] = getattr(ct, k).numpy()
+    b = types.SimpleNamespace(**{k: torch.cat(v) for k, v in cat.items()})
+    opt = ns["HydrogenOptimizer"](max_iter=10)
+    e0 = opt.cal_potential_energy(b).detach().numpy()
+    pos0 = b.pos.numpy().copy()
+    opt.optimize_hydrogen(b)
+    e1 = opt.cal_potential_energy(b).detach().numpy()
+    out.update(n_graphs=np.int64(R - 2), stems=np.array(stems), energy0=e0, energy1=e1, pos1=b.pos.detach().numpy())
+    np.savez_compressed(os.path.join(HERE, "reference_caph_batch.npz"), **out)
+    print(f"cap-H joint LBFGS reference: {R - 2} dipeptides, {len(b.atom_idx)} added H, E {e0.sum():.3f} -> {e1.sum():.3f} kcal/mol, "
+          f"max shift {np.abs(b.pos.detach().numpy() - pos0).max():.4f} A")
+
+
 def main():
     sd = O.load_state_dict(CKPT)
     O.save_weights_npz(sd, os.path.join(HERE, "weights_2ef43f29.npz"))
@@ -355,6 +437,7 @@ def main():
     write_reference_nonbonded(*frs["chig"], *load_protein("chig"))
     write_reference_caph(*frs["chig"], *load_protein("chig"))
     write_reference_caph_lbfgs()
+    write_reference_caph_batch()
 
     model = load_reference_model()
     o64 = O.OracleViSNet(sd, torch.float64)
