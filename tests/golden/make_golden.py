@@ -37,6 +37,9 @@ Writes, next to this file:
                                 hydrogens, as ``optimize_hydrogen`` does on a ``ProteinDataBatch``): the reference's own
                                 CTable filters per dipeptide, concatenated with the offsets of ``ProteinData.__inc__``
                                 (``hydrogen/topology.py:108-126``), fed to its own energy functions / optimiser
+* ``reference_fragment_index.json`` -- protein-atom membership of every dipeptide / ACE-NME from the reference's OWN
+                                ``DipeptideFragment.get_fragments_index`` (``src/Fragmentation/basefrag.py:44-167``,
+                                extracted with ``ast``) on the four example proteins
 * ``reference_outputs.npz``  -- energies/forces produced by the reference's OWN model source
                                 (``/root/reference/src/ViSNet/model``: ``load_model`` -> ``ViSNet.forward``)
                                 executed here with the third-party stand-ins of ``oracle/ref_shims.py``,
@@ -399,6 +402,32 @@ def write_reference_caph_batch():
           f"max shift {np.abs(b.pos.detach().numpy() - pos0).max():.4f} A")
 
 
+def write_reference_fragment_index():
+    import ast
+    import json
+    import types
+    tree = ast.parse(open(f"{REF}/src/Fragmentation/basefrag.py").read())
+    fn = [n for n in ast.walk(tree) if isinstance(n, ast.FunctionDef) and n.name == "get_fragments_index"][0]
+    fn.decorator_list = []
+    ns = {"Atoms": object, "arguments": types.SimpleNamespace(get=lambda: types.SimpleNamespace(verbose=0))}
+    exec(compile(ast.Module(body=[fn], type_ignores=[]), "ref_basefrag", "exec"), ns)
+    out = {}
+    for name in ("chig", "trpcage", "ww", "abd"):
+        prot = read_pdb(f"{REF}/examples/{name}.pdb")
+
+        class FakeAtoms:
+            arrays = {"residuenumbers": np.asarray(prot.resnums), "residuenames": np.asarray(prot.resnames),
+                      "atomtypes": np.asarray(prot.names)}
+
+            def __len__(self):
+                return len(prot)
+
+        dip, an = ns["get_fragments_index"](FakeAtoms())
+        out[name] = {"dipeptides": [[int(i) for i in u] for u in dip], "acenmes": [[int(i) for i in u] for u in an]}
+    with open(os.path.join(HERE, "reference_fragment_index.json"), "w") as fh:
+        json.dump(out, fh, sort_keys=True)
+
+
 def main():
     sd = O.load_state_dict(CKPT)
     O.save_weights_npz(sd, os.path.join(HERE, "weights_2ef43f29.npz"))
@@ -432,6 +461,7 @@ def main():
         json.dump(tables, fh, indent=0, sort_keys=True)
 
     write_reference_partitions(frs)
+    write_reference_fragment_index()
     write_reference_host_logic(*frs["chig"])
     from ai2bmd_b200.fixtures import load_protein
     write_reference_nonbonded(*frs["chig"], *load_protein("chig"))

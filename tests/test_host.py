@@ -272,3 +272,22 @@ def test_bench_roofline_arithmetic():
     assert abs(t["achieved"] - 3 * t["fp32_equivalent_tflops"]) < 1e-9 and t["bound"] == "tensor" and 0 < t["frac"] < 1
     assert b.tensor_roofline(stages, 1000, 1e-3, 1) is None           # adjoint stage on SIMT: no tensor roofline
     assert b.tensor_roofline(["node_fwd0"], 1000, 1e-3, 3) is None
+
+
+@pytest.mark.parametrize("name", ["chig", "trpcage", "ww", "abd"])
+def test_fragment_membership_equals_the_reference_function(golden_dir, name):
+    """Which protein atoms belong to every dipeptide / ACE-NME: the fixtures (ai2bmd_b200/pdbfrag.py) against the output
+    of the reference's own ``DipeptideFragment.get_fragments_index`` (``basefrag.py:44-167``; make_golden.py).  Atom order
+    inside a fragment is this repo's own (the model is permutation-equivariant); the rest of a fragment is added hydrogens."""
+    import json
+    from ai2bmd_b200.fixtures import load_fragments, load_protein
+    ref = json.load(open(os.path.join(golden_dir, "reference_fragment_index.json")))[name]
+    fd, pm = load_fragments(name)
+    _, _, recipe = load_protein(name)
+    assert len(ref["dipeptides"]) + len(ref["acenmes"]) == len(fd)
+    for g in range(len(fd)):
+        real = recipe.real[fd.start[g]:fd.end[g]]
+        want = ref["dipeptides"][g // 2] if g % 2 == 0 else ref["acenmes"][g // 2]
+        assert sorted(real[real >= 0].tolist()) == sorted(want), g
+        n_added = int((real < 0).sum())
+        assert n_added == (fd.end[g] - fd.start[g]) - len(want) and 0 <= n_added <= 5
