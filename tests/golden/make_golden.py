@@ -411,6 +411,11 @@ def write_reference_fragment_index():
     fn.decorator_list = []
     ns = {"Atoms": object, "arguments": types.SimpleNamespace(get=lambda: types.SimpleNamespace(verbose=0))}
     exec(compile(ast.Module(body=[fn], type_ignores=[]), "ref_basefrag", "exec"), ns)
+    tree_h = ast.parse(open(f"{REF}/src/Fragmentation/distancefrag.py").read())
+    fn_h = [n for n in ast.walk(tree_h) if isinstance(n, ast.FunctionDef) and n.name == "get_hydrogen_indices"][0]
+    fn_h.decorator_list = []
+    ns_h = {"Atoms": object, "np": np}
+    exec(compile(ast.Module(body=[fn_h], type_ignores=[]), "ref_distancefrag_h", "exec"), ns_h)
     out = {}
     for name in ("chig", "trpcage", "ww", "abd"):
         prot = read_pdb(f"{REF}/examples/{name}.pdb")
@@ -423,7 +428,15 @@ def write_reference_fragment_index():
                 return len(prot)
 
         dip, an = ns["get_fragments_index"](FakeAtoms())
-        out[name] = {"dipeptides": [[int(i) for i in u] for u in dip], "acenmes": [[int(i) for i in u] for u in an]}
+        # added hydrogens of every dipeptide: (acceptor, removed atom, bond length) from get_hydrogen_indices (distancefrag.py:365-504)
+        fake = FakeAtoms()
+        fake.atom_masks = {a: np.asarray([n == a for n in prot.names]) for a in ("CA", "N", "C", "CB", "CD")}
+        caps = []
+        for k, unit in enumerate(dip):
+            radii, acc, rem = ns_h["get_hydrogen_indices"](fake, k, unit)
+            caps.append([[int(a), int(r), float(b)] for a, r, b in zip(acc, rem, radii.reshape(-1))])
+        out[name] = {"dipeptides": [[int(i) for i in u] for u in dip], "acenmes": [[int(i) for i in u] for u in an],
+                     "added_hydrogens": caps}
     with open(os.path.join(HERE, "reference_fragment_index.json"), "w") as fh:
         json.dump(out, fh, sort_keys=True)
 

@@ -291,3 +291,10 @@ def test_fragment_membership_equals_the_reference_function(golden_dir, name):
         assert sorted(real[real >= 0].tolist()) == sorted(want), g
         n_added = int((real < 0).sum())
         assert n_added == (fd.end[g] - fd.start[g]) - len(want) and 0 <= n_added <= 5
+    # the added hydrogens of every dipeptide: (acceptor, removed atom, bond length) as the reference's own
+    # ``get_hydrogen_indices`` chooses them (``distancefrag.py:365-504``)
+    for k, caps in enumerate(ref["added_hydrogens"]):
+        sl = slice(fd.start[2 * k], fd.end[2 * k])
+        m = recipe.real[sl] < 0
+        mine = sorted((int(a), int(r), round(float(b), 5)) for a, r, b in zip(recipe.acc[sl][m], recipe.rem[sl][m], recipe.blen[sl][m]))
+        assert mine == sorted((a, r, round(b, 5)) for a, r, b in caps), k
