@@ -19,7 +19,7 @@ ViSNet is permutation-equivariant, so atom order inside a fragment does not chan
 from __future__ import annotations
 
 from dataclasses import dataclass
-from typing import List, Tuple
+from typing import List
 
 import numpy as np
 

@@ -8,7 +8,7 @@ import pytest
 from ai2bmd_b200 import build as vbuild
 from ai2bmd_b200 import engine as vengine
 from ai2bmd_b200.calculator import DipeptideBondedCombiner
-from ai2bmd_b200.fragment_data import FragmentData, FragmentInfo
+from ai2bmd_b200.fragment_data import FragmentInfo
 from ai2bmd_b200.parallel import combine_local, partition_fragments, shard_protein_map
 from ai2bmd_b200.weights import pack_weights
 
