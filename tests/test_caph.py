@@ -215,3 +215,36 @@ def test_joint_relaxation_equals_the_reference_batch(golden_dir):
     assert np.abs(out - g["pos1"]).max() <= 2e-6                            # measured: identical in fp32
     # the joint first step is min(1, 1/|g|_1) * lr over ALL hydrogens: the refinement moves them by millis of an Angstrom
     assert 1e-3 < np.abs(g["pos1"] - pos0).max() < 1e-2
+
+
+def _batch_problems(golden_dir):
+    g = np.load(os.path.join(golden_dir, "reference_caph_batch.npz"))
+    problems = []
+    for k in range(int(g["n_graphs"])):
+        pre = f"g{k}_t_"
+        t = {n[len(pre):]: (int(g[n]) if g[n].ndim == 0 else g[n]) for n in g.files if n.startswith(pre)}
+        problems.append((g[f"g{k}_pos0"], t, g[f"g{k}_atom_idx"]))
+    return g, problems
+
+
+def test_c_restatement_on_flat_arrays(golden_dir, gold):
+    """oracle/caph_ref.c (fp32, flat term arrays as a kernel will see them): energy and hydrogen gradient against the
+    Python oracle in fp64, relaxed coordinates against the reference's own optimiser output (single and joint)."""
+    from oracle import caph_c as CC
+    g, problems = _batch_problems(golden_dir)
+    f = CC.flatten(problems)
+    assert f["pos"].shape == (283, 3) and len(f["h_idx"]) == 35 and len(f["pair_a"]) == 695
+    e, grad = CC.energy_grad(f)
+    e64, g64 = 0.0, []
+    for pos, t, aidx in problems:
+        ee, gg = CR.amber_energy_and_grad(pos.astype(np.float64), t, CR.hydrogen_terms(t, aidx))
+        e64 += float(ee)
+        g64.append(gg[aidx])
+    g64 = np.concatenate(g64)
+    assert abs(e - e64) <= 2e-5 * max(1.0, abs(e64))
+    assert np.abs(grad[f["h_idx"]] - g64).max() <= 1e-5 * np.abs(g64).max()
+    x, evals = CC.relax(f)
+    assert np.abs(x - g["pos1"]).max() <= 4e-6 and 2 <= evals <= 12          # measured: 1 ulp, 2 evaluations
+    g1, t1 = gold
+    x1, _ = CC.relax(CC.flatten([(g1["pos0"], t1, g1["atom_idx"])]))
+    assert np.abs(x1 - g1["pos1"]).max() <= 4e-6
