@@ -324,7 +324,7 @@ def write_reference_caph_lbfgs():
           f"{len(out['pairs'])} pairs, {len(out['bonds'])}/{len(out['angles'])}/{len(out['dihedrals'])} bond/angle/dihedral terms")
 
 
-def write_reference_caph_batch():
+def write_reference_caph_batch(name="chig"):
     import ast
     import importlib.util
     import types
@@ -340,7 +340,7 @@ def write_reference_caph_batch():
           "scatter_add": lambda src, index, dim=0: ref_shims._scatter(src, index, dim)}
     exec(compile(ast.Module(body=body, type_ignores=[]), "ref_energies", "exec"), ns)
 
-    prot = read_pdb(f"{REF}/examples/chig.pdb")
+    prot = read_pdb(f"{REF}/examples/{name}.pdb")
     resn = {int(r): n for r, n in zip(prot.resnums, prot.resnames)}
     R = int(prot.resnums.max())
     cat = {k: [] for k in ("pos", "atom_idx", "other_idx", "charge", "bond_force_constant", "bond_equil_value",
@@ -397,8 +397,8 @@ def write_reference_caph_batch():
     opt.optimize_hydrogen(b)
     e1 = opt.cal_potential_energy(b).detach().numpy()
     out.update(n_graphs=np.int64(R - 2), stems=np.array(stems), energy0=e0, energy1=e1, pos1=b.pos.detach().numpy())
-    np.savez_compressed(os.path.join(HERE, "reference_caph_batch.npz"), **out)
-    print(f"cap-H joint LBFGS reference: {R - 2} dipeptides, {len(b.atom_idx)} added H, E {e0.sum():.3f} -> {e1.sum():.3f} kcal/mol, "
+    np.savez_compressed(os.path.join(HERE, "reference_caph_batch.npz" if name == "chig" else f"reference_caph_batch_{name}.npz"), **out)
+    print(f"cap-H joint LBFGS reference ({name}): {R - 2} dipeptides, {len(b.atom_idx)} added H, E {e0.sum():.3f} -> {e1.sum():.3f} kcal/mol, "
           f"max shift {np.abs(b.pos.detach().numpy() - pos0).max():.4f} A")
 
 
@@ -480,7 +480,8 @@ def main():
     write_reference_nonbonded(*frs["chig"], *load_protein("chig"))
     write_reference_caph(*frs["chig"], *load_protein("chig"))
     write_reference_caph_lbfgs()
-    write_reference_caph_batch()
+    write_reference_caph_batch("chig")
+    write_reference_caph_batch("trpcage")      # PRO / GLY neighbours, 13 residue types
 
     model = load_reference_model()
     o64 = O.OracleViSNet(sd, torch.float64)

@@ -217,8 +217,8 @@ def test_joint_relaxation_equals_the_reference_batch(golden_dir):
     assert 1e-3 < np.abs(g["pos1"] - pos0).max() < 1e-2
 
 
-def _batch_problems(golden_dir):
-    g = np.load(os.path.join(golden_dir, "reference_caph_batch.npz"))
+def _batch_problems(golden_dir, name="chig"):
+    g = np.load(os.path.join(golden_dir, "reference_caph_batch.npz" if name == "chig" else f"reference_caph_batch_{name}.npz"))
     problems = []
     for k in range(int(g["n_graphs"])):
         pre = f"g{k}_t_"
@@ -248,3 +248,18 @@ def test_c_restatement_on_flat_arrays(golden_dir, gold):
     g1, t1 = gold
     x1, _ = CC.relax(CC.flatten([(g1["pos0"], t1, g1["atom_idx"])]))
     assert np.abs(x1 - g1["pos1"]).max() <= 4e-6
+
+
+def test_joint_relaxation_on_trpcage(golden_dir):
+    """20 dipeptides, 74 added hydrogens, PRO and GLY neighbours (N-H cap on the N->CD ray, single-hydrogen methyls), ten
+    prmtop tables: Python and C restatements against the reference's own optimiser output."""
+    from oracle import caph_c as CC
+    g, problems = _batch_problems(golden_dir, "trpcage")
+    assert len(problems) == 20 and sum(len(p[2]) for p in problems) == 74
+    assert {"PP", "GG", "WW", "RR"} <= set(g["stems"].tolist())
+    e0 = np.stack([CR.amber_energy(torch.from_numpy(p[0]), p[1], CR.hydrogen_terms(p[1], p[2])).numpy() for p in problems])
+    assert np.abs(e0 - g["energy0"]).max() <= 4e-6 * np.abs(g["energy0"]).max()
+    out = np.concatenate(CR.optimize_hydrogens_batch(problems, max_iter=10))
+    assert np.abs(out - g["pos1"]).max() <= 2e-6
+    x, _ = CC.relax(CC.flatten(problems))
+    assert np.abs(x - g["pos1"]).max() <= 4e-6
