@@ -14,6 +14,7 @@
 #include "../../include/visnet_b200.h"
 #include "k_edge.cuh"
 #include "k_edge_tc.cuh"
+#include "k_fused.cuh"
 #include "k_graph_embed.cuh"
 #include "k_head.cuh"
 #include "k_md.cuh"
@@ -36,28 +37,76 @@ std::string g_create_error;
         }                                                                                            \
     } while (0)
 
-__global__ void protein_scatter_kernel(int n_map, const int* __restrict__ src, const int* __restrict__ dst,
-                                       const float* __restrict__ sign, const float* __restrict__ forces,
-                                       float* __restrict__ ef) {
-    const int m = blockIdx.x * blockDim.x + threadIdx.x;
-    if (m >= n_map) return;
-    const float s = sign[m];
-    const int a = src[m], p = dst[m];
-    atomicAdd(ef + 3 * p + 0, s * forces[3 * a + 0]);
-    atomicAdd(ef + 3 * p + 1, s * forces[3 * a + 1]);
-    atomicAdd(ef + 3 * p + 2, s * forces[3 * a + 2]);
-}
-
-__global__ void protein_energy_kernel(int G, const float* __restrict__ fsign, const float* __restrict__ energy,
-                                      float* __restrict__ out) {
+// ---------------------------------------------------------------------------------------------------------
+// Last launch of an evaluation: per-fragment energies and, when a protein map is set, the signed whole-protein
+// reduction (combiner.py:11-41) as a gather over a CSR of the map sorted by destination atom -- no memset, no
+// atomics, fixed summation order.  Block roles by index:
+//   [0, fb)        warp per fragment:      energy[g] = float(sum_a eatom[a] + mean)         (visnet.py:146-149)
+//   [fb, fb + pb)  thread per protein atom: ef[3p..] = sum_m sign[m] * forces[src[m]]       (combiner.py:38-39)
+//   fb + pb        one block:               ef[3P]   = sum_g frag_sign[g] * energy[g]       (combiner.py:11-21)
+// ---------------------------------------------------------------------------------------------------------
+constexpr int FIN_THREADS = 256;
+__device__ __forceinline__ float fragment_energy(const Workspace& ws, int g, float mean, int lane) {
     double s = 0.0;
-    for (int g = threadIdx.x; g < G; g += 32) s += (double)fsign[g] * (double)energy[g];
+    for (int a = ws.frag_start[g] + lane; a < ws.frag_start[g + 1]; a += 32) s += (double)ws.eatom[a];
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-    if (threadIdx.x == 0) *out = (float)s;
+    return (float)(s + (double)mean);
+}
+__global__ void __launch_bounds__(FIN_THREADS) finalize_kernel(Workspace ws, const float* __restrict__ scalars, int fb, int pb,
+                                                               int n_protein, const int* __restrict__ map_rowptr,
+                                                               const int* __restrict__ map_src, const float* __restrict__ map_sign,
+                                                               const float* __restrict__ frag_sign,
+                                                               const float* __restrict__ forces, float* __restrict__ energy,
+                                                               float* __restrict__ ef) {
+    pdl_entry();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const float mean = __ldg(scalars + 1);
+    const int b = blockIdx.x;
+    if (b < fb) {
+        const int g = b * (FIN_THREADS / 32) + warp;
+        if (g < ws.G) {
+            const float e = fragment_energy(ws, g, mean, lane);
+            if (lane == 0) energy[g] = e;
+        }
+    } else if (b < fb + pb) {
+        const int p = (b - fb) * FIN_THREADS + threadIdx.x;
+        if (p < n_protein) {
+            float fx = 0.f, fy = 0.f, fz = 0.f;
+            for (int m = map_rowptr[p]; m < map_rowptr[p + 1]; m++) {
+                const float s = map_sign[m];
+                const int a = map_src[m];
+                fx = fmaf(s, forces[3 * a], fx); fy = fmaf(s, forces[3 * a + 1], fy); fz = fmaf(s, forces[3 * a + 2], fz);
+            }
+            ef[3 * p] = fx; ef[3 * p + 1] = fy; ef[3 * p + 2] = fz;
+        }
+    } else {
+        __shared__ double red[FIN_THREADS / 32];
+        double acc = 0.0;
+        for (int g = warp; g < ws.G; g += FIN_THREADS / 32) {
+            const float e = fragment_energy(ws, g, mean, lane);
+            acc += (double)frag_sign[g] * (double)e;
+        }
+        if (lane == 0) red[warp] = acc;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double t = 0.0;
+            for (int w = 0; w < FIN_THREADS / 32; w++) t += red[w];
+            ef[3 * (size_t)n_protein] = (float)t;
+        }
+    }
 }
 
 }  // namespace
+
+// Buffers one evaluation reads and writes.  They are kernel arguments, so a captured graph is specific to them.
+struct StepIO {
+    const float* pos = nullptr;   // [N][3]
+    float* energy = nullptr;      // [G]
+    float* forces = nullptr;      // [N][3]
+    float* ef = nullptr;          // [3*n_protein + 1] or nullptr (no whole-protein reduction)
+    bool operator==(const StepIO& o) const { return pos == o.pos && energy == o.energy && forces == o.forces && ef == o.ef; }
+};
 
 struct vb_handle {
     int device = 0;
@@ -79,20 +128,25 @@ struct vb_handle {
     float* d_forces = nullptr;   // [N][3]
     float *h_pos = nullptr, *h_energy = nullptr, *h_forces = nullptr;   // pinned staging
     cudaStream_t own_stream = nullptr;
-    // protein map
+    // protein map, as a CSR over protein (destination) atoms: entries of atom p are map_rowptr[p]..map_rowptr[p+1]
     int n_protein = 0, n_map = 0;
-    int *d_map_src = nullptr, *d_map_dst = nullptr;
+    int *d_map_rowptr = nullptr, *d_map_src = nullptr;
     float *d_map_sign = nullptr, *d_frag_sign = nullptr;
+    float* d_ef = nullptr;       // [3*n_protein + 1] internal whole-protein buffer (diagnostic runs)
+    int* d_flags = nullptr;      // [0]: set by the neighbour stage when a step produced more edges than the workspace holds
     // options
     int use_graph = 1, npw = 0, te_fwd = 0, te_bwd = 32;
     int use_pdl = 0;   // programmatic dependent launch between the stages: measured neutral to slower
     int npw_opt = 0, te_fwd_opt = 0, edge_tc_opt = -1;   // user choices (0 / -1 = choose by problem size)
     int tc_rows_opt = 0, tc_rows = 128;                  // edges per tcgen05 tile (32 / 64 / 96 / 128; MMA M stays 128)
     int node_impl = 1; // 0: warp-per-node kernels (k_node.cuh), 1: CTA-cooperative kernels (k_node2.cuh)
+    int fused = 0, fused_opt = -1;   // 1: one launch per layer and direction (k_fused.cuh); -1 = choose by problem size
     int edge_tc = -1;  // bit 0: forward edge stage on tcgen05, bit 1: adjoint edge stage on tcgen05; -1 = by size
-    // graph cache
-    cudaGraphExec_t graph_exec = nullptr;
+    // graph cache: one instantiated graph per (kind, I/O pointer set); pointers are baked into the captured launches
+    struct GraphEntry { int kind; StepIO io; cudaGraphExec_t exec; };
+    std::vector<GraphEntry> graphs;
     int launches = 0;
+    bool accum_dirty = false;    // a truncated vb_debug_run left accumulators (XA, VA, GQKV, ...) un-consumed
     std::vector<std::string> stage_names;
     // device-resident MD state (k_md.cuh)
     bool md_ready = false;
@@ -109,7 +163,6 @@ struct vb_handle {
     float *d_nb_q = nullptr, *d_nb_sigma = nullptr, *d_nb_eps = nullptr;
     int *d_nb_rowptr = nullptr, *d_nb_col = nullptr;
     double* d_nb_eatom = nullptr;
-    cudaGraphExec_t md_graph = nullptr;  // one whole MD step
 
     void set_error(const char* fmt, ...) {
         char buf[1024];
@@ -120,8 +173,13 @@ struct vb_handle {
         err = buf;
     }
     void drop_graph() {
-        if (graph_exec) { cudaGraphExecDestroy(graph_exec); graph_exec = nullptr; }
-        if (md_graph) { cudaGraphExecDestroy(md_graph); md_graph = nullptr; }
+        for (auto& g : graphs) cudaGraphExecDestroy(g.exec);
+        graphs.clear();
+    }
+    void free_map() {
+        cudaFree(d_map_rowptr); cudaFree(d_map_src); cudaFree(d_map_sign); cudaFree(d_frag_sign); cudaFree(d_ef);
+        d_map_rowptr = d_map_src = nullptr; d_map_sign = d_frag_sign = d_ef = nullptr;
+        n_protein = n_map = 0;
     }
     void free_nb() {
         cudaFree(d_nb_q); cudaFree(d_nb_sigma); cudaFree(d_nb_eps); cudaFree(d_nb_rowptr); cudaFree(d_nb_col); cudaFree(d_nb_eatom);
@@ -234,6 +292,9 @@ void layout_workspace(vb_handle* h, char* base, ArenaPlan& plan, int*& z, int*& 
     carve(plan, base, ws.GQKV, N * 3 * D);
     carve(plan, base, ws.GVNMSG, N * 3 * D);
     carve(plan, base, ws.GTU, N * 6 * D);
+    carve(plan, base, ws.GQKV2, N * 3 * D);
+    carve(plan, base, ws.GVNMSG2, N * 3 * D);
+    carve(plan, base, ws.GTU2, N * 6 * D);
     carve(plan, base, ws.eatom, N);
     carve(plan, base, h->d_pos, N * 3);
     carve(plan, base, h->d_energy, G);
@@ -415,47 +476,115 @@ void edge_bwd(Launcher& Lc, int l) {
     else launch_edge_bwd<32, 8>(Lc, l, 2);
 }
 
-// Enqueue one full evaluation (energy + forces) on Lc.st, reading h->d_pos, writing h->d_energy / d_forces.
-void enqueue_all(Launcher& Lc) {
+void fill_fwd_jobs(const LayerW& lw, int l, TcJob* jobs, int& n) {
+    const size_t chunk = 4 * 8192;
+    n = 0;
+    jobs[n++] = TcJob{lw.tcW1, (int)TC_COL_D0, 0};                       // dk
+    jobs[n++] = TcJob{lw.tcW1 + chunk, (int)TC_COL_D1, 0};               // dv
+    if (l < L - 1) jobs[n++] = TcJob{lw.tcW1 + 2 * chunk, (int)TC_COL_D0, 0};   // f
+    jobs[n++] = TcJob{lw.tcWs, (int)TC_COL_D1, 0};                       // s1
+    jobs[n++] = TcJob{lw.tcWs + chunk, (int)TC_COL_D0, 0};               // s2
+}
+void fill_bwd_jobs(const LayerW& lw, int l, TcJob* jobs, int& n) {
+    const size_t chunk = 4 * 8192;
+    n = 0;
+    jobs[n++] = TcJob{lw.tcWsN, (int)TC_COL_D1, 0};                        // g_m  = g_s1' Ws[0:128]
+    jobs[n++] = TcJob{lw.tcWsN + chunk, (int)TC_COL_D1, 1};                //      + g_s2' Ws[128:256]
+    jobs[n++] = TcJob{lw.tcW1N + chunk, (int)TC_COL_D0, 0};                // g_f  = g_Pdv Wdv
+    jobs[n++] = TcJob{lw.tcW1N, (int)TC_COL_D0, 1};                        //      + g_Pdk Wdk
+    if (l < L - 1) jobs[n++] = TcJob{lw.tcW1N + 2 * chunk, (int)TC_COL_D0, 1};   //      + g_Pf  Wf
+}
+int fused_grid(const vb_handle* h) {
+    const int nblocks = (h->ws.N + FU_NB - 1) / FU_NB;
+    return std::max(1, std::min(nblocks, h->sm_count));
+}
+// edge stage l + node stage l+1 (forward) / node adjoint l+1 + edge adjoint l (backward), one launch each
+void launch_fused_fwd(Launcher& Lc, int l) {
+    vb_handle* h = Lc.h;
+    FusedArgs a{};
+    a.layer = l; a.mw = h->mw; a.ws = h->ws;
+    fill_fwd_jobs(h->mw.layer[l], l, a.jobs, a.njobs);
+    Lc.launch(fused_fwd_kernel, dim3(fused_grid(h)), dim3(TC2_THREADS), TC_SMEM_BYTES, a);
+    Lc.check();
+}
+void launch_fused_bwd(Launcher& Lc, int l) {
+    vb_handle* h = Lc.h;
+    const Workspace& ws = h->ws;
+    FusedArgs a{};
+    a.layer = l; a.mw = h->mw; a.ws = ws;
+    fill_bwd_jobs(h->mw.layer[l], l, a.jobs, a.njobs);
+    float* set[2][3] = {{ws.GQKV, ws.GVNMSG, ws.GTU}, {ws.GQKV2, ws.GVNMSG2, ws.GTU2}};
+    const int pa = l & 1, pc = (l + 1) & 1;
+    a.acc_qkv = set[pa][0]; a.acc_vn = set[pa][1]; a.acc_tu = set[pa][2];
+    a.con_qkv = set[pc][0]; a.con_vn = set[pc][1]; a.con_tu = set[pc][2];
+    Lc.launch(fused_bwd_kernel, dim3(fused_grid(h)), dim3(TC2_THREADS), TC_SMEM_BYTES, a);
+    Lc.check();
+}
+
+void enqueue_finalize(Launcher& Lc, const StepIO& io) {
+    vb_handle* h = Lc.h;
+    const Workspace& ws = h->ws;
+    const bool prot = io.ef != nullptr;
+    const int fb = (ws.G + FIN_THREADS / 32 - 1) / (FIN_THREADS / 32);
+    const int pb = prot ? (h->n_protein + FIN_THREADS - 1) / FIN_THREADS : 0;
+    Lc.launch(finalize_kernel, dim3(fb + pb + (prot ? 1 : 0)), dim3(FIN_THREADS), 0, ws, h->mw.scalars, fb, pb, h->n_protein,
+              h->d_map_rowptr, h->d_map_src, h->d_map_sign, h->d_frag_sign, io.forces, io.energy, io.ef);
+    Lc.check();
+}
+
+// Enqueue one full evaluation (energy + forces [+ whole-protein reduction]) on Lc.st with the given I/O buffers.
+void enqueue_all(Launcher& Lc, const StepIO& io) {
     vb_handle* h = Lc.h;
     Workspace& ws = h->ws;
     const int N = ws.N;
     char name[64];
     if (Lc.next("nbr_build")) {
-        nbr_build_kernel<<<(N + 127) / 128, 128, 0, Lc.st>>>(N, h->d_pos, ws.frag_of, ws.frag_start, h->mw.cutoff,
-                                                           ws.slots, ws.deg, h->d_forces);
+        Lc.launch(nbr_build_kernel, dim3((N + 127) / 128), dim3(128), 0, N, io.pos, ws.frag_of, ws.frag_start, h->mw.cutoff,
+                  ws.slots, ws.deg, io.forces);
         Lc.check();
     }
-    if (Lc.next("rowptr_scan")) { Lc.launch(rowptr_scan_kernel, dim3(1), dim3(1024), 0, N, ws.deg, ws.rowptr); Lc.check(); }
-    if (Lc.next("edge_geom")) { Lc.launch(edge_geom_kernel, dim3((N + 3) / 4), dim3(128), 0, N, h->d_pos, h->mw, ws); Lc.check(); }
+    if (Lc.next("rowptr_scan")) { Lc.launch(rowptr_scan_kernel, dim3(1), dim3(1024), 0, N, ws.deg, ws.rowptr, ws.Ecap, h->d_flags); Lc.check(); }
+    if (Lc.next("edge_geom")) { Lc.launch(edge_geom_kernel, dim3((N + 3) / 4), dim3(128), 0, N, io.pos, h->mw, ws); Lc.check(); }
     if (Lc.next("embed_node")) { Lc.launch(embed_node_kernel, dim3(N), dim3(EMB_THREADS), 0, h->mw, ws); Lc.check(); }
     const int eblocks = std::max(1, std::min(ws.Ecap, h->sm_count * 16));
     if (Lc.next("embed_edge")) { Lc.launch(embed_edge_kernel, dim3(eblocks), dim3(128), 0, h->mw, ws); Lc.check(); }
-    for (int l = 0; l < L; l++) {
-        snprintf(name, sizeof(name), "node_fwd%d", l);
-        if (Lc.next(name)) node_fwd(Lc, l);
-        snprintf(name, sizeof(name), "edge_fwd%d", l);
-        if (Lc.next(name)) edge_fwd(Lc, l);
+    if (h->fused) {
+        // one launch per layer and direction: "fwdL" = edge stage L + node stage L+1, "bwdL" = node adjoint L+1 + edge adjoint L
+        if (Lc.next("node_fwd0")) launch_node_fwd2<4>(Lc, 0);
+        for (int l = 0; l < L; l++) {
+            snprintf(name, sizeof(name), "fwd%d", l);
+            if (Lc.next(name)) launch_fused_fwd(Lc, l);
+        }
+        if (Lc.next("head")) head(Lc);
+        for (int l = L - 1; l >= 0; l--) {
+            snprintf(name, sizeof(name), "bwd%d", l);
+            if (Lc.next(name)) launch_fused_bwd(Lc, l);
+        }
+        if (Lc.next("node_bwd0")) launch_node_bwd2<4>(Lc, 0);
+    } else {
+        for (int l = 0; l < L; l++) {
+            snprintf(name, sizeof(name), "node_fwd%d", l);
+            if (Lc.next(name)) node_fwd(Lc, l);
+            snprintf(name, sizeof(name), "edge_fwd%d", l);
+            if (Lc.next(name)) edge_fwd(Lc, l);
+        }
+        if (Lc.next("node_fwd6")) node_fwd(Lc, L);
+        if (Lc.next("head")) head(Lc);
+        for (int l = L - 1; l >= 0; l--) {
+            snprintf(name, sizeof(name), "node_bwd%d", l + 1);
+            if (Lc.next(name)) node_bwd(Lc, l + 1);
+            snprintf(name, sizeof(name), "edge_bwd%d", l);
+            if (Lc.next(name)) edge_bwd(Lc, l);
+        }
+        if (Lc.next("node_bwd0")) node_bwd(Lc, 0);
     }
-    if (Lc.next("node_fwd6")) node_fwd(Lc, L);
-    if (Lc.next("head")) head(Lc);
-    if (Lc.next("energy_reduce")) {
-        Lc.launch(energy_reduce_kernel, dim3((ws.G + 3) / 4), dim3(128), 0, ws, h->mw.scalars, h->d_energy);
-        Lc.check();
-    }
-    for (int l = L - 1; l >= 0; l--) {
-        snprintf(name, sizeof(name), "node_bwd%d", l + 1);
-        if (Lc.next(name)) node_bwd(Lc, l + 1);
-        snprintf(name, sizeof(name), "edge_bwd%d", l);
-        if (Lc.next(name)) edge_bwd(Lc, l);
-    }
-    if (Lc.next("node_bwd0")) node_bwd(Lc, 0);
     if (Lc.next("embed_edge_bwd")) {
         const int bb = std::max(1, std::min((ws.Ecap + EEB_WARPS - 1) / EEB_WARPS, h->sm_count * 4));
         Lc.launch(embed_edge_bwd_kernel, dim3(bb), dim3(EEB_WARPS * 32), 0, h->mw, ws);
         Lc.check();
     }
-    if (Lc.next("embed_node_bwd")) { Lc.launch(embed_node_bwd_kernel, dim3(N), dim3(ENB_WARPS * 32), 0, h->mw, ws, h->d_forces); Lc.check(); }
+    if (Lc.next("embed_node_bwd")) { Lc.launch(embed_node_bwd_kernel, dim3(N), dim3(ENB_WARPS * 32), 0, h->mw, ws, io.forces); Lc.check(); }
+    if (Lc.next("finalize")) enqueue_finalize(Lc, io);
 }
 
 template <typename K>
@@ -480,6 +609,8 @@ int configure_kernels(vb_handle* h) {
     CUDA_TRY(h, opt_in_smem(edge_bwd_tc_kernel<64>, TC_SMEM_BYTES));
     CUDA_TRY(h, opt_in_smem(edge_bwd_tc_kernel<96>, TC_SMEM_BYTES));
     CUDA_TRY(h, opt_in_smem(edge_bwd_tc_kernel<128>, TC_SMEM_BYTES));
+    CUDA_TRY(h, opt_in_smem(fused_fwd_kernel, TC_SMEM_BYTES));
+    CUDA_TRY(h, opt_in_smem(fused_bwd_kernel, TC_SMEM_BYTES));
 
     CUDA_TRY(h, opt_in_smem(node_fwd2_kernel<4>, sizeof(NodeFwd2Smem<4>)));
     CUDA_TRY(h, opt_in_smem(node_bwd2_kernel<4>, sizeof(NodeBwd2Smem<4>)));
@@ -489,60 +620,90 @@ int configure_kernels(vb_handle* h) {
     return VB_OK;
 }
 
-int ensure_graph_once(vb_handle* h) {
-    if (h->graph_exec) return VB_OK;
-    cudaGraph_t graph = nullptr;
-    CUDA_TRY(h, cudaStreamBeginCapture(h->own_stream, cudaStreamCaptureModeThreadLocal));
-    Launcher Lc{h, h->own_stream, -1, 0, false};
-    enqueue_all(Lc);
-    cudaError_t e_end = cudaStreamEndCapture(h->own_stream, &graph);
-    if (Lc.status != cudaSuccess || e_end != cudaSuccess) {
-        h->set_error("graph capture failed: %s / %s", cudaGetErrorString(Lc.status), cudaGetErrorString(e_end));
+// Accumulators that a producer stage adds into and the consuming stage re-zeroes: clean after a truncated diagnostic run.
+int clean_accumulators(vb_handle* h, cudaStream_t st) {
+    const Workspace& ws = h->ws;
+    const size_t N = ws.N;
+    CUDA_TRY(h, cudaMemsetAsync(ws.XA, 0, N * D * 4, st));
+    CUDA_TRY(h, cudaMemsetAsync(ws.VA, 0, N * 3 * D * 4, st));
+    CUDA_TRY(h, cudaMemsetAsync(ws.GQKV, 0, N * 3 * D * 4, st));
+    CUDA_TRY(h, cudaMemsetAsync(ws.GVNMSG, 0, N * 3 * D * 4, st));
+    CUDA_TRY(h, cudaMemsetAsync(ws.GTU, 0, N * 6 * D * 4, st));
+    CUDA_TRY(h, cudaMemsetAsync(ws.GQKV2, 0, N * 3 * D * 4, st));
+    CUDA_TRY(h, cudaMemsetAsync(ws.GVNMSG2, 0, N * 3 * D * 4, st));
+    CUDA_TRY(h, cudaMemsetAsync(ws.GTU2, 0, N * 6 * D * 4, st));
+    CUDA_TRY(h, cudaMemsetAsync(ws.GX, 0, N * D * 4, st));
+    CUDA_TRY(h, cudaMemsetAsync(ws.GXA, 0, N * D * 4, st));
+    h->accum_dirty = false;
+    return VB_OK;
+}
+
+enum { K_EVAL = 0, K_HOST = 1, K_MD_EVAL = 2, K_MD_STEP = 3 };
+
+// Run `enqueue(stream)` -- a sequence of launches / async copies that depends only on (kind, io) and the handle's
+// configuration -- either directly or as a replay of its cached CUDA graph.  A failed capture always ends the capture
+// (the stream stays usable) and is retried once without programmatic-dependent-launch edges.
+template <typename F>
+int run_cached(vb_handle* h, cudaStream_t st, int kind, const StepIO& io, F&& enqueue) {
+    if (h->accum_dirty) { if (int rc = clean_accumulators(h, st)) return rc; }
+    if (!h->use_graph) return enqueue(st);
+    for (auto& g : h->graphs)
+        if (g.kind == kind && g.io == io) { CUDA_TRY(h, cudaGraphLaunch(g.exec, st)); return VB_OK; }
+    cudaGraphExec_t exec = nullptr;
+    for (int attempt = 0; attempt < 2 && !exec; attempt++) {
+        cudaGraph_t graph = nullptr;
+        CUDA_TRY(h, cudaStreamBeginCapture(h->own_stream, cudaStreamCaptureModeThreadLocal));
+        const int rc = enqueue(h->own_stream);
+        const cudaError_t e_end = cudaStreamEndCapture(h->own_stream, &graph);
+        cudaError_t e_inst = cudaSuccess;
+        if (rc == VB_OK && e_end == cudaSuccess) e_inst = cudaGraphInstantiate(&exec, graph, 0);
         if (graph) cudaGraphDestroy(graph);
-        return VB_ERR_CUDA;
-    }
-    cudaError_t e_inst = cudaGraphInstantiate(&h->graph_exec, graph, 0);
-    cudaGraphDestroy(graph);
-    if (e_inst != cudaSuccess) {
-        h->set_error("cudaGraphInstantiate failed: %s", cudaGetErrorString(e_inst));
-        h->graph_exec = nullptr;
-        return VB_ERR_CUDA;
-    }
-    return VB_OK;
-}
-
-// Programmatic-dependent-launch edges inside a captured graph need a recent driver: if capture or instantiation fails
-// with them, fall back to plain launches once and remember the choice.
-int ensure_graph(vb_handle* h) {
-    int rc = ensure_graph_once(h);
-    if (rc != VB_OK && h->use_pdl) {
-        h->use_pdl = 0;
+        if (rc == VB_OK && e_end == cudaSuccess && e_inst == cudaSuccess) break;
+        exec = nullptr;
         (void)cudaGetLastError();
-        rc = ensure_graph_once(h);
+        if (h->use_pdl && attempt == 0) { h->use_pdl = 0; continue; }
+        if (rc == VB_OK) h->set_error("graph capture failed: %s / %s", cudaGetErrorString(e_end), cudaGetErrorString(e_inst));
+        return VB_ERR_CUDA;
     }
-    return rc;
+    if (h->graphs.size() >= 8) { cudaGraphExecDestroy(h->graphs.front().exec); h->graphs.erase(h->graphs.begin()); }
+    h->graphs.push_back({kind, io, exec});
+    CUDA_TRY(h, cudaGraphLaunch(exec, st));
+    return VB_OK;
 }
 
-// core evaluation on internal buffers, asynchronous on st
-int run_core(vb_handle* h, cudaStream_t st) {
-    if (h->use_graph) {
-        int rc = ensure_graph(h);
-        if (rc != VB_OK) return rc;
-        CUDA_TRY(h, cudaGraphLaunch(h->graph_exec, st));
-    } else {
-        Launcher Lc{h, st, -1, 0, false};
-        enqueue_all(Lc);
-        if (Lc.status != cudaSuccess) {
-            h->set_error("kernel launch failed: %s", cudaGetErrorString(Lc.status));
-            return VB_ERR_CUDA;
-        }
-    }
+int enqueue_eval(vb_handle* h, cudaStream_t st, const StepIO& io) {
+    Launcher Lc{h, st, -1, 0, false};
+    enqueue_all(Lc, io);
+    if (Lc.status != cudaSuccess) { h->set_error("kernel launch failed: %s", cudaGetErrorString(Lc.status)); return VB_ERR_CUDA; }
     return VB_OK;
+}
+
+// one evaluation on the given buffers, asynchronous on st
+int run_eval(vb_handle* h, cudaStream_t st, const StepIO& io) {
+    return run_cached(h, st, K_EVAL, io, [&](cudaStream_t s) -> int { return enqueue_eval(h, s, io); });
+}
+
+StepIO internal_io(vb_handle* h, bool protein) {
+    StepIO io;
+    io.pos = h->d_pos; io.energy = h->d_energy; io.forces = h->d_forces;
+    io.ef = protein ? h->d_ef : nullptr;
+    return io;
+}
+
+// stage names / launch count of one evaluation under the current options (nothing is launched)
+void record_stages(vb_handle* h) {
+    h->stage_names.clear();
+    Launcher Lc{h, nullptr, 0, 0, true};
+    enqueue_all(Lc, internal_io(h, false));
+    h->launches = (int)h->stage_names.size();
 }
 
 void choose_defaults(vb_handle* h) {
     const int N = h->ws.N;
     h->npw = h->npw_opt; h->te_fwd = h->te_fwd_opt; h->edge_tc = h->edge_tc_opt;
+    // fused per-layer launches while the 4-node blocks fit one or two waves of CTAs (latency-bound sizes); larger
+    // batches keep the separate stages with dense 128-edge tiles
+    h->fused = h->fused_opt >= 0 ? h->fused_opt : (((N + FU_NB - 1) / FU_NB <= 2 * h->sm_count) ? 1 : 0);
     if (h->npw == 0) h->npw = (N > 4096) ? 2 : 1;
     if (h->te_fwd == 0) h->te_fwd = ((long long)N * 17 / 64 >= 2LL * h->sm_count) ? 64 : 32;
     // tcgen05 edge kernels (one tile per CTA, 16 compute warps): with the tile length chosen below both stages beat
@@ -626,6 +787,7 @@ int vb_create(const float* weights_host, size_t n_floats, const vb_hparams* hp, 
     if (const char* s = getenv("VB_USE_PDL")) h->use_pdl = atoi(s) ? 1 : 0;
     if (const char* s = getenv("VB_TC_ROWS")) { const int v = atoi(s); if (v == 32 || v == 64 || v == 96 || v == 128) h->tc_rows_opt = v; }
     if (const char* s = getenv("VB_NODE_IMPL")) h->node_impl = atoi(s);
+    if (const char* s = getenv("VB_FUSED")) h->fused_opt = atoi(s) ? 1 : 0;
     *out = h;
     return VB_OK;
 }
@@ -640,7 +802,8 @@ void vb_destroy(vb_handle* h) {
     h->free_md();
     h->free_nb();
     cudaFree(h->arena);
-    cudaFree(h->d_map_src); cudaFree(h->d_map_dst); cudaFree(h->d_map_sign); cudaFree(h->d_frag_sign);
+    h->free_map();
+    cudaFree(h->d_flags);
     cudaFreeHost(h->h_pos); cudaFreeHost(h->h_energy); cudaFreeHost(h->h_forces);
     delete h;
 }
@@ -669,6 +832,7 @@ int vb_set_topology(vb_handle* h, int64_t n_atoms, int64_t n_graphs, const int64
     CUDA_TRY(h, cudaSetDevice(h->device));
     h->drop_graph();
     h->free_md();                 // the MD recipe indexes the fragment atoms of the old topology
+    h->free_map();                // ... and so does the protein map: it must be set again
     h->has_topology = false;
     cudaFree(h->arena); h->arena = nullptr;
     cudaFreeHost(h->h_pos); cudaFreeHost(h->h_energy); cudaFreeHost(h->h_forces);
@@ -692,6 +856,8 @@ int vb_set_topology(vb_handle* h, int64_t n_atoms, int64_t n_graphs, const int64
     layout_workspace(h, h->arena, real, dz, dfo, dfs);
     h->ws.z = dz; h->ws.frag_of = dfo; h->ws.frag_start = dfs;
     CUDA_TRY(h, cudaMemset(h->arena, 0, h->arena_bytes));
+    if (!h->d_flags) CUDA_TRY(h, cudaMalloc(&h->d_flags, sizeof(int) * 4));
+    CUDA_TRY(h, cudaMemset(h->d_flags, 0, sizeof(int) * 4));
     CUDA_TRY(h, cudaMemcpy(dz, z.data(), sizeof(int) * n_atoms, cudaMemcpyHostToDevice));
     CUDA_TRY(h, cudaMemcpy(dfo, frag_of.data(), sizeof(int) * n_atoms, cudaMemcpyHostToDevice));
     CUDA_TRY(h, cudaMemcpy(dfs, frag_start.data(), sizeof(int) * (n_graphs + 1), cudaMemcpyHostToDevice));
@@ -699,11 +865,7 @@ int vb_set_topology(vb_handle* h, int64_t n_atoms, int64_t n_graphs, const int64
     CUDA_TRY(h, cudaMallocHost(&h->h_forces, sizeof(float) * 3 * n_atoms));
     CUDA_TRY(h, cudaMallocHost(&h->h_energy, sizeof(float) * n_graphs));
     choose_defaults(h);
-    // record stage names / launch count
-    h->stage_names.clear();
-    Launcher Lc{h, nullptr, 0, 0, true};
-    enqueue_all(Lc);
-    h->launches = (int)h->stage_names.size();
+    record_stages(h);
     h->has_topology = true;
     return VB_OK;
 }
@@ -713,15 +875,24 @@ int vb_forward(vb_handle* h, const float* pos_dev, float* energy_dev, float* for
     std::lock_guard<std::mutex> lk(h->mu);
     if (!h->has_topology) { h->set_error("vb_forward: call vb_set_topology first"); return VB_ERR_STATE; }
     if (!pos_dev || !energy_dev || !forces_dev) { h->set_error("vb_forward: null buffer"); return VB_ERR_ARG; }
-    cudaStream_t st = (cudaStream_t)stream;
     CUDA_TRY(h, cudaSetDevice(h->device));
-    CUDA_TRY(h, cudaMemcpyAsync(h->d_pos, pos_dev, sizeof(float) * 3 * h->ws.N, cudaMemcpyDeviceToDevice, st));
-    int rc = run_core(h, st);
-    if (rc != VB_OK) return rc;
-    CUDA_TRY(h, cudaMemcpyAsync(energy_dev, h->d_energy, sizeof(float) * h->ws.G, cudaMemcpyDeviceToDevice, st));
-    CUDA_TRY(h, cudaMemcpyAsync(forces_dev, h->d_forces, sizeof(float) * 3 * h->ws.N, cudaMemcpyDeviceToDevice, st));
+    StepIO io;
+    io.pos = pos_dev; io.energy = energy_dev; io.forces = forces_dev;
+    return run_eval(h, (cudaStream_t)stream, io);     // the kernels read / write the caller's buffers directly
+}
+
+namespace {
+int check_edge_overflow(vb_handle* h, const char* who) {
+    if ((int64_t)h->ws.Ecap >= (int64_t)h->ws.N * KNB) return VB_OK;      // worst-case capacity: cannot overflow
+    int flag = 0;
+    CUDA_TRY(h, cudaMemcpy(&flag, h->d_flags, sizeof(int), cudaMemcpyDeviceToHost));
+    if (flag) {
+        h->set_error("%s: a step produced more edges than the max_edges = %d given to vb_set_topology (results invalid)", who, h->ws.Ecap);
+        return VB_ERR_STATE;
+    }
     return VB_OK;
 }
+}  // namespace
 
 int vb_forward_host(vb_handle* h, const float* pos_host, float* energy_host, float* forces_host) {
     if (!h) return VB_ERR_ARG;
@@ -732,20 +903,18 @@ int vb_forward_host(vb_handle* h, const float* pos_host, float* energy_host, flo
     cudaStream_t st = h->own_stream;
     CUDA_TRY(h, cudaSetDevice(h->device));
     memcpy(h->h_pos, pos_host, sizeof(float) * 3 * N);
-    CUDA_TRY(h, cudaMemcpyAsync(h->d_pos, h->h_pos, sizeof(float) * 3 * N, cudaMemcpyHostToDevice, st));
-    int rc = run_core(h, st);
+    // H2D of the positions, every kernel, D2H of energies and forces: one graph replay (pinned staging buffers are fixed)
+    const StepIO io = internal_io(h, false);
+    int rc = run_cached(h, st, K_HOST, io, [&](cudaStream_t s) -> int {
+        CUDA_TRY(h, cudaMemcpyAsync(h->d_pos, h->h_pos, sizeof(float) * 3 * N, cudaMemcpyHostToDevice, s));
+        if (int r = enqueue_eval(h, s, io)) return r;
+        CUDA_TRY(h, cudaMemcpyAsync(h->h_energy, h->d_energy, sizeof(float) * G, cudaMemcpyDeviceToHost, s));
+        CUDA_TRY(h, cudaMemcpyAsync(h->h_forces, h->d_forces, sizeof(float) * 3 * N, cudaMemcpyDeviceToHost, s));
+        return (int)VB_OK;
+    });
     if (rc != VB_OK) return rc;
-    CUDA_TRY(h, cudaMemcpyAsync(h->h_energy, h->d_energy, sizeof(float) * G, cudaMemcpyDeviceToHost, st));
-    CUDA_TRY(h, cudaMemcpyAsync(h->h_forces, h->d_forces, sizeof(float) * 3 * N, cudaMemcpyDeviceToHost, st));
     CUDA_TRY(h, cudaStreamSynchronize(st));
-    if ((int64_t)h->ws.Ecap < (int64_t)N * KNB) {      // caller-trimmed edge capacity is a promise: verify it on this synchronous path
-        int n_edges = 0;
-        CUDA_TRY(h, cudaMemcpy(&n_edges, h->ws.rowptr + N, sizeof(int), cudaMemcpyDeviceToHost));
-        if (n_edges > h->ws.Ecap) {
-            h->set_error("vb_forward_host: %d edges exceed the max_edges = %d given to vb_set_topology (results invalid)", n_edges, h->ws.Ecap);
-            return VB_ERR_STATE;
-        }
-    }
+    if (int r = check_edge_overflow(h, "vb_forward_host")) return r;
     memcpy(energy_host, h->h_energy, sizeof(float) * G);
     memcpy(forces_host, h->h_forces, sizeof(float) * 3 * N);
     return VB_OK;
@@ -756,7 +925,8 @@ int vb_set_protein_map(vb_handle* h, int64_t n_protein_atoms, int64_t n_map, con
     if (!h) return VB_ERR_ARG;
     std::lock_guard<std::mutex> lk(h->mu);
     if (!h->has_topology) { h->set_error("vb_set_protein_map: call vb_set_topology first"); return VB_ERR_STATE; }
-    if (n_protein_atoms <= 0 || n_map < 0 || !frag_sign_host || (n_map > 0 && (!src_atom_host || !dst_atom_host || !sign_host))) {
+    if (n_protein_atoms <= 0 || n_protein_atoms > (1 << 28) || n_map < 0 || !frag_sign_host ||
+        (n_map > 0 && (!src_atom_host || !dst_atom_host || !sign_host))) {
         h->set_error("vb_set_protein_map: bad arguments");
         return VB_ERR_ARG;
     }
@@ -766,21 +936,36 @@ int vb_set_protein_map(vb_handle* h, int64_t n_protein_atoms, int64_t n_map, con
             return VB_ERR_ARG;
         }
     }
-    CUDA_TRY(h, cudaSetDevice(h->device));
-    cudaFree(h->d_map_src); cudaFree(h->d_map_dst); cudaFree(h->d_map_sign); cudaFree(h->d_frag_sign);
-    h->d_map_src = h->d_map_dst = nullptr; h->d_map_sign = h->d_frag_sign = nullptr;
-    const size_t nm = (size_t)std::max<int64_t>(n_map, 1);
-    CUDA_TRY(h, cudaMalloc(&h->d_map_src, sizeof(int) * nm));
-    CUDA_TRY(h, cudaMalloc(&h->d_map_dst, sizeof(int) * nm));
-    CUDA_TRY(h, cudaMalloc(&h->d_map_sign, sizeof(float) * nm));
-    CUDA_TRY(h, cudaMalloc(&h->d_frag_sign, sizeof(float) * h->ws.G));
-    if (n_map > 0) {
-        CUDA_TRY(h, cudaMemcpy(h->d_map_src, src_atom_host, sizeof(int) * n_map, cudaMemcpyHostToDevice));
-        CUDA_TRY(h, cudaMemcpy(h->d_map_dst, dst_atom_host, sizeof(int) * n_map, cudaMemcpyHostToDevice));
-        CUDA_TRY(h, cudaMemcpy(h->d_map_sign, sign_host, sizeof(float) * n_map, cudaMemcpyHostToDevice));
+    // CSR over destination atoms (entries of one atom keep their order in the map): the reduction is a gather
+    const int P = (int)n_protein_atoms;
+    std::vector<int> rowptr(P + 1, 0), src(std::max<int64_t>(n_map, 1));
+    std::vector<float> sgn(std::max<int64_t>(n_map, 1));
+    for (int64_t m = 0; m < n_map; m++) rowptr[dst_atom_host[m] + 1]++;
+    for (int p = 0; p < P; p++) rowptr[p + 1] += rowptr[p];
+    {
+        std::vector<int> fill(rowptr.begin(), rowptr.end() - 1);
+        for (int64_t m = 0; m < n_map; m++) {
+            const int k = fill[dst_atom_host[m]]++;
+            src[k] = src_atom_host[m];
+            sgn[k] = sign_host[m];
+        }
     }
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    CUDA_TRY(h, cudaDeviceSynchronize());
+    h->drop_graph();              // captured launches hold the old map pointers / n_protein
+    h->free_md();                 // the MD state is sized by n_protein
+    h->free_map();
+    CUDA_TRY(h, cudaMalloc(&h->d_map_rowptr, sizeof(int) * (P + 1)));
+    CUDA_TRY(h, cudaMalloc(&h->d_map_src, sizeof(int) * src.size()));
+    CUDA_TRY(h, cudaMalloc(&h->d_map_sign, sizeof(float) * sgn.size()));
+    CUDA_TRY(h, cudaMalloc(&h->d_frag_sign, sizeof(float) * h->ws.G));
+    CUDA_TRY(h, cudaMalloc(&h->d_ef, sizeof(float) * (3 * (size_t)P + 1)));
+    CUDA_TRY(h, cudaMemcpy(h->d_map_rowptr, rowptr.data(), sizeof(int) * (P + 1), cudaMemcpyHostToDevice));
+    CUDA_TRY(h, cudaMemcpy(h->d_map_src, src.data(), sizeof(int) * src.size(), cudaMemcpyHostToDevice));
+    CUDA_TRY(h, cudaMemcpy(h->d_map_sign, sgn.data(), sizeof(float) * sgn.size(), cudaMemcpyHostToDevice));
     CUDA_TRY(h, cudaMemcpy(h->d_frag_sign, frag_sign_host, sizeof(float) * h->ws.G, cudaMemcpyHostToDevice));
-    h->n_protein = (int)n_protein_atoms;
+    CUDA_TRY(h, cudaMemset(h->d_ef, 0, sizeof(float) * (3 * (size_t)P + 1)));
+    h->n_protein = P;
     h->n_map = (int)n_map;
     return VB_OK;
 }
@@ -790,39 +975,24 @@ int vb_forward_protein(vb_handle* h, const float* pos_dev, float* ef_prot_dev, v
     std::lock_guard<std::mutex> lk(h->mu);
     if (!h->has_topology || h->n_protein <= 0) { h->set_error("vb_forward_protein: topology / protein map not set"); return VB_ERR_STATE; }
     if (!pos_dev || !ef_prot_dev) { h->set_error("vb_forward_protein: null buffer"); return VB_ERR_ARG; }
-    cudaStream_t st = (cudaStream_t)stream;
     CUDA_TRY(h, cudaSetDevice(h->device));
-    CUDA_TRY(h, cudaMemcpyAsync(h->d_pos, pos_dev, sizeof(float) * 3 * h->ws.N, cudaMemcpyDeviceToDevice, st));
-    int rc = run_core(h, st);
-    if (rc != VB_OK) return rc;
-    CUDA_TRY(h, cudaMemsetAsync(ef_prot_dev, 0, sizeof(float) * (3 * (size_t)h->n_protein + 1), st));
-    if (h->n_map > 0)
-        protein_scatter_kernel<<<(h->n_map + 255) / 256, 256, 0, st>>>(h->n_map, h->d_map_src, h->d_map_dst,
-                                                                      h->d_map_sign, h->d_forces, ef_prot_dev);
-    protein_energy_kernel<<<1, 32, 0, st>>>(h->ws.G, h->d_frag_sign, h->d_energy, ef_prot_dev + 3 * (size_t)h->n_protein);
-    CUDA_TRY(h, cudaGetLastError());
-    return VB_OK;
+    StepIO io = internal_io(h, false);
+    io.pos = pos_dev; io.ef = ef_prot_dev;            // the signed reduction is the evaluation's last launch
+    return run_eval(h, (cudaStream_t)stream, io);
 }
 
 // ---- device-resident MD (k_md.cuh) ---------------------------------------------------------------------
 namespace {
-// fragment placement -> core evaluation -> signed whole-protein reduction, all on st (inline launches: usable under capture)
-int md_eval_enqueue(vb_handle* h, cudaStream_t st, bool inline_core) {
+StepIO md_io(vb_handle* h) {
+    StepIO io = internal_io(h, false);
+    io.ef = h->md_ef;
+    return io;
+}
+// fragment placement -> evaluation + signed whole-protein reduction [-> non-bonded term], all on st
+int md_eval_enqueue(vb_handle* h, cudaStream_t st) {
     const int N = h->ws.N;
     md_place_kernel<<<(N + 255) / 256, 256, 0, st>>>(N, h->d_real, h->d_acc, h->d_rem, h->d_blen, h->d_mx, h->d_pos);
-    if (inline_core) {
-        Launcher Lc{h, st, -1, 0, false};
-        enqueue_all(Lc);
-        if (Lc.status != cudaSuccess) { h->set_error("kernel launch failed: %s", cudaGetErrorString(Lc.status)); return VB_ERR_CUDA; }
-    } else {
-        int rc = run_core(h, st);
-        if (rc != VB_OK) return rc;
-    }
-    CUDA_TRY(h, cudaMemsetAsync(h->md_ef, 0, sizeof(float) * (3 * (size_t)h->n_protein + 1), st));
-    if (h->n_map > 0)
-        protein_scatter_kernel<<<(h->n_map + 255) / 256, 256, 0, st>>>(h->n_map, h->d_map_src, h->d_map_dst, h->d_map_sign,
-                                                                      h->d_forces, h->md_ef);
-    protein_energy_kernel<<<1, 32, 0, st>>>(h->ws.G, h->d_frag_sign, h->d_energy, h->md_ef + 3 * (size_t)h->n_protein);
+    if (int rc = enqueue_eval(h, st, md_io(h))) return rc;
     if (h->nb_ready && h->nb.hi > h->nb.lo) {      // non-bonded MM term on the same protein coordinates
         nonbonded_kernel<double><<<(h->nb.hi - h->nb.lo + 7) / 8, 256, 0, st>>>(h->nb, h->d_mx, h->md_ef, h->d_nb_eatom);
         nonbonded_energy_kernel<<<1, 256, 0, st>>>(h->nb, h->d_nb_eatom, h->md_ef);
@@ -831,8 +1001,7 @@ int md_eval_enqueue(vb_handle* h, cudaStream_t st, bool inline_core) {
     return VB_OK;
 }
 void md_kick1_enqueue(vb_handle* h, cudaStream_t st) {
-    const int n3 = 3 * h->n_protein;
-    md_kick1_kernel<<<(n3 + 255) / 256, 256, 0, st>>>(h->md, h->d_step, h->d_mmass, h->md_ef, h->d_mx, h->d_mv);
+    md_kick1_kernel<<<1, MD_K1_THREADS, 0, st>>>(h->md, h->d_step, h->d_mmass, h->md_ef, h->d_mx, h->d_mv);
 }
 void md_kick2_enqueue(vb_handle* h, cudaStream_t st) {
     md_kick2_kernel<<<1, MD_K2_THREADS, 0, st>>>(h->md, h->d_step, h->d_mmass, h->md_ef, h->d_mv, h->d_ehist, h->ehist_cap);
@@ -922,7 +1091,7 @@ int vb_md_eval(vb_handle* h, void* stream) {
     std::lock_guard<std::mutex> lk(h->mu);
     if (int rc = md_check(h, "vb_md_eval")) return rc;
     CUDA_TRY(h, cudaSetDevice(h->device));
-    return md_eval_enqueue(h, (cudaStream_t)stream, false);
+    return run_cached(h, (cudaStream_t)stream, K_MD_EVAL, md_io(h), [&](cudaStream_t s) -> int { return md_eval_enqueue(h, s); });
 }
 
 int vb_md_kick1(vb_handle* h, void* stream) {
@@ -952,37 +1121,15 @@ int vb_md_run(vb_handle* h, int64_t n_steps, void* stream) {
     if (n_steps < 0) { h->set_error("vb_md_run: negative step count"); return VB_ERR_ARG; }
     cudaStream_t st = (cudaStream_t)stream;
     CUDA_TRY(h, cudaSetDevice(h->device));
-    if (h->use_graph && !h->md_graph) {
-        for (int attempt = 0; attempt < 2 && !h->md_graph; attempt++) {
-            cudaGraph_t graph = nullptr;
-            CUDA_TRY(h, cudaStreamBeginCapture(h->own_stream, cudaStreamCaptureModeThreadLocal));
-            md_kick1_enqueue(h, h->own_stream);
-            int rc = md_eval_enqueue(h, h->own_stream, true);
-            md_kick2_enqueue(h, h->own_stream);
-            cudaError_t e_end = cudaStreamEndCapture(h->own_stream, &graph);
-            cudaError_t e_inst = cudaSuccess;
-            if (rc == VB_OK && e_end == cudaSuccess) e_inst = cudaGraphInstantiate(&h->md_graph, graph, 0);
-            if (graph) cudaGraphDestroy(graph);
-            if (rc == VB_OK && e_end == cudaSuccess && e_inst == cudaSuccess) break;
-            h->md_graph = nullptr;
-            if (h->use_pdl && attempt == 0) {          // retry once without programmatic launch edges
-                h->use_pdl = 0;
-                (void)cudaGetLastError();
-                continue;
-            }
-            if (rc == VB_OK) h->set_error("MD graph capture failed: %s / %s", cudaGetErrorString(e_end), cudaGetErrorString(e_inst));
-            return VB_ERR_CUDA;
-        }
-    }
-    for (int64_t s = 0; s < n_steps; s++) {
-        if (h->use_graph) {
-            CUDA_TRY(h, cudaGraphLaunch(h->md_graph, st));
-        } else {
-            md_kick1_enqueue(h, st);
-            if (int rc = md_eval_enqueue(h, st, true)) return rc;
-            md_kick2_enqueue(h, st);
+    for (int64_t s = 0; s < n_steps; s++) {          // one graph replay per step
+        int rc = run_cached(h, st, K_MD_STEP, md_io(h), [&](cudaStream_t cs) -> int {
+            md_kick1_enqueue(h, cs);
+            if (int r = md_eval_enqueue(h, cs)) return r;
+            md_kick2_enqueue(h, cs);
             CUDA_TRY(h, cudaGetLastError());
-        }
+            return (int)VB_OK;
+        });
+        if (rc != VB_OK) return rc;
     }
     return VB_OK;
 }
@@ -1105,6 +1252,7 @@ int vb_set_option(vb_handle* h, const char* key, int64_t value) {
     else if (k == "edge_tc" && value >= 0 && value <= 3) h->edge_tc = h->edge_tc_opt = (int)value;
     else if (k == "tc_rows" && (value == 32 || value == 64 || value == 96 || value == 128)) h->tc_rows = h->tc_rows_opt = (int)value;
     else if (k == "node_impl" && (value == 0 || value == 1)) h->node_impl = (int)value;
+    else if (k == "fused" && (value == 0 || value == 1)) h->fused = h->fused_opt = (int)value;
     else if (k == "timeline" && (value == 0 || value == 1)) {
         if (value && !h->d_tl) {
             if (cudaSetDevice(h->device) != cudaSuccess || cudaMalloc(&h->d_tl, sizeof(unsigned long long) * 2 * L * TC_TL_SLOTS) != cudaSuccess) {
@@ -1116,6 +1264,7 @@ int vb_set_option(vb_handle* h, const char* key, int64_t value) {
     }
     else { h->set_error("vb_set_option: unknown key or bad value: %s", key); return VB_ERR_ARG; }
     h->drop_graph();
+    if (h->has_topology) record_stages(h);
     return VB_OK;
 }
 
@@ -1129,6 +1278,12 @@ int64_t vb_get_option(const vb_handle* h, const char* key) {
     if (k == "te_bwd") return h->te_bwd;
     if (k == "edge_tc") return h->edge_tc;
     if (k == "node_impl") return h->node_impl;
+    if (k == "fused") return h->fused;
+    if (k == "edge_overflow") {
+        int flag = 0;
+        if (h->d_flags && cudaMemcpy(&flag, h->d_flags, sizeof(int), cudaMemcpyDeviceToHost) != cudaSuccess) return VB_ERR_CUDA;
+        return flag;
+    }
     if (k == "timeline") return h->timeline;
     if (k == "tc_rows") return h->tc_rows;
     if (k == "n_edges_capacity") return h->ws.Ecap;
@@ -1147,10 +1302,12 @@ int vb_debug_run(vb_handle* h, const float* pos_dev, int n_stages) {
     if (!h->has_topology || !pos_dev) { h->set_error("vb_debug_run: bad state/arguments"); return VB_ERR_STATE; }
     CUDA_TRY(h, cudaSetDevice(h->device));
     CUDA_TRY(h, cudaMemcpy(h->d_pos, pos_dev, sizeof(float) * 3 * h->ws.N, cudaMemcpyDeviceToDevice));
+    if (h->accum_dirty) { if (int rc = clean_accumulators(h, h->own_stream)) return rc; }
     Launcher Lc{h, h->own_stream, n_stages, 0, false};
-    enqueue_all(Lc);
+    enqueue_all(Lc, internal_io(h, h->n_protein > 0));
     if (Lc.status != cudaSuccess) { h->set_error("debug launch failed: %s", cudaGetErrorString(Lc.status)); return VB_ERR_CUDA; }
     CUDA_TRY(h, cudaStreamSynchronize(h->own_stream));
+    h->accum_dirty = n_stages >= 0 && n_stages < (int)h->stage_names.size();   // a consumer stage may not have re-zeroed its accumulators
     return VB_OK;
 }
 
@@ -1168,7 +1325,7 @@ int vb_profile_stages(vb_handle* h, const float* pos_dev, int n_iter, float* ms_
     for (int it = 0; it < n_iter + 1 && rc == VB_OK; it++) {      // iteration 0 is an untimed warm-up
         Launcher Lc{h, h->own_stream, -1, 0, false};
         Lc.events = &ev;
-        enqueue_all(Lc);
+        enqueue_all(Lc, internal_io(h, h->n_protein > 0));
         cudaEventRecord(ev[ns], h->own_stream);
         if (Lc.status != cudaSuccess || cudaStreamSynchronize(h->own_stream) != cudaSuccess) {
             h->set_error("vb_profile_stages: launch failed: %s", cudaGetErrorString(cudaGetLastError()));
@@ -1248,6 +1405,9 @@ int64_t vb_debug_read(vb_handle* h, const char* name, int layer, void* host_dst,
     else BUF("GQKV", ws.GQKV, N * 3 * D, 4)
     else BUF("GVNMSG", ws.GVNMSG, N * 3 * D, 4)
     else BUF("GTU", ws.GTU, N * 6 * D, 4)
+    else BUF("GQKV2", ws.GQKV2, N * 3 * D, 4)
+    else BUF("GVNMSG2", ws.GVNMSG2, N * 3 * D, 4)
+    else BUF("GTU2", ws.GTU2, N * 6 * D, 4)
     else BUF("geom", ws.geom, E * 8, 4)
     else BUF("rbf", ws.rbf, E * NR, 4)
     else BUF("eacc", ws.eacc, E * 4, 4)

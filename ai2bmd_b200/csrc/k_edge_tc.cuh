@@ -23,6 +23,7 @@ constexpr int TC_STAGES = 4;
 constexpr int TC_MAXJOBS = 12;
 constexpr int TC_THREADS = 192;
 constexpr int TC_LT = D + LDS_PAD;   // padded row length of the staging tile (132 floats)
+constexpr int TC_TILE_EXT = 1792;    // floats appended to the staging tile for the fused kernels' node stage (7 KB)
 
 // TMEM column map (512 columns): A hi plane, A lo plane, two accumulators
 constexpr uint32_t TC_COL_AHI = 0, TC_COL_ALO = 128, TC_COL_D0 = 256, TC_COL_D1 = 384;
@@ -36,6 +37,7 @@ struct TcJob {
 struct TcShared {
     alignas(1024) uint8_t ring[TC_STAGES][tc::STAGE_BYTES];
     alignas(16) float tile[TC_TE][TC_LT];
+    float tile_ext[TC_TILE_EXT];        // fused kernels (k_fused.cuh): the node stage's shared rows start at `tile` and may run on into here
     EdgeMeta<TC_TE> meta;
     alignas(8) uint64_t b_full[TC_STAGES];
     uint64_t b_empty[TC_STAGES];
@@ -43,7 +45,6 @@ struct TcShared {
     uint64_t done[TC_MAXJOBS];
     uint32_t tmem_base;
     alignas(16) float eacc[TC_TE][4];   // per-edge adjoint scalars of the current tile: dE/dC, dE/dd[3]
-    float attn[TC_TE][H];               // adjoint kernel: attention pre-activation a_h per edge
     float gattn[TC_TE][H];              // adjoint kernel: dE/da_h per edge
 };
 

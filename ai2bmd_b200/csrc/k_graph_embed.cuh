@@ -39,8 +39,10 @@ __global__ void __launch_bounds__(128) nbr_build_kernel(int N, const float* __re
 }
 
 // K2: exclusive scan of deg -> rowptr (single block; N is small enough that this is latency only).
+// A total above the workspace's edge capacity (a caller-trimmed max_edges that a step exceeded) raises flags[0]; the
+// row pointers are clamped to the capacity, so nothing is written out of bounds and the host can report the overflow.
 __global__ void __launch_bounds__(1024) rowptr_scan_kernel(int N, const int* __restrict__ deg,
-                                                           int* __restrict__ rowptr) {
+                                                           int* __restrict__ rowptr, int ecap, int* __restrict__ flags) {
     pdl_entry();
     __shared__ int wsum[32];
     __shared__ int carry_s;
@@ -70,12 +72,15 @@ __global__ void __launch_bounds__(1024) rowptr_scan_kernel(int N, const int* __r
         __syncthreads();
         const int carry = carry_s;
         const int excl = carry + (warp ? wsum[warp - 1] : 0) + incl - v;
-        if (i < N) rowptr[i] = excl;
+        if (i < N) rowptr[i] = min(excl, ecap);
         __syncthreads();
         if (tid == 1023) carry_s = carry + wsum[31];
         __syncthreads();
     }
-    if (tid == 0) rowptr[N] = carry_s;
+    if (tid == 0) {
+        rowptr[N] = min(carry_s, ecap);
+        if (carry_s > ecap) flags[0] = 1;
+    }
 }
 
 // K3: per-edge geometry + RBF.  One warp per target atom, lane k = neighbour slot k.
@@ -102,11 +107,13 @@ __global__ void __launch_bounds__(128) edge_geom_kernel(int N, const float* __re
             inv_r = __fdiv_rn(1.0f, r);
         }
         C = cutoff_fn(r, mw.cutoff);
-        ws.esrc[e] = j;
-        ws.edst[e] = i;
-        st4(ws.geom + (size_t)e * 8, f4(r, C, dx, dy));
-        st4(ws.geom + (size_t)e * 8 + 4, f4(dz, inv_r, 0.f, 0.f));
-        st4(ws.eacc + (size_t)e * 4, f4s(0.f));
+        if (e < ws.Ecap) {                // beyond a trimmed capacity: dropped (rowptr_scan raised the overflow flag)
+            ws.esrc[e] = j;
+            ws.edst[e] = i;
+            st4(ws.geom + (size_t)e * 8, f4(r, C, dx, dy));
+            st4(ws.geom + (size_t)e * 8 + 4, f4(dz, inv_r, 0.f, 0.f));
+            st4(ws.eacc + (size_t)e * 4, f4s(0.f));
+        }
     }
     const float mu = __ldg(mw.rbf_means + lane), beta = __ldg(mw.rbf_betas + lane);
     const float alpha = 5.0f / mw.cutoff;
@@ -114,7 +121,7 @@ __global__ void __launch_bounds__(128) edge_geom_kernel(int N, const float* __re
         const float rk = __shfl_sync(0xffffffffu, r, k);
         const float Ck = __shfl_sync(0xffffffffu, C, k);
         const float t = expf(-alpha * rk) - mu;
-        ws.rbf[(size_t)(e0 + k) * NR + lane] = Ck * expf(-beta * t * t);
+        if (e0 + k < ws.Ecap) ws.rbf[(size_t)(e0 + k) * NR + lane] = Ck * expf(-beta * t * t);
     }
 }
 

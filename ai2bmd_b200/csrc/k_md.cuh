@@ -64,23 +64,67 @@ __device__ inline MdCoef md_coef(const MdParams& p, double mass) {
     return c;
 }
 
-// first half-kick + drift: one thread per Cartesian component
-__global__ void md_kick1_kernel(MdParams p, const long long* __restrict__ step_ctr, const double* __restrict__ mass,
-                                const float* __restrict__ ef, double* __restrict__ x, double* __restrict__ v) {
-    const int comp = blockIdx.x * blockDim.x + threadIdx.x;
-    if (comp >= 3 * p.n_protein) return;
-    const double m = mass[comp / 3];
-    const MdCoef c = md_coef(p, m);
-    double xi = 0.0, eta = 0.0;
-    if (p.fr > 0.0) md_normals(p, *step_ctr, comp, xi, eta);
-    const double f = (double)ef[comp];
-    double vv = v[comp];
-    vv = vv + (c.c1 * f / m - c.c2 * vv + c.c3 * xi - c.c4 * eta);
-    const double x_old = x[comp];
-    const double x_new = x_old + p.dt * vv + c.c5 * eta;
-    vv = (x_new - x_old - c.c5 * eta) / p.dt;
-    x[comp] = x_new;
-    v[comp] = vv;
+// first half-kick + drift (ase/md/langevin.py step(): v += ..., x += dt v + c5 eta, v recomputed from the positions).
+// With friction > 0 the integrator also keeps the centre of mass where it was (fix_com: old_com saved before the drift,
+// atoms.set_center_of_mass(old_com) after it, THEN the velocity recomputation), so the kernel is one CTA: pass 1 drifts
+// and sums m*x_old, m*x_new in a fixed order, pass 2 shifts every atom by old_com - new_com and recomputes v.
+constexpr int MD_K1_THREADS = 1024;
+__global__ void __launch_bounds__(MD_K1_THREADS) md_kick1_kernel(MdParams p, const long long* __restrict__ step_ctr,
+                                                                 const double* __restrict__ mass, const float* __restrict__ ef,
+                                                                 double* __restrict__ x, double* __restrict__ v) {
+    __shared__ double shift[3];
+    const int n3 = 3 * p.n_protein;
+    const long long step = *step_ctr;
+    const bool fixcm = p.fr > 0.0;
+    double so[3] = {0.0, 0.0, 0.0}, sn[3] = {0.0, 0.0, 0.0}, sm = 0.0;
+    // thread t handles components t, t + T, ...; T is a multiple of 3, so a thread stays on one Cartesian axis
+    constexpr int T = (MD_K1_THREADS / 3) * 3;
+    if (threadIdx.x < T) {
+        for (int comp = threadIdx.x; comp < n3; comp += T) {
+            const double m = mass[comp / 3];
+            const MdCoef c = md_coef(p, m);
+            double xi = 0.0, eta = 0.0;
+            if (p.fr > 0.0) md_normals(p, step, comp, xi, eta);
+            const double f = (double)ef[comp];
+            double vv = v[comp];
+            vv = vv + (c.c1 * f / m - c.c2 * vv + c.c3 * xi - c.c4 * eta);
+            const double x_old = x[comp];
+            const double x_new = x_old + p.dt * vv + c.c5 * eta;
+            x[comp] = x_new;
+            if (fixcm) {
+                v[comp] = x_old;                   // parked until pass 2
+                so[0] += m * x_old; sn[0] += m * x_new;
+                if (comp % 3 == 0) sm += m;
+            } else {
+                v[comp] = (x_new - x_old - c.c5 * eta) / p.dt;
+            }
+        }
+    }
+    if (!fixcm) return;
+    // block reduction per axis (axis of thread t = t % 3), fixed order: warp shuffles cannot be used across axes, so
+    // every thread publishes its partials and three threads sum them serially
+    __shared__ double part_o[MD_K1_THREADS], part_n[MD_K1_THREADS], part_m[MD_K1_THREADS];
+    part_o[threadIdx.x] = so[0]; part_n[threadIdx.x] = sn[0]; part_m[threadIdx.x] = sm;
+    __syncthreads();
+    if (threadIdx.x < 3) {
+        double o = 0.0, n = 0.0, mt = 0.0;
+        for (int t = threadIdx.x; t < T; t += 3) { o += part_o[t]; n += part_n[t]; }
+        for (int t = 0; t < T; t += 3) mt += part_m[t];
+        shift[threadIdx.x] = o / mt - n / mt;      // old_com - new_com
+    }
+    __syncthreads();
+    if (threadIdx.x < T) {
+        for (int comp = threadIdx.x; comp < n3; comp += T) {
+            const double m = mass[comp / 3];
+            const MdCoef c = md_coef(p, m);
+            double xi = 0.0, eta = 0.0;
+            md_normals(p, step, comp, xi, eta);
+            const double x_old = v[comp];
+            const double x_new = x[comp] + shift[comp % 3];
+            x[comp] = x_new;
+            v[comp] = (x_new - x_old - c.c5 * eta) / p.dt;
+        }
+    }
 }
 
 // fragment atoms follow the protein: real atoms copy, cap hydrogens sit at P[acc] + unit(P[rem] - P[acc]) * blen

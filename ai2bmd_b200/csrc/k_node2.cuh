@@ -26,28 +26,27 @@ struct NodeFwd2Smem {
 // ---------------------------------------------------------------------------------------------
 // forward node stage k (same contract as node_fwd_kernel)
 // ---------------------------------------------------------------------------------------------
-template <int NB>
-__global__ void __launch_bounds__(N2Cfg<NB>::THREADS) node_fwd2_kernel(NodeArgs a) {
-    pdl_entry();
+// Body shared by the stand-alone kernel below and by the fused per-layer kernel (k_fused.cuh): the N2Cfg<NB>::WARPS
+// warps with threadIdx.x < N2Cfg<NB>::THREADS run it for nodes [n0, n0 + NB); `sync` is a barrier among exactly those
+// threads (__syncthreads in the stand-alone kernel, a named barrier of the compute warps in the fused one).
+template <int NB, typename SyncF>
+__device__ __forceinline__ void node_fwd2_body(const ModelW& mw, const Workspace& ws, const int k, const int n0,
+                                               float* dyn_smem, SyncF sync) {
     constexpr int N2_WARPS = N2Cfg<NB>::WARPS, N2_THREADS = N2Cfg<NB>::THREADS;
     using S = NodeFwd2Smem<NB>;
     constexpr int LDA = S::LDA;
     constexpr int N2_RB = N2Rows<NB>::RB;
-    extern __shared__ __align__(16) float dyn_smem[];
     S& sm = *reinterpret_cast<S*>(dyn_smem);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, col = lane * 4;
-    const int k = a.layer;
-    const Workspace& ws = a.ws;
-    const int n0 = blockIdx.x * NB;
     const int nn = min(NB, ws.N - n0);            // valid nodes in this CTA
 
     if (k >= 1) {
-        const LayerW& lw = a.mw.layer[k - 1];
+        const LayerW& lw = mw.layer[k - 1];
         for (int idx = threadIdx.x; idx < NB * 32; idx += N2_THREADS) {
             const int nd = idx >> 5, c4 = (idx & 31) * 4;
             st4(&sm.xs[nd][c4], nd < nn ? ld4(ws.XA + (size_t)(n0 + nd) * D + c4) : f4s(0.f));
         }
-        __syncthreads();
+        sync();
         // o = xa Wo^T + bo : units = 3 chunks x NB/8 row blocks (x 4 K-quarters in the 16-warp variant)
         if constexpr (NB <= 4) {
             for (int u = warp; u < 12; u += N2_WARPS) {
@@ -62,7 +61,7 @@ __global__ void __launch_bounds__(N2Cfg<NB>::THREADS) node_fwd2_kernel(NodeArgs 
                     else st4(&sm.osp[kq - 1][r][ch * D + col], arr4(acc[r]));
                 }
             }
-            __syncthreads();
+            sync();
             for (int idx = threadIdx.x; idx < NB * 96; idx += N2_THREADS) {      // fixed-order sum of the K-quarters
                 const int r = idx / 96, c4 = (idx % 96) * 4;
                 st4(&sm.os[r][c4], (ld4(&sm.os[r][c4]) + ld4(&sm.osp[0][r][c4])) + (ld4(&sm.osp[1][r][c4]) + ld4(&sm.osp[2][r][c4])));
@@ -77,7 +76,7 @@ __global__ void __launch_bounds__(N2Cfg<NB>::THREADS) node_fwd2_kernel(NodeArgs 
                 for (int r = 0; r < N2_RB; r++) st4(&sm.os[rb * N2_RB + r][ch * D + col], arr4(acc[r]));
             }
         }
-        __syncthreads();
+        sync();
     }
     // per-node phase: residual update, LayerNorm, VecLayerNorm (warp per node)
     for (int nd = warp; nd < NB; nd += N2_WARPS) {
@@ -108,7 +107,7 @@ __global__ void __launch_bounds__(N2Cfg<NB>::THREADS) node_fwd2_kernel(NodeArgs 
             for (int s = 0; s < 3; s++) st4(ws.VA + ((size_t)node * 3 + s) * D + col, f4s(0.f));
         }
         if (k < L) {
-            const LayerW& lw = a.mw.layer[k];
+            const LayerW& lw = mw.layer[k];
             st4(&sm.xs[nd][col], ln_forward(x, lw.ln_w, lw.ln_b, lane));
             float4 vn[3];
             vecln_forward(vec, vn, lw.vln_w, lane);
@@ -120,8 +119,8 @@ __global__ void __launch_bounds__(N2Cfg<NB>::THREADS) node_fwd2_kernel(NodeArgs 
         }
     }
     if (k >= L) return;
-    __syncthreads();
-    const LayerW& lw = a.mw.layer[k];
+    sync();
+    const LayerW& lw = mw.layer[k];
     // GEMM units: [0, UQ): qkv ; [UQ, UQ+UV): vec_proj ; then w_trg|w_src
     constexpr int UQ = 3 * (NB / N2_RB), UV = 3 * (3 * NB / N2_RB), UT = 2 * (3 * NB / N2_RB);
     const int nunits = UQ + UV + ((k < L - 1) ? UT : 0);
@@ -156,7 +155,7 @@ __global__ void __launch_bounds__(N2Cfg<NB>::THREADS) node_fwd2_kernel(NodeArgs 
             }
         }
     }
-    __syncthreads();     // V123 rows of this CTA are visible block-wide
+    sync();     // V123 rows of this CTA are visible block-wide
     for (int nd = warp; nd < nn; nd += N2_WARPS) {
         const size_t r3 = (size_t)(n0 + nd) * 3;
         float4 vd = f4s(0.f);
@@ -164,6 +163,13 @@ __global__ void __launch_bounds__(N2Cfg<NB>::THREADS) node_fwd2_kernel(NodeArgs 
         for (int s = 0; s < 3; s++) vd = vd + ld4(ws.V123[k] + (r3 + s) * 3 * D + col) * ld4(ws.V123[k] + (r3 + s) * 3 * D + D + col);
         st4(ws.VDOT[k] + (size_t)(n0 + nd) * D + col, vd);
     }
+}
+
+template <int NB>
+__global__ void __launch_bounds__(N2Cfg<NB>::THREADS) node_fwd2_kernel(NodeArgs a) {
+    pdl_entry();
+    extern __shared__ __align__(16) float dyn_smem[];
+    node_fwd2_body<NB>(a.mw, a.ws, a.layer, (int)blockIdx.x * NB, dyn_smem, [] { __syncthreads(); });
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -184,26 +190,25 @@ struct NodeBwd2Smem {
     float part_v[5][3 * NB][D];                   // partial products of the vector rows (3 + 2 K-chunks)
 };
 
-template <int NB>
-__global__ void __launch_bounds__(N2Cfg<NB>::THREADS) node_bwd2_kernel(NodeArgs a) {
-    pdl_entry();
+// Body (see node_fwd2_body).  GQKV / GVNMSG / GTU are the accumulators the edge adjoint of layer k added into; they are
+// consumed and re-zeroed here (the fused pipeline alternates between two sets, the stand-alone one uses ws.G*).
+template <int NB, typename SyncF>
+__device__ __forceinline__ void node_bwd2_body(const ModelW& mw, const Workspace& ws, const int k, const int n0,
+                                               float* __restrict__ GQKV, float* __restrict__ GVNMSG, float* __restrict__ GTU,
+                                               float* dyn_smem, SyncF sync) {
     constexpr int N2_WARPS = N2Cfg<NB>::WARPS;
     using S = NodeBwd2Smem<NB>;
     constexpr int LD3 = S::LD3, LD2 = S::LD2;
     constexpr int N2_RB = N2Rows<NB>::RB;
-    extern __shared__ __align__(16) float dyn_smem[];
     S& sm = *reinterpret_cast<S*>(dyn_smem);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, col = lane * 4;
-    const int k = a.layer;
-    const Workspace& ws = a.ws;
-    const int n0 = blockIdx.x * NB;
     const int nn = min(NB, ws.N - n0);
     const bool has_a = (k <= L - 1), has_b = (k >= 1);
     const bool has_tu = (k < L - 1);
     const float4 z4 = f4s(0.f);
 
     if (has_a) {
-        const LayerW& lw = a.mw.layer[k];
+        const LayerW& lw = mw.layer[k];
         // stage the A-operand rows (warp per node)
         for (int nd = warp; nd < NB; nd += N2_WARPS) {
             const int node = n0 + nd;
@@ -212,7 +217,7 @@ __global__ void __launch_bounds__(N2Cfg<NB>::THREADS) node_bwd2_kernel(NodeArgs 
             const float* orow = ws.O[k] + (size_t)node * 3 * D;
             const float4 o1 = ok ? ld4(orow + col) : z4, o2 = ok ? ld4(orow + D + col) : z4;
             const float4 g_vdot = gx * o2;
-            const float* gq = ws.GQKV + (size_t)node * 3 * D;
+            const float* gq = GQKV + (size_t)node * 3 * D;
             st4(&sm.gq[nd][col], ok ? ld4(gq + col) : z4);
             st4(&sm.gq[nd][D + col], ok ? ld4(gq + D + col) : z4);
             st4(&sm.gq[nd][2 * D + col], ok ? ld4(gq + 2 * D + col) : z4);
@@ -225,13 +230,13 @@ __global__ void __launch_bounds__(N2Cfg<NB>::THREADS) node_bwd2_kernel(NodeArgs 
                 st4(&sm.gvp[nd * 3 + s][D + col], g_vdot * (ok ? ld4(vrow + col) : z4));
                 st4(&sm.gvp[nd * 3 + s][2 * D + col], gv * o1);
                 if (has_tu) {
-                    const float* gt = ws.GTU + r3 * 2 * D;
+                    const float* gt = GTU + r3 * 2 * D;
                     st4(&sm.gtu[nd * 3 + s][col], ok ? ld4(gt + col) : z4);
                     st4(&sm.gtu[nd * 3 + s][D + col], ok ? ld4(gt + D + col) : z4);
                 }
             }
         }
-        __syncthreads();
+        sync();
         // units: scalar rows x 3 K-chunks (Wqkv) ; vector rows x (3 K-chunks Wvec + 2 K-chunks Wtu)
         constexpr int UX = 3 * S::NXB;
         const int kv = has_tu ? 5 : 3;
@@ -252,7 +257,7 @@ __global__ void __launch_bounds__(N2Cfg<NB>::THREADS) node_bwd2_kernel(NodeArgs 
                 for (int r = 0; r < N2_RB; r++) st4(&sm.part_v[kc][rb * N2_RB + r][col], arr4(acc[r]));
             }
         }
-        __syncthreads();
+        sync();
     }
     // per-node phase
     for (int nd = warp; nd < NB; nd += N2_WARPS) {
@@ -262,13 +267,13 @@ __global__ void __launch_bounds__(N2Cfg<NB>::THREADS) node_bwd2_kernel(NodeArgs 
 #pragma unroll
         for (int s = 0; s < 3; s++) gvec[s] = ok ? ld4(ws.GVEC + ((size_t)node * 3 + s) * D + col) : z4;
         if (has_a && ok) {
-            const LayerW& lw = a.mw.layer[k];
+            const LayerW& lw = mw.layer[k];
             const float4 gxn = (ld4(&sm.part_x[0][nd][col]) + ld4(&sm.part_x[1][nd][col])) + ld4(&sm.part_x[2][nd][col]);
             float4 vin[3], gout[3], gv[3];
 #pragma unroll
             for (int s = 0; s < 3; s++) {
                 const int row = nd * 3 + s;
-                float4 g = ld4(ws.GVNMSG + ((size_t)node * 3 + s) * D + col);
+                float4 g = ld4(GVNMSG + ((size_t)node * 3 + s) * D + col);
                 g = g + ((ld4(&sm.part_v[0][row][col]) + ld4(&sm.part_v[1][row][col])) + ld4(&sm.part_v[2][row][col]));
                 if (has_tu) g = g + (ld4(&sm.part_v[3][row][col]) + ld4(&sm.part_v[4][row][col]));
                 gout[s] = g;
@@ -280,14 +285,14 @@ __global__ void __launch_bounds__(N2Cfg<NB>::THREADS) node_bwd2_kernel(NodeArgs 
             gx = gx + ln_backward(ld4(ws.X[k] + (size_t)node * D + col), gxn, lw.ln_w, lane);
         }
         if (ok) {
-            float* gq = ws.GQKV + (size_t)node * 3 * D;
+            float* gq = GQKV + (size_t)node * 3 * D;
             st4(gq + col, z4); st4(gq + D + col, z4); st4(gq + 2 * D + col, z4);
 #pragma unroll
             for (int s = 0; s < 3; s++) {
                 const size_t r3 = (size_t)node * 3 + s;
-                st4(ws.GVNMSG + r3 * D + col, z4);
-                st4(ws.GTU + r3 * 2 * D + col, z4);
-                st4(ws.GTU + r3 * 2 * D + D + col, z4);
+                st4(GVNMSG + r3 * D + col, z4);
+                st4(GTU + r3 * 2 * D + col, z4);
+                st4(GTU + r3 * 2 * D + D + col, z4);
                 st4(ws.GVEC + r3 * D + col, gvec[s]);
             }
             st4(ws.GX + (size_t)node * D + col, gx);
@@ -304,9 +309,9 @@ __global__ void __launch_bounds__(N2Cfg<NB>::THREADS) node_bwd2_kernel(NodeArgs 
         }
     }
     if (!has_b) return;
-    __syncthreads();
+    sync();
     {
-        const LayerW& lw = a.mw.layer[k - 1];
+        const LayerW& lw = mw.layer[k - 1];
         for (int u = warp; u < 3 * S::NXB; u += N2_WARPS) {
             const int kc = u % 3, rb = u / 3;
             float acc[N2_RB][4];
@@ -316,10 +321,17 @@ __global__ void __launch_bounds__(N2Cfg<NB>::THREADS) node_bwd2_kernel(NodeArgs 
             for (int r = 0; r < N2_RB; r++) st4(&sm.part_x[kc][rb * N2_RB + r][col], arr4(acc[r]));
         }
     }
-    __syncthreads();
+    sync();
     for (int nd = warp; nd < nn; nd += N2_WARPS)
         st4(ws.GXA + (size_t)(n0 + nd) * D + col,
             (ld4(&sm.part_x[0][nd][col]) + ld4(&sm.part_x[1][nd][col])) + ld4(&sm.part_x[2][nd][col]));
+}
+
+template <int NB>
+__global__ void __launch_bounds__(N2Cfg<NB>::THREADS) node_bwd2_kernel(NodeArgs a) {
+    pdl_entry();
+    extern __shared__ __align__(16) float dyn_smem[];
+    node_bwd2_body<NB>(a.mw, a.ws, a.layer, (int)blockIdx.x * NB, a.ws.GQKV, a.ws.GVNMSG, a.ws.GTU, dyn_smem, [] { __syncthreads(); });
 }
 
 }  // namespace vb

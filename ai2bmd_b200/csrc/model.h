@@ -99,6 +99,10 @@ struct Workspace {
     float* GQKV;            // [N][384]
     float* GVNMSG;          // [N][3][128]
     float* GTU;             // [N][3][256]
+    // second accumulator set of the fused per-layer adjoint (k_fused.cuh): layer l adds into set l&1, consumes set (l+1)&1
+    float* GQKV2;           // [N][384]
+    float* GVNMSG2;         // [N][3][128]
+    float* GTU2;            // [N][3][256]
     float* eatom;           // [N]
 };
 

@@ -54,12 +54,17 @@ class BondedForceField:
 
 
 class Langevin:
-    """ASE-style Langevin integrator (``fixcm=True``); ``friction=0`` reduces to velocity Verlet."""
+    """ASE-style Langevin integrator, restating ``ase/md/langevin.py`` ``Langevin.step`` of ASE 3.22 with
+    ``fixcm=True`` (recalled; ASE is not in the image): half-kick, drift, centre of mass put back where it was,
+    velocities recomputed from the positions, forces, half-kick, centre-of-mass velocity removed.
+    ``friction=0`` reduces to velocity Verlet (no random numbers, no centre-of-mass handling)."""
 
     def __init__(self, positions, numbers, force_fn, dt_fs=1.0, temperature_K=300.0, friction_per_fs=0.001, seed=0,
-                 normal_source=None):
+                 normal_source=None, zero_com_momentum=False):
         """``normal_source(step) -> (xi, eta)`` overrides the numpy generator for the per-step normals (used to
-        drive this host integrator with the device's Philox stream in the parity tests)."""
+        drive this host integrator with the device's Philox stream in the parity tests).  ``zero_com_momentum``
+        removes the centre-of-mass momentum of the Maxwell-Boltzmann draw; the reference does not
+        (``simulator.py:96`` calls ``MaxwellBoltzmannDistribution`` only, no ``Stationary``)."""
         self.normal_source = normal_source
         self.nsteps = 0
         self.x = np.array(positions, dtype=np.float64)
@@ -69,9 +74,10 @@ class Langevin:
         self.T = temperature_K * KB
         self.fr = friction_per_fs / FS
         self.rng = np.random.default_rng(seed)
-        # Maxwell-Boltzmann start (simulator.py:96), centre-of-mass motion removed
+        # Maxwell-Boltzmann start (simulator.py:96)
         self.v = self.rng.standard_normal(self.x.shape) * np.sqrt(self.T / self.m)
-        self.v -= (self.v * self.m).sum(0) / self.m.sum()
+        if zero_com_momentum:
+            self.v -= (self.v * self.m).sum(0) / self.m.sum()
         self.energy, self.f = force_fn(self.x)
         dt, fr = self.dt, self.fr
         sigma = np.sqrt(2 * self.T * fr / self.m)
@@ -96,6 +102,9 @@ class Langevin:
         self.v = self.v + (self.c1 * self.f / self.m - self.c2 * self.v + self.c3 * xi - self.c4 * eta)
         x_old = self.x
         self.x = self.x + self.dt * self.v + self.c5 * eta
+        if self.fr > 0:     # fix_com: the centre of mass stays where it was before the drift (atoms.set_center_of_mass(old_com))
+            msum = self.m.sum()
+            self.x = self.x + ((self.m * x_old).sum(0) / msum - (self.m * self.x).sum(0) / msum)
         self.v = (self.x - x_old - self.c5 * eta) / self.dt
         self.energy, self.f = self.force_fn(self.x)
         self.v = self.v + (self.c1 * self.f / self.m - self.c2 * self.v + self.c3 * xi - self.c4 * eta)
@@ -145,7 +154,7 @@ class DeviceLangevin:
 
     def __init__(self, state_dict, frags: FragmentData, pm: ProteinMap, recipe: FragmentRecipe, positions, numbers,
                  dt_fs=1.0, temperature_K=300.0, friction_per_fs=0.001, seed=0, device: int = 0, velocities=None,
-                 group=None, engine: Engine = None):
+                 group=None, engine: Engine = None, zero_com_momentum=False):
         import torch
         self.torch, self.group = torch, group
         self.n = pm.n_protein
@@ -167,7 +176,8 @@ class DeviceLangevin:
             rng = np.random.default_rng(seed)
             m = self.masses[:, None]
             velocities = rng.standard_normal(x.shape) * np.sqrt(self.kT / m)
-            velocities -= (velocities * m).sum(0) / m.sum()
+            if zero_com_momentum:
+                velocities -= (velocities * m).sum(0) / m.sum()
         engine.md_set_state(x, velocities, 0)
         self._eval()
 

@@ -358,7 +358,7 @@ def run_ours(args):
             if world > 1:
                 dist.all_reduce(t_md, op=dist.ReduceOp.MAX)
             md_device = {"value": args.steps / float(t_md.item()), "unit": "steps/s", "temperature_K": dmd.temperature(),
-                         "launches_per_step": shard.engine.launches_per_forward + 6,
+                         "launches_per_step": shard.engine.launches_per_forward,
                          "what": "Langevin (dt 1 fs, 300 K, friction 0.001/fs) entirely on the device: half-kick + drift, "
                                  "cap-H placement, engine, signed reduction" + (", NCCL all-reduce" if world > 1 else "") +
                                  ", half-kick; " + ("one CUDA graph replay per step" if world == 1 else "phases enqueued by the host around the engine's graph") +
@@ -476,8 +476,8 @@ def run_ours(args):
         "value_l2_warm": args.steps / float(t_warm.item()),
         "wall_s_timed_region": wall,
         "e2e": e2e,
-        "gpu_launches": args.steps * (shard.engine.launches_per_forward + 3),
-        "launches_per_step": shard.engine.launches_per_forward + 3,
+        "gpu_launches": args.steps * shard.engine.launches_per_forward,
+        "launches_per_step": shard.engine.launches_per_forward,
         "clocks": clock_info,
         "roofline": roofline,
         "cpu_baseline": cpu,

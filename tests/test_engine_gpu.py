@@ -150,7 +150,102 @@ def test_graph_replay_equals_eager_and_tile_variants(real_weights, chig):
         eng.set_option(key, val)
         e2, f2 = eng.forward_host(fd.pos)
         assert np.abs(f0 - f2).max() <= 2e-5 and (np.abs(e0 - e2) <= e_tol(e0)).all(), key
-    assert 30 <= eng.launches_per_forward <= 40
+    assert 15 <= eng.launches_per_forward <= 40
+
+
+@pytest.mark.parametrize("name", ["ww", "abd"])
+def test_parity_ww_abd_against_fp64_oracle(model, real_weights, name):
+    """The two larger example proteins (69 / 93 fragments), full energy / force parity against the fp64 oracle."""
+    fd, _ = load_fragments(name)
+    oracle = O.OracleViSNet({k: torch.from_numpy(v) for k, v in real_weights.items()}, torch.float64)
+    e_ref, f_ref = oracle.energy_and_forces(fd.z, fd.pos, fd.batch)
+    e, f = model.dl_potential_loader(fd)
+    assert (np.abs(e - e_ref.numpy()) <= e_tol(e_ref.numpy())).all()
+    assert np.abs(f - f_ref.numpy()).max() <= f_tol(f_ref.numpy())
+
+
+def test_parity_c5_conformers_against_fp64_oracle(model, real_weights):
+    """Config C5 (Protein-Unit conformer batch): 32 of the 2048 conformers against the fp64 oracle."""
+    from ai2bmd_b200.synth import conformer_batch
+    fd = conformer_batch(32, seed=1)
+    oracle = O.OracleViSNet({k: torch.from_numpy(v) for k, v in real_weights.items()}, torch.float64)
+    e_ref, f_ref = oracle.energy_and_forces(fd.z, fd.pos, fd.batch)
+    e, f = model.dl_potential_loader(fd)
+    assert (np.abs(e - e_ref.numpy()) <= e_tol(e_ref.numpy())).all()
+    assert np.abs(f - f_ref.numpy()).max() <= f_tol(f_ref.numpy())
+
+
+@pytest.mark.parametrize("key", ["chig", "trpcage", "dense44"])
+def test_fused_and_separate_launch_plans_agree(real_weights, reference_outputs, key):
+    """One launch per layer (k_fused.cuh) against the separate node / edge stages, and both against the fp64 anchor."""
+    r = reference_outputs
+    fd = _case(r, key)
+    out = {}
+    for fused in (0, 1):
+        eng = Engine(real_weights, 0)
+        eng.set_option("fused", fused)
+        eng.set_topology(fd.z, fd.batch, n_graphs=len(fd))
+        assert eng.get_option("fused") == fused
+        out[fused] = eng.forward_host(fd.pos)
+        e2, f2 = eng.forward_host(fd.pos)              # graph replay on re-zeroed accumulators
+        assert np.abs(f2 - out[fused][1]).max() <= 2e-5 * max(1.0, np.abs(f2).max())
+    e64, f64 = r[f"{key}_e64"], r[f"{key}_f64"]
+    for fused in (0, 1):
+        e, f = out[fused]
+        assert np.abs(f - f64).max() <= 2e-5 * np.abs(f64).max() + 5e-5, fused
+        assert (np.abs(e.reshape(e64.shape) - e64) <= 2e-6 * np.abs(e64).max() + 4e-3).all(), fused
+    assert out[1][0].shape == out[0][0].shape
+    assert eng.launches_per_forward <= 24
+
+
+def test_fused_plan_persistent_ctas_many_blocks(real_weights):
+    """More 4-node blocks than SMs: every CTA of the fused kernels loops over several blocks (and sub-tile parities)."""
+    fd = synthetic_batch(96, seed=3)
+    outs = []
+    for fused in (0, 1):
+        eng = Engine(real_weights, 0)
+        eng.set_option("fused", fused)
+        eng.set_topology(fd.z, fd.batch)
+        outs.append(eng.forward_host(fd.pos))
+    (e0, f0), (e1, f1) = outs
+    assert np.isfinite(e1).all() and np.isfinite(f1).all()
+    assert (np.abs(e1 - e0) <= e_tol(e0)).all()
+    assert np.abs(f1 - f0).max() <= 5e-5
+
+
+def test_trimmed_edge_capacity_overflow_is_reported(real_weights, chig):
+    fd, _ = chig
+    eng = Engine(real_weights, 0)
+    eng.set_topology(fd.z, fd.batch, max_edges=1000)            # Chignolin has ~6.7k edges
+    with pytest.raises(RuntimeError, match="max_edges"):
+        eng.forward_host(fd.pos)
+    assert eng.get_option("edge_overflow") == 1
+    eng.set_topology(fd.z, fd.batch)                             # full capacity: fine again, flag cleared
+    e, f = eng.forward_host(fd.pos)
+    assert np.isfinite(f).all() and eng.get_option("edge_overflow") == 0
+
+
+def test_protein_map_change_invalidates_md_state(real_weights, chig):
+    """vb_set_protein_map after vb_md_setup drops the captured step and the MD state (sized by the old map)."""
+    from ai2bmd_b200.fixtures import load_protein
+    fd, pm = chig
+    prot_pos, prot_z, recipe = load_protein("chig")
+    eng = Engine(real_weights, 0)
+    eng.set_topology(fd.z, fd.batch)
+    eng.set_protein_map(pm.n_protein, pm.src_atom, pm.dst_atom, pm.sign, pm.frag_sign)
+    ef = torch.zeros(3 * pm.n_protein + 1, device="cuda")
+    eng.md_setup(np.ones(pm.n_protein), recipe.real, recipe.acc, recipe.rem, recipe.blen, 0.1, 0.025, 0.0, 0, ef.data_ptr())
+    eng.md_set_state(prot_pos, np.zeros_like(prot_pos), 0)
+    eng.md_eval()
+    eng.md_run(2)
+    torch.cuda.synchronize()
+    eng.set_protein_map(pm.n_protein, pm.src_atom, pm.dst_atom, pm.sign, pm.frag_sign)
+    with pytest.raises(RuntimeError, match="vb_md_setup first"):
+        eng.md_run(1)
+    eng.set_topology(fd.z, fd.batch)                             # ... and a new topology drops the map itself
+    pos = torch.from_numpy(fd.pos).cuda()
+    with pytest.raises(RuntimeError, match="protein map"):
+        eng.forward_protein_device(pos.data_ptr(), ef.data_ptr())
 
 
 def test_device_pointer_entry_point(real_weights, chig):
