@@ -49,10 +49,22 @@ class ViSNetModel:
             raise ValueError("model_path must be provided")
         return cls(load_state_dict(kwargs["model_path"]), device=kwargs.get("device", "cuda:0"))
 
-    def _ensure_topology(self, frag: FragmentData):
+    @classmethod
+    def from_engine(cls, engine: Engine, device: str, frag: FragmentData):
+        """Wrap an engine whose topology is already ``frag``'s (e.g. a shard's engine with its protein map set)."""
+        self = cls.__new__(cls)
+        self.device, self.engine = device, engine
+        self._topo_key = self._key(frag)[0]
+        return self
+
+    @staticmethod
+    def _key(frag: FragmentData):
         z = np.ascontiguousarray(frag.z, dtype=np.int64)
         batch = np.ascontiguousarray(frag.batch, dtype=np.int64)
-        key = (z.size, hash(z.tobytes()), hash(batch.tobytes()))
+        return (z.size, hash(z.tobytes()), hash(batch.tobytes())), z, batch
+
+    def _ensure_topology(self, frag: FragmentData):
+        key, z, batch = self._key(frag)
         if key != self._topo_key:
             self.engine.set_topology(z, batch, n_graphs=len(frag))
             self._topo_key = key

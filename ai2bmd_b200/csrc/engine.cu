@@ -13,6 +13,7 @@
 
 #include "../../include/visnet_b200.h"
 #include "k_edge.cuh"
+#include "k_comm.cuh"
 #include "k_edge_tc.cuh"
 #include "k_fused.cuh"
 #include "k_graph_embed.cuh"
@@ -134,6 +135,12 @@ struct vb_handle {
     float *d_map_sign = nullptr, *d_frag_sign = nullptr;
     float* d_ef = nullptr;       // [3*n_protein + 1] internal whole-protein buffer (diagnostic runs)
     int* d_flags = nullptr;      // [0]: set by the neighbour stage when a step produced more edges than the workspace holds
+    // NVLink peer-memory all-reduce (k_comm.cuh): window in this rank's HBM + IPC mappings of every peer's window
+    bool comm_ready = false;
+    int comm_auto = 1;           // append the all-reduce to every evaluation that produces the whole-protein buffer
+    void* comm_base = nullptr;
+    void* comm_peer[COMM_MAX_WORLD] = {};
+    CommParams comm{};
     // options
     int use_graph = 1, npw = 0, te_fwd = 0, te_bwd = 32;
     int use_pdl = 0;   // programmatic dependent launch between the stages: measured neutral to slower
@@ -180,6 +187,13 @@ struct vb_handle {
         cudaFree(d_map_rowptr); cudaFree(d_map_src); cudaFree(d_map_sign); cudaFree(d_frag_sign); cudaFree(d_ef);
         d_map_rowptr = d_map_src = nullptr; d_map_sign = d_frag_sign = d_ef = nullptr;
         n_protein = n_map = 0;
+    }
+    void free_comm() {
+        for (int r = 0; r < COMM_MAX_WORLD; r++)
+            if (comm_peer[r] && r != comm.rank) cudaIpcCloseMemHandle(comm_peer[r]);
+        cudaFree(comm_base); cudaFree(comm.counters);
+        comm_base = nullptr; comm = CommParams{}; comm_ready = false;
+        for (auto& p : comm_peer) p = nullptr;
     }
     void free_nb() {
         cudaFree(d_nb_q); cudaFree(d_nb_sigma); cudaFree(d_nb_eps); cudaFree(d_nb_rowptr); cudaFree(d_nb_col); cudaFree(d_nb_eatom);
@@ -671,16 +685,27 @@ int run_cached(vb_handle* h, cudaStream_t st, int kind, const StepIO& io, F&& en
     return VB_OK;
 }
 
-int enqueue_eval(vb_handle* h, cudaStream_t st, const StepIO& io) {
+// all-reduce of buf[n] over the connected ranks (k_comm.cuh), one launch on st
+int enqueue_allreduce(vb_handle* h, cudaStream_t st, float* buf, long long n) {
+    if (n > h->comm.max_floats) { h->set_error("all-reduce of %lld floats exceeds the window (%lld)", n, h->comm.max_floats); return VB_ERR_ARG; }
+    const int ctas = (int)std::max<long long>(1, std::min<long long>((n + COMM_THREADS - 1) / COMM_THREADS, COMM_MAX_CTAS));
+    comm_allreduce_kernel<<<ctas, COMM_THREADS, 0, st>>>(h->comm, buf, n);
+    CUDA_TRY(h, cudaGetLastError());
+    return VB_OK;
+}
+
+// every launch of one evaluation; with `reduce` the whole-protein buffer is all-reduced over the connected ranks last
+int enqueue_eval(vb_handle* h, cudaStream_t st, const StepIO& io, bool reduce = false) {
     Launcher Lc{h, st, -1, 0, false};
     enqueue_all(Lc, io);
     if (Lc.status != cudaSuccess) { h->set_error("kernel launch failed: %s", cudaGetErrorString(Lc.status)); return VB_ERR_CUDA; }
+    if (reduce && io.ef && h->comm_ready && h->comm_auto) return enqueue_allreduce(h, st, io.ef, 3LL * h->n_protein + 1);
     return VB_OK;
 }
 
 // one evaluation on the given buffers, asynchronous on st
 int run_eval(vb_handle* h, cudaStream_t st, const StepIO& io) {
-    return run_cached(h, st, K_EVAL, io, [&](cudaStream_t s) -> int { return enqueue_eval(h, s, io); });
+    return run_cached(h, st, K_EVAL, io, [&](cudaStream_t s) -> int { return enqueue_eval(h, s, io, true); });
 }
 
 StepIO internal_io(vb_handle* h, bool protein) {
@@ -701,9 +726,9 @@ void record_stages(vb_handle* h) {
 void choose_defaults(vb_handle* h) {
     const int N = h->ws.N;
     h->npw = h->npw_opt; h->te_fwd = h->te_fwd_opt; h->edge_tc = h->edge_tc_opt;
-    // fused per-layer launches while the 4-node blocks fit one or two waves of CTAs (latency-bound sizes); larger
-    // batches keep the separate stages with dense 128-edge tiles
-    h->fused = h->fused_opt >= 0 ? h->fused_opt : (((N + FU_NB - 1) / FU_NB <= 2 * h->sm_count) ? 1 : 0);
+    // fused per-layer launches (k_fused.cuh) are opt-in: inside a graph a launch boundary costs ~1-2 us, less than what the
+    // fused kernels lose to the 96-register budget of a 576-thread CTA running the node GEMMs (profiles/README.md)
+    h->fused = h->fused_opt >= 0 ? h->fused_opt : 0;
     if (h->npw == 0) h->npw = (N > 4096) ? 2 : 1;
     if (h->te_fwd == 0) h->te_fwd = ((long long)N * 17 / 64 >= 2LL * h->sm_count) ? 64 : 32;
     // tcgen05 edge kernels (one tile per CTA, 16 compute warps): with the tile length chosen below both stages beat
@@ -801,6 +826,7 @@ void vb_destroy(vb_handle* h) {
     cudaFree(h->d_tl);
     h->free_md();
     h->free_nb();
+    h->free_comm();
     cudaFree(h->arena);
     h->free_map();
     cudaFree(h->d_flags);
@@ -998,6 +1024,7 @@ int md_eval_enqueue(vb_handle* h, cudaStream_t st) {
         nonbonded_energy_kernel<<<1, 256, 0, st>>>(h->nb, h->d_nb_eatom, h->md_ef);
     }
     CUDA_TRY(h, cudaGetLastError());
+    if (h->comm_ready && h->comm_auto) return enqueue_allreduce(h, st, h->md_ef, 3LL * h->n_protein + 1);
     return VB_OK;
 }
 void md_kick1_enqueue(vb_handle* h, cudaStream_t st) {
@@ -1227,6 +1254,69 @@ int vb_nonbonded(vb_handle* h, const float* prot_pos_dev, float* ef_prot_dev, vo
 }
 
 
+// ---- NVLink peer-memory all-reduce (k_comm.cuh) ------------------------------------------------------------------
+int vb_comm_init(vb_handle* h, int rank, int world, int64_t max_floats, void* ipc_handle_out) {
+    if (!h) return VB_ERR_ARG;
+    std::lock_guard<std::mutex> lk(h->mu);
+    if (world < 1 || world > COMM_MAX_WORLD || rank < 0 || rank >= world || max_floats <= 0 || !ipc_handle_out) {
+        h->set_error("vb_comm_init: bad arguments (world <= %d)", COMM_MAX_WORLD);
+        return VB_ERR_ARG;
+    }
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    CUDA_TRY(h, cudaDeviceSynchronize());
+    h->drop_graph();
+    h->free_comm();
+    const size_t flag_bytes = ((size_t)2 * world * sizeof(int) + 255) & ~(size_t)255;
+    const size_t bytes = flag_bytes + (size_t)2 * world * (size_t)max_floats * sizeof(float);
+    CUDA_TRY(h, cudaMalloc(&h->comm_base, bytes));
+    CUDA_TRY(h, cudaMemset(h->comm_base, 0, bytes));
+    CUDA_TRY(h, cudaMalloc(&h->comm.counters, 4 * sizeof(unsigned int)));
+    CUDA_TRY(h, cudaMemset(h->comm.counters, 0, 4 * sizeof(unsigned int)));
+    h->comm.rank = rank; h->comm.world = world; h->comm.max_floats = max_floats;
+    cudaIpcMemHandle_t hd;
+    CUDA_TRY(h, cudaIpcGetMemHandle(&hd, h->comm_base));
+    memcpy(ipc_handle_out, &hd, sizeof(hd));
+    return VB_OK;
+}
+
+int vb_comm_connect(vb_handle* h, const void* all_handles) {
+    if (!h) return VB_ERR_ARG;
+    std::lock_guard<std::mutex> lk(h->mu);
+    if (!h->comm_base || !all_handles) { h->set_error("vb_comm_connect: call vb_comm_init first"); return VB_ERR_STATE; }
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    const int world = h->comm.world;
+    const size_t flag_bytes = ((size_t)2 * world * sizeof(int) + 255) & ~(size_t)255;
+    for (int r = 0; r < world; r++) {
+        void* base = h->comm_base;
+        if (r != h->comm.rank) {
+            cudaIpcMemHandle_t hd;
+            memcpy(&hd, static_cast<const char*>(all_handles) + (size_t)r * sizeof(hd), sizeof(hd));
+            cudaError_t e = cudaIpcOpenMemHandle(&base, hd, cudaIpcMemLazyEnablePeerAccess);
+            if (e != cudaSuccess) {
+                h->set_error("vb_comm_connect: cudaIpcOpenMemHandle for rank %d failed: %s (GPUs without peer access?)", r, cudaGetErrorString(e));
+                (void)cudaGetLastError();
+                return VB_ERR_CUDA;
+            }
+        }
+        h->comm_peer[r] = base;
+        h->comm.flags[r] = reinterpret_cast<int*>(base);
+        h->comm.slots[r] = reinterpret_cast<float*>(static_cast<char*>(base) + flag_bytes);
+    }
+    h->comm_ready = true;
+    h->drop_graph();
+    return VB_OK;
+}
+
+int vb_comm_allreduce(vb_handle* h, float* buf_dev, int64_t n, void* stream) {
+    if (!h) return VB_ERR_ARG;
+    std::lock_guard<std::mutex> lk(h->mu);
+    if (!h->comm_ready) { h->set_error("vb_comm_allreduce: call vb_comm_init / vb_comm_connect first"); return VB_ERR_STATE; }
+    if (!buf_dev || n <= 0) { h->set_error("vb_comm_allreduce: bad arguments"); return VB_ERR_ARG; }
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    return enqueue_allreduce(h, (cudaStream_t)stream, buf_dev, n);
+}
+
 int vb_get_edges(vb_handle* h, int32_t* slots_host, int32_t* deg_host) {
     if (!h) return VB_ERR_ARG;
     std::lock_guard<std::mutex> lk(h->mu);
@@ -1253,6 +1343,7 @@ int vb_set_option(vb_handle* h, const char* key, int64_t value) {
     else if (k == "tc_rows" && (value == 32 || value == 64 || value == 96 || value == 128)) h->tc_rows = h->tc_rows_opt = (int)value;
     else if (k == "node_impl" && (value == 0 || value == 1)) h->node_impl = (int)value;
     else if (k == "fused" && (value == 0 || value == 1)) h->fused = h->fused_opt = (int)value;
+    else if (k == "comm_auto" && (value == 0 || value == 1)) h->comm_auto = (int)value;
     else if (k == "timeline" && (value == 0 || value == 1)) {
         if (value && !h->d_tl) {
             if (cudaSetDevice(h->device) != cudaSuccess || cudaMalloc(&h->d_tl, sizeof(unsigned long long) * 2 * L * TC_TL_SLOTS) != cudaSuccess) {
@@ -1279,6 +1370,8 @@ int64_t vb_get_option(const vb_handle* h, const char* key) {
     if (k == "edge_tc") return h->edge_tc;
     if (k == "node_impl") return h->node_impl;
     if (k == "fused") return h->fused;
+    if (k == "comm_auto") return h->comm_auto;
+    if (k == "comm_ready") return h->comm_ready ? 1 : 0;
     if (k == "edge_overflow") {
         int flag = 0;
         if (h->d_flags && cudaMemcpy(&flag, h->d_flags, sizeof(int), cudaMemcpyDeviceToHost) != cudaSuccess) return VB_ERR_CUDA;

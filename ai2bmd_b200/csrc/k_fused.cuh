@@ -34,9 +34,17 @@ constexpr int FU_NB = 4;                 // nodes per block: a 4-node block has 
 static_assert(sizeof(NodeFwd2Smem<FU_NB>) <= sizeof(float) * (TC_TE * TC_LT + TC_TILE_EXT), "node stage rows must fit the staging tile");
 static_assert(sizeof(NodeBwd2Smem<FU_NB>) <= sizeof(float) * (TC_TE * TC_LT + TC_TILE_EXT), "node adjoint rows must fit the staging tile");
 static_assert(N2Cfg<FU_NB>::WARPS == TC2_CWARPS, "the node stage runs on the compute warps");
-constexpr int FU_RPW = TC_TE / TC2_CWARPS;   // 8 row slots per compute warp: row(r) = r * 16 + warp
+constexpr int FU_RPW = TC_TE / TC2_CWARPS;   // up to 8 rows per compute warp
 
-__device__ __forceinline__ int fu_row(int r, int warp) { return r * TC2_CWARPS + warp; }
+// Rows of a sub-tile are dealt to the compute warps in contiguous runs of rpw = ceil(nvalid / 16): consecutive rows mostly
+// share their target node, so a warp's target-side gathers of one batch coalesce into one L2 request.  Row slot r of a
+// warp is row warp * rpw + r (valid while r < rpw and the row is below nvalid).
+struct FuRows {
+    int rpw, base, nvalid;
+    __device__ __forceinline__ FuRows(int nvalid_, int warp) : rpw((nvalid_ + TC2_CWARPS - 1) / TC2_CWARPS), base(warp * rpw), nvalid(nvalid_) {}
+    __device__ __forceinline__ int row(int r) const { return base + r; }
+    __device__ __forceinline__ bool ok(int r) const { return r < rpw && base + r < nvalid; }
+};
 
 // number of sub-tiles this CTA will run (identical in the producer, the MMA issuer and the compute warps)
 __device__ __forceinline__ int fu_count_tiles(const Workspace& ws) {
@@ -122,6 +130,7 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) fused_fwd_kernel(const __grid_
             for (int e0 = eb; e0 < ee; e0 += TC_TE, t++) {
                 const uint32_t tpar = (uint32_t)(t & 1);
                 const int nvalid = min(TC_TE, ee - e0);
+                const FuRows R(nvalid, warp);
                 // ---- load f tile + meta (coalesced) ----
                 for (int idx = threadIdx.x; idx < nvalid * 32; idx += TC2_CTHREADS) {
                     const int row = idx >> 5, c4 = (idx & 31) * 4;
@@ -144,9 +153,9 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) fused_fwd_kernel(const __grid_
                     const float4 bb = ldg4(lw.b1 + col);
 #pragma unroll
                     for (int r = 0; r < FU_RPW; r++) {
-                        const int row = fu_row(r, warp);
+                        const int row = R.row(r);
                         Areg[r] = 0.f;
-                        if (row < nvalid) {
+                        if (R.ok(r)) {
                             const float4 qi = ldg4(QKV + (size_t)sh.meta.dst[row] * 3 * D + col);
                             const float4 kj = ldg4(QKV + (size_t)sh.meta.src[row] * 3 * D + D + col);
                             const float4 P = ld4(&sh.tile[row][col]) + bb;
@@ -168,8 +177,8 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) fused_fwd_kernel(const __grid_
                     const float4 bb = ldg4(lw.b1 + D + col);
 #pragma unroll
                     for (int r = 0; r < FU_RPW; r++) {
-                        const int row = fu_row(r, warp);
-                        if (row < nvalid) {
+                        const int row = R.row(r);
+                        if (R.ok(r)) {
                             const float4 vj = ldg4(QKV + (size_t)sh.meta.src[row] * 3 * D + 2 * D + col);
                             const float4 P = ld4(&sh.tile[row][col]) + bb;
                             st4(&sh.tile[row][col], vj * silu4(P) * Areg[r]);
@@ -200,12 +209,12 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) fused_fwd_kernel(const __grid_
                     const float4 bb = ldg4(lw.b1 + 2 * D + col);
 #pragma unroll 1
                     for (int rb = 0; rb < FU_RPW; rb += 2) {       // gathers of 2 rows in flight before the first global store
-                        if (fu_row(rb, warp) >= nvalid) break;
+                        if (!R.ok(rb)) break;
                         float4 tir[2][3], ujr[2][3], fin[2];
 #pragma unroll
                         for (int u = 0; u < 2; u++) {
-                            const int row = fu_row(rb + u, warp);
-                            const bool ok = row < nvalid;
+                            const int row = R.row(rb + u);
+                            const bool ok = R.ok(rb + u);
                             const size_t i3 = (size_t)sh.meta.dst[ok ? row : 0] * 3, j3 = (size_t)sh.meta.src[ok ? row : 0] * 3;
                             fin[u] = ok ? ldg4(Fin + (size_t)(e0 + row) * D + col) : f4s(0.f);
 #pragma unroll
@@ -216,8 +225,8 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) fused_fwd_kernel(const __grid_
                         }
 #pragma unroll
                         for (int u = 0; u < 2; u++) {
-                            const int row = fu_row(rb + u, warp);
-                            if (row < nvalid) {
+                            const int row = R.row(rb + u);
+                            if (R.ok(rb + u)) {
                                 const float4 dd = sh.meta.d[row];
                                 const float4 Pf = ld4(&sh.tile[row][col]) + bb;
                                 const float4 fp = silu4(Pf);
@@ -301,7 +310,7 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) fused_fwd_kernel(const __grid_
                 csync();                                              // tile / meta free; XA / VA updates visible CTA-wide
             }
             // ---- node stage l + 1 of this block (its xa / va are complete) ----
-            node_fwd2_body<FU_NB>(a.mw, ws, l + 1, n0, reinterpret_cast<float*>(&sh.tile[0][0]), [] { csync(); });
+            node_fwd2_body<FU_NB, 2>(a.mw, ws, l + 1, n0, reinterpret_cast<float*>(&sh.tile[0][0]), [] { csync(); });
             csync();                                                  // node-stage shared rows (aliasing the tile) are free
         }
     }
@@ -349,24 +358,25 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) fused_bwd_kernel(const __grid_
         for (int b = blockIdx.x; b < nblocks; b += gridDim.x) {
             const int n0 = b * FU_NB, n1 = min(n0 + FU_NB, ws.N);
             // ---- node adjoint l + 1 of this block: consumes the accumulators of parity (l+1)&1, writes GX / GVEC / GXA ----
-            node_bwd2_body<FU_NB>(a.mw, ws, l + 1, n0, a.con_qkv, a.con_vn, a.con_tu, reinterpret_cast<float*>(&sh.tile[0][0]),
+            node_bwd2_body<FU_NB, 2>(a.mw, ws, l + 1, n0, a.con_qkv, a.con_vn, a.con_tu, reinterpret_cast<float*>(&sh.tile[0][0]),
                                   [] { csync(); });
             csync();                                                  // GVEC / GXA of the block visible; node rows (aliasing the tile) free
             const int eb = ws.rowptr[n0], ee = ws.rowptr[n1];
             for (int e0 = eb; e0 < ee; e0 += TC_TE, t++) {
                 const uint32_t tpar = (uint32_t)(t & 1);
                 const int nvalid = min(TC_TE, ee - e0);
+                const FuRows R(nvalid, warp);
                 load_edge_meta<TC_TE, TC2_CTHREADS>(sh.meta, ws, e0, nvalid);
                 csync();
                 // ---- s1 half: g_Spre[:, 0:128] -> tile -> A ; source-side g_vn ----
 #pragma unroll 1
                 for (int rb = 0; rb < FU_RPW; rb += RB4) {
-                    if (fu_row(rb, warp) >= nvalid) break;
+                    if (!R.ok(rb)) break;
                     float4 sp[RB4], gM[RB4][3], vn[RB4][3];
 #pragma unroll
                     for (int u = 0; u < RB4; u++) {
-                        const int row = fu_row(rb + u, warp);
-                        const int rr = row < nvalid ? row : 0;
+                        const int row = R.row(rb + u);
+                        const int rr = R.ok(rb + u) ? row : 0;
                         const size_t e = (size_t)(e0 + rr);
                         const size_t i3 = (size_t)sh.meta.dst[rr] * 3, j3 = (size_t)sh.meta.src[rr] * 3;
                         sp[u] = ldg4(SP + e * 2 * D + col);
@@ -375,8 +385,8 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) fused_bwd_kernel(const __grid_
                     }
 #pragma unroll
                     for (int u = 0; u < RB4; u++) {
-                        const int row = fu_row(rb + u, warp);
-                        if (row < nvalid) {
+                        const int row = R.row(rb + u);
+                        if (R.ok(rb + u)) {
                             const size_t j3 = (size_t)sh.meta.src[row] * 3;
                             const float4 s1 = silu4(sp[u]);
                             const float4 gs1 = gM[u][0] * vn[u][0] + gM[u][1] * vn[u][1] + gM[u][2] * vn[u][2];
@@ -394,8 +404,8 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) fused_bwd_kernel(const __grid_
                 // ---- s2 half ----
 #pragma unroll 4
                 for (int r = 0; r < FU_RPW; r++) {
-                    const int row = fu_row(r, warp);
-                    if (row < nvalid) {
+                    const int row = R.row(r);
+                    if (R.ok(r)) {
                         const size_t e = (size_t)(e0 + row);
                         const size_t i3 = (size_t)sh.meta.dst[row] * 3;
                         const float4 dd = sh.meta.d[row];
@@ -420,13 +430,13 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) fused_bwd_kernel(const __grid_
                 csync();
 #pragma unroll 1
                 for (int rb = 0; rb < FU_RPW; rb += RB4) {
-                    if (fu_row(rb, warp) >= nvalid) break;
+                    if (!R.ok(rb)) break;
                     float4 gxa[RB4], vjr[RB4], pdvr[RB4];
                     float avr[RB4];
 #pragma unroll
                     for (int u = 0; u < RB4; u++) {
-                        const int row = fu_row(rb + u, warp);
-                        const int rr = row < nvalid ? row : 0;
+                        const int row = R.row(rb + u);
+                        const int rr = R.ok(rb + u) ? row : 0;
                         const size_t e = (size_t)(e0 + rr);
                         gxa[u] = ld4(GXA + (size_t)sh.meta.dst[rr] * D + col);
                         vjr[u] = ldg4(QKV + (size_t)sh.meta.src[rr] * 3 * D + 2 * D + col);
@@ -435,8 +445,8 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) fused_bwd_kernel(const __grid_
                     }
 #pragma unroll
                     for (int u = 0; u < RB4; u++) {
-                        const int row = fu_row(rb + u, warp);
-                        if (row < nvalid) {                              // warp-uniform
+                        const int row = R.row(rb + u);
+                        if (R.ok(rb + u)) {                              // warp-uniform
                             const size_t j = sh.meta.src[row];
                             const float Ce = sh.meta.C[row];
                             const float av = avr[u], sa = silu_(av), A = sa * Ce;
@@ -458,12 +468,12 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) fused_bwd_kernel(const __grid_
                 // ---- adjoint of a_h = sum q_i k_j dk : first g_Pdk (next A operand), then the g_q tile ----
 #pragma unroll 1
                 for (int rb = 0; rb < FU_RPW; rb += RB4) {
-                    if (fu_row(rb, warp) >= nvalid) break;
+                    if (!R.ok(rb)) break;
                     float4 pdkr[RB4], qir[RB4], kjr[RB4];
 #pragma unroll
                     for (int u = 0; u < RB4; u++) {
-                        const int row = fu_row(rb + u, warp);
-                        const int rr = row < nvalid ? row : 0;
+                        const int row = R.row(rb + u);
+                        const int rr = R.ok(rb + u) ? row : 0;
                         const size_t e = (size_t)(e0 + rr);
                         pdkr[u] = ldg4(P1 + e * 3 * D + col);
                         qir[u] = ldg4(QKV + (size_t)sh.meta.dst[rr] * 3 * D + col);
@@ -471,8 +481,8 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) fused_bwd_kernel(const __grid_
                     }
 #pragma unroll
                     for (int u = 0; u < RB4; u++) {
-                        const int row = fu_row(rb + u, warp);
-                        if (row < nvalid) {
+                        const int row = R.row(rb + u);
+                        if (R.ok(rb + u)) {
                             const size_t j = sh.meta.src[row];
                             const float4 dk = silu4(pdkr[u]);
                             const float gav = sh.gattn[row][hd];
@@ -488,8 +498,8 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) fused_bwd_kernel(const __grid_
                 csync();
 #pragma unroll 4
                 for (int r = 0; r < FU_RPW; r++) {
-                    const int row = fu_row(r, warp);
-                    if (row < nvalid) {
+                    const int row = R.row(r);
+                    if (R.ok(r)) {
                         const size_t e = (size_t)(e0 + row);
                         const float4 dk = silu4(ldg4(P1 + e * 3 * D + col));
                         const float4 kj = ldg4(QKV + (size_t)sh.meta.src[row] * 3 * D + D + col);
@@ -510,12 +520,12 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) fused_bwd_kernel(const __grid_
                     csync();
 #pragma unroll 1
                     for (int rb = 0; rb < FU_RPW; rb += 2) {
-                        if (fu_row(rb, warp) >= nvalid) break;
+                        if (!R.ok(rb)) break;
                         float4 gfr[2], pfr[2], tir[2][3], ujr[2][3];
 #pragma unroll
                         for (int u = 0; u < 2; u++) {
-                            const int row = fu_row(rb + u, warp);
-                            const int rr = row < nvalid ? row : 0;
+                            const int row = R.row(rb + u);
+                            const int rr = R.ok(rb + u) ? row : 0;
                             const size_t e = (size_t)(e0 + rr);
                             const size_t i3 = (size_t)sh.meta.dst[rr] * 3, j3 = (size_t)sh.meta.src[rr] * 3;
                             gfr[u] = ld4(ws.GF + e * D + col);
@@ -528,8 +538,8 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) fused_bwd_kernel(const __grid_
                         }
 #pragma unroll
                         for (int u = 0; u < 2; u++) {
-                            const int row = fu_row(rb + u, warp);
-                            if (row < nvalid) {
+                            const int row = R.row(rb + u);
+                            if (R.ok(rb + u)) {
                                 const size_t j3 = (size_t)sh.meta.src[row] * 3;
                                 const float4 dd = sh.meta.d[row];
                                 const float4 gfn = gfr[u], pf = pfr[u];
@@ -567,8 +577,8 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) fused_bwd_kernel(const __grid_
                     csync();
 #pragma unroll 4
                     for (int r = 0; r < FU_RPW; r++) {
-                        const int row = fu_row(r, warp);
-                        if (row < nvalid) {
+                        const int row = R.row(r);
+                        if (R.ok(r)) {
                             const size_t e = (size_t)(e0 + row);
                             const float4 gfn = ld4(ws.GF + e * D + col);
                             st4(&sh.tile[row][col], gfn * silu4(ldg4(P1 + e * 3 * D + 2 * D + col)));   // g_wdot
@@ -620,8 +630,8 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) fused_bwd_kernel(const __grid_
                 csync();
 #pragma unroll 4
                 for (int r = 0; r < FU_RPW; r++) {
-                    const int row = fu_row(r, warp);
-                    if (row < nvalid) {
+                    const int row = R.row(r);
+                    if (R.ok(r)) {
                         float* g = ws.GF + (size_t)(e0 + row) * D + col;
                         float4 v = ld4(&sh.tile[row][col]);
                         if (upd) v = v + ld4(g);

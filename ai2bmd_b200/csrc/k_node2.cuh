@@ -29,7 +29,7 @@ struct NodeFwd2Smem {
 // Body shared by the stand-alone kernel below and by the fused per-layer kernel (k_fused.cuh): the N2Cfg<NB>::WARPS
 // warps with threadIdx.x < N2Cfg<NB>::THREADS run it for nodes [n0, n0 + NB); `sync` is a barrier among exactly those
 // threads (__syncthreads in the stand-alone kernel, a named barrier of the compute warps in the fused one).
-template <int NB, typename SyncF>
+template <int NB, int NBUF = 4, typename SyncF>
 __device__ __forceinline__ void node_fwd2_body(const ModelW& mw, const Workspace& ws, const int k, const int n0,
                                                float* dyn_smem, SyncF sync) {
     constexpr int N2_WARPS = N2Cfg<NB>::WARPS, N2_THREADS = N2Cfg<NB>::THREADS;
@@ -54,7 +54,7 @@ __device__ __forceinline__ void node_fwd2_body(const ModelW& mw, const Workspace
                 float acc[N2_RB][4];
                 if (kq == 0) acc_set_bias<N2_RB>(acc, lw.bo + ch * D, lane);
                 else acc_zero<N2_RB>(acc);
-                warp_gemm<N2_RB, D / 4, LDA, 4>(acc, &sm.xs[0][kq * (D / 4)], lw.WoT + (size_t)kq * (D / 4) * 3 * D + ch * D, 3 * D, lane);
+                warp_gemm<N2_RB, D / 4, LDA, NBUF>(acc, &sm.xs[0][kq * (D / 4)], lw.WoT + (size_t)kq * (D / 4) * 3 * D + ch * D, 3 * D, lane);
 #pragma unroll
                 for (int r = 0; r < N2_RB; r++) {
                     if (kq == 0) st4(&sm.os[r][ch * D + col], arr4(acc[r]));
@@ -71,7 +71,7 @@ __device__ __forceinline__ void node_fwd2_body(const ModelW& mw, const Workspace
                 const int ch = u % 3, rb = u / 3;
                 float acc[N2_RB][4];
                 acc_set_bias<N2_RB>(acc, lw.bo + ch * D, lane);
-                warp_gemm<N2_RB, D, LDA, (NB <= 8 ? 4 : 2)>(acc, &sm.xs[rb * N2_RB][0], lw.WoT + ch * D, 3 * D, lane);
+                warp_gemm<N2_RB, D, LDA, (NB <= 8 ? NBUF : 2)>(acc, &sm.xs[rb * N2_RB][0], lw.WoT + ch * D, 3 * D, lane);
 #pragma unroll
                 for (int r = 0; r < N2_RB; r++) st4(&sm.os[rb * N2_RB + r][ch * D + col], arr4(acc[r]));
             }
@@ -129,7 +129,7 @@ __device__ __forceinline__ void node_fwd2_body(const ModelW& mw, const Workspace
         if (u < UQ) {
             const int ch = u % 3, rb = u / 3;
             acc_set_bias<N2_RB>(acc, lw.bqkv + ch * D, lane);
-            warp_gemm<N2_RB, D, LDA, (NB <= 8 ? 4 : 2)>(acc, &sm.xs[rb * N2_RB][0], lw.WqkvT + ch * D, 3 * D, lane);
+            warp_gemm<N2_RB, D, LDA, (NB <= 8 ? NBUF : 2)>(acc, &sm.xs[rb * N2_RB][0], lw.WqkvT + ch * D, 3 * D, lane);
 #pragma unroll
             for (int r = 0; r < N2_RB; r++) {
                 const int nd = rb * N2_RB + r;
@@ -138,7 +138,7 @@ __device__ __forceinline__ void node_fwd2_body(const ModelW& mw, const Workspace
         } else if (u < UQ + UV) {
             const int v = u - UQ, ch = v % 3, rb = v / 3;
             acc_zero<N2_RB>(acc);
-            warp_gemm<N2_RB, D, LDA, (NB <= 8 ? 4 : 2)>(acc, &sm.vs[rb * N2_RB][0], lw.WvecT + ch * D, 3 * D, lane);
+            warp_gemm<N2_RB, D, LDA, (NB <= 8 ? NBUF : 2)>(acc, &sm.vs[rb * N2_RB][0], lw.WvecT + ch * D, 3 * D, lane);
 #pragma unroll
             for (int r = 0; r < N2_RB; r++) {
                 const int row = rb * N2_RB + r;                  // = nd*3 + s
@@ -147,7 +147,7 @@ __device__ __forceinline__ void node_fwd2_body(const ModelW& mw, const Workspace
         } else {
             const int v = u - UQ - UV, ch = v % 2, rb = v / 2;
             acc_zero<N2_RB>(acc);
-            warp_gemm<N2_RB, D, LDA, (NB <= 8 ? 4 : 2)>(acc, &sm.vs[rb * N2_RB][0], lw.WtuT + ch * D, 2 * D, lane);
+            warp_gemm<N2_RB, D, LDA, (NB <= 8 ? NBUF : 2)>(acc, &sm.vs[rb * N2_RB][0], lw.WtuT + ch * D, 2 * D, lane);
 #pragma unroll
             for (int r = 0; r < N2_RB; r++) {
                 const int row = rb * N2_RB + r;
@@ -169,7 +169,7 @@ template <int NB>
 __global__ void __launch_bounds__(N2Cfg<NB>::THREADS) node_fwd2_kernel(NodeArgs a) {
     pdl_entry();
     extern __shared__ __align__(16) float dyn_smem[];
-    node_fwd2_body<NB>(a.mw, a.ws, a.layer, (int)blockIdx.x * NB, dyn_smem, [] { __syncthreads(); });
+    node_fwd2_body<NB, 4>(a.mw, a.ws, a.layer, (int)blockIdx.x * NB, dyn_smem, [] { __syncthreads(); });
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -192,7 +192,7 @@ struct NodeBwd2Smem {
 
 // Body (see node_fwd2_body).  GQKV / GVNMSG / GTU are the accumulators the edge adjoint of layer k added into; they are
 // consumed and re-zeroed here (the fused pipeline alternates between two sets, the stand-alone one uses ws.G*).
-template <int NB, typename SyncF>
+template <int NB, int NBUF = 4, typename SyncF>
 __device__ __forceinline__ void node_bwd2_body(const ModelW& mw, const Workspace& ws, const int k, const int n0,
                                                float* __restrict__ GQKV, float* __restrict__ GVNMSG, float* __restrict__ GTU,
                                                float* dyn_smem, SyncF sync) {
@@ -246,13 +246,13 @@ __device__ __forceinline__ void node_bwd2_body(const ModelW& mw, const Workspace
             acc_zero<N2_RB>(acc);
             if (u < UX) {
                 const int kc = u % 3, rb = u / 3;
-                warp_gemm<N2_RB, D, LD3, 4>(acc, &sm.gq[rb * N2_RB][kc * D], lw.WqkvN + (size_t)kc * D * D, D, lane);
+                warp_gemm<N2_RB, D, LD3, NBUF>(acc, &sm.gq[rb * N2_RB][kc * D], lw.WqkvN + (size_t)kc * D * D, D, lane);
 #pragma unroll
                 for (int r = 0; r < N2_RB; r++) st4(&sm.part_x[kc][rb * N2_RB + r][col], arr4(acc[r]));
             } else {
                 const int v = u - UX, kc = v % kv, rb = v / kv;
-                if (kc < 3) warp_gemm<N2_RB, D, LD3, 4>(acc, &sm.gvp[rb * N2_RB][kc * D], lw.WvecN + (size_t)kc * D * D, D, lane);
-                else        warp_gemm<N2_RB, D, LD2, 4>(acc, &sm.gtu[rb * N2_RB][(kc - 3) * D], lw.WtuN + (size_t)(kc - 3) * D * D, D, lane);
+                if (kc < 3) warp_gemm<N2_RB, D, LD3, NBUF>(acc, &sm.gvp[rb * N2_RB][kc * D], lw.WvecN + (size_t)kc * D * D, D, lane);
+                else        warp_gemm<N2_RB, D, LD2, NBUF>(acc, &sm.gtu[rb * N2_RB][(kc - 3) * D], lw.WtuN + (size_t)(kc - 3) * D * D, D, lane);
 #pragma unroll
                 for (int r = 0; r < N2_RB; r++) st4(&sm.part_v[kc][rb * N2_RB + r][col], arr4(acc[r]));
             }
@@ -316,7 +316,7 @@ __device__ __forceinline__ void node_bwd2_body(const ModelW& mw, const Workspace
             const int kc = u % 3, rb = u / 3;
             float acc[N2_RB][4];
             acc_zero<N2_RB>(acc);
-            warp_gemm<N2_RB, D, LD3, 4>(acc, &sm.gq[rb * N2_RB][kc * D], lw.WoN + (size_t)kc * D * D, D, lane);
+            warp_gemm<N2_RB, D, LD3, NBUF>(acc, &sm.gq[rb * N2_RB][kc * D], lw.WoN + (size_t)kc * D * D, D, lane);
 #pragma unroll
             for (int r = 0; r < N2_RB; r++) st4(&sm.part_x[kc][rb * N2_RB + r][col], arr4(acc[r]));
         }
@@ -331,7 +331,7 @@ template <int NB>
 __global__ void __launch_bounds__(N2Cfg<NB>::THREADS) node_bwd2_kernel(NodeArgs a) {
     pdl_entry();
     extern __shared__ __align__(16) float dyn_smem[];
-    node_bwd2_body<NB>(a.mw, a.ws, a.layer, (int)blockIdx.x * NB, a.ws.GQKV, a.ws.GVNMSG, a.ws.GTU, dyn_smem, [] { __syncthreads(); });
+    node_bwd2_body<NB, 4>(a.mw, a.ws, a.layer, (int)blockIdx.x * NB, a.ws.GQKV, a.ws.GVNMSG, a.ws.GTU, dyn_smem, [] { __syncthreads(); });
 }
 
 }  // namespace vb

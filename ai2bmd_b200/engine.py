@@ -30,6 +30,7 @@ EXPORTED_SYMBOLS = [
     "vb_set_option", "vb_get_option", "vb_num_stages", "vb_stage_name", "vb_debug_run", "vb_debug_read", "vb_profile_stages", "vb_tc_selftest",
     "vb_md_setup", "vb_md_set_normals", "vb_md_set_state", "vb_md_kick1", "vb_md_eval", "vb_md_kick2", "vb_md_run", "vb_md_get_state",
     "vb_set_nonbonded", "vb_nonbonded",
+    "vb_comm_init", "vb_comm_connect", "vb_comm_allreduce",
 ]
 
 
@@ -97,6 +98,12 @@ def load_library(path: Optional[str] = None):
     lib.vb_set_nonbonded.argtypes = [vp, i64, vp, vp, vp, vp, vp, i64, i64]
     lib.vb_nonbonded.restype = C.c_int
     lib.vb_nonbonded.argtypes = [vp, vp, vp, vp]
+    lib.vb_comm_init.restype = C.c_int
+    lib.vb_comm_init.argtypes = [vp, C.c_int, C.c_int, i64, vp]
+    lib.vb_comm_connect.restype = C.c_int
+    lib.vb_comm_connect.argtypes = [vp, vp]
+    lib.vb_comm_allreduce.restype = C.c_int
+    lib.vb_comm_allreduce.argtypes = [vp, vp, i64, vp]
     lib.vb_md_get_state.restype = C.c_int
     lib.vb_md_get_state.argtypes = [vp, vp, vp, vp, vp, i64]
     if path == _build.LIB_PATH:
@@ -188,6 +195,21 @@ class Engine:
 
     def forward_protein_device(self, pos_ptr: int, ef_ptr: int, stream_ptr: int = 0):
         self._check(self.lib.vb_forward_protein(self.h, pos_ptr, ef_ptr, stream_ptr), "vb_forward_protein")
+
+    # ---- NVLink peer-memory all-reduce (include/visnet_b200.h: vb_comm_*) ----
+    def comm_init(self, rank: int, world: int, max_floats: int) -> bytes:
+        """Allocate this rank's window; returns its 64-byte CUDA IPC handle (exchange it with every other rank)."""
+        buf = C.create_string_buffer(64)
+        self._check(self.lib.vb_comm_init(self.h, int(rank), int(world), int(max_floats), buf), "vb_comm_init")
+        return bytes(buf.raw)
+
+    def comm_connect(self, handles) -> None:
+        """``handles``: the IPC handles of all ranks in rank order (this rank's own included)."""
+        blob = b"".join(bytes(x) for x in handles)
+        self._check(self.lib.vb_comm_connect(self.h, C.c_char_p(blob)), "vb_comm_connect")
+
+    def comm_allreduce(self, buf_ptr: int, n: int, stream_ptr: int = 0):
+        self._check(self.lib.vb_comm_allreduce(self.h, buf_ptr, int(n), stream_ptr), "vb_comm_allreduce")
 
     # ---- non-bonded MM term ----
     def set_nonbonded(self, charges, sigmas_nm, epsilons_kj, excl_rowptr, excl_col, atom_lo: int = 0, atom_hi: int = -1):

@@ -181,10 +181,15 @@ class DeviceLangevin:
         engine.md_set_state(x, velocities, 0)
         self._eval()
 
+    @property
+    def _native_comm(self):
+        """True when the engine all-reduces the force buffer itself (peer-memory all-reduce inside the step graph)."""
+        return self.group is not None and self.engine.get_option("comm_ready") == 1 and self.engine.get_option("comm_auto") == 1
+
     def _eval(self):
         sp = self.stream.cuda_stream
         self.engine.md_eval(sp)
-        if self.group is not None:
+        if self.group is not None and not self._native_comm:
             self.torch.distributed.all_reduce(self.ef, group=self.group)
 
     def set_normals(self, pool):
@@ -198,7 +203,7 @@ class DeviceLangevin:
 
     def run(self, n_steps: int):
         sp = self.stream.cuda_stream
-        if self.group is None:
+        if self.group is None or self._native_comm:      # whole step (incl. the all-reduce) = one graph replay
             self.engine.md_run(n_steps, sp)
             return
         for _ in range(n_steps):

@@ -112,9 +112,15 @@ class ShardedBondedCalculator:
 
 
 class DeviceShard:
-    """Device-resident shard: engine + protein map + persistent torch buffers; one NCCL all-reduce/step."""
+    """Device-resident shard: engine + protein map + persistent torch buffers; one all-reduce per step.
 
-    def __init__(self, state_dict, frags: FragmentData, pm: ProteinMap, rank: int, world_size: int, device: int):
+    With ``native_comm`` (default) the ranks exchange CUDA IPC handles once (``torch.distributed`` is only the host
+    transport for those 64 bytes) and every evaluation then ends with the engine's own one-shot all-reduce over NVLink
+    peer memory, captured in the step's CUDA graph (``csrc/k_comm.cuh``).  If peer mapping is not possible on this box
+    the ranks fall back -- together -- to ``torch.distributed.all_reduce`` (NCCL) enqueued after the evaluation."""
+
+    def __init__(self, state_dict, frags: FragmentData, pm: ProteinMap, rank: int, world_size: int, device: int,
+                 native_comm: bool = True):
         import torch
         from .engine import Engine
         self.torch = torch
@@ -122,6 +128,8 @@ class DeviceShard:
         self.device = torch.device("cuda", device)
         self.ef = torch.zeros(3 * pm.n_protein + 1, dtype=torch.float32, device=self.device)
         self.engine = None
+        self.comm_engine = None
+        self.native = False
         local = self.plan.local_fragments(frags)
         if local is not None:
             self.engine = Engine(state_dict, device)
@@ -129,6 +137,33 @@ class DeviceShard:
             m = self.plan.local_map
             self.engine.set_protein_map(m.n_protein, m.src_atom, m.dst_atom, m.sign, m.frag_sign)
             self.pos = torch.from_numpy(np.ascontiguousarray(local.pos, dtype=np.float32)).to(self.device)
+        if world_size > 1 and native_comm:
+            import torch.distributed as dist
+            self.comm_engine = self.engine if self.engine is not None else Engine(state_dict, device)   # empty shard: comm only
+            ok = 1
+            try:
+                handle = self.comm_engine.comm_init(rank, world_size, 3 * pm.n_protein + 1)
+            except RuntimeError:
+                handle, ok = b"\0" * 64, 0
+            handles = [None] * world_size
+            dist.all_gather_object(handles, handle)
+            if ok:
+                try:
+                    self.comm_engine.comm_connect(handles)
+                except RuntimeError:
+                    ok = 0
+            flag = torch.tensor([ok], dtype=torch.int32, device=self.device)
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN)          # all ranks use the peer-memory path, or none does
+            self.native = bool(int(flag.item()))
+            if not self.native:
+                self.comm_engine.set_option("comm_auto", 0)
+
+    @property
+    def collective(self) -> str:
+        if self.plan.world_size == 1:
+            return "none (single GPU)"
+        return ("one-shot all-reduce over NVLink peer memory, last kernel of the step graph (k_comm.cuh)" if self.native
+                else "torch.distributed.all_reduce (NCCL), enqueued by the host after the step graph")
 
     def set_positions(self, frag_pos_host: np.ndarray):
         """Upload this rank's slice of the packed fragment positions (pinned -> device)."""
@@ -141,10 +176,12 @@ class DeviceShard:
         torch = self.torch
         stream = torch.cuda.current_stream(self.device).cuda_stream
         if self.engine is not None:
-            self.engine.forward_protein_device(self.pos.data_ptr(), self.ef.data_ptr(), stream)
+            self.engine.forward_protein_device(self.pos.data_ptr(), self.ef.data_ptr(), stream)   # native: reduces too
         else:
             self.ef.zero_()
-        if all_reduce and self.plan.world_size > 1:
+            if self.native and all_reduce:
+                self.comm_engine.comm_allreduce(self.ef.data_ptr(), self.ef.numel(), stream)
+        if all_reduce and self.plan.world_size > 1 and not self.native:
             import torch.distributed as dist
             dist.all_reduce(self.ef, op=dist.ReduceOp.SUM)
         return self.ef

@@ -47,6 +47,8 @@ def parse():
     ap.add_argument("--no-flush", action="store_true", help="keep L2 warm between timed steps (diagnostic)")
     ap.add_argument("--fragments", type=int, default=512, help="fragment count of the synthetic c4 batch")
     ap.add_argument("--skip-cpu-baseline", action="store_true")
+    ap.add_argument("--nccl", action="store_true", help="N > 1: torch.distributed all-reduce instead of the peer-memory one")
+    ap.add_argument("--no-c4", action="store_true", help="N > 1: skip the 512-fragment strong-scaling leg")
     return ap.parse_args()
 
 
@@ -76,35 +78,72 @@ def load_weights():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
-    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """SM clock and throttle reasons sampled every 20 ms through NVML (in-process thread; works the same under torchrun)
+    while ``loaded`` is set, i.e. during the warm-up and the timed GPU regions; nvidia-smi is the fallback."""
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap",
+               0x80: "hw_power_brake_slowdown"}
 
     def __init__(self, index=0):
-        self.rows, self.proc, self.index = [], None, index
+        self.index, self.sm, self.mx, self.mask = index, [], [], 0
+        self.loaded, self._stop, self.thread, self.how = False, False, None, None
+
+    def _nvml_index(self):
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        if vis:
+            ids = [v.strip() for v in vis.split(",") if v.strip()]
+            if self.index < len(ids) and ids[self.index].isdigit():
+                return int(ids[self.index])
+        return self.index
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "200"],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            threading.Thread(target=self._read, daemon=True).start()
+            import pynvml
+            pynvml.nvmlInit()
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(self._nvml_index())
+            self.nv, self.how = pynvml, "nvml, 20 ms period"
+            self.max_clock = int(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
         except Exception:
-            self.proc = None
+            self.nv, self.how = None, "nvidia-smi -lms 100"
+        self.thread = threading.Thread(target=self._run_nvml if self.nv else self._run_smi, daemon=True)
+        self.thread.start()
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append([x.strip() for x in line.split(",")])
+    def _run_nvml(self):
+        nv = self.nv
+        reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
+        while not self._stop:
+            if self.loaded:
+                try:
+                    self.sm.append(int(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                    self.mx.append(self.max_clock)
+                    self.mask |= int(reasons(self.h))
+                except Exception:
+                    pass
+            time.sleep(0.02)
+
+    def _run_smi(self):
+        q = "clocks.sm,clocks.max.sm,clocks_event_reasons.active"
+        try:
+            proc = subprocess.Popen(["nvidia-smi", "-i", str(self._nvml_index()), f"--query-gpu={q}", "--format=csv,noheader,nounits",
+                                     "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            return
+        for line in proc.stdout:
+            if self._stop:
+                break
+            r = [x.strip() for x in line.split(",")]
+            if self.loaded and len(r) >= 3 and r[0].isdigit():
+                self.sm.append(int(r[0])); self.mx.append(int(r[1]) if r[1].isdigit() else 0)
+                try:
+                    self.mask |= int(r[2], 16)
+                except ValueError:
+                    pass
+        proc.terminate()
 
     def stop(self):
-        if self.proc:
-            self.proc.terminate()
-        sm = [int(r[0]) for r in self.rows if r and r[0].isdigit()]
-        mx = [int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()]
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({n for r in self.rows if len(r) >= 6 for n, v in zip(names, r[2:6]) if v.lower().startswith("active")})
-        return {"sm_mhz": int(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(sm)}
+        self._stop = True
+        names = sorted(n for bit, n in self.REASONS.items() if self.mask & bit)
+        return {"sm_mhz": int(np.median(self.sm)) if self.sm else None, "sm_max_mhz": max(self.mx) if self.mx else None,
+                "reasons": names, "samples": len(self.sm), "how": self.how}
 
 
 def algorithmic_bytes(stage, n_atoms, n_edges):
@@ -218,7 +257,7 @@ def run_reference(args):
         "impl": "reference", "metric": "MD steps/sec", "value": value, "unit": "steps/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "example-PDB geometry, shipped checkpoint weights",
-        "config": {"workload": f"{desc}: G={len(fd)} N={len(fd.z)}", "device": "host CPU"},
+        "config": {"workload": workload_string(desc, fd), "device": "host CPU"},
         "cpu_baseline": {"value": value, "unit": "steps/s", "cores": threads, "host_threads_available": avail,
                          "kind": "port", "sample": sample_desc},
         "e2e": {"value": value, "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -226,11 +265,49 @@ def run_reference(args):
     print(json.dumps(line))
 
 
+def workload_string(desc, fd):
+    """Identical in both arms (the driver compares the strings)."""
+    return f"{desc}: G={len(fd)} N={len(fd.z)}"
+
+
+def time_shard_steps(torch, dist, shard, steps, warmup, world, flush=None):
+    """Device time of `steps` evaluations of a DeviceShard (CUDA events around each step, max over ranks), seconds."""
+    stream = torch.cuda.current_stream()
+    for _ in range(max(3, warmup)):
+        shard.step()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    for a, b in ev:
+        if flush is not None:
+            flush.fill_(1.0)
+        a.record(stream)
+        shard.step()
+        b.record(stream)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t = torch.tensor([sum(a.elapsed_time(b) for a, b in ev) / 1e3], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def golden_reference(workload):
+    """Outputs of the reference's own model source on this workload (tests/golden/make_golden.py), if committed."""
+    path = os.path.join(ROOT, "tests", "golden", "reference_outputs.npz")
+    if workload not in ("chig", "trpcage") or not os.path.exists(path):
+        return None
+    r = np.load(path)
+    return {"e": r[f"{workload}_ref_e"], "f": r[f"{workload}_ref_f"], "e64": r[f"{workload}_e64"], "f64": r[f"{workload}_f64"]}
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
     from ai2bmd_b200.calculator import ViSNetModel
-    from ai2bmd_b200.parallel import DeviceShard
+    from ai2bmd_b200.parallel import DeviceShard, combine_local
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -247,7 +324,7 @@ def run_ours(args):
     sd = load_weights()
     n_atoms, n_frag = len(fd.z), len(fd)
 
-    shard = DeviceShard(sd, fd, pm, rank, world, local)
+    shard = DeviceShard(sd, fd, pm, rank, world, local, native_comm=not args.nccl)
     stream = torch.cuda.current_stream()
     flush = None if args.no_flush else torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device="cuda")
 
@@ -256,30 +333,16 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---- device-resident timing (value) ----
-    for _ in range(max(3, args.warmup)):
-        shard.step()
-    barrier()
     clocks = ClockSampler(local)
     if rank == 0:
         clocks.start()
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    barrier()
+    clocks.loaded = True
+    # ---- device-resident timing (value): CUDA events around each step, L2 flushed before each, max over ranks ----
     wall0 = time.perf_counter()
-    for a, b in ev:
-        if flush is not None:
-            flush.fill_(1.0)
-        a.record(stream)
-        shard.step()
-        b.record(stream)
-    barrier()
+    t_dev = time_shard_steps(torch, dist, shard, args.steps, args.warmup, world, flush)
     wall = time.perf_counter() - wall0
-    t_dev = sum(a.elapsed_time(b) for a, b in ev) / 1e3          # seconds, this rank
-    t = torch.tensor([t_dev], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    t_dev = float(t.item())
     ef = shard.ef.clone()
+    n_edges_local = int(shard.engine.get_edges()[1].sum()) if shard.engine is not None else 0   # edges of the timed positions
     # ---- warm-L2 variant (diagnostic) ----
     barrier()
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -291,17 +354,34 @@ def run_ours(args):
     t_warm = torch.tensor([a.elapsed_time(b) / 1e3], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t_warm, op=dist.ReduceOp.MAX)
-    clock_info = clocks.stop() if rank == 0 else None
+    # ---- the collective alone (N > 1): all-reduce of the [3*N_prot + 1] buffer, device time per call ----
+    comm = None
+    if world > 1:
+        buf = torch.zeros(3 * pm.n_protein + 1, dtype=torch.float32, device="cuda")
+
+        def one_reduce():
+            if shard.native:
+                shard.comm_engine.comm_allreduce(buf.data_ptr(), buf.numel(), stream.cuda_stream)
+            else:
+                dist.all_reduce(buf)
+        for _ in range(5):
+            one_reduce()
+        barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(stream)
+        for _ in range(50):
+            one_reduce()
+        b.record(stream)
+        barrier()
+        t_c = torch.tensor([a.elapsed_time(b) / 50.0 * 1e3], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t_c, op=dist.ReduceOp.MAX)
+        comm = {"us_per_allreduce": float(t_c.item()), "bytes": 4 * (3 * pm.n_protein + 1), "how": shard.collective}
 
     # ---- end-to-end through the reference-facing call, host buffers (rank-local shard + all-reduce) ----
-    e2e = None
     local_frags = shard.plan.local_fragments(fd)
     model = None
     if local_frags is not None:
-        model = ViSNetModel.__new__(ViSNetModel)                 # reuse the shard's engine (same weights/device)
-        model.device, model.engine, model._topo_key = f"cuda:{local}", shard.engine, None
-        model._ensure_topology(local_frags)                       # same topology: no re-allocation cost in the loop
-    from ai2bmd_b200.parallel import combine_local
+        model = ViSNetModel.from_engine(shard.engine, f"cuda:{local}", local_frags)   # the shard's engine, topology already set
     ef_host = torch.zeros(3 * pm.n_protein + 1, dtype=torch.float32).pin_memory()
     ef_dev = torch.zeros(3 * pm.n_protein + 1, dtype=torch.float32, device="cuda")
 
@@ -312,7 +392,10 @@ def run_ours(args):
             loc = combine_local(shard.plan.local_map, e, f) if model is not None else np.zeros(3 * pm.n_protein + 1, np.float32)
             ef_host.copy_(torch.from_numpy(loc))
             ef_dev.copy_(ef_host, non_blocking=True)
-            dist.all_reduce(ef_dev)
+            if shard.native:
+                shard.comm_engine.comm_allreduce(ef_dev.data_ptr(), ef_dev.numel(), stream.cuda_stream)
+            else:
+                dist.all_reduce(ef_dev)
             ef_host.copy_(ef_dev)
         return None
 
@@ -357,12 +440,47 @@ def run_ours(args):
             t_md = torch.tensor([a.elapsed_time(b) / 1e3], dtype=torch.float64, device="cuda")
             if world > 1:
                 dist.all_reduce(t_md, op=dist.ReduceOp.MAX)
+            one_graph = world == 1 or shard.native
             md_device = {"value": args.steps / float(t_md.item()), "unit": "steps/s", "temperature_K": dmd.temperature(),
-                         "launches_per_step": shard.engine.launches_per_forward,
+                         "launches_per_step": shard.engine.launches_per_forward + 3 + (1 if world > 1 else 0),
                          "what": "Langevin (dt 1 fs, 300 K, friction 0.001/fs) entirely on the device: half-kick + drift, "
-                                 "cap-H placement, engine, signed reduction" + (", NCCL all-reduce" if world > 1 else "") +
-                                 ", half-kick; " + ("one CUDA graph replay per step" if world == 1 else "phases enqueued by the host around the engine's graph") +
+                                 "cap-H placement, engine, signed reduction" + (", all-reduce" if world > 1 else "") +
+                                 ", half-kick; " + ("one CUDA graph replay per step" if one_graph else "phases enqueued by the host around the engine's graph") +
                                  ", no host synchronisation, L2 in the loop's steady state"}
+    clocks.loaded = False
+    clock_info = clocks.stop() if rank == 0 else None
+
+    # ---- parity of the N-GPU result against the reference-source golden vectors (same tolerance as the tests) ----
+    gold = golden_reference(args.workload)
+    parity = None
+    if gold is not None:
+        ref_ef = combine_local(pm, gold["e"].reshape(-1), gold["f"])
+        got = ef.cpu().numpy()
+        dF = np.abs(got[:-1] - ref_ef[:-1])
+        tol_f = 5e-5 + 2e-5 * float(np.abs(ref_ef[:-1]).max())
+        tol_e = 4e-3 * n_frag
+        parity = {"against": "whole-protein E/F combined from the outputs of the reference's own model source "
+                             "(tests/golden/reference_outputs.npz)",
+                  "force_mae_eV_per_A": float(dF.mean()), "force_max_abs_eV_per_A": float(dF.max()),
+                  "energy_abs_err_eV": float(abs(got[-1] - ref_ef[-1])), "tol_force": tol_f, "tol_energy": tol_e,
+                  "parity_ok": bool(dF.max() <= tol_f and abs(got[-1] - ref_ef[-1]) <= tol_e)}
+
+    # ---- N > 1: the synthetic 512-fragment batch (config C4) at N GPUs and at 1 GPU in the same run ----
+    scale_c4 = None
+    if world > 1 and not args.no_c4:
+        fd4, pm4, desc4 = load_workload("c4", 512)
+        sh4 = DeviceShard(sd, fd4, pm4, rank, world, local, native_comm=not args.nccl)
+        t4n = time_shard_steps(torch, dist, sh4, 10, 3, world, flush) / 10.0
+        t41 = None
+        if rank == 0:
+            one = DeviceShard(sd, fd4, pm4, 0, 1, local)
+            t41 = time_shard_steps(torch, dist, one, 10, 3, 1, flush) / 10.0
+            del one
+        barrier()
+        scale_c4 = {"workload": workload_string(desc4, fd4), "ms_per_step_n_gpus": t4n * 1e3,
+                    "ms_per_step_1_gpu": t41 * 1e3 if t41 else None, "speedup": (t41 / t4n) if t41 else None,
+                    "collective": sh4.collective}
+        del sh4
 
     if rank != 0:
         if world > 1:
@@ -370,8 +488,7 @@ def run_ours(args):
         return
 
     # ---- per-kernel times + roofline (rank 0, its shard) ----
-    slots, deg = shard.engine.get_edges()
-    n_edges = int(deg.sum())
+    n_edges = n_edges_local
     prof = shard.engine.profile_stages(shard.pos.data_ptr(), n_iter=5)
     total_ms = sum(ms for _, ms in prof)
     fam = {}
@@ -394,11 +511,23 @@ def run_ours(args):
                 "kernel_ms": fam_ms[top_fam] / len(launches), "algorithmic_bytes": ab / len(launches) if ab else None,
                 "achieved": achieved, "peak": peak, "peak_kind": peak_kind, "unit": "GB/s",
                 "frac": (achieved / peak) if achieved else None, "traffic": traffic,
-                "note": "algorithmic bytes = SURVEY 8d fused lower bound per launch; this stage is contraction/latency bound, "
-                        "not HBM bound (DESIGN.md section 5); workloads below ~2k atoms are L2 resident",
+                "note": "algorithmic bytes = SURVEY 8d fused lower bound per launch (N, E of the timed positions); this stage is "
+                        "contraction/latency bound, not HBM bound (DESIGN.md section 5); workloads below ~2k atoms are L2 resident",
                 "share_of_step": fam_ms[top_fam] / total_ms,
                 "tensor": tensor_roofline([n for n, _ in launches], n_edges, t_fam, shard.engine.get_option("edge_tc")),
                 "family_ms": {k: round(v, 4) for k, v in sorted(fam_ms.items(), key=lambda x: -x[1])}}
+
+    # ---- force / energy error against the reference-source golden vectors, per fragment atom (the metric's second half) ----
+    accuracy = None
+    if gold is not None and world == 1:
+        e_h, f_h = shard.engine.forward_host(fd.pos)
+        accuracy = {"force_mae_vs_reference_eV_per_A": float(np.abs(f_h - gold["f"]).mean()),
+                    "force_max_abs_vs_reference_eV_per_A": float(np.abs(f_h - gold["f"]).max()),
+                    "energy_mae_vs_reference_eV": float(np.abs(e_h.reshape(-1) - gold["e"].reshape(-1)).mean()),
+                    "force_mae_vs_fp64_oracle_eV_per_A": float(np.abs(f_h - gold["f64"]).mean()),
+                    "energy_mae_vs_fp64_oracle_eV": float(np.abs(e_h.reshape(-1) - gold["e64"].reshape(-1)).mean()),
+                    "reference": "fp32 outputs of the reference's own ViSNet.forward source on the same fragments "
+                                 "(tests/golden/make_golden.py); fp64 oracle = oracle/visnet_ref.py"}
 
     # ---- CPU baseline (bounded sample) ----
     cpu = None
@@ -415,6 +544,25 @@ def run_ours(args):
                "sample": f"{n_eval} evaluations of {len(sample)}/{len(fd)} fragments ({len(sample.z)} atoms) by the "
                          f"pure-PyTorch CPU oracle, fp32, {threads} threads (fastest of the candidates tried); "
                          f"scaled by atom count"}
+
+    # ---- B1: the same oracle as eager PyTorch on this B200 -- "the reference on a modern GPU" ----
+    gpu_eager = None
+    if not args.skip_cpu_baseline and world == 1:
+        from oracle import visnet_ref as O
+        sample = fd if len(fd.z) <= 800 else fd[0:24]
+        m_gpu = O.OracleCalculatorModel({k: torch.from_numpy(np.asarray(v)) for k, v in sd.items()}, device="cuda")
+        for _ in range(2):
+            m_gpu.dl_potential_loader(sample)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        n_eval = 5
+        for _ in range(n_eval):
+            m_gpu.dl_potential_loader(sample)
+        torch.cuda.synchronize()
+        sec = (time.perf_counter() - t0) / n_eval * (len(fd.z) / len(sample.z))
+        gpu_eager = {"value": 1.0 / sec, "unit": "steps/s", "kind": "port, eager PyTorch ops on cuda:0 (autograd forces), "
+                     "host numpy in/out, neighbour list by the canonical CPU rule",
+                     "sample": f"{n_eval} evaluations of {len(sample)}/{len(fd)} fragments, scaled by atom count"}
 
     # ---- the MD loop that drives the path (host integrator, 1 GPU, real example proteins only) ----
     md_loop = None
@@ -461,26 +609,37 @@ def run_ours(args):
                      "what": "all-pairs LJ + Coulomb with dipeptide exclusions (vb_nonbonded), not part of `value`"}
 
     value = args.steps / t_dev
+    edge_tc = shard.engine.get_option("edge_tc")
     line = {
         "metric": "MD steps/sec", "value": value, "unit": "steps/s", "n_gpus": world, "steps": args.steps,
         "warmup": max(3, args.warmup), "ms_per_step": t_dev / args.steps * 1e3, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f32",
         "data": "example-PDB geometry (real for chig/trpcage/ww/abd, synthetic rotations+jitter for c4/c5), shipped checkpoint weights",
-        "config": {"workload": f"{desc}: G={n_frag} N={n_atoms} E={n_edges if world == 1 else 'sharded'} N_prot={pm.n_protein}",
-                   "parallelism": f"fragments sharded over {world} GPU(s), 1 NCCL all-reduce/step" if world > 1 else "single GPU",
+        "config": {"workload": workload_string(desc, fd),
+                   "edges": n_edges if world == 1 else f"{n_edges} on rank 0 (sharded)", "n_protein": pm.n_protein,
+                   "step": "one hot-path evaluation (neighbour list, ViSNet energy + analytic forces of every fragment, signed "
+                           "whole-protein reduction" + (", all-reduce" if world > 1 else "") + "); the integrator update is NOT in "
+                           "`value` -- `md_device` is the same step with the Langevin update on the device",
+                   "parallelism": f"fragments sharded over {world} GPU(s); {shard.collective}" if world > 1 else "single GPU",
                    "l2": "flushed (256 MiB write) before every timed step" if flush is not None else "warm",
                    "timing": "CUDA events around each step on the launching stream, max over ranks",
                    "cuda_graph": True,
-                   "edge_kernels": "tcgen05 (TMEM accumulators, TMA weight ring, 3xTF32)" if shard.engine.get_option("edge_tc") == 3
-                                   else ("fp32 SIMT" if shard.engine.get_option("edge_tc") == 0 else f"mixed ({shard.engine.get_option('edge_tc')})")},
+                   "launch_plan": "fused per-layer kernels" if shard.engine.get_option("fused") == 1 else "separate node / edge stages",
+                   "edge_kernels": "tcgen05 (TMEM accumulators, TMA weight ring, 3xTF32)" if edge_tc == 3
+                                   else ("fp32 SIMT" if edge_tc == 0 else f"mixed ({edge_tc})")},
         "value_l2_warm": args.steps / float(t_warm.item()),
         "wall_s_timed_region": wall,
         "e2e": e2e,
-        "gpu_launches": args.steps * shard.engine.launches_per_forward,
-        "launches_per_step": shard.engine.launches_per_forward,
+        "gpu_launches": args.steps * (shard.engine.launches_per_forward + (1 if world > 1 and shard.native else 0)),
+        "launches_per_step": shard.engine.launches_per_forward + (1 if world > 1 and shard.native else 0),
         "clocks": clock_info,
         "roofline": roofline,
         "cpu_baseline": cpu,
+        "gpu_eager_baseline": gpu_eager,
+        "accuracy": accuracy,
+        "parity": parity,
+        "comm": comm,
+        "scale_c4": scale_c4,
         "md_loop": md_loop,
         "md_device": md_device,
         "nonbonded": nonbonded,

@@ -133,6 +133,20 @@ int vb_set_nonbonded(vb_handle* h, int64_t n_protein_atoms, const float* charges
  * adds the term too. */
 int vb_nonbonded(vb_handle* h, const float* prot_pos_dev, float* ef_prot_dev, void* stream);
 
+/* ---- One-shot all-reduce over NVLink peer memory ---------------------------------------------
+ * One process per GPU.  vb_comm_init allocates this rank's window (2 parities x world slots of max_floats) and returns
+ * its 64-byte CUDA IPC handle; the caller exchanges the handles of all ranks (any host transport: torch.distributed,
+ * MPI, a file) and passes them, in rank order, to vb_comm_connect.  From then on every evaluation that produces the
+ * whole-protein buffer (vb_forward_protein, vb_md_eval, vb_md_run) ends with the all-reduce as ONE more kernel of its
+ * CUDA graph: peer stores into every rank's window, a system-scope flag per sender, a fixed-order sum (bit-identical on
+ * all ranks).  Option "comm_auto" 0 turns the automatic step off; vb_comm_allreduce runs it on any device buffer.
+ * Replaces: the host-side gather of the per-device results (ThreadPoolExecutor + numpy concatenation,
+ *           src/Calculators/bonded.py:74-89) ahead of combiner.py:38-39, and the NCCL all-reduce a caller would
+ *           otherwise enqueue from the host every step.  Needs peer access between the GPUs (NVLink / NVSwitch). */
+int vb_comm_init(vb_handle* h, int rank, int world, int64_t max_floats, void* ipc_handle_out /* 64 bytes */);
+int vb_comm_connect(vb_handle* h, const void* all_handles /* world x 64 bytes, rank order */);
+int vb_comm_allreduce(vb_handle* h, float* buf_dev, int64_t n, void* stream);
+
 /* Copy the current neighbour list to the host: slots[N*32] (source index or -1), deg[N].
  * Replaces: the edge_index returned by torch_cluster.radius_graph at src/ViSNet/model/utils.py:260-266. */
 int vb_get_edges(vb_handle* h, int32_t* slots_host, int32_t* deg_host);
@@ -141,7 +155,10 @@ int vb_get_edges(vb_handle* h, int32_t* slots_host, int32_t* deg_host);
 int vb_launches_per_forward(const vb_handle* h);
 /* Tuning knobs: "use_graph" 0/1, "use_pdl" 0/1 (programmatic dependent launch between the stages, default off), "npw" 1/2, "te_fwd" 32/64, "te_bwd" 32/64, "node_impl" 0/1,
  * "edge_tc" bit0 = forward / bit1 = adjoint edge stage on tcgen05, "tc_rows" 32/64/96/128 edges per tcgen05 tile
- * (defaults: chosen by problem size), "timeline" 0/1 in-kernel phase stamps of the tcgen05 edge kernels. */
+ * (defaults: chosen by problem size), "timeline" 0/1 in-kernel phase stamps of the tcgen05 edge kernels,
+ * "fused" 0/1 one launch per layer and direction (edge stage + node stage of a 4-node block; default: by size),
+ * "comm_auto" 0/1.  vb_get_option also answers "edge_overflow" (1 after a step exceeded a trimmed max_edges) and
+ * "comm_ready". */
 int vb_set_option(vb_handle* h, const char* key, int64_t value);
 int64_t vb_get_option(const vb_handle* h, const char* key);   /* resolved value (after vb_set_topology) */
 
@@ -157,7 +174,7 @@ int vb_profile_stages(vb_handle* h, const float* pos_dev, int n_iter, float* ms_
  * weight image (ai2bmd_b200.weights.tc_image); repeated `reps` times inside one launch; *ms_out = kernel time. */
 int vb_tc_selftest(int device, const float* a_host, const float* img_host, float* d_host, int reps, float* ms_out);
 /* Copy an internal buffer to the host.  name: "X","V","F","VN","QKV","V123","VDOT","TU","O" (per layer),
- * "XA","VA","GX","GVEC","GF","GXA","GQKV","GVNMSG","GTU","geom","rbf","eacc","grbf","esrc","edst","rowptr",
+ * "XA","VA","GX","GVEC","GF","GXA","GQKV","GVNMSG","GTU","GQKV2","GVNMSG2","GTU2","geom","rbf","eacc","grbf","esrc","edst","rowptr",
  * "eatom","energy","forces".  Returns the number of bytes copied (<= cap_bytes) or a negative status. */
 int64_t vb_debug_read(vb_handle* h, const char* name, int layer, void* host_dst, int64_t cap_bytes);
 

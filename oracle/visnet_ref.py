@@ -262,9 +262,12 @@ def vec_layer_norm_max_min(vec: torch.Tensor, weight: torch.Tensor) -> torch.Ten
 class OracleViSNet:
     """Functional restatement; weights are held in ``dtype`` (fp32 default, fp64 for anchors)."""
 
-    def __init__(self, state_dict: Dict[str, torch.Tensor], dtype=torch.float32):
+    def __init__(self, state_dict: Dict[str, torch.Tensor], dtype=torch.float32, device="cpu"):
+        """``device="cuda"`` runs the same eager PyTorch ops on a GPU (the PyTorch-eager proxy for
+        "the reference on a modern GPU"); the neighbour list is still the canonical CPU rule."""
         self.dtype = dtype
-        self.sd = {k: v.to(dtype) for k, v in state_dict.items()}
+        self.device = torch.device(device)
+        self.sd = {k: v.to(dtype).to(self.device) for k, v in state_dict.items()}
         self.cutoff = HP["cutoff"]
         self.D, self.L, self.H = HP["D"], HP["L"], HP["H"]
 
@@ -300,8 +303,10 @@ class OracleViSNet:
             slots, deg = radius_graph_canonical(pos.detach().cpu().numpy().astype(np.float32),
                                                 batch.cpu().numpy(), self.cutoff, HP["max_nbr"])
             edge_index = torch.from_numpy(slots_to_edge_index(slots, deg))
+        edge_index = edge_index.to(pos.device)
         src, dst = edge_index[0], edge_index[1]
         pos = pos.to(self.dtype)
+        dev = pos.device
 
         def keep(name, t):
             if cap is not None:
@@ -321,9 +326,9 @@ class OracleViSNet:
         w_e = (rbf @ sd[p + "distance_proj.weight"].T + sd[p + "distance_proj.bias"]) * cut.unsqueeze(1)
         msg = w_e * sd[p + "embedding.weight"][z][src]
         msg = msg * mask.unsqueeze(1).to(msg.dtype)          # self-loops removed (utils.py:298-302)
-        agg = torch.zeros(n, D, dtype=self.dtype).index_add_(0, dst, msg)
+        agg = torch.zeros(n, D, dtype=self.dtype, device=dev).index_add_(0, dst, msg)
         x = torch.cat([x0, agg], dim=1) @ sd[p + "combine.weight"].T + sd[p + "combine.bias"]
-        vec = torch.zeros(n, 3, D, dtype=self.dtype)
+        vec = torch.zeros(n, 3, D, dtype=self.dtype, device=dev)
         p = rm + "edge_embedding."
         f = (x[dst] + x[src]) * (rbf @ sd[p + "edge_proj.weight"].T + sd[p + "edge_proj.bias"])
         keep("x_emb", x), keep("f_emb", f)
@@ -350,8 +355,8 @@ class OracleViSNet:
             s = silu(m @ sd[p + "s_proj.weight"].T + sd[p + "s_proj.bias"])
             s1, s2 = torch.split(s, D, dim=1)
             vmsg = vn[src] * s1.unsqueeze(1) + s2.unsqueeze(1) * d.unsqueeze(2)
-            xa = torch.zeros(n, D, dtype=self.dtype).index_add_(0, dst, m)
-            va = torch.zeros(n, 3, D, dtype=self.dtype).index_add_(0, dst, vmsg)
+            xa = torch.zeros(n, D, dtype=self.dtype, device=dev).index_add_(0, dst, m)
+            va = torch.zeros(n, 3, D, dtype=self.dtype, device=dev).index_add_(0, dst, vmsg)
             keep(f"m{l}", m), keep(f"xa{l}", xa), keep(f"va{l}", va)
             if not last:
                 # edge_update (visnet_block.py:290-295)
@@ -395,15 +400,15 @@ class OracleViSNet:
         x = x + sd["prior_model.atomref.weight"][z]
         keep("e_atom", x)
         g = int(batch.max().item()) + 1 if n_graphs is None else n_graphs
-        out = torch.zeros(g, 1, dtype=self.dtype).index_add_(0, batch, x)
+        out = torch.zeros(g, 1, dtype=self.dtype, device=dev).index_add_(0, batch, x)
         out = out + sd["mean"]
         return out
 
     def energy_and_forces(self, z, pos, batch, edge_index=None, cap=None):
         """visnet.py:135-166: E[G,1], F[N,3] = -dE/dpos (autograd)."""
-        z = torch.as_tensor(z, dtype=torch.long)
-        batch = torch.as_tensor(batch, dtype=torch.long)
-        pos = torch.as_tensor(pos).to(self.dtype).clone().requires_grad_(True)
+        z = torch.as_tensor(z, dtype=torch.long).to(self.device)
+        batch = torch.as_tensor(batch, dtype=torch.long).to(self.device)
+        pos = torch.as_tensor(pos).to(self.dtype).to(self.device).clone().requires_grad_(True)
         with torch.enable_grad():
             out = self.forward(z, pos, batch, edge_index=edge_index, cap=cap)
             (dy,) = torch.autograd.grad([out], [pos], grad_outputs=[torch.ones_like(out)],
@@ -418,11 +423,11 @@ class OracleCalculatorModel:
     """Restatement of ``ViSNetModel`` (``src/Calculators/visnet_calculator.py:22-63``) over the oracle:
     ``dl_potential_loader(FragmentData) -> (e[G,1] f32, f[N,3] f32)`` as numpy arrays."""
 
-    def __init__(self, state_dict, dtype=torch.float32):
-        self.model = OracleViSNet(state_dict, dtype)
+    def __init__(self, state_dict, dtype=torch.float32, device="cpu"):
+        self.model = OracleViSNet(state_dict, dtype, device)
 
     def dl_potential_loader(self, frag):
         e, f = self.model.energy_and_forces(torch.from_numpy(np.asarray(frag.z, dtype=np.int64)),
                                             torch.from_numpy(np.asarray(frag.pos, dtype=np.float32)),
                                             torch.from_numpy(np.asarray(frag.batch, dtype=np.int64)))
-        return (e.reshape(-1, 1).to(torch.float32).numpy(), f.reshape(-1, 3).to(torch.float32).numpy())
+        return (e.reshape(-1, 1).to(torch.float32).cpu().numpy(), f.reshape(-1, 3).to(torch.float32).cpu().numpy())
