@@ -13,6 +13,7 @@
 
 #include "../../include/visnet_b200.h"
 #include "k_edge.cuh"
+#include "k_caph.cuh"
 #include "k_comm.cuh"
 #include "k_edge_tc.cuh"
 #include "k_fused.cuh"
@@ -135,6 +136,10 @@ struct vb_handle {
     float *d_map_sign = nullptr, *d_frag_sign = nullptr;
     float* d_ef = nullptr;       // [3*n_protein + 1] internal whole-protein buffer (diagnostic runs)
     int* d_flags = nullptr;      // [0]: set by the neighbour stage when a step produced more edges than the workspace holds
+    // cap-hydrogen refinement (k_caph.cuh): flat term arrays + scratch in one device allocation
+    bool caph_ready = false;
+    CaphDev caph{};
+    void* caph_mem = nullptr;
     // NVLink peer-memory all-reduce (k_comm.cuh): window in this rank's HBM + IPC mappings of every peer's window
     bool comm_ready = false;
     int comm_auto = 1;           // append the all-reduce to every evaluation that produces the whole-protein buffer
@@ -187,6 +192,10 @@ struct vb_handle {
         cudaFree(d_map_rowptr); cudaFree(d_map_src); cudaFree(d_map_sign); cudaFree(d_frag_sign); cudaFree(d_ef);
         d_map_rowptr = d_map_src = nullptr; d_map_sign = d_frag_sign = d_ef = nullptr;
         n_protein = n_map = 0;
+    }
+    void free_caph() {
+        cudaFree(caph_mem);
+        caph_mem = nullptr; caph = CaphDev{}; caph_ready = false;
     }
     void free_comm() {
         for (int r = 0; r < COMM_MAX_WORLD; r++)
@@ -827,6 +836,7 @@ void vb_destroy(vb_handle* h) {
     h->free_md();
     h->free_nb();
     h->free_comm();
+    h->free_caph();
     cudaFree(h->arena);
     h->free_map();
     cudaFree(h->d_flags);
@@ -859,6 +869,7 @@ int vb_set_topology(vb_handle* h, int64_t n_atoms, int64_t n_graphs, const int64
     h->drop_graph();
     h->free_md();                 // the MD recipe indexes the fragment atoms of the old topology
     h->free_map();                // ... and so does the protein map: it must be set again
+    h->free_caph();               // ... and the hydrogen-refinement terms
     h->has_topology = false;
     cudaFree(h->arena); h->arena = nullptr;
     cudaFreeHost(h->h_pos); cudaFreeHost(h->h_energy); cudaFreeHost(h->h_forces);
@@ -1018,6 +1029,7 @@ StepIO md_io(vb_handle* h) {
 int md_eval_enqueue(vb_handle* h, cudaStream_t st) {
     const int N = h->ws.N;
     md_place_kernel<<<(N + 255) / 256, 256, 0, st>>>(N, h->d_real, h->d_acc, h->d_rem, h->d_blen, h->d_mx, h->d_pos);
+    if (h->caph_ready) caph_relax_kernel<<<1, CAPH_THREADS, 0, st>>>(h->caph, h->d_pos);   // hydrogen refinement, in place
     if (int rc = enqueue_eval(h, st, md_io(h))) return rc;
     if (h->nb_ready && h->nb.hi > h->nb.lo) {      // non-bonded MM term on the same protein coordinates
         nonbonded_kernel<double><<<(h->nb.hi - h->nb.lo + 7) / 8, 256, 0, st>>>(h->nb, h->d_mx, h->md_ef, h->d_nb_eatom);
@@ -1254,6 +1266,115 @@ int vb_nonbonded(vb_handle* h, const float* prot_pos_dev, float* ef_prot_dev, vo
 }
 
 
+// ---- cap-hydrogen refinement (k_caph.cuh) --------------------------------------------------------------------------
+int vb_set_caph(vb_handle* h, const vb_caph_problem* pr) {
+    if (!h) return VB_ERR_ARG;
+    std::lock_guard<std::mutex> lk(h->mu);
+    if (!h->has_topology) { h->set_error("vb_set_caph: call vb_set_topology first"); return VB_ERR_STATE; }
+    if (!pr) { h->set_error("vb_set_caph: null problem"); return VB_ERR_ARG; }
+    const int64_t N = h->ws.N;
+    auto bad = [&](const char* what) { h->set_error("vb_set_caph: %s", what); return VB_ERR_ARG; };
+    if (pr->n_h < 0 || pr->n_bonds < 0 || pr->n_angles < 0 || pr->n_dih < 0 || pr->n_pairs < 0 || pr->n_mirror < 0) return bad("negative count");
+    if (pr->max_iter < 1 || pr->max_iter > 64) return bad("max_iter must be in [1, 64]");
+    if (!(pr->scnb > 0.f) || !(pr->scee > 0.f) || !(pr->lr > 0.f)) return bad("scnb, scee and lr must be positive");
+    const int64_t n_terms = pr->n_bonds + pr->n_angles + pr->n_dih + pr->n_pairs;
+    if (n_terms > (1 << 27) || pr->n_h > (1 << 26)) return bad("problem too large");
+    auto check_idx = [&](const int32_t* a, int64_t count, const char* what) {
+        if (count > 0 && !a) { h->set_error("vb_set_caph: %s is null", what); return false; }
+        for (int64_t i = 0; i < count; i++)
+            if (a[i] < 0 || a[i] >= N) { h->set_error("vb_set_caph: %s[%lld] = %d is not a fragment atom", what, (long long)i, a[i]); return false; }
+        return true;
+    };
+    if (!check_idx(pr->h_idx, pr->n_h, "h_idx") || !check_idx(pr->bond_ij, 2 * pr->n_bonds, "bond_ij") ||
+        !check_idx(pr->angle_ijk, 3 * pr->n_angles, "angle_ijk") || !check_idx(pr->dih_ijkl, 4 * pr->n_dih, "dih_ijkl") ||
+        !check_idx(pr->pair_ij, 2 * pr->n_pairs, "pair_ij") || !check_idx(pr->mirror_dst, pr->n_mirror, "mirror_dst") ||
+        !check_idx(pr->mirror_src, pr->n_mirror, "mirror_src"))
+        return VB_ERR_ARG;
+    if ((pr->n_bonds && (!pr->bond_k || !pr->bond_r0)) || (pr->n_angles && (!pr->angle_k || !pr->angle_t0)) ||
+        (pr->n_dih && (!pr->dih_k || !pr->dih_n || !pr->dih_p)) || (pr->n_pairs && (!pr->pair_a || !pr->pair_b || !pr->pair_qq)))
+        return bad("null parameter array");
+    // gather table: for every optimised hydrogen the scratch rows (term * 4 + slot) that carry a gradient on it
+    std::vector<int> slot_of(N, -1);
+    for (int64_t i = 0; i < pr->n_h; i++) {
+        if (slot_of[pr->h_idx[i]] >= 0) return bad("h_idx lists an atom twice");
+        slot_of[pr->h_idx[i]] = (int)i;
+    }
+    std::vector<std::vector<int>> rows(pr->n_h);
+    int64_t term = 0;
+    auto scan = [&](const int32_t* idx, int64_t count, int width) {
+        for (int64_t t = 0; t < count; t++, term++)
+            for (int k = 0; k < width; k++) {
+                const int hs = slot_of[idx[t * width + k]];
+                if (hs >= 0) rows[hs].push_back((int)(term * 4 + k));
+            }
+    };
+    scan(pr->bond_ij, pr->n_bonds, 2);
+    scan(pr->angle_ijk, pr->n_angles, 3);
+    scan(pr->dih_ijkl, pr->n_dih, 4);
+    scan(pr->pair_ij, pr->n_pairs, 2);
+    std::vector<int> gat_rowptr(pr->n_h + 1, 0), gat_entry;
+    for (int64_t i = 0; i < pr->n_h; i++) {
+        gat_rowptr[i + 1] = gat_rowptr[i] + (int)rows[i].size();
+        gat_entry.insert(gat_entry.end(), rows[i].begin(), rows[i].end());
+    }
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    CUDA_TRY(h, cudaDeviceSynchronize());
+    h->drop_graph();
+    h->free_caph();
+    // one allocation, carved in 256-byte steps
+    struct Piece { const void* src; size_t bytes; size_t off; };
+    std::vector<Piece> pieces;
+    size_t total = 0;
+    auto add = [&](const void* src, size_t bytes) {
+        pieces.push_back({src, bytes, total});
+        total += (std::max<size_t>(bytes, 4) + 255) & ~(size_t)255;
+        return pieces.size() - 1;
+    };
+    const size_t nh = (size_t)pr->n_h, n3 = 3 * nh;
+    const size_t i_h = add(pr->h_idx, 4 * nh);
+    const size_t i_bij = add(pr->bond_ij, 8 * (size_t)pr->n_bonds), i_bk = add(pr->bond_k, 4 * (size_t)pr->n_bonds), i_br = add(pr->bond_r0, 4 * (size_t)pr->n_bonds);
+    const size_t i_aijk = add(pr->angle_ijk, 12 * (size_t)pr->n_angles), i_ak = add(pr->angle_k, 4 * (size_t)pr->n_angles), i_at = add(pr->angle_t0, 4 * (size_t)pr->n_angles);
+    const size_t i_dijkl = add(pr->dih_ijkl, 16 * (size_t)pr->n_dih), i_dk = add(pr->dih_k, 4 * (size_t)pr->n_dih), i_dn = add(pr->dih_n, 4 * (size_t)pr->n_dih), i_dp = add(pr->dih_p, 4 * (size_t)pr->n_dih);
+    const size_t i_pij = add(pr->pair_ij, 8 * (size_t)pr->n_pairs), i_pa = add(pr->pair_a, 4 * (size_t)pr->n_pairs), i_pb = add(pr->pair_b, 4 * (size_t)pr->n_pairs), i_pq = add(pr->pair_qq, 4 * (size_t)pr->n_pairs);
+    const size_t i_md = add(pr->mirror_dst, 4 * (size_t)pr->n_mirror), i_ms = add(pr->mirror_src, 4 * (size_t)pr->n_mirror);
+    const size_t i_gr = add(gat_rowptr.data(), 4 * gat_rowptr.size()), i_ge = add(gat_entry.data(), 4 * gat_entry.size());
+    const size_t i_tg = add(nullptr, 4 * 12 * (size_t)n_terms);
+    const size_t i_vec = add(nullptr, 4 * (2 * (size_t)pr->max_iter + 4) * n3);
+    const size_t i_ev = add(nullptr, 4);
+    CUDA_TRY(h, cudaMalloc(&h->caph_mem, total));
+    CUDA_TRY(h, cudaMemset(h->caph_mem, 0, total));
+    char* base = static_cast<char*>(h->caph_mem);
+    for (const Piece& pc : pieces)
+        if (pc.src && pc.bytes) CUDA_TRY(h, cudaMemcpy(base + pc.off, pc.src, pc.bytes, cudaMemcpyHostToDevice));
+    auto ip = [&](size_t i) { return reinterpret_cast<const int*>(base + pieces[i].off); };
+    auto fp = [&](size_t i) { return reinterpret_cast<const float*>(base + pieces[i].off); };
+    CaphDev& c = h->caph;
+    c.n_h = (int)pr->n_h; c.h_idx = ip(i_h);
+    c.n_bonds = (int)pr->n_bonds; c.bond_ij = ip(i_bij); c.bond_k = fp(i_bk); c.bond_r0 = fp(i_br);
+    c.n_angles = (int)pr->n_angles; c.angle_ijk = ip(i_aijk); c.angle_k = fp(i_ak); c.angle_t0 = fp(i_at);
+    c.n_dih = (int)pr->n_dih; c.dih_ijkl = ip(i_dijkl); c.dih_k = fp(i_dk); c.dih_n = fp(i_dn); c.dih_p = fp(i_dp);
+    c.n_pairs = (int)pr->n_pairs; c.pair_ij = ip(i_pij); c.pair_a = fp(i_pa); c.pair_b = fp(i_pb); c.pair_qq = fp(i_pq);
+    c.n_mirror = (int)pr->n_mirror; c.mirror_dst = ip(i_md); c.mirror_src = ip(i_ms);
+    c.gat_rowptr = ip(i_gr); c.gat_entry = ip(i_ge);
+    c.scnb = pr->scnb; c.scee = pr->scee; c.max_iter = pr->max_iter; c.lr = pr->lr; c.tol_grad = pr->tol_grad; c.tol_change = pr->tol_change;
+    c.tg = reinterpret_cast<float*>(base + pieces[i_tg].off);
+    c.vec = reinterpret_cast<float*>(base + pieces[i_vec].off);
+    c.evals_out = reinterpret_cast<int*>(base + pieces[i_ev].off);
+    h->caph_ready = true;
+    return VB_OK;
+}
+
+int vb_caph_relax(vb_handle* h, float* pos_dev, void* stream) {
+    if (!h) return VB_ERR_ARG;
+    std::lock_guard<std::mutex> lk(h->mu);
+    if (!h->caph_ready) { h->set_error("vb_caph_relax: call vb_set_caph first"); return VB_ERR_STATE; }
+    if (!pos_dev) { h->set_error("vb_caph_relax: null buffer"); return VB_ERR_ARG; }
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    caph_relax_kernel<<<1, CAPH_THREADS, 0, (cudaStream_t)stream>>>(h->caph, pos_dev);
+    CUDA_TRY(h, cudaGetLastError());
+    return VB_OK;
+}
+
 // ---- NVLink peer-memory all-reduce (k_comm.cuh) ------------------------------------------------------------------
 int vb_comm_init(vb_handle* h, int rank, int world, int64_t max_floats, void* ipc_handle_out) {
     if (!h) return VB_ERR_ARG;
@@ -1371,6 +1492,13 @@ int64_t vb_get_option(const vb_handle* h, const char* key) {
     if (k == "node_impl") return h->node_impl;
     if (k == "fused") return h->fused;
     if (k == "comm_auto") return h->comm_auto;
+    if (k == "caph_ready") return h->caph_ready ? 1 : 0;
+    if (k == "caph_evals") {           // energy evaluations of the last refinement (synchronises)
+        int v = 0;
+        if (!h->caph_ready || cudaDeviceSynchronize() != cudaSuccess ||
+            cudaMemcpy(&v, h->caph.evals_out, sizeof(int), cudaMemcpyDeviceToHost) != cudaSuccess) return VB_ERR_STATE;
+        return v;
+    }
     if (k == "comm_ready") return h->comm_ready ? 1 : 0;
     if (k == "edge_overflow") {
         int flag = 0;

@@ -23,6 +23,17 @@ class _HParams(C.Structure):
                 ("num_rbf", C.c_int32), ("max_num_neighbors", C.c_int32), ("cutoff", C.c_float)]
 
 
+class _CaphProblem(C.Structure):
+    _fields_ = [("n_h", C.c_int64), ("h_idx", C.c_void_p),
+                ("n_bonds", C.c_int64), ("bond_ij", C.c_void_p), ("bond_k", C.c_void_p), ("bond_r0", C.c_void_p),
+                ("n_angles", C.c_int64), ("angle_ijk", C.c_void_p), ("angle_k", C.c_void_p), ("angle_t0", C.c_void_p),
+                ("n_dih", C.c_int64), ("dih_ijkl", C.c_void_p), ("dih_k", C.c_void_p), ("dih_n", C.c_void_p), ("dih_p", C.c_void_p),
+                ("n_pairs", C.c_int64), ("pair_ij", C.c_void_p), ("pair_a", C.c_void_p), ("pair_b", C.c_void_p), ("pair_qq", C.c_void_p),
+                ("n_mirror", C.c_int64), ("mirror_dst", C.c_void_p), ("mirror_src", C.c_void_p),
+                ("scnb", C.c_float), ("scee", C.c_float), ("max_iter", C.c_int32),
+                ("lr", C.c_float), ("tol_grad", C.c_float), ("tol_change", C.c_float)]
+
+
 # every symbol include/visnet_b200.h declares (tests check that the library exports each of them)
 EXPORTED_SYMBOLS = [
     "vb_weight_manifest", "vb_create", "vb_destroy", "vb_last_error", "vb_set_topology", "vb_forward",
@@ -31,6 +42,7 @@ EXPORTED_SYMBOLS = [
     "vb_md_setup", "vb_md_set_normals", "vb_md_set_state", "vb_md_kick1", "vb_md_eval", "vb_md_kick2", "vb_md_run", "vb_md_get_state",
     "vb_set_nonbonded", "vb_nonbonded",
     "vb_comm_init", "vb_comm_connect", "vb_comm_allreduce",
+    "vb_set_caph", "vb_caph_relax",
 ]
 
 
@@ -104,6 +116,10 @@ def load_library(path: Optional[str] = None):
     lib.vb_comm_connect.argtypes = [vp, vp]
     lib.vb_comm_allreduce.restype = C.c_int
     lib.vb_comm_allreduce.argtypes = [vp, vp, i64, vp]
+    lib.vb_set_caph.restype = C.c_int
+    lib.vb_set_caph.argtypes = [vp, C.POINTER(_CaphProblem)]
+    lib.vb_caph_relax.restype = C.c_int
+    lib.vb_caph_relax.argtypes = [vp, vp, vp]
     lib.vb_md_get_state.restype = C.c_int
     lib.vb_md_get_state.argtypes = [vp, vp, vp, vp, vp, i64]
     if path == _build.LIB_PATH:
@@ -195,6 +211,32 @@ class Engine:
 
     def forward_protein_device(self, pos_ptr: int, ef_ptr: int, stream_ptr: int = 0):
         self._check(self.lib.vb_forward_protein(self.h, pos_ptr, ef_ptr, stream_ptr), "vb_forward_protein")
+
+    # ---- cap-hydrogen refinement (include/visnet_b200.h: vb_set_caph / vb_caph_relax) ----
+    def set_caph(self, problem):
+        """``problem``: an :class:`ai2bmd_b200.caph.CapHProblem` (flat term arrays over the packed fragment atoms)."""
+        keep, p = [], _CaphProblem()
+
+        def arr(a, dtype):
+            a = np.ascontiguousarray(a, dtype=dtype)
+            keep.append(a)
+            return a.ctypes.data if a.size else None
+
+        p.n_h, p.h_idx = len(problem.h_idx), arr(problem.h_idx, np.int32)
+        p.n_bonds, p.bond_ij, p.bond_k, p.bond_r0 = len(problem.bond_k), arr(problem.bond_ij, np.int32), arr(problem.bond_k, np.float32), arr(problem.bond_r0, np.float32)
+        p.n_angles, p.angle_ijk, p.angle_k, p.angle_t0 = len(problem.angle_k), arr(problem.angle_ijk, np.int32), arr(problem.angle_k, np.float32), arr(problem.angle_t0, np.float32)
+        p.n_dih, p.dih_ijkl, p.dih_k = len(problem.dih_k), arr(problem.dih_ijkl, np.int32), arr(problem.dih_k, np.float32)
+        p.dih_n, p.dih_p = arr(problem.dih_n, np.float32), arr(problem.dih_p, np.float32)
+        p.n_pairs, p.pair_ij, p.pair_a = len(problem.pair_a), arr(problem.pair_ij, np.int32), arr(problem.pair_a, np.float32)
+        p.pair_b, p.pair_qq = arr(problem.pair_b, np.float32), arr(problem.pair_qq, np.float32)
+        p.n_mirror, p.mirror_dst, p.mirror_src = len(problem.mirror_dst), arr(problem.mirror_dst, np.int32), arr(problem.mirror_src, np.int32)
+        p.scnb, p.scee, p.max_iter = float(problem.scnb), float(problem.scee), int(problem.max_iter)
+        p.lr, p.tol_grad, p.tol_change = float(problem.lr), float(problem.tol_grad), float(problem.tol_change)
+        self._check(self.lib.vb_set_caph(self.h, C.byref(p)), "vb_set_caph")
+
+    def caph_relax(self, pos_ptr: int, stream_ptr: int = 0):
+        """Refine the added hydrogens of a packed fragment position buffer (device pointer) in place; asynchronous."""
+        self._check(self.lib.vb_caph_relax(self.h, pos_ptr, stream_ptr), "vb_caph_relax")
 
     # ---- NVLink peer-memory all-reduce (include/visnet_b200.h: vb_comm_*) ----
     def comm_init(self, rank: int, world: int, max_floats: int) -> bytes:

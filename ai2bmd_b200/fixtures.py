@@ -23,3 +23,24 @@ def load_protein(name: str):
     """(protein positions [n,3] f64, atomic numbers [n], FragmentRecipe) of an example protein."""
     g = np.load(os.path.join(GOLDEN, f"fragments_{name}.npz"))
     return g["prot_pos"], g["prot_z"], FragmentRecipe(g["rc_real"], g["rc_acc"], g["rc_rem"], g["rc_blen"])
+
+
+def load_capped_protein(name: str):
+    """The example protein as a :class:`ai2bmd_b200.pdbfrag.CappedProtein` (names, residues, elements, positions)."""
+    from .pdbfrag import CappedProtein
+    g = np.load(os.path.join(GOLDEN, f"fragments_{name}.npz"))
+    el = {1: "H", 6: "C", 7: "N", 8: "O", 16: "S"}
+    return CappedProtein([str(x) for x in g["prot_names"]], [str(x) for x in g["prot_resnames"]], g["prot_resnums"].astype(np.int64),
+                         [el[int(z)] for z in g["prot_z"]], g["prot_pos"])
+
+
+def load_caph_tables(name: str):
+    """[(parsed prmtop table, atom names)] per dipeptide of an example protein, as stored next to the reference's own
+    refinement output (tests/golden/reference_caph_batch*.npz), plus that file."""
+    g = np.load(os.path.join(GOLDEN, "reference_caph_batch.npz" if name == "chig" else f"reference_caph_batch_{name}.npz"))
+    tables = []
+    for k in range(int(g["n_graphs"])):
+        pre = f"g{k}_t_"
+        t = {n[len(pre):]: (int(g[n]) if g[n].ndim == 0 else g[n]) for n in g.files if n.startswith(pre)}
+        tables.append((t, [str(x) for x in g[f"g{k}_names"]]))
+    return tables, g

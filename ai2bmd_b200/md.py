@@ -28,10 +28,12 @@ MASSES = {1: 1.008, 6: 12.011, 7: 14.007, 8: 15.999, 16: 32.06}
 class BondedForceField:
     """Whole-protein bonded energy/forces from the fragment batch (device-side reduction)."""
 
-    def __init__(self, state_dict, frags: FragmentData, pm: ProteinMap, recipe: FragmentRecipe, device: int = 0):
+    def __init__(self, state_dict, frags: FragmentData, pm: ProteinMap, recipe: FragmentRecipe, device: int = 0, refine=None):
+        """``refine(frag_pos) -> frag_pos``: optional host-side refinement of the placed fragment coordinates (the parity
+        tests pass the CPU restatement of the cap-hydrogen LBFGS here to check the device loop that runs it in-kernel)."""
         import torch
         self.torch = torch
-        self.recipe, self.pm = recipe, pm
+        self.recipe, self.pm, self.refine = recipe, pm, refine
         self.engine = Engine(state_dict, device)
         self.engine.set_topology(frags.z, frags.batch, n_graphs=len(frags))
         self.engine.set_protein_map(pm.n_protein, pm.src_atom, pm.dst_atom, pm.sign, pm.frag_sign)
@@ -44,7 +46,10 @@ class BondedForceField:
 
     def __call__(self, prot_pos: np.ndarray):
         """(E [eV], F [n_protein,3] eV/A) for the given protein coordinates."""
-        self.pos_host.numpy()[:] = self.recipe.positions(prot_pos)
+        frag_pos = self.recipe.positions(prot_pos)
+        if getattr(self, "refine", None) is not None:
+            frag_pos = self.refine(frag_pos)
+        self.pos_host.numpy()[:] = frag_pos
         self.pos_dev.copy_(self.pos_host, non_blocking=True)
         self.engine.forward_protein_device(self.pos_dev.data_ptr(), self.ef_dev.data_ptr(), self.stream.cuda_stream)
         self.ef_host.copy_(self.ef_dev, non_blocking=True)
@@ -154,7 +159,9 @@ class DeviceLangevin:
 
     def __init__(self, state_dict, frags: FragmentData, pm: ProteinMap, recipe: FragmentRecipe, positions, numbers,
                  dt_fs=1.0, temperature_K=300.0, friction_per_fs=0.001, seed=0, device: int = 0, velocities=None,
-                 group=None, engine: Engine = None, zero_com_momentum=False):
+                 group=None, engine: Engine = None, zero_com_momentum=False, caph=None):
+        """``caph``: an :class:`ai2bmd_b200.caph.CapHProblem` -- the added hydrogens are then refined every step on the
+        device (one LBFGS call on the Amber terms, ``csrc/k_caph.cuh``) between their placement and the evaluation."""
         import torch
         self.torch, self.group = torch, group
         self.n = pm.n_protein
@@ -167,6 +174,8 @@ class DeviceLangevin:
             engine.set_topology(frags.z, frags.batch, n_graphs=len(frags))
             engine.set_protein_map(pm.n_protein, pm.src_atom, pm.dst_atom, pm.sign, pm.frag_sign)
         self.engine = engine
+        if caph is not None:
+            engine.set_caph(caph)
         self.ef = torch.zeros(3 * self.n + 1, dtype=torch.float32, device=dev)
         self.stream = torch.cuda.current_stream(dev)
         engine.md_setup(self.masses, recipe.real, recipe.acc, recipe.rem, recipe.blen, dt_fs * FS, self.kT, self.fr,

@@ -133,6 +133,33 @@ int vb_set_nonbonded(vb_handle* h, int64_t n_protein_atoms, const float* charges
  * adds the term too. */
 int vb_nonbonded(vb_handle* h, const float* prot_pos_dev, float* ef_prot_dev, void* stream);
 
+/* ---- Per-step refinement of the added (cap) hydrogens -----------------------------------
+ * One LBFGS call (lr, max_iter, tolerance_grad, tolerance_change; no line search, fresh state) on the Amber energy of all
+ * dipeptides, moving only the added hydrogens -- what the reference runs every MD step between placing them and the
+ * ViSNet evaluation.  The problem is given as flat term arrays whose atom indices address the PACKED FRAGMENT position
+ * buffer [N][3] of vb_set_topology: every term that contains an optimised hydrogen, with its own parameters (Amber
+ * units: kcal/mol, Angstrom, radians; qq = product of prmtop charges).  mirror_dst/mirror_src: fragment atoms that are
+ * copies of relaxed ones (the ACE-NME fragments take their hydrogens from the neighbouring dipeptides,
+ * src/Fragmentation/distancefrag.py:286-307) and are re-copied after the relaxation.
+ * Replaces: HydrogenOptimizer.optimize_hydrogen + the five energy terms, src/Fragmentation/hydrogen/energies.py:9-60,
+ *           211-242 (tables: hydrogen/ctable.py:58-240), called from DistanceFragment.get_fragments,
+ *           src/Fragmentation/distancefrag.py:56-92.  Host helper that builds the arrays from prmtop tables:
+ *           ai2bmd_b200/caph.py.  Once set, vb_md_eval / vb_md_run refine after placing the fragment atoms. */
+typedef struct {
+    int64_t n_h;      const int32_t* h_idx;                                              /* optimised hydrogens        */
+    int64_t n_bonds;  const int32_t* bond_ij;   const float* bond_k;  const float* bond_r0;      /* [n][2]             */
+    int64_t n_angles; const int32_t* angle_ijk; const float* angle_k; const float* angle_t0;     /* [n][3]             */
+    int64_t n_dih;    const int32_t* dih_ijkl;  const float* dih_k;   const float* dih_n; const float* dih_p;  /* [n][4] */
+    int64_t n_pairs;  const int32_t* pair_ij;   const float* pair_a;  const float* pair_b; const float* pair_qq;
+    int64_t n_mirror; const int32_t* mirror_dst; const int32_t* mirror_src;
+    float scnb, scee;                 /* 1-4 scaling of the reference's HydrogenOptimizer: 1.2, 2.0                  */
+    int32_t max_iter;                 /* 10 in the reference                                                         */
+    float lr, tol_grad, tol_change;   /* 0.1, 0.1, 0.01 in the reference                                             */
+} vb_caph_problem;
+int vb_set_caph(vb_handle* h, const vb_caph_problem* problem);          /* host pointers, copied */
+/* Refine a packed fragment position buffer in place (device pointer), asynchronous on `stream`. */
+int vb_caph_relax(vb_handle* h, float* pos_dev, void* stream);
+
 /* ---- One-shot all-reduce over NVLink peer memory ---------------------------------------------
  * One process per GPU.  vb_comm_init allocates this rank's window (2 parities x world slots of max_floats) and returns
  * its 64-byte CUDA IPC handle; the caller exchanges the handles of all ranks (any host transport: torch.distributed,
@@ -157,8 +184,8 @@ int vb_launches_per_forward(const vb_handle* h);
  * "edge_tc" bit0 = forward / bit1 = adjoint edge stage on tcgen05, "tc_rows" 32/64/96/128 edges per tcgen05 tile
  * (defaults: chosen by problem size), "timeline" 0/1 in-kernel phase stamps of the tcgen05 edge kernels,
  * "fused" 0/1 one launch per layer and direction (edge stage + node stage of a 4-node block; default: by size),
- * "comm_auto" 0/1.  vb_get_option also answers "edge_overflow" (1 after a step exceeded a trimmed max_edges) and
- * "comm_ready". */
+ * "comm_auto" 0/1.  vb_get_option also answers "edge_overflow" (1 after a step exceeded a trimmed max_edges),
+ * "comm_ready", "caph_ready" and "caph_evals" (energy evaluations of the last hydrogen refinement). */
 int vb_set_option(vb_handle* h, const char* key, int64_t value);
 int64_t vb_get_option(const vb_handle* h, const char* key);   /* resolved value (after vb_set_topology) */
 

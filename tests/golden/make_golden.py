@@ -383,6 +383,7 @@ def write_reference_caph_batch(name="chig"):
         o_atom += ct.natom; o_bnd += ct.numbnd; o_ang += ct.numang; o_dih += ct.nptra
         o_lj += ct.ntypes * (ct.ntypes + 1) // 2
         out[f"g{g}_pos0"], out[f"g{g}_atom_idx"], out[f"g{g}_src"] = pos, aidx_np, src
+        out[f"g{g}_names"] = np.array(CR.prmtop_atom_names(open(path).read()))
         for k in ("natom", "ntypes", "numbnd", "numang", "nptra"):
             out[f"g{g}_t_{k}"] = np.int64(getattr(ct, k))
         for k in ("charge", "atomic_number", "atom_type_idx", "number_excluded_atoms", "nonbonded_parm_index",
@@ -455,7 +456,8 @@ def main():
                             end=fd.end, batch=fd.batch, n_protein=pm.n_protein, src_atom=pm.src_atom,
                             dst_atom=pm.dst_atom, sign=pm.sign, frag_sign=pm.frag_sign,
                             prot_pos=prot.positions, prot_z=np.array([zmap[e] for e in prot.elements]),
-                            rc_real=rc.real, rc_acc=rc.acc, rc_rem=rc.rem, rc_blen=rc.blen)
+                            rc_real=rc.real, rc_acc=rc.acc, rc_rem=rc.rem, rc_blen=rc.blen,
+                            prot_names=np.array(prot.names), prot_resnames=np.array(prot.resnames), prot_resnums=prot.resnums)
 
     # the reference's own fragment composition tables (numpy-only module) + residue sequences of the examples
     import importlib.util

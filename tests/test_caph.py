@@ -263,3 +263,49 @@ def test_joint_relaxation_on_trpcage(golden_dir):
     assert np.abs(out - g["pos1"]).max() <= 2e-6
     x, _ = CC.relax(CC.flatten(problems))
     assert np.abs(x - g["pos1"]).max() <= 4e-6
+
+
+# ---- product-side host logic (ai2bmd_b200/caph.py): flat term arrays over the packed fragment atoms --------------------
+@pytest.mark.parametrize("name,n_h,n_pairs", [("chig", 35, 695), ("trpcage", 74, None)])
+def test_product_problem_builder_against_the_reference_output(name, n_h, n_pairs):
+    """``caph.build_problem`` (name-based table layout, terms, ACE-NME mirrors) feeds the C restatement: relaxing the PACKED
+    fragment buffer with its arrays reproduces the coordinates of the reference's own optimiser."""
+    from ai2bmd_b200 import caph
+    from ai2bmd_b200.fixtures import load_capped_protein, load_caph_tables, load_fragments, load_protein
+    from oracle import caph_c as CC
+    fd, pm = load_fragments(name)
+    _, _, recipe = load_protein(name)
+    prot = load_capped_protein(name)
+    tables, g = load_caph_tables(name)
+    pr = caph.build_problem(prot, fd, recipe, tables)
+    assert len(pr.h_idx) == n_h and (n_pairs is None or len(pr.pair_a) == n_pairs)
+    # the layout puts every table atom on the fragment atom with the same first-approximation coordinates
+    for k, t2f in enumerate(pr.table_to_frag):
+        assert np.abs(fd.pos[t2f] - g[f"g{k}_pos0"]).max() <= 2e-6
+        assert sorted(t2f.tolist()) == list(range(int(fd.start[2 * k]), int(fd.end[2 * k])))
+    # every added hydrogen of an ACE-NME fragment mirrors a dipeptide hydrogen at the same place
+    assert len(pr.mirror_dst) == int((recipe.real[np.isin(fd.batch, np.arange(1, len(fd), 2))] < 0).sum())
+    assert np.abs(fd.pos[pr.mirror_dst] - fd.pos[pr.mirror_src]).max() <= 1e-5
+    flat = {"pos": fd.pos.copy(), "h_idx": pr.h_idx.astype(np.int64)}
+    for key in ("bond_ij", "angle_ijk", "dih_ijkl", "pair_ij"):
+        flat[key] = np.ascontiguousarray(getattr(pr, key), dtype=np.int64)
+    for key in ("bond_k", "bond_r0", "angle_k", "angle_t0", "dih_k", "dih_n", "dih_p", "pair_a", "pair_b", "pair_qq"):
+        flat[key] = np.ascontiguousarray(getattr(pr, key), dtype=np.float32)
+    x, evals = CC.relax(flat)
+    pos1 = g["pos1"]
+    off = 0
+    for k, t2f in enumerate(pr.table_to_frag):
+        assert np.abs(x[t2f] - pos1[off:off + len(t2f)]).max() <= 4e-6
+        off += len(t2f)
+    assert 2 <= evals <= 12
+
+
+def test_product_prmtop_parser_equals_the_oracle_parser():
+    from ai2bmd_b200 import caph
+    a, b = caph.parse_prmtop(MINI_PRMTOP), CR.parse_prmtop(MINI_PRMTOP)
+    assert a.keys() == b.keys()
+    for k in a:
+        assert np.array_equal(np.asarray(a[k]), np.asarray(b[k])), k
+    ta, tb = caph.hydrogen_terms(a, [0]), CR.hydrogen_terms(b, [0])
+    for k in ta:
+        assert np.array_equal(ta[k], tb[k]), k

@@ -298,3 +298,23 @@ def test_fragment_membership_equals_the_reference_function(golden_dir, name):
         m = recipe.real[sl] < 0
         mine = sorted((int(a), int(r), round(float(b), 5)) for a, r, b in zip(recipe.acc[sl][m], recipe.rem[sl][m], recipe.blen[sl][m]))
         assert mine == sorted((a, r, round(b, 5)) for a, r, b in caps), k
+
+
+def test_host_langevin_keeps_the_centre_of_mass_in_place():
+    """ASE 3.22 Langevin.step with fix_com: the centre of mass is put back after the drift and its velocity removed after
+    the second half-kick, so 100 steps in a force field with a net force leave it where it started."""
+    from ai2bmd_b200.md import Langevin
+    rng = np.random.default_rng(0)
+    z = np.array([1, 6, 7, 8, 16, 1, 6, 1])
+    x0 = rng.normal(size=(8, 3)) * 2.0
+
+    def force_fn(x):
+        return 0.0, -0.3 * (x - 1.0) + np.array([0.2, -0.1, 0.05])          # harmonic well + a constant net force
+
+    md = Langevin(x0, z, force_fn, dt_fs=1.0, temperature_K=300.0, friction_per_fs=0.01, seed=4)
+    com0 = (md.m * x0).sum(0) / md.m.sum()
+    assert np.abs((md.m * md.v).sum(0)).max() > 1e-3                       # the Maxwell-Boltzmann draw is not made stationary
+    md.run(100)
+    assert np.abs((md.m * md.x).sum(0) / md.m.sum() - com0).max() <= 1e-12
+    assert np.abs((md.m * md.v).sum(0)).max() <= 1e-12
+    assert np.abs(md.x - x0).max() > 1e-2

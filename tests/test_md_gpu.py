@@ -102,6 +102,9 @@ def test_device_integrator_matches_host_integrator_langevin(real_weights):
     assert np.abs(x - host.x).max() <= X_TOL and np.abs(v - host.v).max() <= V_TOL
     m = dev.masses[:, None]
     assert np.abs((m * v).sum(0)).max() <= 1e-9                      # centre of mass at rest
+    com0 = (m * prot_pos).sum(0) / m.sum()                           # ... and where it started (ASE fix_com restores the position too)
+    assert np.abs((m * x).sum(0) / m.sum() - com0).max() <= 1e-9
+    assert np.abs((host.m * host.x).sum(0) / host.m.sum() - com0).max() <= 1e-9
     # externally supplied normals take the same path
     pool = np.stack([np.stack(src(s)) for s in range(n, n + 5)])     # [5, 2, n, 3]
     dev.set_normals(pool)
