@@ -23,6 +23,7 @@
 #include "k_nonbonded.cuh"
 #include "k_node.cuh"
 #include "k_node2.cuh"
+#include "k_node_tc.cuh"
 
 using namespace vb;
 
@@ -153,6 +154,7 @@ struct vb_handle {
     int tc_rows_opt = 0, tc_rows = 128;                  // edges per tcgen05 tile (32 / 64 / 96 / 128; MMA M stays 128)
     int node_impl = 1; // 0: warp-per-node kernels (k_node.cuh), 1: CTA-cooperative kernels (k_node2.cuh)
     int fused = 0, fused_opt = -1;   // 1: one launch per layer and direction (k_fused.cuh); -1 = choose by problem size
+    int node_tc = 0, node_tc_opt = -1;   // 1: node stage on tensor cores (k_node_tc.cuh); -1 = choose by problem size
     int edge_tc = -1;  // bit 0: forward edge stage on tcgen05, bit 1: adjoint edge stage on tcgen05; -1 = by size
     // graph cache: one instantiated graph per (kind, I/O pointer set); pointers are baked into the captured launches
     struct GraphEntry { int kind; StepIO io; cudaGraphExec_t exec; };
@@ -311,7 +313,11 @@ void layout_workspace(vb_handle* h, char* base, ArenaPlan& plan, int*& z, int*& 
     carve(plan, base, ws.GX, N * D);
     carve(plan, base, ws.GVEC, N * 3 * D);
     carve(plan, base, ws.GF, E * D);
-    carve(plan, base, ws.GXA, N * D);
+    carve(plan, base, ws.GXA, 3 * N * D);
+    carve(plan, base, ws.XN, N * D);
+    carve(plan, base, ws.PX, 3 * N * D);
+    carve(plan, base, ws.PV, 5 * 3 * N * D);
+    carve(plan, base, ws.GO, N * 3 * D);
     carve(plan, base, ws.GQKV, N * 3 * D);
     carve(plan, base, ws.GVNMSG, N * 3 * D);
     carve(plan, base, ws.GTU, N * 6 * D);
@@ -544,6 +550,90 @@ void launch_fused_bwd(Launcher& Lc, int l) {
     Lc.check();
 }
 
+// ---- node stage on tensor cores (k_node_tc.cuh) --------------------------------------------------------------
+void node_tc_common(const vb_handle* h, NodeTcArgs& a, int k) {
+    a.layer = k; a.mw = h->mw; a.ws = h->ws;
+    a.tx = (h->ws.N + TC_TE - 1) / TC_TE;
+    a.tv = (3 * h->ws.N + TC_TE - 1) / TC_TE;
+    a.njx = 3; a.njv = 5; a.jx = 1; a.jv = 1;
+}
+void node_tc_jobs(TcJob* jobs, const float* img, int n) {
+    for (int c = 0; c < n; c++) jobs[c] = TcJob{img + (size_t)c * 4 * 8192, 0, 0};
+}
+int node_tc_grid(const NodeTcArgs& a) { return a.tx * (a.njx / a.jx) + a.tv * (a.njv / a.jv); }
+// one job per CTA while that still fits ~2 waves (each CTA then streams a single weight image); otherwise a CTA runs all
+// chunks of its row tile on one staged A operand
+bool node_tc_split(const vb_handle* h, const NodeTcArgs& a) { return a.tx * a.njx + a.tv * a.njv <= 2 * h->sm_count; }
+
+void launch_node_oproj_tc(Launcher& Lc, int k) {           // O[k-1] = xa Wo[k-1]^T + bo
+    vb_handle* h = Lc.h;
+    NodeTcArgs a{};
+    node_tc_common(h, a, k);
+    a.tv = 0;
+    node_tc_jobs(a.jobs_x, h->mw.layer[k - 1].tcWo, 3);
+    if (!node_tc_split(h, a)) a.jx = 3;
+    Lc.launch(node_tc_kernel<NT_OPROJ>, dim3(node_tc_grid(a)), dim3(TC2_THREADS), TC_SMEM_BYTES, a);
+    Lc.check();
+}
+void launch_node_norm_fwd(Launcher& Lc, int k) {
+    vb_handle* h = Lc.h;
+    Lc.launch(node_norm_fwd_kernel, dim3((h->ws.N + NN_WARPS - 1) / NN_WARPS), dim3(NN_WARPS * 32), 0, k, h->mw, h->ws);
+    Lc.check();
+}
+void launch_node_proj_tc(Launcher& Lc, int k) {            // [q|k|v], [v1|v2|v3|t|u] of stage k
+    vb_handle* h = Lc.h;
+    NodeTcArgs a{};
+    node_tc_common(h, a, k);
+    node_tc_jobs(a.jobs_x, h->mw.layer[k].tcWqkv, 3);
+    node_tc_jobs(a.jobs_v, h->mw.layer[k].tcWvt, 5);
+    if (k == 0) a.tv = 0;                                   // vec = 0 at the first layer: V123 / TU / VN stay zero
+    if (k == L - 1) a.njv = 3;                              // no edge update in the last layer: t, u unused
+    if (!node_tc_split(h, a)) { a.jx = a.njx; a.jv = a.njv; }
+    Lc.launch(node_tc_kernel<NT_PROJ>, dim3(node_tc_grid(a)), dim3(TC2_THREADS), TC_SMEM_BYTES, a);
+    Lc.check();
+}
+void launch_node_bwdA_tc(Launcher& Lc, int k) {            // K-chunk partials of the stage-k adjoint contractions
+    vb_handle* h = Lc.h;
+    NodeTcArgs a{};
+    node_tc_common(h, a, k);
+    node_tc_jobs(a.jobs_x, h->mw.layer[k].tcWqkvN, 3);
+    node_tc_jobs(a.jobs_v, h->mw.layer[k].tcWvtN, 5);
+    if (k == L - 1) a.njv = 3;
+    a.acc_qkv = h->ws.GQKV; a.acc_tu = h->ws.GTU;
+    Lc.launch(node_tc_kernel<NT_BWDA>, dim3(node_tc_grid(a)), dim3(TC2_THREADS), TC_SMEM_BYTES, a);
+    Lc.check();
+}
+void launch_node_norm_bwd(Launcher& Lc, int k) {
+    vb_handle* h = Lc.h;
+    Lc.launch(node_norm_bwd_kernel, dim3((h->ws.N + NN_WARPS - 1) / NN_WARPS), dim3(NN_WARPS * 32), 0, k, h->mw, h->ws,
+              h->ws.GQKV, h->ws.GVNMSG, h->ws.GTU);
+    Lc.check();
+}
+void launch_node_bwdB_tc(Launcher& Lc, int k) {            // dE/dxa partials = [g_o1 | g_x vdot | g_x] Wo[k-1]
+    vb_handle* h = Lc.h;
+    NodeTcArgs a{};
+    node_tc_common(h, a, k);
+    a.tv = 0;
+    node_tc_jobs(a.jobs_x, h->mw.layer[k - 1].tcWoN, 3);
+    Lc.launch(node_tc_kernel<NT_BWDB>, dim3(node_tc_grid(a)), dim3(TC2_THREADS), TC_SMEM_BYTES, a);
+    Lc.check();
+}
+// stage k of the node forward / adjoint as launches named for the stage checks
+void node_fwd_tc(Launcher& Lc, int k) {
+    char name[64];
+    if (k >= 1) { snprintf(name, sizeof(name), "oproj%d", k); if (Lc.next(name)) launch_node_oproj_tc(Lc, k); }
+    snprintf(name, sizeof(name), "norm%d", k);
+    if (Lc.next(name)) launch_node_norm_fwd(Lc, k);
+    if (k < L) { snprintf(name, sizeof(name), "proj%d", k); if (Lc.next(name)) launch_node_proj_tc(Lc, k); }
+}
+void node_bwd_tc(Launcher& Lc, int k) {
+    char name[64];
+    if (k <= L - 1) { snprintf(name, sizeof(name), "bwdA%d", k); if (Lc.next(name)) launch_node_bwdA_tc(Lc, k); }
+    snprintf(name, sizeof(name), "bnorm%d", k);
+    if (Lc.next(name)) launch_node_norm_bwd(Lc, k);
+    if (k >= 1) { snprintf(name, sizeof(name), "bwdB%d", k); if (Lc.next(name)) launch_node_bwdB_tc(Lc, k); }
+}
+
 void enqueue_finalize(Launcher& Lc, const StepIO& io) {
     vb_handle* h = Lc.h;
     const Workspace& ws = h->ws;
@@ -584,6 +674,21 @@ void enqueue_all(Launcher& Lc, const StepIO& io) {
             if (Lc.next(name)) launch_fused_bwd(Lc, l);
         }
         if (Lc.next("node_bwd0")) launch_node_bwd2<4>(Lc, 0);
+    } else if (h->node_tc) {
+        // node stage on tensor cores: three launches per stage (GEMM tiles / warp-per-node glue / GEMM tiles)
+        for (int l = 0; l < L; l++) {
+            node_fwd_tc(Lc, l);
+            snprintf(name, sizeof(name), "edge_fwd%d", l);
+            if (Lc.next(name)) edge_fwd(Lc, l);
+        }
+        node_fwd_tc(Lc, L);
+        if (Lc.next("head")) head(Lc);
+        for (int l = L - 1; l >= 0; l--) {
+            node_bwd_tc(Lc, l + 1);
+            snprintf(name, sizeof(name), "edge_bwd%d", l);
+            if (Lc.next(name)) edge_bwd(Lc, l);
+        }
+        node_bwd_tc(Lc, 0);
     } else {
         for (int l = 0; l < L; l++) {
             snprintf(name, sizeof(name), "node_fwd%d", l);
@@ -634,6 +739,10 @@ int configure_kernels(vb_handle* h) {
     CUDA_TRY(h, opt_in_smem(edge_bwd_tc_kernel<128>, TC_SMEM_BYTES));
     CUDA_TRY(h, opt_in_smem(fused_fwd_kernel, TC_SMEM_BYTES));
     CUDA_TRY(h, opt_in_smem(fused_bwd_kernel, TC_SMEM_BYTES));
+    CUDA_TRY(h, opt_in_smem(node_tc_kernel<NT_OPROJ>, TC_SMEM_BYTES));
+    CUDA_TRY(h, opt_in_smem(node_tc_kernel<NT_PROJ>, TC_SMEM_BYTES));
+    CUDA_TRY(h, opt_in_smem(node_tc_kernel<NT_BWDA>, TC_SMEM_BYTES));
+    CUDA_TRY(h, opt_in_smem(node_tc_kernel<NT_BWDB>, TC_SMEM_BYTES));
 
     CUDA_TRY(h, opt_in_smem(node_fwd2_kernel<4>, sizeof(NodeFwd2Smem<4>)));
     CUDA_TRY(h, opt_in_smem(node_bwd2_kernel<4>, sizeof(NodeBwd2Smem<4>)));
@@ -656,7 +765,7 @@ int clean_accumulators(vb_handle* h, cudaStream_t st) {
     CUDA_TRY(h, cudaMemsetAsync(ws.GVNMSG2, 0, N * 3 * D * 4, st));
     CUDA_TRY(h, cudaMemsetAsync(ws.GTU2, 0, N * 6 * D * 4, st));
     CUDA_TRY(h, cudaMemsetAsync(ws.GX, 0, N * D * 4, st));
-    CUDA_TRY(h, cudaMemsetAsync(ws.GXA, 0, N * D * 4, st));
+    CUDA_TRY(h, cudaMemsetAsync(ws.GXA, 0, 3 * N * D * 4, st));
     h->accum_dirty = false;
     return VB_OK;
 }
@@ -738,6 +847,11 @@ void choose_defaults(vb_handle* h) {
     // fused per-layer launches (k_fused.cuh) are opt-in: inside a graph a launch boundary costs ~1-2 us, less than what the
     // fused kernels lose to the 96-register budget of a 576-thread CTA running the node GEMMs (profiles/README.md)
     h->fused = h->fused_opt >= 0 ? h->fused_opt : 0;
+    // node stage on tensor cores for batches whose row tiles fill the machine (the three-launch TC stage has a higher
+    // fixed latency than the single SIMT kernel; crossover measured, profiles/README.md)
+    h->node_tc = h->node_tc_opt >= 0 ? h->node_tc_opt : (N >= 4096 ? 1 : 0);
+    if (h->fused) h->node_tc = 0;
+    h->ws.gxa_parts = h->node_tc ? 3 : 1;
     if (h->npw == 0) h->npw = (N > 4096) ? 2 : 1;
     if (h->te_fwd == 0) h->te_fwd = ((long long)N * 17 / 64 >= 2LL * h->sm_count) ? 64 : 32;
     // tcgen05 edge kernels (one tile per CTA, 16 compute warps): with the tile length chosen below both stages beat
@@ -822,6 +936,7 @@ int vb_create(const float* weights_host, size_t n_floats, const vb_hparams* hp, 
     if (const char* s = getenv("VB_TC_ROWS")) { const int v = atoi(s); if (v == 32 || v == 64 || v == 96 || v == 128) h->tc_rows_opt = v; }
     if (const char* s = getenv("VB_NODE_IMPL")) h->node_impl = atoi(s);
     if (const char* s = getenv("VB_FUSED")) h->fused_opt = atoi(s) ? 1 : 0;
+    if (const char* s = getenv("VB_NODE_TC")) h->node_tc_opt = atoi(s) ? 1 : 0;
     *out = h;
     return VB_OK;
 }
@@ -1463,7 +1578,8 @@ int vb_set_option(vb_handle* h, const char* key, int64_t value) {
     else if (k == "edge_tc" && value >= 0 && value <= 3) h->edge_tc = h->edge_tc_opt = (int)value;
     else if (k == "tc_rows" && (value == 32 || value == 64 || value == 96 || value == 128)) h->tc_rows = h->tc_rows_opt = (int)value;
     else if (k == "node_impl" && (value == 0 || value == 1)) h->node_impl = (int)value;
-    else if (k == "fused" && (value == 0 || value == 1)) h->fused = h->fused_opt = (int)value;
+    else if (k == "fused" && (value == 0 || value == 1)) { h->fused = h->fused_opt = (int)value; if (value) h->node_tc = 0; h->ws.gxa_parts = h->node_tc ? 3 : 1; }
+    else if (k == "node_tc" && (value == 0 || value == 1)) { h->node_tc = h->node_tc_opt = (int)value; if (value) h->fused = 0; h->ws.gxa_parts = h->node_tc ? 3 : 1; }
     else if (k == "comm_auto" && (value == 0 || value == 1)) h->comm_auto = (int)value;
     else if (k == "timeline" && (value == 0 || value == 1)) {
         if (value && !h->d_tl) {
@@ -1491,6 +1607,7 @@ int64_t vb_get_option(const vb_handle* h, const char* key) {
     if (k == "edge_tc") return h->edge_tc;
     if (k == "node_impl") return h->node_impl;
     if (k == "fused") return h->fused;
+    if (k == "node_tc") return h->node_tc;
     if (k == "comm_auto") return h->comm_auto;
     if (k == "caph_ready") return h->caph_ready ? 1 : 0;
     if (k == "caph_evals") {           // energy evaluations of the last refinement (synchronises)
@@ -1623,6 +1740,7 @@ int64_t vb_debug_read(vb_handle* h, const char* name, int layer, void* host_dst,
     else BUF("GVEC", ws.GVEC, N * 3 * D, 4)
     else BUF("GF", ws.GF, E * D, 4)
     else BUF("GXA", ws.GXA, N * D, 4)
+    else BUF("GXA3", ws.GXA, 3 * N * D, 4)
     else BUF("GQKV", ws.GQKV, N * 3 * D, 4)
     else BUF("GVNMSG", ws.GVNMSG, N * 3 * D, 4)
     else BUF("GTU", ws.GTU, N * 6 * D, 4)

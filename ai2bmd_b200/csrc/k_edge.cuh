@@ -293,7 +293,7 @@ __global__ void __launch_bounds__(NW * 32) edge_bwd_kernel(EdgeArgs a) {
         // ---- g_m = g_xa_i + g_Spre Ws ----
 #pragma unroll
         for (int r = 0; r < R; r++) {
-            const float4 t = ldg4(ws.GXA + (size_t)meta.dst[r0 + r] * D + col);
+            const float4 t = load_gxa(ws, (size_t)meta.dst[r0 + r], col);
             acc[r][0] = t.x; acc[r][1] = t.y; acc[r][2] = t.z; acc[r][3] = t.w;
         }
         warp_gemm<R, 2 * D, LEQ>(acc, Ss + r0 * LEQ, lw.WsN, D, lane);

@@ -43,6 +43,7 @@ struct TcShared {
     uint64_t b_empty[TC_STAGES];
     uint64_t go[TC_MAXJOBS];
     uint64_t done[TC_MAXJOBS];
+    uint64_t b_tile;                    // per-edge feature rows landed in `tile` (one arrival + byte count per compute warp)
     uint32_t tmem_base;
     alignas(16) float eacc[TC_TE][4];   // per-edge adjoint scalars of the current tile: dE/dC, dE/dd[3]
     float gattn[TC_TE][H];              // adjoint kernel: dE/da_h per edge
@@ -229,6 +230,7 @@ __device__ __forceinline__ uint32_t tc2_setup(TcShared& sh, int njobs) {
     if (threadIdx.x == 0) {
         for (int s = 0; s < TC_STAGES; s++) { tc::mbar_init(&sh.b_full[s], 1); tc::mbar_init(&sh.b_empty[s], 1); }
         for (int j = 0; j < njobs; j++) { tc::mbar_init(&sh.go[j], TC2_CTHREADS); tc::mbar_init(&sh.done[j], 1); }
+        tc::mbar_init(&sh.b_tile, TC2_CWARPS);
         tc::fence_barrier_init();
     }
     if (warp == TC2_CWARPS) tc::tmem_alloc(&sh.tmem_base, 512);
@@ -327,12 +329,24 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) edge_fwd_tc_kernel(const __gri
             const uint32_t tpar = (uint32_t)(it & 1);
             const int e0 = ((int)blockIdx.x + it * (int)gridDim.x) * ROWS;
             const int nvalid = min(ROWS, E - e0);
-            // ---- load f tile + meta (coalesced) ----
-            for (int idx = threadIdx.x; idx < ROWS * 32; idx += TC2_CTHREADS) {
-                const int row = idx >> 5, c4 = (idx & 31) * 4;
-                st4(&sh.tile[row][c4], row < nvalid ? ldg4(Fin + (size_t)(e0 + row) * D + c4) : f4s(0.f));
+            // ---- per-edge feature rows -> staging tile by TMA bulk copies (one 512 B row each, padded rows in shared
+            //      memory), completion on an mbarrier; the next tile of this CTA is prefetched into L2 meanwhile ----
+            {
+                constexpr int RW = ROWS / TC2_CWARPS;                 // rows a warp issues
+                const int w0 = warp * RW, wn = max(0, min(RW, nvalid - w0));
+                if (lane == 0) {
+                    if (wn > 0) tc::mbar_arrive_expect_tx(&sh.b_tile, (uint32_t)wn * D * 4);
+                    else tc::mbar_arrive(&sh.b_tile);
+                }
+                __syncwarp();
+                if (lane < wn) tc::tma_load_1d(&sh.tile[w0 + lane][0], Fin + (size_t)(e0 + w0 + lane) * D, D * 4, &sh.b_tile);
+                if (threadIdx.x == 0 && it + 1 < my_tiles) {
+                    const int en = ((int)blockIdx.x + (it + 1) * (int)gridDim.x) * ROWS;
+                    tc::tma_prefetch_l2(Fin + (size_t)en * D, (uint32_t)min(ROWS, E - en) * D * 4);
+                }
             }
             load_edge_meta<TC_TE, TC2_CTHREADS>(sh.meta, ws, e0, nvalid);
+            tc::mbar_wait(&sh.b_tile, tpar);
             csync();
             TC_TL(2);
             tc2_tile_to_a<ROWS>(sh, tmem, warp, lane);
@@ -590,6 +604,14 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) edge_bwd_tc_kernel(const __gri
             const int e0 = ((int)blockIdx.x + it * (int)gridDim.x) * ROWS;
             const int nvalid = min(ROWS, E - e0);
             load_edge_meta<TC_TE, TC2_CTHREADS>(sh.meta, ws, e0, nvalid);
+            if (threadIdx.x < 4 && it + 1 < my_tiles) {               // next tile's stored pre-activations / g_f rows -> L2
+                const int en = ((int)blockIdx.x + (it + 1) * (int)gridDim.x) * ROWS;
+                const uint32_t nn = (uint32_t)min(ROWS, E - en);
+                if (threadIdx.x == 0) tc::tma_prefetch_l2(P1 + (size_t)en * 3 * D, nn * 3 * D * 4);
+                else if (threadIdx.x == 1) tc::tma_prefetch_l2(SP + (size_t)en * 2 * D, nn * 2 * D * 4);
+                else if (threadIdx.x == 2) { if (upd) tc::tma_prefetch_l2(ws.GF + (size_t)en * D, nn * D * 4); }
+                else tc::tma_prefetch_l2(ATT + (size_t)en * H, nn * H * 4);
+            }
             csync();
             TC_TL(2);
             // ---- s1 half: g_Spre[:, 0:128] -> tile -> A ; source-side g_vn ----
@@ -666,7 +688,7 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) edge_bwd_tc_kernel(const __gri
                 for (int u = 0; u < RB4; u++) {
                     const int row = r0 + rb + u;
                     const size_t e = (size_t)(e0 + (row < nvalid ? row : 0));
-                    gxa[u] = ldg4(ws.GXA + (size_t)sh.meta.dst[row] * D + col);
+                    gxa[u] = load_gxa(ws, (size_t)sh.meta.dst[row], col);
                     vjr[u] = ldg4(QKV + (size_t)sh.meta.src[row] * 3 * D + 2 * D + col);
                     pdvr[u] = ldg4(P1 + e * 3 * D + D + col);
                     avr[u] = row < nvalid ? __ldg(ATT + e * H + hd) : 0.f;

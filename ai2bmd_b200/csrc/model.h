@@ -40,7 +40,14 @@ namespace vb {
     X(tcW1, 3 * 4 * 8192)      /* forward  [dk | dv | f]   : 3 chunks                    */        \
     X(tcWs, 2 * 4 * 8192)      /* forward  [s1 | s2]       : 2 chunks                    */        \
     X(tcWsN, 2 * 4 * 8192)     /* adjoint  g_m = g_s Ws    : K-chunks s1-part, s2-part   */        \
-    X(tcW1N, 3 * 4 * 8192)     /* adjoint  g_f += g_P W1   : K-chunks dk, dv, f parts    */
+    X(tcW1N, 3 * 4 * 8192)     /* adjoint  g_f += g_P W1   : K-chunks dk, dv, f parts    */        \
+    /* node stage on tensor cores (k_node_tc.cuh): forward column chunks / adjoint K chunks */                 \
+    X(tcWo, 3 * 4 * 8192)      /* forward  o = xa Wo^T     : chunks o1, o2, o3           */        \
+    X(tcWqkv, 3 * 4 * 8192)    /* forward  [q | k | v]                                    */        \
+    X(tcWvt, 5 * 4 * 8192)     /* forward  [v1 | v2 | v3 | t | u] (t, u zeros in the last layer) */ \
+    X(tcWoN, 3 * 4 * 8192)     /* adjoint  g_xa = g_o Wo   : K-chunks                     */        \
+    X(tcWqkvN, 3 * 4 * 8192)   /* adjoint  g_xn = g_qkv Wqkv                              */        \
+    X(tcWvtN, 5 * 4 * 8192)    /* adjoint  g_vn = g_v123 Wvec + g_tu Wtu                  */
 
 struct LayerW {
 #define X(name, count) const float* name;
@@ -95,7 +102,8 @@ struct Workspace {
     float* GX;              // [N][128]
     float* GVEC;            // [N][3][128]
     float* GF;              // [Ecap][128]
-    float* GXA;             // [N][128]
+    float* GXA;             // [gxa_parts][N][128]  dE/dxa; with the tensor-core node stage three K-chunk partials (summed by the edge adjoint)
+    int gxa_parts;          // 1 or 3
     float* GQKV;            // [N][384]
     float* GVNMSG;          // [N][3][128]
     float* GTU;             // [N][3][256]
@@ -104,6 +112,18 @@ struct Workspace {
     float* GVNMSG2;         // [N][3][128]
     float* GTU2;            // [N][3][256]
     float* eatom;           // [N]
+    // tensor-core node stage (k_node_tc.cuh)
+    float* XN;              // [N][128]      LayerNorm(x) of the current stage
+    float* PX;              // [3][N][128]   partial products of g_qkv Wqkv (one per 128-deep K chunk)
+    float* PV;              // [5][3N][128]  partial products of g_v123 Wvec (3) and g_tu Wtu (2)
+    float* GO;              // [N][384]      [g_o1 | g_x vdot | g_x]
 };
+
+// dE/dxa of a node: the sum of its partials in a fixed order
+__device__ __forceinline__ float4 load_gxa(const Workspace& ws, size_t node, int col) {
+    float4 v = ld4(ws.GXA + node * D + col);
+    if (ws.gxa_parts == 3) v = (v + ld4(ws.GXA + ((size_t)ws.N + node) * D + col)) + ld4(ws.GXA + (2 * (size_t)ws.N + node) * D + col);
+    return v;
+}
 
 }  // namespace vb

@@ -52,6 +52,11 @@ __device__ __forceinline__ void tma_load_1d(void* smem_dst, const void* gmem_src
                  : "memory");
 }
 
+// bulk prefetch global -> L2 (SASS: UBLKPF.L2): address and size multiples of 16 bytes
+__device__ __forceinline__ void tma_prefetch_l2(const void* gmem_src, uint32_t bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gmem_src), "r"(bytes) : "memory");
+}
+
 // ---- TMEM allocation (one full warp executes these) -------------------------------------------------
 __device__ __forceinline__ void tmem_alloc(uint32_t* smem_result, uint32_t ncols) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_result)), "r"(ncols)

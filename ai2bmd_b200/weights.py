@@ -21,13 +21,18 @@ def load_state_dict(path: str) -> Dict[str, np.ndarray]:
         z = np.load(path)
         return {k: np.asarray(z[k], dtype=np.float32) for k in z.files}
     import torch
-    ck = torch.load(path, map_location="cpu", weights_only=True)
+    try:
+        ck = torch.load(path, map_location="cpu", weights_only=True)
+    except Exception as e:      # Lightning checkpoints may pickle non-tensor objects in hyper_parameters
+        raise RuntimeError(f"{path}: torch.load(weights_only=True) refused the file ({e}); the reference loads it with full "
+                           "unpickling -- for a TRUSTED file, re-save its state_dict (or an .npz of it) and load that") from e
     hp = ck.get("hyper_parameters", {})
     if hp:
         want = dict(embedding_dimension=128, num_layers=6, num_heads=8, num_rbf=32, lmax=1, max_num_neighbors=32,
-                    vecnorm_type="max_min", rbf_type="expnorm", activation="silu", attn_activation="silu")
+                    vecnorm_type="max_min", rbf_type="expnorm", activation="silu", attn_activation="silu", cutoff=5.0,
+                    max_z=100, prior_model="Atomref", reduce_op="add", derivative=True)
         for k, v in want.items():
-            if hp.get(k) != v:
+            if k in hp and hp[k] != v:
                 raise ValueError(f"checkpoint hyper-parameter {k}={hp.get(k)!r} is not the supported {v!r}")
     return {re.sub(r"^model\.", "", k): v.float().numpy() for k, v in ck["state_dict"].items()}
 
@@ -60,8 +65,10 @@ def _named_arrays(sd: Dict[str, np.ndarray]) -> Dict[str, np.ndarray]:
     out["h0_U2T"], out["h0_b2"], out["h0_U2N"] = u2.T, f(o0 + "update_net.2.bias"), u2
     out["h1_u2"] = f(o1 + "update_net.2.weight")[0]
     out["h1_b2"] = np.array([f(o1 + "update_net.2.bias")[0], 0, 0, 0], dtype=np.float32)
-    out["atomref"] = f("prior_model.atomref.weight").reshape(-1)
-    out["scalars"] = np.array([float(sd["std"]), float(sd["mean"]), 0, 0], dtype=np.float32)
+    # absent prior / standardisation tensors mean "no prior", std 1, mean 0 (visnet.py:141-149)
+    out["atomref"] = (f("prior_model.atomref.weight").reshape(-1) if "prior_model.atomref.weight" in sd
+                      else np.zeros(100, dtype=np.float32))
+    out["scalars"] = np.array([float(sd.get("std", 1.0)), float(sd.get("mean", 0.0)), 0, 0], dtype=np.float32)
     for l in range(L):
         p = rm + f"vis_mp_layers.{l}."
         last = l == L - 1
@@ -89,6 +96,14 @@ def _named_arrays(sd: Dict[str, np.ndarray]) -> Dict[str, np.ndarray]:
         out[k + "tcWs"] = np.concatenate([tc_image(ws[c * D:(c + 1) * D]) for c in range(2)])
         out[k + "tcWsN"] = np.concatenate([tc_image(ws[c * D:(c + 1) * D].T) for c in range(2)])
         out[k + "tcW1N"] = np.concatenate([tc_image(w1[c * D:(c + 1) * D].T) for c in range(3)])
+        # node stage on tensor cores (k_node_tc.cuh)
+        wvt = np.concatenate([wv, wtu], 0)                      # [v1 | v2 | v3 | t | u] : [640, 128]
+        out[k + "tcWo"] = np.concatenate([tc_image(wo[c * D:(c + 1) * D]) for c in range(3)])
+        out[k + "tcWqkv"] = np.concatenate([tc_image(wqkv[c * D:(c + 1) * D]) for c in range(3)])
+        out[k + "tcWvt"] = np.concatenate([tc_image(wvt[c * D:(c + 1) * D]) for c in range(5)])
+        out[k + "tcWoN"] = np.concatenate([tc_image(wo[c * D:(c + 1) * D].T) for c in range(3)])
+        out[k + "tcWqkvN"] = np.concatenate([tc_image(wqkv[c * D:(c + 1) * D].T) for c in range(3)])
+        out[k + "tcWvtN"] = np.concatenate([tc_image(wvt[c * D:(c + 1) * D].T) for c in range(5)])
     return out
 
 

@@ -198,6 +198,39 @@ def test_fused_and_separate_launch_plans_agree(real_weights, reference_outputs, 
     assert eng.launches_per_forward <= 24
 
 
+@pytest.mark.parametrize("key", ["chig", "trpcage", "dense44"])
+def test_tensor_core_node_stage_agrees(real_weights, reference_outputs, key):
+    """Node stage as tcgen05 GEMM tiles (k_node_tc.cuh, one job per CTA at these sizes) against the fp64 anchor."""
+    r = reference_outputs
+    fd = _case(r, key)
+    eng = Engine(real_weights, 0)
+    eng.set_option("node_tc", 1)
+    eng.set_topology(fd.z, fd.batch, n_graphs=len(fd))
+    assert eng.get_option("node_tc") == 1
+    e, f = eng.forward_host(fd.pos)
+    e2, f2 = eng.forward_host(fd.pos)
+    assert np.abs(f2 - f).max() <= 2e-5 * max(1.0, np.abs(f).max())
+    e64, f64 = r[f"{key}_e64"], r[f"{key}_f64"]
+    assert np.abs(f - f64).max() <= 2e-5 * np.abs(f64).max() + 5e-5
+    assert (np.abs(e.reshape(e64.shape) - e64) <= 2e-6 * np.abs(e64).max() + 4e-3).all()
+
+
+def test_tensor_core_node_stage_all_chunks_per_cta(real_weights):
+    """A batch large enough that every CTA runs all column chunks of its row tile on one staged A operand (default plan
+    of the 512-fragment config) against the SIMT node stage."""
+    fd = synthetic_batch(160, seed=5)
+    outs = []
+    for node_tc in (0, 1):
+        eng = Engine(real_weights, 0)
+        eng.set_option("node_tc", node_tc)
+        eng.set_topology(fd.z, fd.batch)
+        outs.append(eng.forward_host(fd.pos))
+    (e0, f0), (e1, f1) = outs
+    assert np.isfinite(e1).all() and np.isfinite(f1).all()
+    assert (np.abs(e1 - e0) <= e_tol(e0)).all()
+    assert np.abs(f1 - f0).max() <= 5e-5
+
+
 def test_fused_plan_persistent_ctas_many_blocks(real_weights):
     """More 4-node blocks than SMs: every CTA of the fused kernels loops over several blocks (and sub-tile parities)."""
     fd = synthetic_batch(96, seed=3)

@@ -14,7 +14,7 @@ sys.path.insert(0, os.path.join(ROOT, "tools"))
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.parametrize("opts", ["fused=0", "fused=1", "fused=0,edge_tc=0"])
+@pytest.mark.parametrize("opts", ["fused=0", "fused=1", "fused=0,edge_tc=0", "node_tc=1"])
 @pytest.mark.parametrize("weights", ["real", "3"])
 def test_every_stage_against_the_fp64_adjoint_oracle(opts, weights):
     from stage_check import stage_report
@@ -24,3 +24,4 @@ def test_every_stage_against_the_fp64_adjoint_oracle(opts, weights):
     stages = {s for s, _, _ in worst}
     assert "head" in stages and "embed_node_bwd" in stages and "finalize" in stages
     assert ("fwd3" in stages) == ("fused=1" in opts)
+    assert ("proj3" in stages and "bwdB2" in stages) == ("node_tc=1" in opts)

@@ -118,6 +118,33 @@ def stage_report(frags="chig", weights="real", max_frags=0, opts=""):
             report(st, "f0", rd("F", 0, (N * 32, D))[:E], S["f_in0"])
         elif st.startswith("node_fwd"):
             node_fwd_checks(st, int(st[8:]))
+        elif st.startswith("oproj"):            # tensor-core node stage: O of the previous layer
+            k = int(st[5:])
+            report(st, f"o{k-1}", rd("O", k - 1, (N, 3 * D)), S[f"o{k-1}"])
+        elif st.startswith("norm"):
+            k = int(st[4:])
+            if k >= 1:
+                report(st, f"x_in{k}", rd("X", k, (N, D)), S[f"x_in{k}"] if k < L else S["x_out"])
+                report(st, f"vec_in{k}", rd("V", k, (N, 3, D)), S[f"vec_in{k}"] if k < L else S["vec_out"])
+                report(st, f"vdot{k-1}", rd("VDOT", k - 1, (N, D)), S[f"vdot{k-1}"])
+            if k < L:
+                report(st, "vn", rd("VN", k, (N, 3, D)), S[f"vn{k}"])
+        elif st.startswith("proj"):
+            k = int(st[4:])
+            report(st, "qkv", rd("QKV", k, (N, 3 * D)), cat(S[f"q{k}"], S[f"k{k}"], S[f"v{k}"]))
+            report(st, "v123", rd("V123", k, (N, 3, 3 * D)), cat(S[f"v1{k}"], S[f"v2{k}"], S[f"v3{k}"]))
+            if k < L - 1:
+                report(st, "tu", rd("TU", k, (N, 3, 2 * D)), cat(S[f"t{k}"], S[f"u{k}"]))
+        elif st.startswith("bnorm"):
+            k = int(st[5:])
+            if k <= L - 1:
+                report(st, f"gx_in{k}", rd("GX", 0, (N, D)), B[f"gx_in{k}"])
+                report(st, f"gvec_in{k}", rd("GVEC", 0, (N, 3, D)), B[f"gvec_in{k}"])
+        elif st.startswith("bwdB"):
+            k = int(st[4:])
+            report(st, f"g_xa{k-1}", rd("GXA3", 0, (3, N, D)).sum(0), B[f"g_xa{k-1}"])
+        elif st.startswith("bwdA"):
+            pass                                 # K-chunk partials only; their sums are checked at bnorm
         elif st.startswith("edge_fwd"):
             l = int(st[8:])
             report(st, "xa", rd("XA", 0, (N, D)), S[f"xa{l}"])
