@@ -447,6 +447,36 @@ def run_ours(args):
                                  "cap-H placement, engine, signed reduction" + (", all-reduce" if world > 1 else "") +
                                  ", half-kick; " + ("one CUDA graph replay per step" if one_graph else "phases enqueued by the host around the engine's graph") +
                                  ", no host synchronisation, L2 in the loop's steady state"}
+    # ---- per-step cap-hydrogen refinement: cost of the LBFGS kernel alone and of the MD step with it ----
+    caph_info = None
+    if world == 1 and md_device is not None and args.workload in ("chig", "trpcage"):
+        from ai2bmd_b200 import caph as caph_mod
+        from ai2bmd_b200.fixtures import load_capped_protein, load_caph_tables
+        tables, _ = load_caph_tables(args.workload)
+        problem = caph_mod.build_problem(load_capped_protein(args.workload), fd, recipe, tables)
+        shard.engine.set_caph(problem)
+        ptmp = shard.pos.clone()
+        for _ in range(3):
+            shard.engine.caph_relax(ptmp.data_ptr(), stream.cuda_stream)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(stream)
+        for _ in range(50):
+            ptmp.copy_(shard.pos)
+            shard.engine.caph_relax(ptmp.data_ptr(), stream.cuda_stream)
+        b.record(stream)
+        torch.cuda.synchronize()
+        us = a.elapsed_time(b) / 50 * 1e3
+        dmd.run(5)
+        barrier()
+        a.record(stream)
+        dmd.run(args.steps)
+        b.record(stream)
+        barrier()
+        caph_info = {"us_per_refinement": us, "hydrogens": int(len(problem.h_idx)), "terms": int(len(problem.bond_k) + len(problem.angle_k) + len(problem.dih_k) + len(problem.pair_a)),
+                     "energy_evaluations": shard.engine.get_option("caph_evals"),
+                     "md_device_with_refinement_steps_per_s": args.steps / (a.elapsed_time(b) / 1e3),
+                     "what": "one LBFGS call (lr 0.1, max_iter 10, tolerances 0.1 / 0.01) on the Amber terms of all dipeptides, added "
+                             "hydrogens only, one CTA (csrc/k_caph.cuh); folded into the device MD step after the placement"}
     clocks.loaded = False
     clock_info = clocks.stop() if rank == 0 else None
 
@@ -642,6 +672,7 @@ def run_ours(args):
         "scale_c4": scale_c4,
         "md_loop": md_loop,
         "md_device": md_device,
+        "caph": caph_info,
         "nonbonded": nonbonded,
         "checksum": {"E_prot_eV": float(ef[-1].item()), "F_abs_sum": float(ef[:-1].abs().sum().item())},
     }
