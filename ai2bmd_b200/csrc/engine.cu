@@ -178,6 +178,7 @@ struct vb_handle {
     int *d_nb_rowptr = nullptr, *d_nb_col = nullptr;
     double* d_nb_eatom = nullptr;
 
+    bool has_topology_sizes() const { return ws.N > 0; }
     void set_error(const char* fmt, ...) {
         char buf[1024];
         va_list ap;
@@ -563,7 +564,7 @@ void node_tc_jobs(TcJob* jobs, const float* img, int n) {
 int node_tc_grid(const NodeTcArgs& a) { return a.tx * (a.njx / a.jx) + a.tv * (a.njv / a.jv); }
 // one job per CTA while that still fits ~2 waves (each CTA then streams a single weight image); otherwise a CTA runs all
 // chunks of its row tile on one staged A operand
-bool node_tc_split(const vb_handle* h, const NodeTcArgs& a) { return a.tx * a.njx + a.tv * a.njv <= 2 * h->sm_count; }
+bool node_tc_split(const vb_handle* h, const NodeTcArgs&) { return h->ws.gxa_parts == 3; }   // one decision per topology (set_gxa_parts)
 
 void launch_node_oproj_tc(Launcher& Lc, int k) {           // O[k-1] = xa Wo[k-1]^T + bo
     vb_handle* h = Lc.h;
@@ -600,13 +601,17 @@ void launch_node_bwdA_tc(Launcher& Lc, int k) {            // K-chunk partials o
     node_tc_jobs(a.jobs_v, h->mw.layer[k].tcWvtN, 5);
     if (k == L - 1) a.njv = 3;
     a.acc_qkv = h->ws.GQKV; a.acc_tu = h->ws.GTU;
+    if (!node_tc_split(h, a)) { a.jx = a.njx; a.jv = a.njv; }   // all K chunks in one CTA, accumulated in TMEM
     Lc.launch(node_tc_kernel<NT_BWDA>, dim3(node_tc_grid(a)), dim3(TC2_THREADS), TC_SMEM_BYTES, a);
     Lc.check();
 }
 void launch_node_norm_bwd(Launcher& Lc, int k) {
     vb_handle* h = Lc.h;
+    NodeTcArgs a{};
+    node_tc_common(h, a, k);
+    if (k == L - 1) a.njv = 3;
     Lc.launch(node_norm_bwd_kernel, dim3((h->ws.N + NN_WARPS - 1) / NN_WARPS), dim3(NN_WARPS * 32), 0, k, h->mw, h->ws,
-              h->ws.GQKV, h->ws.GVNMSG, h->ws.GTU);
+              h->ws.GQKV, h->ws.GVNMSG, h->ws.GTU, node_tc_split(h, a) ? 1 : 0);
     Lc.check();
 }
 void launch_node_bwdB_tc(Launcher& Lc, int k) {            // dE/dxa partials = [g_o1 | g_x vdot | g_x] Wo[k-1]
@@ -615,6 +620,7 @@ void launch_node_bwdB_tc(Launcher& Lc, int k) {            // dE/dxa partials = 
     node_tc_common(h, a, k);
     a.tv = 0;
     node_tc_jobs(a.jobs_x, h->mw.layer[k - 1].tcWoN, 3);
+    if (h->ws.gxa_parts == 1) a.jx = 3;                        // accumulate the three K chunks in TMEM: one complete dE/dxa
     Lc.launch(node_tc_kernel<NT_BWDB>, dim3(node_tc_grid(a)), dim3(TC2_THREADS), TC_SMEM_BYTES, a);
     Lc.check();
 }
@@ -833,6 +839,15 @@ StepIO internal_io(vb_handle* h, bool protein) {
     return io;
 }
 
+// dE/dxa arrives as three K-chunk partials only when the tensor-core node stage runs one chunk per CTA (small systems)
+void set_gxa_parts(vb_handle* h) {
+    h->ws.gxa_parts = 1;
+    if (h->node_tc && h->has_topology_sizes()) {
+        const int tx = (h->ws.N + TC_TE - 1) / TC_TE, tv = (3 * h->ws.N + TC_TE - 1) / TC_TE;
+        if (tx * 3 + tv * 5 <= 2 * h->sm_count) h->ws.gxa_parts = 3;
+    }
+}
+
 // stage names / launch count of one evaluation under the current options (nothing is launched)
 void record_stages(vb_handle* h) {
     h->stage_names.clear();
@@ -847,11 +862,12 @@ void choose_defaults(vb_handle* h) {
     // fused per-layer launches (k_fused.cuh) are opt-in: inside a graph a launch boundary costs ~1-2 us, less than what the
     // fused kernels lose to the 96-register budget of a 576-thread CTA running the node GEMMs (profiles/README.md)
     h->fused = h->fused_opt >= 0 ? h->fused_opt : 0;
-    // node stage on tensor cores for batches whose row tiles fill the machine (the three-launch TC stage has a higher
-    // fixed latency than the single SIMT kernel; crossover measured, profiles/README.md)
-    h->node_tc = h->node_tc_opt >= 0 ? h->node_tc_opt : (N >= 4096 ? 1 : 0);
+    // node stage on tensor cores from ~600 atoms on (measured, graph replay: Chignolin 391 atoms 0.78 -> 0.82 ms slower,
+    // Trp-cage 737 atoms 1.08 -> 0.97 ms, WW 2.07 -> 1.81, ABD 2.22 -> 1.98, 512 fragments 13.8 -> 12.3: the three-launch
+    // stage has a higher fixed latency than the single SIMT kernel, profiles/README.md)
+    h->node_tc = h->node_tc_opt >= 0 ? h->node_tc_opt : (N >= 600 ? 1 : 0);
     if (h->fused) h->node_tc = 0;
-    h->ws.gxa_parts = h->node_tc ? 3 : 1;
+    set_gxa_parts(h);
     if (h->npw == 0) h->npw = (N > 4096) ? 2 : 1;
     if (h->te_fwd == 0) h->te_fwd = ((long long)N * 17 / 64 >= 2LL * h->sm_count) ? 64 : 32;
     // tcgen05 edge kernels (one tile per CTA, 16 compute warps): with the tile length chosen below both stages beat
@@ -1578,8 +1594,8 @@ int vb_set_option(vb_handle* h, const char* key, int64_t value) {
     else if (k == "edge_tc" && value >= 0 && value <= 3) h->edge_tc = h->edge_tc_opt = (int)value;
     else if (k == "tc_rows" && (value == 32 || value == 64 || value == 96 || value == 128)) h->tc_rows = h->tc_rows_opt = (int)value;
     else if (k == "node_impl" && (value == 0 || value == 1)) h->node_impl = (int)value;
-    else if (k == "fused" && (value == 0 || value == 1)) { h->fused = h->fused_opt = (int)value; if (value) h->node_tc = 0; h->ws.gxa_parts = h->node_tc ? 3 : 1; }
-    else if (k == "node_tc" && (value == 0 || value == 1)) { h->node_tc = h->node_tc_opt = (int)value; if (value) h->fused = 0; h->ws.gxa_parts = h->node_tc ? 3 : 1; }
+    else if (k == "fused" && (value == 0 || value == 1)) { h->fused = h->fused_opt = (int)value; if (value) h->node_tc = 0; set_gxa_parts(h); }
+    else if (k == "node_tc" && (value == 0 || value == 1)) { h->node_tc = h->node_tc_opt = (int)value; if (value) h->fused = 0; set_gxa_parts(h); }
     else if (k == "comm_auto" && (value == 0 || value == 1)) h->comm_auto = (int)value;
     else if (k == "timeline" && (value == 0 || value == 1)) {
         if (value && !h->d_tl) {

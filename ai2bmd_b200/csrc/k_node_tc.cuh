@@ -56,10 +56,11 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) node_tc_kernel(const __grid_co
     const int total_rows = is_x ? ws.N : 3 * ws.N;
     const int row0 = tile * TC_TE;
     const int nvalid = min(TC_TE, total_rows - row0);
+    constexpr bool KCHUNKS = (MODE == NT_BWDA || MODE == NT_BWDB);     // jobs = K chunks accumulated into one product
     if (threadIdx.x < nj) {
         TcJob j = is_x ? a.jobs_x[j0 + threadIdx.x] : a.jobs_v[j0 + threadIdx.x];
-        j.d_col = (threadIdx.x & 1) ? (int)TC_COL_D1 : (int)TC_COL_D0;
-        j.accumulate = 0;
+        j.d_col = (!KCHUNKS && (threadIdx.x & 1)) ? (int)TC_COL_D1 : (int)TC_COL_D0;
+        j.accumulate = (KCHUNKS && threadIdx.x > 0) ? 1 : 0;
         jl[threadIdx.x] = j;
     }
     const uint32_t tmem = tc2_setup(sh, nj);           // (its __syncthreads publishes jl)
@@ -69,61 +70,88 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) node_tc_kernel(const __grid_co
     } else if (warp == TC2_CWARPS + 1) {
         if (lane == 0) tc_mma_issuer(sh, jl, nj, 1, tmem, nullptr);
     } else {
-        // ---- A operand rows -> staging tile (warp per row, lane owns 4 channels: coalesced 512 B rows) ----
-        for (int r = warp; r < nvalid; r += TC2_CWARPS) {
-            const size_t row = (size_t)(row0 + r);
-            float4 v;
-            if (MODE == NT_OPROJ) {
-                v = ld4(ws.XA + row * D + col);
-            } else if (MODE == NT_PROJ) {
-                v = is_x ? ld4(ws.XN + row * D + col) : ld4(ws.VN[k] + row * D + col);
-            } else if (MODE == NT_BWDA) {
-                if (is_x) {
-                    v = ld4(a.acc_qkv + row * 3 * D + j0 * D + col);
-                } else if (j0 >= 3) {
-                    v = ld4(a.acc_tu + row * 2 * D + (j0 - 3) * D + col);
-                } else {
-                    const size_t node = row / 3;
-                    const float* orow = ws.O[k] + node * 3 * D;
-                    if (j0 == 2) {
-                        v = ld4(ws.GVEC + row * D + col) * ld4(orow + col);                         // g_vec * o1
-                    } else {
-                        const float4 g_vdot = ld4(ws.GX + node * D + col) * ld4(orow + D + col);    // g_x * o2
-                        v = g_vdot * ld4(ws.V123[k] + row * 3 * D + (j0 == 0 ? D : 0) + col);       // * v2 | * v1
-                    }
-                }
-            } else {
-                v = ld4(ws.GO + row * 3 * D + j0 * D + col);
-            }
-            st4(&sh.tile[r][col], v);
-        }
-        csync();
-        fu_tile_to_a(sh, tmem, warp, lane, nvalid);
-        tc2_go(sh, 0);
-        if (nj > 1) tc2_go(sh, 1);
-        for (int j = 0; j < nj; j++) {
-            tc::mbar_wait(&sh.done[j], 0u);
-            tc::fence_after_sync();
-            csync();                                          // the tile is free (A copied / previous chunk stored)
-            fu_d_to_tile(sh, tmem, (j & 1) ? TC_COL_D1 : TC_COL_D0, warp, lane, nvalid);
-            tc::fence_before_sync();
-            csync();
-            if (j + 2 < nj) tc::mbar_arrive(&sh.go[j + 2]);   // this accumulator is drained: the chunk after next may start
-            const int jj = j0 + j;
+        // A operand rows of job jj -> staging tile (warp per row, lane owns 4 channels: coalesced 512 B rows)
+        auto load_a = [&](int jj) {
             for (int r = warp; r < nvalid; r += TC2_CWARPS) {
                 const size_t row = (size_t)(row0 + r);
-                float4 v = ld4(&sh.tile[r][col]);
+                float4 v;
                 if (MODE == NT_OPROJ) {
-                    st4(ws.O[k - 1] + row * 3 * D + jj * D + col, v + ldg4(a.mw.layer[k - 1].bo + jj * D + col));
+                    v = ld4(ws.XA + row * D + col);
                 } else if (MODE == NT_PROJ) {
-                    if (is_x) st4(ws.QKV[k] + row * 3 * D + jj * D + col, v + ldg4(a.mw.layer[k].bqkv + jj * D + col));
-                    else if (jj < 3) st4(ws.V123[k] + row * 3 * D + jj * D + col, v);
-                    else st4(ws.TU[k] + row * 2 * D + (jj - 3) * D + col, v);
+                    v = is_x ? ld4(ws.XN + row * D + col) : ld4(ws.VN[k] + row * D + col);
                 } else if (MODE == NT_BWDA) {
-                    if (is_x) st4(ws.PX + ((size_t)jj * ws.N + row) * D + col, v);
-                    else st4(ws.PV + ((size_t)jj * 3 * ws.N + row) * D + col, v);
+                    if (is_x) {
+                        v = ld4(a.acc_qkv + row * 3 * D + jj * D + col);
+                    } else if (jj >= 3) {
+                        v = ld4(a.acc_tu + row * 2 * D + (jj - 3) * D + col);
+                    } else {
+                        const size_t node = row / 3;
+                        const float* orow = ws.O[k] + node * 3 * D;
+                        if (jj == 2) {
+                            v = ld4(ws.GVEC + row * D + col) * ld4(orow + col);                         // g_vec * o1
+                        } else {
+                            const float4 g_vdot = ld4(ws.GX + node * D + col) * ld4(orow + D + col);    // g_x * o2
+                            v = g_vdot * ld4(ws.V123[k] + row * 3 * D + (jj == 0 ? D : 0) + col);       // * v2 | * v1
+                        }
+                    }
                 } else {
-                    st4(ws.GXA + ((size_t)jj * ws.N + row) * D + col, v);
+                    v = ld4(ws.GO + row * 3 * D + jj * D + col);
+                }
+                st4(&sh.tile[r][col], v);
+            }
+        };
+        if (!KCHUNKS) {
+            // ---- column chunks of one product: one A operand, accumulators alternate between D0 and D1 ----
+            load_a(0);
+            csync();
+            fu_tile_to_a(sh, tmem, warp, lane, nvalid);
+            tc2_go(sh, 0);
+            if (nj > 1) tc2_go(sh, 1);
+            for (int j = 0; j < nj; j++) {
+                tc::mbar_wait(&sh.done[j], 0u);
+                tc::fence_after_sync();
+                csync();                                          // the tile is free (A copied / previous chunk stored)
+                fu_d_to_tile(sh, tmem, (j & 1) ? TC_COL_D1 : TC_COL_D0, warp, lane, nvalid);
+                tc::fence_before_sync();
+                csync();
+                if (j + 2 < nj) tc::mbar_arrive(&sh.go[j + 2]);   // this accumulator is drained: the chunk after next may start
+                const int jj = j0 + j;
+                for (int r = warp; r < nvalid; r += TC2_CWARPS) {
+                    const size_t row = (size_t)(row0 + r);
+                    const float4 v = ld4(&sh.tile[r][col]);
+                    if (MODE == NT_OPROJ) {
+                        st4(ws.O[k - 1] + row * 3 * D + jj * D + col, v + ldg4(a.mw.layer[k - 1].bo + jj * D + col));
+                    } else {
+                        if (is_x) st4(ws.QKV[k] + row * 3 * D + jj * D + col, v + ldg4(a.mw.layer[k].bqkv + jj * D + col));
+                        else if (jj < 3) st4(ws.V123[k] + row * 3 * D + jj * D + col, v);
+                        else st4(ws.TU[k] + row * 2 * D + (jj - 3) * D + col, v);
+                    }
+                }
+            }
+        } else {
+            // ---- K chunks of one product: every chunk has its own A operand, all accumulate into D0; with one chunk per
+            //      CTA the result is the partial of chunk j0 (the glue kernel / the edge adjoint sums the partials) ----
+            for (int j = 0; j < nj; j++) {
+                load_a(j0 + j);
+                csync();
+                if (j > 0) { tc::mbar_wait(&sh.done[j - 1], 0u); tc::fence_after_sync(); }   // A planes no longer read
+                fu_tile_to_a(sh, tmem, warp, lane, nvalid);
+                tc2_go(sh, j);
+                csync();                                          // the tile may take the next chunk's rows
+            }
+            tc::mbar_wait(&sh.done[nj - 1], 0u);
+            tc::fence_after_sync();
+            fu_d_to_tile(sh, tmem, TC_COL_D0, warp, lane, nvalid);
+            tc::fence_before_sync();
+            csync();
+            for (int r = warp; r < nvalid; r += TC2_CWARPS) {
+                const size_t row = (size_t)(row0 + r);
+                const float4 v = ld4(&sh.tile[r][col]);
+                if (MODE == NT_BWDA) {
+                    if (is_x) st4(ws.PX + ((size_t)j0 * ws.N + row) * D + col, v);
+                    else st4(ws.PV + ((size_t)j0 * 3 * ws.N + row) * D + col, v);
+                } else {
+                    st4(ws.GXA + ((size_t)j0 * ws.N + row) * D + col, v);
                 }
             }
         }
@@ -179,8 +207,10 @@ __global__ void __launch_bounds__(NN_WARPS * 32) node_norm_fwd_kernel(int k, Mod
 // ---------------------------------------------------------------------------------------------------------
 // backward glue (warp per node): the per-node phase of node_bwd2_body around the partial products
 // ---------------------------------------------------------------------------------------------------------
+// `split`: the products arrive as one partial per K chunk (3 scalar, 3 + 2 vector) to be summed here; otherwise chunk 0
+// holds the complete product (the GEMM CTA accumulated its chunks in TMEM).
 __global__ void __launch_bounds__(NN_WARPS * 32) node_norm_bwd_kernel(int k, ModelW mw, Workspace ws, float* __restrict__ GQKV,
-                                                                      float* __restrict__ GVNMSG, float* __restrict__ GTU) {
+                                                                      float* __restrict__ GVNMSG, float* __restrict__ GTU, int split) {
     pdl_entry();
     const int lane = threadIdx.x & 31, col = lane * 4;
     const int node = blockIdx.x * NN_WARPS + (threadIdx.x >> 5);
@@ -193,14 +223,19 @@ __global__ void __launch_bounds__(NN_WARPS * 32) node_norm_bwd_kernel(int k, Mod
     for (int s = 0; s < 3; s++) gvec[s] = ld4(ws.GVEC + ((size_t)node * 3 + s) * D + col);
     if (has_a) {
         const LayerW& lw = mw.layer[k];
-        const float4 gxn = (ld4(ws.PX + (0 * N + node) * D + col) + ld4(ws.PX + (1 * N + node) * D + col)) + ld4(ws.PX + (2 * N + node) * D + col);
+        float4 gxn = ld4(ws.PX + (0 * N + node) * D + col);
+        if (split) gxn = (gxn + ld4(ws.PX + (1 * N + node) * D + col)) + ld4(ws.PX + (2 * N + node) * D + col);
         float4 vin[3], gout[3], gv[3];
 #pragma unroll
         for (int s = 0; s < 3; s++) {
             const size_t r3 = (size_t)node * 3 + s;
             float4 g = ld4(GVNMSG + r3 * D + col);
-            g = g + ((ld4(ws.PV + (0 * 3 * N + r3) * D + col) + ld4(ws.PV + (1 * 3 * N + r3) * D + col)) + ld4(ws.PV + (2 * 3 * N + r3) * D + col));
-            if (has_tu) g = g + (ld4(ws.PV + (3 * 3 * N + r3) * D + col) + ld4(ws.PV + (4 * 3 * N + r3) * D + col));
+            if (split) {
+                g = g + ((ld4(ws.PV + (0 * 3 * N + r3) * D + col) + ld4(ws.PV + (1 * 3 * N + r3) * D + col)) + ld4(ws.PV + (2 * 3 * N + r3) * D + col));
+                if (has_tu) g = g + (ld4(ws.PV + (3 * 3 * N + r3) * D + col) + ld4(ws.PV + (4 * 3 * N + r3) * D + col));
+            } else {
+                g = g + ld4(ws.PV + r3 * D + col);
+            }
             gout[s] = g;
             vin[s] = ld4(ws.V[k] + r3 * D + col);
         }

@@ -12,9 +12,14 @@ A compact restatement of the reference's one-off fragmentation tables, far enoug
 * signed force map (+ dipeptide atoms, - ACE-NME atoms, added hydrogens dropped):
   ``distancefrag.py:335-353``, ``src/Calculators/combiner.py:38-39``
 
-Not restated (out of scope for the ViSNet hot path): the AMBER atom
-permutation (``seq_dict.pkl``), the LBFGS relaxation of the added hydrogens, CYX-CYX fused pairs.
-ViSNet is permutation-equivariant, so atom order inside a fragment does not change energies/forces.
+* CYX-CYX pairs: the two dipeptides of a disulfide bridge are evaluated as ONE graph; the second one (by residue number)
+  stays in the batch as an empty fragment: ``distancefrag.py:185-238``, pairing rule ``get_cystine_bonds`` ``:804-844``
+
+Atom order inside a fragment is this module's own (leading cap group, residue, trailing cap group, added hydrogens after
+the real atoms of their group); the reference reorders every dipeptide into AMBER order through ``seq_dict.pkl``
+(``distancefrag.py:506-737``).  ViSNet is permutation-equivariant, so energies and forces do not depend on it as long as no
+atom has more than 32 candidates inside the cutoff (the first-32-by-index rule is order dependent: ``neighbour_cap_margin``
+reports the margin, and the AMBER order of a dipeptide is available through ``ai2bmd_b200.caph.table_layout``).
 """
 from __future__ import annotations
 
@@ -98,6 +103,50 @@ def _cap_h(pos, acceptor, removed, acc_elem):
     return _Cap(acceptor, removed, _RCOV[acc_elem] + _RCOV["H"])
 
 
+def cystine_pairs(prot: CappedProtein, centres) -> dict:
+    """``{dipeptide i: dipeptide j}`` for the dipeptides (indices into ``centres``, the centre residue numbers) whose centre
+    residue is CYX, paired by the shortest SG-SG distance exactly as ``DistanceFragment.get_cystine_bonds`` does
+    (``distancefrag.py:804-844``): walk the CYX dipeptides in order, take each one's nearest SG partner unless either of the
+    two is already paired."""
+    cyx, sg = [], []
+    for k, c in enumerate(centres):
+        members = [i for i in range(len(prot)) if prot.resnums[i] == c]
+        if prot.resnames[members[0]] != "CYX":
+            continue
+        s_atoms = [i for i in members if prot.names[i] == "SG"]
+        if len(s_atoms) != 1:
+            raise ValueError(f"CYX residue {c} has {len(s_atoms)} SG atoms")
+        cyx.append(k)
+        sg.append(s_atoms[0])
+    if len(cyx) % 2:
+        raise ValueError("odd number of CYX residues")
+    if not cyx:
+        return {}
+    P = np.asarray(prot.positions, dtype=np.float64)[sg]
+    dist = np.linalg.norm(P[None, :] - P[:, None], axis=-1)
+    np.fill_diagonal(dist, np.inf)
+    pairs = {}
+    for i, j in enumerate(np.argmin(dist, axis=-1)):
+        if i in pairs or int(j) in pairs:
+            continue
+        pairs[i] = int(j)
+    return {cyx[i]: cyx[j] for i, j in pairs.items()}
+
+
+def neighbour_cap_margin(frags: FragmentData, cutoff: float = 5.0, cap: int = 32) -> int:
+    """``cap`` minus the largest number of atoms (itself included) any atom has strictly inside the cutoff within its own
+    fragment.  Non-negative: no neighbour list is truncated, so the atom order inside the fragments cannot change the
+    result; negative: the first-32-by-index rule drops neighbours and the reference's AMBER order matters."""
+    worst = 0
+    for g in range(len(frags)):
+        p = np.asarray(frags.pos[int(frags.start[g]):int(frags.end[g])], dtype=np.float32)
+        if len(p) == 0:
+            continue
+        d2 = ((p[:, None, :] - p[None, :, :]) ** 2).sum(-1)
+        worst = max(worst, int((d2 < np.float32(cutoff) ** 2).sum(1).max()))
+    return cap - worst
+
+
 def fragment_protein(prot: CappedProtein, with_recipe: bool = False):
     R = int(prot.resnums.max())
     assert len(set(prot.resnums.tolist())) == R, "residue numbers are not continuous"
@@ -151,6 +200,11 @@ def fragment_protein(prot: CappedProtein, with_recipe: bool = False):
         if k < na:
             # ACE-NME k: leading group of dipeptide k+1 (from residue k+2) + trailing group of dipeptide k (k+3)
             frags.append((-1.0, lead_group(centre) + trail_group(centre + 1)))
+
+    # disulfide bridges: the pair is one graph, the partner's slot stays as an empty fragment (distancefrag.py:185-238)
+    for i, j in cystine_pairs(prot, [k + 2 for k in range(nd)]).items():
+        frags[2 * i] = (frags[2 * i][0], frags[2 * i][1] + frags[2 * j][1])
+        frags[2 * j] = (frags[2 * j][0], [])
 
     z, batch, start, end = [], [], [], []
     src, dst, sgn, fsgn = [], [], [], []

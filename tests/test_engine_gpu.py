@@ -228,7 +228,7 @@ def test_tensor_core_node_stage_all_chunks_per_cta(real_weights):
     (e0, f0), (e1, f1) = outs
     assert np.isfinite(e1).all() and np.isfinite(f1).all()
     assert (np.abs(e1 - e0) <= e_tol(e0)).all()
-    assert np.abs(f1 - f0).max() <= 5e-5
+    assert np.abs(f1 - f0).max() <= f_tol(f0)            # two fp32-level evaluations of jittered conformers (|F| up to tens of eV/A)
 
 
 def test_fused_plan_persistent_ctas_many_blocks(real_weights):

@@ -1,12 +1,9 @@
 set -x
 mkdir -p gpurun_out
-timeout 1500 python -m pytest tests -m gpu -q > gpurun_out/r02e_pytest.log 2>&1; echo "pytest rc=$?" >> gpurun_out/r02e_pytest.log
-for w in trpcage ww abd; do
-  for o in 0 1; do
-    timeout 300 python tools/stage_times.py --workload $w --opts node_tc=$o --out gpurun_out/r02e_stages_${w}_nodetc$o.txt > /dev/null 2>> gpurun_out/r02e.err
-  done
-done
-timeout 300 python tools/stage_times.py --workload c4 --opts node_tc=1 --iters 5 --out gpurun_out/r02e_stages_c4_nodetc.txt > /dev/null 2>> gpurun_out/r02e.err
-timeout 300 python tools/stage_times.py --workload chig --out gpurun_out/r02e_stages_chig.txt > /dev/null 2>> gpurun_out/r02e.err
-tail -25 gpurun_out/r02e_pytest.log
-for f in gpurun_out/r02e_stages_*.txt; do echo $f; tail -n 2 $f; done
+nvidia-smi -L > gpurun_out/r02f_gpus.txt
+timeout 900 python -m pytest tests/test_multigpu.py -m gpu -x -q > gpurun_out/r02f_pytest_multigpu.log 2>&1; echo "pytest rc=$?" >> gpurun_out/r02f_pytest_multigpu.log
+timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 50 --warmup 5 > gpurun_out/r02f_bench_chig_n2.json 2> gpurun_out/r02f_bench_chig_n2.err
+timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus 2 --steps 50 --warmup 5 --nccl --no-c4 > gpurun_out/r02f_bench_chig_n2_nccl.json 2> gpurun_out/r02f_bench_chig_n2_nccl.err
+tail -20 gpurun_out/r02f_pytest_multigpu.log
+tail -3 gpurun_out/r02f_bench_chig_n2.err
+head -c 1500 gpurun_out/r02f_bench_chig_n2.json
