@@ -44,3 +44,19 @@ def load_caph_tables(name: str):
         t = {n[len(pre):]: (int(g[n]) if g[n].ndim == 0 else g[n]) for n in g.files if n.startswith(pre)}
         tables.append((t, [str(x) for x in g[f"g{k}_names"]]))
     return tables, g
+
+
+def load_synthetic_cyx():
+    """The WW-domain example with four SER turned into CYX (OG -> SG) -- the reference ships no CYX-containing example --
+    exactly as tests/golden/make_golden.py builds it for the reference's own pairing function; returns (protein, golden)."""
+    import json
+    from .pdbfrag import CappedProtein
+    prot = load_capped_protein("ww")
+    gold = json.load(open(os.path.join(GOLDEN, "reference_cyx.json")))
+    names, resn, elem = list(prot.names), list(prot.resnames), list(prot.elements)
+    for i in range(len(prot)):
+        if int(prot.resnums[i]) in gold["cyx_residues"]:
+            resn[i] = "CYX"
+            if names[i] == "OG":
+                names[i], elem[i] = "SG", "S"
+    return CappedProtein(names, resn, prot.resnums, elem, prot.positions), gold

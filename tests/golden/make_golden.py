@@ -442,6 +442,47 @@ def write_reference_fragment_index():
         json.dump(out, fh, sort_keys=True)
 
 
+def synthetic_cyx_protein(prot):
+    """The WW-domain example with four SER residues turned into two disulfide-bridged CYX (OG -> SG): the reference ships no
+    CYX-containing example; only names / elements change, geometry stays."""
+    ser = sorted({int(r) for r, n in zip(prot.resnums, prot.resnames) if n == "SER"})
+    pick = ser[:4]
+    assert len(pick) == 4, ser
+    names, resn, elem = list(prot.names), list(prot.resnames), list(prot.elements)
+    for i in range(len(prot)):
+        if int(prot.resnums[i]) in pick:
+            resn[i] = "CYX"
+            if names[i] == "OG":
+                names[i], elem[i] = "SG", "S"
+    return type(prot)(names, resn, prot.resnums, elem, prot.positions), pick
+
+
+def write_reference_cyx():
+    """Pairing of disulfide-bridged dipeptides by the reference's own ``get_cystine_bonds`` (distancefrag.py:804-844)
+    on the synthetic CYX protein, with the dipeptide atom lists of the reference's own ``get_fragments_index``."""
+    import ast
+    import json
+    import types
+    prot, pick = synthetic_cyx_protein(read_pdb(f"{REF}/examples/ww.pdb"))
+    tree = ast.parse(open(f"{REF}/src/Fragmentation/distancefrag.py").read())
+    fn = [n for n in ast.walk(tree) if isinstance(n, ast.FunctionDef) and n.name == "get_cystine_bonds"][0]
+    fn.decorator_list = []
+    ns = {"np": np, "Protein": object, "arguments": types.SimpleNamespace(get=lambda: types.SimpleNamespace(verbose=0))}
+    exec(compile(ast.Module(body=[fn], type_ignores=[]), "ref_cyx", "exec"), ns)
+    dips = json.load(open(os.path.join(HERE, "reference_fragment_index.json")))["ww"]["dipeptides"]
+
+    class FakeProt:
+        arrays = {"atomtypes": np.asarray(prot.names), "residuenames": np.asarray(prot.resnames)}
+
+        def get_positions(self):
+            return np.asarray(prot.positions)
+
+    pairs = ns["get_cystine_bonds"](FakeProt(), dips)
+    with open(os.path.join(HERE, "reference_cyx.json"), "w") as fh:
+        json.dump({"cyx_residues": pick, "pairs": {str(int(k)): int(v) for k, v in pairs.items()}}, fh, sort_keys=True)
+    print(f"CYX pairing reference: residues {pick} -> dipeptide pairs {pairs}")
+
+
 def main():
     sd = O.load_state_dict(CKPT)
     O.save_weights_npz(sd, os.path.join(HERE, "weights_2ef43f29.npz"))
@@ -477,6 +518,7 @@ def main():
 
     write_reference_partitions(frs)
     write_reference_fragment_index()
+    write_reference_cyx()
     write_reference_host_logic(*frs["chig"])
     from ai2bmd_b200.fixtures import load_protein
     write_reference_nonbonded(*frs["chig"], *load_protein("chig"))

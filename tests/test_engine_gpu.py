@@ -129,6 +129,26 @@ def test_edge_cases_tiny_graphs(real_weights):
     assert np.abs(f[0]).max() == 0 and np.abs(f[4:]).max() == 0      # isolated atoms feel no force
 
 
+def test_cystine_pair_as_one_graph_with_an_empty_fragment(model, real_weights):
+    """Disulfide-bridged dipeptides packed as one (large) graph + the partner's empty slot (distancefrag.py:185-238)."""
+    from ai2bmd_b200.fixtures import load_synthetic_cyx
+    from ai2bmd_b200.pdbfrag import fragment_protein
+    prot, _ = load_synthetic_cyx()
+    fd, pm = fragment_protein(prot)
+    sizes = fd.end - fd.start
+    assert (sizes == 0).any() and sizes.max() > 44
+    oracle = O.OracleViSNet({k: torch.from_numpy(v) for k, v in real_weights.items()}, torch.float64)
+    e_ref, f_ref = oracle.forward_all(fd) if hasattr(oracle, "forward_all") else oracle.energy_and_forces(fd.z, fd.pos, fd.batch)
+    e, f = model.dl_potential_loader(fd)
+    assert e.shape == (len(fd), 1)
+    er = np.zeros(len(fd)); er[:len(e_ref)] = e_ref.numpy()[:, 0]
+    assert (np.abs(e[:, 0] - er) <= e_tol(er)).all() and (e[sizes == 0, 0] == 0).all()
+    assert np.abs(f - f_ref.numpy()).max() <= f_tol(f_ref.numpy())
+    slots, deg = model.engine.get_edges()
+    s_ref, d_ref = O.radius_graph_canonical(fd.pos, fd.batch)
+    assert np.array_equal(deg, d_ref) and np.array_equal(slots, s_ref)
+
+
 def test_batch_composition_independence(model, chig):
     fd, _ = chig
     e_all, f_all = model.dl_potential_loader(fd)

@@ -1,5 +1,6 @@
 """Host-side logic: FragmentData semantics, fixtures, weight packing, C-ABI symbol table, loud failure."""
 import ctypes
+import json
 import os
 
 import numpy as np
@@ -11,6 +12,8 @@ from ai2bmd_b200.calculator import DipeptideBondedCombiner
 from ai2bmd_b200.fragment_data import FragmentInfo
 from ai2bmd_b200.parallel import combine_local, partition_fragments, shard_protein_map
 from ai2bmd_b200.weights import pack_weights
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
 ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
 
@@ -318,3 +321,35 @@ def test_host_langevin_keeps_the_centre_of_mass_in_place():
     assert np.abs((md.m * md.x).sum(0) / md.m.sum() - com0).max() <= 1e-12
     assert np.abs((md.m * md.v).sum(0)).max() <= 1e-12
     assert np.abs(md.x - x0).max() > 1e-2
+
+
+def test_cystine_pairing_equals_the_reference_function():
+    """CYX-CYX dipeptides are paired by the reference's own ``get_cystine_bonds`` (golden) and packed as ONE graph, the
+    partner's slot staying in the batch as an empty fragment (distancefrag.py:185-238)."""
+    from ai2bmd_b200.fixtures import load_fragments, load_synthetic_cyx
+    from ai2bmd_b200.pdbfrag import cystine_pairs, fragment_protein
+    prot, gold = load_synthetic_cyx()
+    R = int(prot.resnums.max())
+    pairs = cystine_pairs(prot, [k + 2 for k in range(R - 2)])
+    assert {str(k): v for k, v in pairs.items()} == gold["pairs"]
+    fd, pm, rc = fragment_protein(prot, with_recipe=True)
+    fd0, pm0 = load_fragments("ww")
+    assert len(fd) == len(fd0) and len(fd.z) == len(fd0.z)            # same atoms, regrouped
+    sizes, sizes0 = fd.end - fd.start, fd0.end - fd0.start
+    assert (sizes[[2 * j for j in pairs.values() if j not in pairs]] == 0).all()
+    assert sizes.sum() == sizes0.sum() and (sizes == 0).sum() >= 1 and sizes.max() > sizes0.max()
+    # the whole-protein map still addresses every real fragment atom exactly once
+    assert len(pm.src_atom) == len(pm0.src_atom) and len(set(pm.src_atom.tolist())) == len(pm.src_atom)
+    assert np.array_equal(np.sort(pm.dst_atom), np.sort(pm0.dst_atom))
+    assert (np.diff(fd.batch) >= 0).all() and set(np.unique(fd.batch).tolist()) == set(np.flatnonzero(sizes > 0).tolist())
+
+
+def test_example_fragments_never_exceed_the_neighbour_cap():
+    """The engine keeps, like the reference, the FIRST 32 candidates by atom index.  This repository orders the atoms of a
+    fragment differently from the reference's AMBER permutation, which is harmless exactly as long as no atom has more
+    than 32 atoms (itself included) inside the cutoff -- fail loudly the day a fixture crosses that line."""
+    from ai2bmd_b200.fixtures import load_fragments
+    from ai2bmd_b200.pdbfrag import neighbour_cap_margin
+    for name in ("chig", "trpcage", "ww", "abd"):
+        fd, _ = load_fragments(name)
+        assert neighbour_cap_margin(fd) >= 0, f"{name}: an atom has more than 32 candidates: atom order now matters"
