@@ -263,7 +263,7 @@ def test_fused_plan_persistent_ctas_many_blocks(real_weights):
     (e0, f0), (e1, f1) = outs
     assert np.isfinite(e1).all() and np.isfinite(f1).all()
     assert (np.abs(e1 - e0) <= e_tol(e0)).all()
-    assert np.abs(f1 - f0).max() <= 5e-5
+    assert np.abs(f1 - f0).max() <= f_tol(f0)            # two fp32-level evaluations of jittered conformers
 
 
 def test_trimmed_edge_capacity_overflow_is_reported(real_weights, chig):

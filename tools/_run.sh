@@ -1,7 +1,5 @@
 set -x
 mkdir -p gpurun_out
-timeout 1500 python -m pytest tests -m gpu -q > gpurun_out/r02_pytest_gpu.log 2>&1; echo "pytest rc=$?" >> gpurun_out/r02_pytest_gpu.log
-tail -5 gpurun_out/r02_pytest_gpu.log
-python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/r02_smoke.log 2>&1; tail -2 gpurun_out/r02_smoke.log
 bash tools/record_run.sh r02 > gpurun_out/r02_record.log 2>&1
 tail -5 gpurun_out/r02_record.log
+du -sh gpurun_out

@@ -15,18 +15,24 @@ timeout 120 python tools/stage_times.py --workload chig --out $out/${tag}_stages
 timeout 120 python tools/stage_times.py --workload chig --max-frags 1 --out $out/${tag}_stages_1frag.txt > /dev/null 2>&1
 timeout 120 python tools/stage_times.py --workload c4 --iters 5 --out $out/${tag}_stages_c4.txt > /dev/null 2>&1
 timeout 120 python tools/tc_timeline.py --workload chig > $out/${tag}_timeline_chig.txt 2>&1
+# --set full captures are summarised ON THE BOX (metrics + top source lines) and the reports deleted: gpurun brings back
+# at most 64 MiB
+capture() {   # capture <kernel regex> <workload> <launch-skip> <count>
+  rep=/tmp/${tag}_$1_$2
+  timeout 400 ncu --set full --clock-control none --import-source on -k regex:$1 --launch-skip $3 -c $4 -f -o $rep \
+    python bench.py --workload $2 --steps 2 --warmup 1 --skip-cpu-baseline > $out/ncu_full_$1_$2.log 2>&1
+  python tools/ncu_summary.py full $rep.ncu-rep $out/${tag}_$1_$2_full.txt > /dev/null 2>&1
+  python tools/ncu_lines.py $rep.ncu-rep 25 > $out/${tag}_$1_$2_lines.txt 2>&1
+  rm -f $rep.ncu-rep
+}
 for w in chig c4; do
   timeout 400 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $out/${tag}_launches_$w.csv \
     python bench.py --workload $w --steps 2 --warmup 1 --skip-cpu-baseline > $out/ncu_list_$w.log 2>&1
-  for k in edge_fwd_tc edge_bwd_tc; do
-    timeout 400 ncu --set full --clock-control none --import-source on -k regex:$k --launch-skip 14 -c 2 -f -o $out/${tag}_${k}_$w \
-      python bench.py --workload $w --steps 2 --warmup 1 --skip-cpu-baseline > $out/ncu_full_${k}_$w.log 2>&1
-  done
+  capture edge_fwd_tc $w 14 2
+  capture edge_bwd_tc $w 14 2
 done
-timeout 400 ncu --set full --clock-control none --import-source on -k regex:node_tc_kernel --launch-skip 20 -c 4 -f -o $out/${tag}_node_tc_c4 \
-  python bench.py --workload c4 --steps 2 --warmup 1 --skip-cpu-baseline > $out/ncu_full_node_tc_c4.log 2>&1
-timeout 400 ncu --set full --clock-control none --import-source on -k regex:node_bwd2 --launch-skip 8 -c 2 -f -o $out/${tag}_node_bwd2_chig \
-  python bench.py --workload chig --steps 2 --warmup 1 --skip-cpu-baseline > $out/ncu_full_node_bwd2_chig.log 2>&1
+capture node_tc_kernel c4 20 4
+capture node_bwd2 chig 8 2
 for t in memcheck racecheck; do
   timeout 600 compute-sanitizer --tool $t python tools/sanitize_run.py 3 4 node_tc=1 > $out/${tag}_${t}_nodetc.log 2>&1
 done
