@@ -330,7 +330,7 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) edge_fwd_tc_kernel(const __gri
             const int e0 = ((int)blockIdx.x + it * (int)gridDim.x) * ROWS;
             const int nvalid = min(ROWS, E - e0);
             // ---- per-edge feature rows -> staging tile by TMA bulk copies (one 512 B row each, padded rows in shared
-            //      memory), completion on an mbarrier; the next tile of this CTA is prefetched into L2 meanwhile ----
+            //      memory), completion on an mbarrier ----
             {
                 constexpr int RW = ROWS / TC2_CWARPS;                 // rows a warp issues
                 const int w0 = warp * RW, wn = max(0, min(RW, nvalid - w0));
@@ -340,10 +340,6 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) edge_fwd_tc_kernel(const __gri
                 }
                 __syncwarp();
                 if (lane < wn) tc::tma_load_1d(&sh.tile[w0 + lane][0], Fin + (size_t)(e0 + w0 + lane) * D, D * 4, &sh.b_tile);
-                if (threadIdx.x == 0 && it + 1 < my_tiles) {
-                    const int en = ((int)blockIdx.x + (it + 1) * (int)gridDim.x) * ROWS;
-                    tc::tma_prefetch_l2(Fin + (size_t)en * D, (uint32_t)min(ROWS, E - en) * D * 4);
-                }
             }
             load_edge_meta<TC_TE, TC2_CTHREADS>(sh.meta, ws, e0, nvalid);
             tc::mbar_wait(&sh.b_tile, tpar);
@@ -512,6 +508,10 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) edge_fwd_tc_kernel(const __gri
                 }
             }
             TC_TL(15);
+            if (threadIdx.x == 0 && it + 1 < my_tiles) {             // next tile's feature rows -> L2 (bulk prefetch), shortly before use
+                const int en = ((int)blockIdx.x + (it + 1) * (int)gridDim.x) * ROWS;
+                tc::tma_prefetch_l2(Fin + (size_t)en * D, (uint32_t)min(ROWS, E - en) * D * 4);
+            }
             // ---- s2 (D0): va_i += sum_e s2 * d ----
             tc::mbar_wait(&sh.done[J_S2], tpar);
             tc::fence_after_sync();
@@ -604,14 +604,6 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) edge_bwd_tc_kernel(const __gri
             const int e0 = ((int)blockIdx.x + it * (int)gridDim.x) * ROWS;
             const int nvalid = min(ROWS, E - e0);
             load_edge_meta<TC_TE, TC2_CTHREADS>(sh.meta, ws, e0, nvalid);
-            if (threadIdx.x < 4 && it + 1 < my_tiles) {               // next tile's stored pre-activations / g_f rows -> L2
-                const int en = ((int)blockIdx.x + (it + 1) * (int)gridDim.x) * ROWS;
-                const uint32_t nn = (uint32_t)min(ROWS, E - en);
-                if (threadIdx.x == 0) tc::tma_prefetch_l2(P1 + (size_t)en * 3 * D, nn * 3 * D * 4);
-                else if (threadIdx.x == 1) tc::tma_prefetch_l2(SP + (size_t)en * 2 * D, nn * 2 * D * 4);
-                else if (threadIdx.x == 2) { if (upd) tc::tma_prefetch_l2(ws.GF + (size_t)en * D, nn * D * 4); }
-                else tc::tma_prefetch_l2(ATT + (size_t)en * H, nn * H * 4);
-            }
             csync();
             TC_TL(2);
             // ---- s1 half: g_Spre[:, 0:128] -> tile -> A ; source-side g_vn ----
@@ -889,6 +881,15 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) edge_bwd_tc_kernel(const __gri
                 }
             }
             TC_TL(19);
+            // next tile's stored pre-activations -> L2 (bulk prefetch, UBLKPF).  Issued late in the tile: a whole tile ahead
+            // the rows were evicted again before their use (ncu: DRAM reads 1.0 -> 1.7 GB per launch on the 512-fragment batch)
+            if (threadIdx.x < 3 && it + 1 < my_tiles) {
+                const int en = ((int)blockIdx.x + (it + 1) * (int)gridDim.x) * ROWS;
+                const uint32_t nn = (uint32_t)min(ROWS, E - en);
+                if (threadIdx.x == 0) tc::tma_prefetch_l2(SP + (size_t)en * 2 * D, nn * 2 * D * 4);
+                else if (threadIdx.x == 1) tc::tma_prefetch_l2(P1 + (size_t)en * 3 * D, nn * 3 * D * 4);
+                else tc::tma_prefetch_l2(ATT + (size_t)en * H, nn * H * 4);
+            }
             // ---- g_f = g_f_next + [g_Pdk|g_Pdv|g_Pf] W1 ----
             wait_done(J_LAST, tpar);
             TC_TL(20);
