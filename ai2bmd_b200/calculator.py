@@ -55,6 +55,7 @@ class ViSNetModel:
         self = cls.__new__(cls)
         self.device, self.engine = device, engine
         self._topo_key = self._key(frag)[0]
+        self._calibrated = True
         return self
 
     @staticmethod
@@ -68,11 +69,15 @@ class ViSNetModel:
         if key != self._topo_key:
             self.engine.set_topology(z, batch, n_graphs=len(frag))
             self._topo_key = key
+            self._calibrated = False
 
     def dl_potential_loader(self, frag_data: FragmentData) -> Tuple[np.ndarray, np.ndarray]:
         """``FragmentData -> (e[G,1] float32 eV, f[N,3] float32 eV/A)`` as numpy arrays."""
         self._ensure_topology(frag_data)
         e, f = self.engine.forward_host(np.asarray(frag_data.pos, dtype=np.float32))
+        if not getattr(self, "_calibrated", True):      # once per topology: tile length from the real edge count
+            self.engine.set_option("calibrate", 1)
+            self._calibrated = True
         return e.reshape(-1, 1), f.reshape(-1, 3)
 
 

@@ -151,7 +151,9 @@ struct vb_handle {
     int use_graph = 1, npw = 0, te_fwd = 0, te_bwd = 32;
     int use_pdl = 0;   // programmatic dependent launch between the stages: measured neutral to slower
     int npw_opt = 0, te_fwd_opt = 0, edge_tc_opt = -1;   // user choices (0 / -1 = choose by problem size)
-    int tc_rows_opt = 0, tc_rows = 128;                  // edges per tcgen05 tile (32 / 64 / 96 / 128; MMA M stays 128)
+    int tc_rows_opt = 0, tc_rows = 128;                  // kernel variant: capacity of a tcgen05 tile (32 / 64 / 96 / 128; MMA M stays 128)
+    int tile_rows = 128;                                 // edges per tile actually used (<= tc_rows): whole waves of CTAs
+    long long edges_plan = 0;                            // edge count the tile length was planned for (estimate or calibrated)
     int node_impl = 1; // 0: warp-per-node kernels (k_node.cuh), 1: CTA-cooperative kernels (k_node2.cuh)
     int fused = 0, fused_opt = -1;   // 1: one launch per layer and direction (k_fused.cuh); -1 = choose by problem size
     int node_tc = 0, node_tc_opt = -1;   // 1: node stage on tensor cores (k_node_tc.cuh); -1 = choose by problem size
@@ -460,8 +462,9 @@ void launch_edge_fwd_tc(Launcher& Lc, int l) {
     a.jobs[n++] = TcJob{lw.tcWs + chunk, (int)TC_COL_D0, 0};               // s2
     a.njobs = n;
     a.tl = h->timeline ? h->d_tl + (size_t)l * TC_TL_SLOTS : nullptr;
+    a.tile_rows = h->tile_rows;
     const int rows = h->tc_rows;
-    const int tiles = (h->ws.Ecap + rows - 1) / rows;
+    const int tiles = (h->ws.Ecap + h->tile_rows - 1) / h->tile_rows;
     const int blocks = std::max(1, std::min(tiles, h->sm_count));
     if (rows == 32) Lc.launch(edge_fwd_tc_kernel<32>, dim3(blocks), dim3(TC2_THREADS), TC_SMEM_BYTES, a);
     else if (rows == 64) Lc.launch(edge_fwd_tc_kernel<64>, dim3(blocks), dim3(TC2_THREADS), TC_SMEM_BYTES, a);
@@ -490,8 +493,9 @@ void launch_edge_bwd_tc(Launcher& Lc, int l) {
     if (upd) a.jobs[n++] = TcJob{lw.tcW1N + 2 * chunk, (int)TC_COL_D0, 1};   //      + g_Pf  Wf
     a.njobs = n;
     a.tl = h->timeline ? h->d_tl + (size_t)(L + l) * TC_TL_SLOTS : nullptr;
+    a.tile_rows = h->tile_rows;
     const int rows = h->tc_rows;
-    const int tiles = (h->ws.Ecap + rows - 1) / rows;
+    const int tiles = (h->ws.Ecap + h->tile_rows - 1) / h->tile_rows;
     const int blocks = std::max(1, std::min(tiles, h->sm_count));
     if (rows == 32) Lc.launch(edge_bwd_tc_kernel<32>, dim3(blocks), dim3(TC2_THREADS), TC_SMEM_BYTES, a);
     else if (rows == 64) Lc.launch(edge_bwd_tc_kernel<64>, dim3(blocks), dim3(TC2_THREADS), TC_SMEM_BYTES, a);
@@ -664,7 +668,12 @@ void enqueue_all(Launcher& Lc, const StepIO& io) {
     }
     if (Lc.next("rowptr_scan")) { Lc.launch(rowptr_scan_kernel, dim3(1), dim3(1024), 0, N, ws.deg, ws.rowptr, ws.Ecap, h->d_flags); Lc.check(); }
     if (Lc.next("edge_geom")) { Lc.launch(edge_geom_kernel, dim3((N + 3) / 4), dim3(128), 0, N, io.pos, h->mw, ws); Lc.check(); }
-    if (Lc.next("embed_node")) { Lc.launch(embed_node_kernel, dim3(N), dim3(EMB_THREADS), 0, h->mw, ws); Lc.check(); }
+    const bool batch = N > 8 * h->sm_count;             // batches: several nodes per CTA share the embedding weights
+    if (Lc.next("embed_node")) {
+        if (batch) Lc.launch(embed_node_kernel<8>, dim3((N + 7) / 8), dim3(EMB_THREADS), 0, h->mw, ws);
+        else Lc.launch(embed_node_kernel<1>, dim3(N), dim3(EMB_THREADS), 0, h->mw, ws);
+        Lc.check();
+    }
     const int eblocks = std::max(1, std::min(ws.Ecap, h->sm_count * 16));
     if (Lc.next("embed_edge")) { Lc.launch(embed_edge_kernel, dim3(eblocks), dim3(128), 0, h->mw, ws); Lc.check(); }
     if (h->fused) {
@@ -717,7 +726,10 @@ void enqueue_all(Launcher& Lc, const StepIO& io) {
         Lc.launch(embed_edge_bwd_kernel, dim3(bb), dim3(EEB_WARPS * 32), 0, h->mw, ws);
         Lc.check();
     }
-    if (Lc.next("embed_node_bwd")) { Lc.launch(embed_node_bwd_kernel, dim3(N), dim3(ENB_WARPS * 32), 0, h->mw, ws, io.forces); Lc.check(); }
+    if (Lc.next("embed_node_bwd")) {
+        Lc.launch(embed_node_bwd_kernel, dim3(batch ? std::min(N, 5 * h->sm_count) : N), dim3(ENB_WARPS * 32), 0, h->mw, ws, io.forces);
+        Lc.check();
+    }
     if (Lc.next("finalize")) enqueue_finalize(Lc, io);
 }
 
@@ -856,6 +868,27 @@ void record_stages(vb_handle* h) {
     h->launches = (int)h->stage_names.size();
 }
 
+// Tile length of the tcgen05 edge kernels: the per-tile latency is mostly per-row SIMT phases, so the edges are cut into
+// k whole waves of equally long tiles (k = fewest waves with tiles <= 128 edges) instead of 128-edge tiles plus a ragged last
+// wave: 32,028 edges (ABD) -> 292 tiles of 110 instead of 251 of 128 (two rounds either way, each 14 % shorter); Chignolin
+// 143 tiles of 47 instead of 105 of 64.  `edges` is an estimate (17 per atom, +3 % margin) until vb_set_option("calibrate")
+// replaces it by the count of the last evaluation.
+void plan_tiles(vb_handle* h, long long edges) {
+    const long long sm = h->sm_count;
+    const long long padded = edges + edges * 3 / 100 + 1;
+    const long long waves = std::max<long long>(1, (padded + sm * 128 - 1) / (sm * 128));
+    long long rows = (padded + sm * waves - 1) / (sm * waves);
+    rows = std::min<long long>(128, std::max<long long>(16, rows));
+    if (h->tc_rows_opt > 0) {                      // user-fixed tile capacity: full tiles of that length (round-1 behaviour)
+        h->tc_rows = h->tc_rows_opt;
+        h->tile_rows = h->tc_rows_opt;
+    } else {
+        h->tc_rows = rows <= 32 ? 32 : rows <= 64 ? 64 : rows <= 96 ? 96 : 128;
+        h->tile_rows = (int)rows;
+    }
+    h->edges_plan = edges;
+}
+
 void choose_defaults(vb_handle* h) {
     const int N = h->ws.N;
     h->npw = h->npw_opt; h->te_fwd = h->te_fwd_opt; h->edge_tc = h->edge_tc_opt;
@@ -874,18 +907,7 @@ void choose_defaults(vb_handle* h) {
     // the fp32 SIMT kernels at every size measured, down to a single 26-atom fragment (tools/tc_crossover.py,
     // profiles/README.md); the SIMT kernels stay selectable ("edge_tc" 0..2) as the independent implementation
     if (h->edge_tc < 0) h->edge_tc = 3;
-    // short tiles spread a small system over more SMs (the per-tile latency is mostly the per-row SIMT phases):
-    // the longest tile that still fits the estimated edge count into one wave of CTAs
-    h->tc_rows = h->tc_rows_opt;
-    if (h->tc_rows == 0) {
-        const long long est_edges = (long long)N * 17;
-        h->tc_rows = 128;
-        if ((est_edges + 127) / 128 < h->sm_count) {
-            if ((est_edges + 95) / 96 <= h->sm_count) h->tc_rows = 96;
-            if ((est_edges + 63) / 64 <= h->sm_count) h->tc_rows = 64;
-            if ((est_edges + 31) / 32 <= h->sm_count) h->tc_rows = 32;
-        }
-    }
+    plan_tiles(h, h->edges_plan > 0 ? h->edges_plan : (long long)N * 17);
 }
 
 }  // namespace
@@ -1006,6 +1028,7 @@ int vb_set_topology(vb_handle* h, int64_t n_atoms, int64_t n_graphs, const int64
     cudaFreeHost(h->h_pos); cudaFreeHost(h->h_energy); cudaFreeHost(h->h_forces);
     h->h_pos = h->h_energy = h->h_forces = nullptr;
     h->ws = Workspace{};
+    h->edges_plan = 0;
     h->ws.N = (int)n_atoms;
     h->ws.G = (int)n_graphs;
     const int64_t worst = n_atoms * KNB;
@@ -1592,7 +1615,21 @@ int vb_set_option(vb_handle* h, const char* key, int64_t value) {
     else if (k == "te_fwd" && (value == 32 || value == 64)) h->te_fwd = h->te_fwd_opt = (int)value;
     else if (k == "te_bwd" && (value == 32 || value == 64)) h->te_bwd = (int)value;
     else if (k == "edge_tc" && value >= 0 && value <= 3) h->edge_tc = h->edge_tc_opt = (int)value;
-    else if (k == "tc_rows" && (value == 32 || value == 64 || value == 96 || value == 128)) h->tc_rows = h->tc_rows_opt = (int)value;
+    else if (k == "tc_rows" && (value == 0 || value == 32 || value == 64 || value == 96 || value == 128)) {
+        h->tc_rows_opt = (int)value;
+        if (h->has_topology) plan_tiles(h, h->edges_plan > 0 ? h->edges_plan : (long long)h->ws.N * 17);
+    }
+    else if (k == "calibrate" && value == 1) {
+        // re-plan the tile length from the edge count of the last evaluation (synchronises)
+        if (!h->has_topology) { h->set_error("vb_set_option: calibrate needs a topology"); return VB_ERR_STATE; }
+        int e = 0;
+        if (cudaSetDevice(h->device) != cudaSuccess || cudaDeviceSynchronize() != cudaSuccess ||
+            cudaMemcpy(&e, h->ws.rowptr + h->ws.N, sizeof(int), cudaMemcpyDeviceToHost) != cudaSuccess) {
+            h->set_error("vb_set_option: calibrate failed: %s", cudaGetErrorString(cudaGetLastError()));
+            return VB_ERR_CUDA;
+        }
+        if (e > 0) plan_tiles(h, e);
+    }
     else if (k == "node_impl" && (value == 0 || value == 1)) h->node_impl = (int)value;
     else if (k == "fused" && (value == 0 || value == 1)) { h->fused = h->fused_opt = (int)value; if (value) h->node_tc = 0; set_gxa_parts(h); }
     else if (k == "node_tc" && (value == 0 || value == 1)) { h->node_tc = h->node_tc_opt = (int)value; if (value) h->fused = 0; set_gxa_parts(h); }
@@ -1640,6 +1677,7 @@ int64_t vb_get_option(const vb_handle* h, const char* key) {
     }
     if (k == "timeline") return h->timeline;
     if (k == "tc_rows") return h->tc_rows;
+    if (k == "tile_rows") return h->tile_rows;
     if (k == "n_edges_capacity") return h->ws.Ecap;
     return VB_ERR_ARG;
 }

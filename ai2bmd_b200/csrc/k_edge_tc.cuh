@@ -218,6 +218,7 @@ struct EdgeTcArgs {
     Workspace ws;
     TcJob jobs[TC_MAXJOBS];
     int njobs;
+    int tile_rows;              // edges per tile, <= the kernel's ROWS
     unsigned long long* tl;     // optional timeline (SM clock stamps of CTA 0, first tile); nullptr = off
 };
 constexpr int TC_TL_SLOTS = 64;  // [0,32): compute thread 0 phase stamps ; [32,48): MMA issuer (go seen / MMAs issued per job)
@@ -304,7 +305,8 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) edge_fwd_tc_kernel(const __gri
     constexpr int RPW = ROWS / TC2_CWARPS;      // rows per compute warp in the coalesced phases
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, col = lane * 4;
     const int E = ws.rowptr[ws.N];
-    const int ntiles_total = (E + ROWS - 1) / ROWS;
+    const int trows = min(ROWS, max(16, a.tile_rows));          // edges per tile (<= ROWS, chosen on the host so the tiles fill whole waves)
+    const int ntiles_total = (E + trows - 1) / trows;
     const int my_tiles = ((int)blockIdx.x < ntiles_total) ? (ntiles_total - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
     if (a.tl != nullptr && blockIdx.x == 0 && threadIdx.x == 0) a.tl[0] = (unsigned long long)clock64();
     const uint32_t tmem = tc2_setup(sh, a.njobs);
@@ -323,12 +325,14 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) edge_fwd_tc_kernel(const __gri
         float* __restrict__ P1 = ws.P1[l];
         float* __restrict__ SP = ws.SP[l];
         float* __restrict__ ATT = ws.ATT[l];
-        const int r0 = warp * RPW;
         const int cch = threadIdx.x & (D - 1), grp = threadIdx.x >> 7;      // aggregation role: channel, target parity
         for (int it = 0; it < my_tiles; it++) {
             const uint32_t tpar = (uint32_t)(it & 1);
-            const int e0 = ((int)blockIdx.x + it * (int)gridDim.x) * ROWS;
-            const int nvalid = min(ROWS, E - e0);
+            const int e0 = ((int)blockIdx.x + it * (int)gridDim.x) * trows;
+            const int nvalid = min(trows, E - e0);
+            // rows are dealt to the compute warps in contiguous runs of rpw = ceil(nvalid / 16): a tile shorter than ROWS
+            // keeps every warp busy (slot s of a warp is row warp * rpw + s, valid while s < rpw and the row exists)
+            const int rpw = (nvalid + TC2_CWARPS - 1) / TC2_CWARPS, r0 = warp * rpw;
             // ---- per-edge feature rows -> staging tile by TMA bulk copies (one 512 B row each, padded rows in shared
             //      memory), completion on an mbarrier ----
             {
@@ -363,13 +367,14 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) edge_fwd_tc_kernel(const __gri
                 const float4 bb = ldg4(lw.b1 + col);
 #pragma unroll
                 for (int r = 0; r < RPW; r++) {
+                    if (r >= rpw) break;
                     const int row = r0 + r;
                     const float4 qi = ldg4(QKV + (size_t)sh.meta.dst[row] * 3 * D + col);
                     const float4 kj = ldg4(QKV + (size_t)sh.meta.src[row] * 3 * D + D + col);
                     const float4 P = ld4(&sh.tile[row][col]) + bb;
                     const float av = quad_sum(hsum4(qi * kj * silu4(P)));
                     Areg[r] = silu_(av) * sh.meta.C[row];
-                    if (row < nvalid) {
+                    if ((r < rpw && row < nvalid)) {
                         st4(P1 + (size_t)(e0 + row) * 3 * D + col, P);
                         if ((lane & 3) == 0) ATT[(size_t)(e0 + row) * H + (lane >> 2)] = av;
                     }
@@ -389,11 +394,12 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) edge_fwd_tc_kernel(const __gri
                 const float4 bb = ldg4(lw.b1 + D + col);
 #pragma unroll
                 for (int r = 0; r < RPW; r++) {
+                    if (r >= rpw) break;
                     const int row = r0 + r;
                     const float4 vj = ldg4(QKV + (size_t)sh.meta.src[row] * 3 * D + 2 * D + col);
                     const float4 P = ld4(&sh.tile[row][col]) + bb;
                     st4(&sh.tile[row][col], vj * silu4(P) * Areg[r]);
-                    if (row < nvalid) st4(P1 + (size_t)(e0 + row) * 3 * D + D + col, P);
+                    if ((r < rpw && row < nvalid)) st4(P1 + (size_t)(e0 + row) * 3 * D + D + col, P);
                 }
             }
             csync();
@@ -425,12 +431,13 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) edge_fwd_tc_kernel(const __gri
                 const float4 bb = ldg4(lw.b1 + 2 * D + col);
 #pragma unroll 1
                 for (int rb = 0; rb < RPW; rb += 2) {       // gathers of 2 rows in flight before the first global store
+                    if (rb >= rpw) break;
                     float4 tir[2][3], ujr[2][3], fin[2];
 #pragma unroll
                     for (int u = 0; u < 2; u++) {
                         const int row = r0 + rb + u;
                         const size_t i3 = (size_t)sh.meta.dst[row] * 3, j3 = (size_t)sh.meta.src[row] * 3;
-                        fin[u] = row < nvalid ? ldg4(Fin + (size_t)(e0 + row) * D + col) : f4s(0.f);
+                        fin[u] = (rb + u < rpw && row < nvalid) ? ldg4(Fin + (size_t)(e0 + row) * D + col) : f4s(0.f);
 #pragma unroll
                         for (int s = 0; s < 3; s++) {
                             tir[u][s] = ldg4(TU + (i3 + s) * 2 * D + col);
@@ -447,7 +454,7 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) edge_fwd_tc_kernel(const __gri
                         const float4 a2 = ujr[u][0] * dd.x + ujr[u][1] * dd.y + ujr[u][2] * dd.z;
                         const float4 wdot = (tir[u][0] - a1 * dd.x) * (ujr[u][0] - a2 * dd.x) + (tir[u][1] - a1 * dd.y) * (ujr[u][1] - a2 * dd.y) +
                                             (tir[u][2] - a1 * dd.z) * (ujr[u][2] - a2 * dd.z);
-                        if (row < nvalid) {
+                        if ((rb + u < rpw && row < nvalid)) {
                             st4(P1 + (size_t)(e0 + row) * 3 * D + 2 * D + col, Pf);
                             st4(Fout + (size_t)(e0 + row) * D + col, fin[u] + fp * wdot);
                         }
@@ -509,8 +516,8 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) edge_fwd_tc_kernel(const __gri
             }
             TC_TL(15);
             if (threadIdx.x == 0 && it + 1 < my_tiles) {             // next tile's feature rows -> L2 (bulk prefetch), shortly before use
-                const int en = ((int)blockIdx.x + (it + 1) * (int)gridDim.x) * ROWS;
-                tc::tma_prefetch_l2(Fin + (size_t)en * D, (uint32_t)min(ROWS, E - en) * D * 4);
+                const int en = ((int)blockIdx.x + (it + 1) * (int)gridDim.x) * trows;
+                tc::tma_prefetch_l2(Fin + (size_t)en * D, (uint32_t)min(trows, E - en) * D * 4);
             }
             // ---- s2 (D0): va_i += sum_e s2 * d ----
             tc::mbar_wait(&sh.done[J_S2], tpar);
@@ -579,7 +586,8 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) edge_bwd_tc_kernel(const __gri
     constexpr int RB4 = (RPW % 4 == 0) ? 4 : 2;     // rows whose loads are issued together
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, col = lane * 4, hd = lane >> 2;
     const int E = ws.rowptr[ws.N];
-    const int ntiles_total = (E + ROWS - 1) / ROWS;
+    const int trows = min(ROWS, max(16, a.tile_rows));          // edges per tile (<= ROWS, chosen on the host so the tiles fill whole waves)
+    const int ntiles_total = (E + trows - 1) / trows;
     const int my_tiles = ((int)blockIdx.x < ntiles_total) ? (ntiles_total - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
     if (a.tl != nullptr && blockIdx.x == 0 && threadIdx.x == 0) a.tl[0] = (unsigned long long)clock64();
     const uint32_t tmem = tc2_setup(sh, a.njobs);
@@ -596,13 +604,15 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) edge_bwd_tc_kernel(const __gri
         const float* __restrict__ P1 = ws.P1[l];
         const float* __restrict__ SP = ws.SP[l];
         const float* __restrict__ ATT = ws.ATT[l];
-        const int r0 = warp * RPW;
         const int cch = threadIdx.x & (D - 1), grp = threadIdx.x >> 7;
         auto wait_done = [&](int j, uint32_t tpar) { tc::mbar_wait(&sh.done[j], tpar); tc::fence_after_sync(); };
         for (int it = 0; it < my_tiles; it++) {
             const uint32_t tpar = (uint32_t)(it & 1);
-            const int e0 = ((int)blockIdx.x + it * (int)gridDim.x) * ROWS;
-            const int nvalid = min(ROWS, E - e0);
+            const int e0 = ((int)blockIdx.x + it * (int)gridDim.x) * trows;
+            const int nvalid = min(trows, E - e0);
+            // rows are dealt to the compute warps in contiguous runs of rpw = ceil(nvalid / 16): a tile shorter than ROWS
+            // keeps every warp busy (slot s of a warp is row warp * rpw + s, valid while s < rpw and the row exists)
+            const int rpw = (nvalid + TC2_CWARPS - 1) / TC2_CWARPS, r0 = warp * rpw;
             load_edge_meta<TC_TE, TC2_CTHREADS>(sh.meta, ws, e0, nvalid);
             csync();
             TC_TL(2);
@@ -610,11 +620,12 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) edge_bwd_tc_kernel(const __gri
             // (loads of 4 rows are issued together: the atomics below are compiler barriers for load hoisting)
 #pragma unroll 1
             for (int rb = 0; rb < RPW; rb += RB4) {
+                if (rb >= rpw) break;
                 float4 sp[RB4], gM[RB4][3], vn[RB4][3];
 #pragma unroll
                 for (int u = 0; u < RB4; u++) {
                     const int row = r0 + rb + u;
-                    const size_t e = (size_t)(e0 + (row < nvalid ? row : 0));
+                    const size_t e = (size_t)(e0 + ((rb + u < rpw && row < nvalid) ? row : 0));
                     const size_t i3 = (size_t)sh.meta.dst[row] * 3, j3 = (size_t)sh.meta.src[row] * 3;
                     sp[u] = ldg4(SP + e * 2 * D + col);
 #pragma unroll
@@ -623,11 +634,11 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) edge_bwd_tc_kernel(const __gri
 #pragma unroll
                 for (int u = 0; u < RB4; u++) {
                     const int row = r0 + rb + u;
-                    const bool ok = row < nvalid;
+                    const bool ok = (rb + u < rpw && row < nvalid);
                     const size_t j3 = (size_t)sh.meta.src[row] * 3;
                     const float4 s1 = silu4(sp[u]);
                     const float4 gs1 = gM[u][0] * vn[u][0] + gM[u][1] * vn[u][1] + gM[u][2] * vn[u][2];
-                    st4(&sh.tile[row][col], ok ? gs1 * dsilu4(sp[u]) : f4s(0.f));
+                    if (rb + u < rpw) st4(&sh.tile[row][col], ok ? gs1 * dsilu4(sp[u]) : f4s(0.f));   // (a slot past the run is the next warp's row)
                     if (ok) {
                         red4(ws.GVNMSG + (j3 + 0) * D + col, gM[u][0] * s1);
                         red4(ws.GVNMSG + (j3 + 1) * D + col, gM[u][1] * s1);
@@ -644,8 +655,9 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) edge_bwd_tc_kernel(const __gri
             // ---- s2 half ----
 #pragma unroll 4
             for (int r = 0; r < RPW; r++) {
+                if (r >= rpw) break;
                 const int row = r0 + r;
-                const bool ok = row < nvalid;
+                const bool ok = (r < rpw && row < nvalid);
                 const size_t e = (size_t)(e0 + (ok ? row : 0));
                 const size_t i3 = (size_t)sh.meta.dst[row] * 3;
                 const float4 dd = sh.meta.d[row];
@@ -674,31 +686,33 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) edge_bwd_tc_kernel(const __gri
             TC_TL(9);
 #pragma unroll 1
             for (int rb = 0; rb < RPW; rb += RB4) {
+                if (rb >= rpw) break;
                 float4 gxa[RB4], vjr[RB4], pdvr[RB4];
                 float avr[RB4];
 #pragma unroll
                 for (int u = 0; u < RB4; u++) {
                     const int row = r0 + rb + u;
-                    const size_t e = (size_t)(e0 + (row < nvalid ? row : 0));
+                    const size_t e = (size_t)(e0 + ((rb + u < rpw && row < nvalid) ? row : 0));
                     gxa[u] = load_gxa(ws, (size_t)sh.meta.dst[row], col);
                     vjr[u] = ldg4(QKV + (size_t)sh.meta.src[row] * 3 * D + 2 * D + col);
                     pdvr[u] = ldg4(P1 + e * 3 * D + D + col);
-                    avr[u] = row < nvalid ? __ldg(ATT + e * H + hd) : 0.f;
+                    avr[u] = (rb + u < rpw && row < nvalid) ? __ldg(ATT + e * H + hd) : 0.f;
                 }
 #pragma unroll
                 for (int u = 0; u < RB4; u++) {
                     const int row = r0 + rb + u;
-                    const bool ok = row < nvalid;
+                    const bool ok = (rb + u < rpw && row < nvalid);
                     const size_t j = sh.meta.src[row];
                     const float Ce = sh.meta.C[row];
                     const float av = avr[u], sa = silu_(av), A = sa * Ce;
                     const float4 gm = ld4(&sh.tile[row][col]) + gxa[u];
                     const float4 dv = silu4(pdvr[u]);
-                    st4(&sh.tile[row][col], ok ? gm * vjr[u] * A * dsilu4(pdvr[u]) : f4s(0.f));      // g_Pdv
+                    const bool mine = rb + u < rpw;                 // a slot past the run is the next warp's row: no shared writes
+                    if (mine) st4(&sh.tile[row][col], ok ? gm * vjr[u] * A * dsilu4(pdvr[u]) : f4s(0.f));      // g_Pdv
                     const float gA = quad_sum(hsum4(gm * vjr[u] * dv));
-                    if ((lane & 3) == 0) sh.gattn[row][hd] = gA * Ce * dsilu_(av);
+                    if (mine && (lane & 3) == 0) sh.gattn[row][hd] = gA * Ce * dsilu_(av);
                     const float gc = warp_sum((lane & 3) == 0 ? gA * sa : 0.f);
-                    if (lane == 0) sh.eacc[row][0] = gc;
+                    if (mine && lane == 0) sh.eacc[row][0] = gc;
                     if (ok) red4(ws.GQKV + j * 3 * D + 2 * D + col, gm * dv * A);
                 }
             }
@@ -711,11 +725,12 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) edge_bwd_tc_kernel(const __gri
             // ---- adjoint of a_h = sum q_i k_j dk : first g_Pdk (next A operand), then the g_q tile ----
 #pragma unroll 1
             for (int rb = 0; rb < RPW; rb += RB4) {
+                if (rb >= rpw) break;
                 float4 pdkr[RB4], qir[RB4], kjr[RB4];
 #pragma unroll
                 for (int u = 0; u < RB4; u++) {
                     const int row = r0 + rb + u;
-                    const size_t e = (size_t)(e0 + (row < nvalid ? row : 0));
+                    const size_t e = (size_t)(e0 + ((rb + u < rpw && row < nvalid) ? row : 0));
                     pdkr[u] = ldg4(P1 + e * 3 * D + col);
                     qir[u] = ldg4(QKV + (size_t)sh.meta.dst[row] * 3 * D + col);
                     kjr[u] = ldg4(QKV + (size_t)sh.meta.src[row] * 3 * D + D + col);
@@ -723,11 +738,11 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) edge_bwd_tc_kernel(const __gri
 #pragma unroll
                 for (int u = 0; u < RB4; u++) {
                     const int row = r0 + rb + u;
-                    const bool ok = row < nvalid;
+                    const bool ok = (rb + u < rpw && row < nvalid);
                     const size_t j = sh.meta.src[row];
                     const float4 dk = silu4(pdkr[u]);
                     const float gav = sh.gattn[row][hd];
-                    st4(&sh.tile[row][col], ok ? qir[u] * kjr[u] * gav * dsilu4(pdkr[u]) : f4s(0.f));   // g_Pdk
+                    if (rb + u < rpw) st4(&sh.tile[row][col], ok ? qir[u] * kjr[u] * gav * dsilu4(pdkr[u]) : f4s(0.f));   // g_Pdk
                     if (ok) red4(ws.GQKV + j * 3 * D + D + col, qir[u] * dk * gav);
                 }
             }
@@ -741,8 +756,9 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) edge_bwd_tc_kernel(const __gri
             csync();
 #pragma unroll 4
             for (int r = 0; r < RPW; r++) {
+                if (r >= rpw) break;
                 const int row = r0 + r;
-                const size_t e = (size_t)(e0 + (row < nvalid ? row : 0));
+                const size_t e = (size_t)(e0 + ((r < rpw && row < nvalid) ? row : 0));
                 const float4 dk = silu4(ldg4(P1 + e * 3 * D + col));
                 const float4 kj = ldg4(QKV + (size_t)sh.meta.src[row] * 3 * D + D + col);
                 st4(&sh.tile[row][col], kj * dk * sh.gattn[row][hd]);                    // per-edge g_q contribution
@@ -765,11 +781,12 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) edge_bwd_tc_kernel(const __gri
                 csync();
 #pragma unroll 1
                 for (int rb = 0; rb < RPW; rb += 2) {
+                    if (rb >= rpw) break;
                     float4 gfr[2], pfr[2], tir[2][3], ujr[2][3];
 #pragma unroll
                     for (int u = 0; u < 2; u++) {
                         const int row = r0 + rb + u;
-                        const bool ok = row < nvalid;
+                        const bool ok = (rb + u < rpw && row < nvalid);
                         const size_t e = (size_t)(e0 + (ok ? row : 0));
                         const size_t i3 = (size_t)sh.meta.dst[row] * 3, j3 = (size_t)sh.meta.src[row] * 3;
                         gfr[u] = ok ? ld4(ws.GF + e * D + col) : f4s(0.f);
@@ -783,7 +800,7 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) edge_bwd_tc_kernel(const __gri
 #pragma unroll
                     for (int u = 0; u < 2; u++) {
                         const int row = r0 + rb + u;
-                        const bool ok = row < nvalid;
+                        const bool ok = (rb + u < rpw && row < nvalid);
                         const size_t e = (size_t)(e0 + (ok ? row : 0));
                         const size_t j3 = (size_t)sh.meta.src[row] * 3;
                         const float4 dd = sh.meta.d[row];
@@ -797,7 +814,7 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) edge_bwd_tc_kernel(const __gri
                         for (int s = 0; s < 3; s++) { w1[s] = tir[u][s] - a1 * dv3[s]; w2[s] = ujr[u][s] - a2 * dv3[s]; }
                         const float4 wdot = w1[0] * w2[0] + w1[1] * w2[1] + w1[2] * w2[2];
                         const float4 gwd = gfn * fp;
-                        st4(&sh.tile[row][col], gfn * wdot * dsilu4(pf));                    // g_Pf
+                        if (rb + u < rpw) st4(&sh.tile[row][col], gfn * wdot * dsilu4(pf));                    // g_Pf
                         const float4 c1 = gwd * (w2[0] * dd.x + w2[1] * dd.y + w2[2] * dd.z);
                         const float4 c2 = gwd * (w1[0] * dd.x + w1[1] * dd.y + w1[2] * dd.z);
                         float gdl[3];
@@ -808,7 +825,7 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) edge_bwd_tc_kernel(const __gri
                             gu[s] = gw2 - c2 * dv3[s];
                             gdl[s] = warp_sum(hsum4(tir[u][s] * c1 + a1 * gw1 + ujr[u][s] * c2 + a2 * gw2));
                         }
-                        if (lane == 0) { sh.eacc[row][1] -= gdl[0]; sh.eacc[row][2] -= gdl[1]; sh.eacc[row][3] -= gdl[2]; }
+                        if (lane == 0 && rb + u < rpw) { sh.eacc[row][1] -= gdl[0]; sh.eacc[row][2] -= gdl[1]; sh.eacc[row][3] -= gdl[2]; }
                         if (ok) {
                             red4(ws.GTU + (j3 + 0) * 2 * D + D + col, gu[0]);
                             red4(ws.GTU + (j3 + 1) * 2 * D + D + col, gu[1]);
@@ -827,8 +844,9 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) edge_bwd_tc_kernel(const __gri
                 csync();
 #pragma unroll 4
                 for (int r = 0; r < RPW; r++) {
+                    if (r >= rpw) break;
                     const int row = r0 + r;
-                    const bool ok = row < nvalid;
+                    const bool ok = (r < rpw && row < nvalid);
                     const size_t e = (size_t)(e0 + (ok ? row : 0));
                     const float4 gfn = ok ? ld4(ws.GF + e * D + col) : f4s(0.f);
                     st4(&sh.tile[row][col], gfn * silu4(ldg4(P1 + e * 3 * D + 2 * D + col)));   // g_wdot
@@ -884,8 +902,8 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) edge_bwd_tc_kernel(const __gri
             // next tile's stored pre-activations -> L2 (bulk prefetch, UBLKPF).  Issued late in the tile: a whole tile ahead
             // the rows were evicted again before their use (ncu: DRAM reads 1.0 -> 1.7 GB per launch on the 512-fragment batch)
             if (threadIdx.x < 3 && it + 1 < my_tiles) {
-                const int en = ((int)blockIdx.x + (it + 1) * (int)gridDim.x) * ROWS;
-                const uint32_t nn = (uint32_t)min(ROWS, E - en);
+                const int en = ((int)blockIdx.x + (it + 1) * (int)gridDim.x) * trows;
+                const uint32_t nn = (uint32_t)min(trows, E - en);
                 if (threadIdx.x == 0) tc::tma_prefetch_l2(SP + (size_t)en * 2 * D, nn * 2 * D * 4);
                 else if (threadIdx.x == 1) tc::tma_prefetch_l2(P1 + (size_t)en * 3 * D, nn * 3 * D * 4);
                 else tc::tma_prefetch_l2(ATT + (size_t)en * H, nn * H * 4);
@@ -900,8 +918,9 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) edge_bwd_tc_kernel(const __gri
             TC_TL(21);
 #pragma unroll 4
             for (int r = 0; r < RPW; r++) {
+                if (r >= rpw) break;
                 const int row = r0 + r;
-                if (row < nvalid) {
+                if ((r < rpw && row < nvalid)) {
                     float* g = ws.GF + (size_t)(e0 + row) * D + col;
                     float4 v = ld4(&sh.tile[row][col]);
                     if (upd) v = v + ld4(g);

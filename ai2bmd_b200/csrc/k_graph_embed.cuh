@@ -130,26 +130,22 @@ __global__ void __launch_bounds__(128) edge_geom_kernel(int N, const float* __re
 //   agg_i[c] = sum_{e->i, j!=i} (rbf_e . Wd[c,:] + bd[c]) * C_e * nb_emb[z_j][c]
 //   x_i = [emb[z_i] | agg_i] Wc^T + bc
 // ---------------------------------------------------------------------------------------------
-// One node per 256-thread block (thread = channel x K-half): the per-edge loop and the final K = 256 product are serial
-// latency chains, so both are split in two and the halves summed in a fixed order through shared memory.
+// NB consecutive nodes per 256-thread block (thread = channel x K-half): the per-edge loop and the final K = 256 product
+// are serial latency chains, so both are split in two and the halves summed in a fixed order through shared memory.
+// NB = 1 for small systems (one wave of per-node CTAs, shortest chain); NB = 8 for batches, where every CTA streaming the
+// 128 KB combine weight for a single node made the kernel L2-bound (14k nodes: 1.8 GB of L2 -> SM traffic): a weight row is
+// now loaded once per CTA and used for all NB nodes.
 constexpr int EMB_THREADS = 2 * D;
+template <int NB>
 __global__ void __launch_bounds__(EMB_THREADS) embed_node_kernel(ModelW mw, Workspace ws) {
     pdl_entry();
-    __shared__ float cat[2 * D];
-    __shared__ float part[D];
+    __shared__ float cat[NB][2 * D];
+    __shared__ float part[NB][D];
     __shared__ int sj[KNB];
     __shared__ int sz[KNB];
     __shared__ float sC[KNB];
     const int c = threadIdx.x & (D - 1), half = threadIdx.x >> 7;
-    const int i = blockIdx.x;
-    if (i >= ws.N) return;
-    const int e0 = ws.rowptr[i], dg = ws.rowptr[i + 1] - e0;
-    if (threadIdx.x < dg) {                         // edge metadata first: breaks the esrc -> z -> embedding load chain
-        const int j = ws.esrc[e0 + threadIdx.x];
-        sj[threadIdx.x] = j;
-        sz[threadIdx.x] = ws.z[j];
-        sC[threadIdx.x] = ws.geom[(size_t)(e0 + threadIdx.x) * 8 + 1];
-    }
+    const int n0 = blockIdx.x * NB;
     float wd[NR];
 #pragma unroll
     for (int k = 0; k < NR; k += 4) {
@@ -157,40 +153,77 @@ __global__ void __launch_bounds__(EMB_THREADS) embed_node_kernel(ModelW mw, Work
         wd[k] = w.x; wd[k + 1] = w.y; wd[k + 2] = w.z; wd[k + 3] = w.w;
     }
     const float bd = __ldg(mw.bd + c);
-    const float x0 = __ldg(mw.emb + ws.z[i] * D + c);
-    __syncthreads();
-    float acc = 0.f;
-#pragma unroll 2
-    for (int k2 = half; k2 < dg; k2 += 2) {         // even edges on one half, odd edges on the other
-        if (sj[k2] == i) continue;
-        const float nb = __ldg(mw.nb_emb + sz[k2] * D + c);
-        float dp = bd;
-#pragma unroll
-        for (int k = 0; k < NR; k += 4) {
-            const float4 rb = ldg4(ws.rbf + (size_t)(e0 + k2) * NR + k);
-            dp = fmaf(rb.x, wd[k], dp); dp = fmaf(rb.y, wd[k + 1], dp);
-            dp = fmaf(rb.z, wd[k + 2], dp); dp = fmaf(rb.w, wd[k + 3], dp);
+    for (int nb = 0; nb < NB; nb++) {
+        const int i = n0 + nb;
+        if (i >= ws.N) {                                 // (block-uniform)
+            if (half == 0) { cat[nb][c] = 0.f; cat[nb][D + c] = 0.f; }
+            continue;
         }
-        acc = fmaf(dp * sC[k2], nb, acc);
-    }
-    if (half == 1) part[c] = acc;
-    __syncthreads();
-    if (half == 0) { cat[c] = x0; cat[D + c] = acc + part[c]; }
-    __syncthreads();
-    // x_i = [emb | agg] Wc^T + bc : each half takes 128 of the 256 k's, 8 independent chains
-    float o[8];
-#pragma unroll
-    for (int u = 0; u < 8; u++) o[u] = 0.f;
-    const int kb = half * D;
+        const int e0 = ws.rowptr[i], dg = ws.rowptr[i + 1] - e0;
+        if (threadIdx.x < dg) {                         // edge metadata first: breaks the esrc -> z -> embedding load chain
+            const int j = ws.esrc[e0 + threadIdx.x];
+            sj[threadIdx.x] = j;
+            sz[threadIdx.x] = ws.z[j];
+            sC[threadIdx.x] = ws.geom[(size_t)(e0 + threadIdx.x) * 8 + 1];
+        }
+        const float x0 = __ldg(mw.emb + ws.z[i] * D + c);
+        __syncthreads();
+        float acc = 0.f;
 #pragma unroll 2
-    for (int k = 0; k < D; k += 8) {
+        for (int k2 = half; k2 < dg; k2 += 2) {         // even edges on one half, odd edges on the other
+            if (sj[k2] == i) continue;
+            const float nbv = __ldg(mw.nb_emb + sz[k2] * D + c);
+            float dp = bd;
 #pragma unroll
-        for (int u = 0; u < 8; u++) o[u] = fmaf(cat[kb + k + u], __ldg(mw.WcT + (size_t)(kb + k + u) * D + c), o[u]);
+            for (int k = 0; k < NR; k += 4) {
+                const float4 rb = ldg4(ws.rbf + (size_t)(e0 + k2) * NR + k);
+                dp = fmaf(rb.x, wd[k], dp); dp = fmaf(rb.y, wd[k + 1], dp);
+                dp = fmaf(rb.z, wd[k + 2], dp); dp = fmaf(rb.w, wd[k + 3], dp);
+            }
+            acc = fmaf(dp * sC[k2], nbv, acc);
+        }
+        if (half == 1) part[nb][c] = acc;
+        __syncthreads();                                // (also: sj / sz / sC free for the next node)
+        if (half == 0) { cat[nb][c] = x0; cat[nb][D + c] = acc + part[nb][c]; }
     }
-    const float sum = ((o[0] + o[1]) + (o[2] + o[3])) + ((o[4] + o[5]) + (o[6] + o[7]));
-    if (half == 1) part[c] = sum;
     __syncthreads();
-    if (half == 0) ws.X[0][(size_t)i * D + c] = (__ldg(mw.bc + c) + sum) + part[c];
+    // x_i = [emb | agg] Wc^T + bc : each half takes 128 of the 256 k's
+    const int kb = half * D;
+    if constexpr (NB == 1) {
+        float o[8];
+#pragma unroll
+        for (int u = 0; u < 8; u++) o[u] = 0.f;
+#pragma unroll 2
+        for (int k = 0; k < D; k += 8) {
+#pragma unroll
+            for (int u = 0; u < 8; u++) o[u] = fmaf(cat[0][kb + k + u], __ldg(mw.WcT + (size_t)(kb + k + u) * D + c), o[u]);
+        }
+        const float sum = ((o[0] + o[1]) + (o[2] + o[3])) + ((o[4] + o[5]) + (o[6] + o[7]));
+        if (half == 1) part[0][c] = sum;
+        __syncthreads();
+        if (half == 0 && n0 < ws.N) ws.X[0][(size_t)n0 * D + c] = (__ldg(mw.bc + c) + sum) + part[0][c];
+    } else {
+        float o[NB];
+#pragma unroll
+        for (int nb = 0; nb < NB; nb++) o[nb] = 0.f;
+#pragma unroll 8
+        for (int k = 0; k < D; k++) {
+            const float w = __ldg(mw.WcT + (size_t)(kb + k) * D + c);
+#pragma unroll
+            for (int nb = 0; nb < NB; nb++) o[nb] = fmaf(cat[nb][kb + k], w, o[nb]);
+        }
+        if (half == 1) {
+#pragma unroll
+            for (int nb = 0; nb < NB; nb++) part[nb][c] = o[nb];
+        }
+        __syncthreads();
+        if (half == 0) {
+            const float bcv = __ldg(mw.bc + c);
+#pragma unroll
+            for (int nb = 0; nb < NB; nb++)
+                if (n0 + nb < ws.N) ws.X[0][(size_t)(n0 + nb) * D + c] = (bcv + o[nb]) + part[nb][c];
+        }
+    }
 }
 
 // K5: edge embedding  f0_e[c] = (x_i[c] + x_j[c]) * (rbf_e . We[c,:] + be[c]).   thread = channel.
@@ -281,15 +314,18 @@ __global__ void __launch_bounds__(ENB_WARPS * 32) embed_node_bwd_kernel(ModelW m
     __shared__ __align__(16) float gwe_s[ENB_WARPS][D];
     __shared__ float fi_s[ENB_WARPS][3];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, col = lane * 4;
-    const int i = blockIdx.x;
-    if (i >= ws.N) return;
-    if (threadIdx.x < D) gx_s[threadIdx.x] = ws.GX[(size_t)i * D + threadIdx.x];
-    for (int idx = threadIdx.x; idx < D * NR; idx += ENB_WARPS * 32) {
+    for (int idx = threadIdx.x; idx < D * NR; idx += ENB_WARPS * 32) {      // once per CTA (a CTA walks several nodes of a batch)
         const int cc = idx / NR, k = idx % NR;
         const float w = __ldg(mw.WdN + idx);
         WdT_s[k][cc] = w;
         WdN_s[cc][k] = w;
     }
+    const float alpha = 5.0f / mw.cutoff;
+    const float mu = __ldg(mw.rbf_means + lane), beta = __ldg(mw.rbf_betas + lane);
+    const float4 bd = ldg4(mw.bd + col);
+    for (int i = blockIdx.x; i < ws.N; i += gridDim.x) {
+    __syncthreads();                                    // previous node's shared rows are consumed; weights visible
+    if (threadIdx.x < D) gx_s[threadIdx.x] = ws.GX[(size_t)i * D + threadIdx.x];
     __syncthreads();
     // g_agg = (gx_i Wc)[128:256]: K split over the warps (16 k's each, all loads in flight), fixed-order sum
     {
@@ -304,9 +340,6 @@ __global__ void __launch_bounds__(ENB_WARPS * 32) embed_node_bwd_kernel(ModelW m
     float4 g_agg = f4s(0.f);
 #pragma unroll
     for (int w = 0; w < ENB_WARPS; w++) g_agg = g_agg + ld4(&gagg_s[w][col]);
-    const float4 bd = ldg4(mw.bd + col);
-    const float alpha = 5.0f / mw.cutoff;
-    const float mu = __ldg(mw.rbf_means + lane), beta = __ldg(mw.rbf_betas + lane);
     float fix = 0.f, fiy = 0.f, fiz = 0.f;
     const int e1 = ws.rowptr[i + 1];
     for (int e = ws.rowptr[i] + warp; e < e1; e += ENB_WARPS) {
@@ -358,21 +391,7 @@ __global__ void __launch_bounds__(ENB_WARPS * 32) embed_node_bwd_kernel(ModelW m
         for (int w = 0; w < ENB_WARPS; w++) t += fi_s[w][threadIdx.x];
         atomicAdd(forces + 3 * i + threadIdx.x, t);
     }
-}
-
-// per-fragment energy: E_g = sum_a e_atom[a] + mean   (one warp per fragment; visnet.py:146-149).
-// The <= 44 per-atom terms are summed in double and rounded once, so the result does not depend on order.
-__global__ void __launch_bounds__(128) energy_reduce_kernel(Workspace ws, const float* __restrict__ scalars,
-                                                            float* __restrict__ energy) {
-    pdl_entry();
-    const int lane = threadIdx.x & 31;
-    const int g = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (g >= ws.G) return;
-    double s = 0.0;
-    for (int a = ws.frag_start[g] + lane; a < ws.frag_start[g + 1]; a += 32) s += (double)ws.eatom[a];
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-    if (lane == 0) energy[g] = (float)(s + (double)__ldg(scalars + 1));
+    }
 }
 
 }  // namespace vb

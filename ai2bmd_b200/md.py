@@ -37,6 +37,8 @@ class BondedForceField:
         self.engine = Engine(state_dict, device)
         self.engine.set_topology(frags.z, frags.batch, n_graphs=len(frags))
         self.engine.set_protein_map(pm.n_protein, pm.src_atom, pm.dst_atom, pm.sign, pm.frag_sign)
+        self.engine.forward_host(np.asarray(frags.pos, dtype=np.float32))       # start geometry: real edge count for the tile plan
+        self.engine.set_option("calibrate", 1)
         dev = torch.device("cuda", device)
         self.pos_host = torch.empty((len(frags.z), 3), dtype=torch.float32).pin_memory()
         self.pos_dev = torch.empty((len(frags.z), 3), dtype=torch.float32, device=dev)
@@ -173,6 +175,8 @@ class DeviceLangevin:
             engine = Engine(state_dict, device)
             engine.set_topology(frags.z, frags.batch, n_graphs=len(frags))
             engine.set_protein_map(pm.n_protein, pm.src_atom, pm.dst_atom, pm.sign, pm.frag_sign)
+            engine.forward_host(np.asarray(frags.pos, dtype=np.float32))
+            engine.set_option("calibrate", 1)
         self.engine = engine
         if caph is not None:
             engine.set_caph(caph)

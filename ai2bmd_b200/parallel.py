@@ -137,6 +137,11 @@ class DeviceShard:
             m = self.plan.local_map
             self.engine.set_protein_map(m.n_protein, m.src_atom, m.dst_atom, m.sign, m.frag_sign)
             self.pos = torch.from_numpy(np.ascontiguousarray(local.pos, dtype=np.float32)).to(self.device)
+            # one evaluation of the start geometry, then plan the edge-tile length from its real edge count
+            e0 = torch.empty(len(local), dtype=torch.float32, device=self.device)
+            f0 = torch.empty((len(local.z), 3), dtype=torch.float32, device=self.device)
+            self.engine.forward_device(self.pos.data_ptr(), e0.data_ptr(), f0.data_ptr(), torch.cuda.current_stream(self.device).cuda_stream)
+            self.engine.set_option("calibrate", 1)
         if world_size > 1 and native_comm:
             import torch.distributed as dist
             self.comm_engine = self.engine if self.engine is not None else Engine(state_dict, device)   # empty shard: comm only

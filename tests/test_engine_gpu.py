@@ -101,6 +101,29 @@ def test_parity_every_edge_kernel_variant(real_weights, reference_outputs, key, 
     assert (np.abs(e.reshape(e64.shape) - e64) <= tol).all()
 
 
+@pytest.mark.parametrize("key", ["chig", "trpcage", "dense44"])
+def test_parity_planned_tile_lengths(real_weights, reference_outputs, key):
+    """Default plan: tiles of equal, odd length that fill whole waves of CTAs (rows dealt to the warps in runs of
+    ceil(nvalid / 16)), first from the 17-edges-per-atom estimate, then calibrated to the real edge count."""
+    r = reference_outputs
+    fd = _case(r, key)
+    eng = Engine(real_weights, 0)
+    eng.set_topology(fd.z, fd.batch, n_graphs=len(fd))
+    e64, f64 = r[f"{key}_e64"], r[f"{key}_f64"]
+    seen = []
+    for calibrated in (False, True):
+        if calibrated:
+            eng.set_option("calibrate", 1)
+        rows, cap = eng.get_option("tile_rows"), eng.get_option("tc_rows")
+        assert 16 <= rows <= cap <= 128
+        seen.append(rows)
+        e, f = eng.forward_host(fd.pos)
+        assert np.abs(f - f64).max() <= 2e-5 * np.abs(f64).max() + 5e-5, (calibrated, rows)
+        assert (np.abs(e.reshape(e64.shape) - e64) <= 2e-6 * np.abs(e64).max() + 4e-3).all(), (calibrated, rows)
+    n_edges = int(eng.get_edges()[1].sum())
+    assert -(-n_edges // seen[1]) <= 148 * max(1, -(-n_edges // (148 * 128)))      # the calibrated tiles fill whole waves
+
+
 @pytest.mark.parametrize("seed", [0, 7])
 def test_parity_random_weights(seed, chig):
     fd, _ = chig

@@ -39,6 +39,9 @@ def main():
     e = torch.empty(len(fd), device="cuda")
     f = torch.empty(len(fd.z), 3, device="cuda")
     st = torch.cuda.current_stream()
+    eng.forward_device(pos.data_ptr(), e.data_ptr(), f.data_ptr(), st.cuda_stream)
+    if "tc_rows" not in args.opts:
+        eng.set_option("calibrate", 1)
     prof = eng.profile_stages(pos.data_ptr(), n_iter=args.iters)
     for _ in range(5):
         eng.forward_device(pos.data_ptr(), e.data_ptr(), f.data_ptr(), st.cuda_stream)
@@ -49,7 +52,7 @@ def main():
     b.record(st)
     torch.cuda.synchronize()
     lines = [f"workload {args.workload}: {desc}: G={len(fd)} N={len(fd.z)}  options: {args.opts or 'defaults'} "
-             f"(fused={eng.get_option('fused')}, edge_tc={eng.get_option('edge_tc')}, tc_rows={eng.get_option('tc_rows')})"]
+             f"(fused={eng.get_option('fused')}, edge_tc={eng.get_option('edge_tc')}, tc_rows={eng.get_option('tc_rows')}, tile_rows={eng.get_option('tile_rows')})"]
     for name, ms in prof:
         lines.append(f"{name:24s} {ms * 1e3:8.1f} us")
     lines.append(f"{'sum (eager, per-launch events)':32s} {sum(ms for _, ms in prof) * 1e3:8.1f} us  ({len(prof)} launches)")
