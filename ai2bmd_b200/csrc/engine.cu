@@ -157,6 +157,7 @@ struct vb_handle {
     int node_impl = 1; // 0: warp-per-node kernels (k_node.cuh), 1: CTA-cooperative kernels (k_node2.cuh)
     int fused = 0, fused_opt = -1;   // 1: one launch per layer and direction (k_fused.cuh); -1 = choose by problem size
     int node_tc = 0, node_tc_opt = -1;   // 1: node stage on tensor cores (k_node_tc.cuh); -1 = choose by problem size
+    int embed_batch_opt = -1;            // embedding kernels: several nodes per CTA (1), one (0), by size (-1)
     int edge_tc = -1;  // bit 0: forward edge stage on tcgen05, bit 1: adjoint edge stage on tcgen05; -1 = by size
     // graph cache: one instantiated graph per (kind, I/O pointer set); pointers are baked into the captured launches
     struct GraphEntry { int kind; StepIO io; cudaGraphExec_t exec; };
@@ -668,7 +669,9 @@ void enqueue_all(Launcher& Lc, const StepIO& io) {
     }
     if (Lc.next("rowptr_scan")) { Lc.launch(rowptr_scan_kernel, dim3(1), dim3(1024), 0, N, ws.deg, ws.rowptr, ws.Ecap, h->d_flags); Lc.check(); }
     if (Lc.next("edge_geom")) { Lc.launch(edge_geom_kernel, dim3((N + 3) / 4), dim3(128), 0, N, io.pos, h->mw, ws); Lc.check(); }
-    const bool batch = N > 8 * h->sm_count;             // batches: several nodes per CTA share the embedding weights
+    // batches: several nodes per CTA share the embedding weights ("embed_batch": bit 0 forward kernel, bit 1 adjoint kernel)
+    const bool batch = h->embed_batch_opt >= 0 ? (h->embed_batch_opt & 1) : N > 8 * h->sm_count;
+    const bool batch_bwd = h->embed_batch_opt >= 0 ? (h->embed_batch_opt & 2) != 0 : N > 8 * h->sm_count;
     if (Lc.next("embed_node")) {
         if (batch) Lc.launch(embed_node_kernel<8>, dim3((N + 7) / 8), dim3(EMB_THREADS), 0, h->mw, ws);
         else Lc.launch(embed_node_kernel<1>, dim3(N), dim3(EMB_THREADS), 0, h->mw, ws);
@@ -727,7 +730,7 @@ void enqueue_all(Launcher& Lc, const StepIO& io) {
         Lc.check();
     }
     if (Lc.next("embed_node_bwd")) {
-        Lc.launch(embed_node_bwd_kernel, dim3(batch ? std::min(N, 5 * h->sm_count) : N), dim3(ENB_WARPS * 32), 0, h->mw, ws, io.forces);
+        Lc.launch(embed_node_bwd_kernel, dim3(batch_bwd ? std::min(N, 5 * h->sm_count) : N), dim3(ENB_WARPS * 32), 0, h->mw, ws, io.forces);
         Lc.check();
     }
     if (Lc.next("finalize")) enqueue_finalize(Lc, io);
@@ -868,17 +871,21 @@ void record_stages(vb_handle* h) {
     h->launches = (int)h->stage_names.size();
 }
 
-// Tile length of the tcgen05 edge kernels: the per-tile latency is mostly per-row SIMT phases, so the edges are cut into
-// k whole waves of equally long tiles (k = fewest waves with tiles <= 128 edges) instead of 128-edge tiles plus a ragged last
-// wave: 32,028 edges (ABD) -> 292 tiles of 110 instead of 251 of 128 (two rounds either way, each 14 % shorter); Chignolin
-// 143 tiles of 47 instead of 105 of 64.  `edges` is an estimate (17 per atom, +3 % margin) until vb_set_option("calibrate")
-// replaces it by the count of the last evaluation.
+// Tile length of the tcgen05 edge kernels.  A tile's latency is a fixed part (every CTA streams the layer's weights
+// L2 -> shared memory, barriers, TMEM round trips) plus per-row SIMT phases in which each of the 16 compute warps owns
+// ceil(rows / 16) rows.  So the edges are cut into the fewest whole waves of tiles <= 128 edges, and the tile length is
+// the smallest MULTIPLE OF 16 that still fits those waves: Chignolin (6.7k edges) 141 tiles of 48 instead of 105 of 64,
+// WW (19.7k) 247 tiles of 80 in two even waves instead of 154 of 128 (one full wave + 6 tiles).  Lengths between
+// multiples of 16 were measured slower (more CTAs, same rows per warp: Trp-cage 88 vs 96 +3 %), and so was 112 instead
+// of 128 (ABD +2 %, 512 fragments +2.5 %): from 7 rows per warp on the full tile is kept.  `edges` is an estimate (17 per
+// atom, +3 % margin) until vb_set_option("calibrate") replaces it by the count of the last evaluation.
 void plan_tiles(vb_handle* h, long long edges) {
     const long long sm = h->sm_count;
     const long long padded = edges + edges * 3 / 100 + 1;
     const long long waves = std::max<long long>(1, (padded + sm * 128 - 1) / (sm * 128));
-    long long rows = (padded + sm * waves - 1) / (sm * waves);
-    rows = std::min<long long>(128, std::max<long long>(16, rows));
+    long long rpw = (padded + sm * waves * 16 - 1) / (sm * waves * 16);
+    if (rpw >= 7) rpw = 8;
+    const long long rows = 16 * std::min<long long>(8, std::max<long long>(1, rpw));
     if (h->tc_rows_opt > 0) {                      // user-fixed tile capacity: full tiles of that length (round-1 behaviour)
         h->tc_rows = h->tc_rows_opt;
         h->tile_rows = h->tc_rows_opt;
@@ -1634,6 +1641,7 @@ int vb_set_option(vb_handle* h, const char* key, int64_t value) {
     else if (k == "fused" && (value == 0 || value == 1)) { h->fused = h->fused_opt = (int)value; if (value) h->node_tc = 0; set_gxa_parts(h); }
     else if (k == "node_tc" && (value == 0 || value == 1)) { h->node_tc = h->node_tc_opt = (int)value; if (value) h->fused = 0; set_gxa_parts(h); }
     else if (k == "comm_auto" && (value == 0 || value == 1)) h->comm_auto = (int)value;
+    else if (k == "embed_batch" && value >= -1 && value <= 3) h->embed_batch_opt = (int)value;
     else if (k == "timeline" && (value == 0 || value == 1)) {
         if (value && !h->d_tl) {
             if (cudaSetDevice(h->device) != cudaSuccess || cudaMalloc(&h->d_tl, sizeof(unsigned long long) * 2 * L * TC_TL_SLOTS) != cudaSuccess) {

@@ -339,6 +339,25 @@ class Engine:
         self._check(self.lib.vb_profile_stages(self.h, pos_ptr, int(n_iter), ms.ctypes.data), "vb_profile_stages")
         return list(zip(names, ms.tolist()))
 
+    def vecln_near_ties(self, rel_gap: float = 1e-5) -> np.ndarray:
+        """Atoms of the LAST evaluation that sit on a derivative kink of the model (diagnostic).
+
+        VecLayerNorm(max_min) (reference ``src/ViSNet/model/utils.py:165-215``) normalises the channel norms of an atom's
+        vector features by their max and min over the 128 channels, so the gradient of the energy is routed through the
+        argmax / argmin channel.  Where the two largest (or two smallest) channel norms agree to fp32 rounding the
+        argmax flips with the rounding order and the force on that fragment jumps by up to ~1e-2 eV/A -- in the
+        reference as much as here.  Returns the sorted atom indices whose top-two or bottom-two channel norms in any
+        layer differ by less than ``rel_gap`` relative; callers comparing two evaluation orders (tests,
+        plan-vs-plan checks) exclude the fragments of these atoms.
+        """
+        n = self.n_atoms
+        hit = np.zeros(n, dtype=bool)
+        for k in range(1, 6):                     # the vector features entering layer 0 are identically zero
+            v = self.debug_read("V", k, (n, 3, 128)).astype(np.float64)
+            srt = np.sort(np.sqrt((v * v).sum(1)), axis=1)
+            hit |= ((srt[:, -1] - srt[:, -2]) < rel_gap * srt[:, -1]) | ((srt[:, 1] - srt[:, 0]) < rel_gap * srt[:, 1])
+        return np.flatnonzero(hit)
+
     def debug_read(self, name: str, layer: int, shape, dtype=np.float32) -> np.ndarray:
         out = np.empty(shape, dtype=dtype)
         n = self._check(self.lib.vb_debug_read(self.h, name.encode(), int(layer), out.ctypes.data, out.nbytes),

@@ -103,8 +103,9 @@ def test_parity_every_edge_kernel_variant(real_weights, reference_outputs, key, 
 
 @pytest.mark.parametrize("key", ["chig", "trpcage", "dense44"])
 def test_parity_planned_tile_lengths(real_weights, reference_outputs, key):
-    """Default plan: tiles of equal, odd length that fill whole waves of CTAs (rows dealt to the warps in runs of
-    ceil(nvalid / 16)), first from the 17-edges-per-atom estimate, then calibrated to the real edge count."""
+    """Default plan: tiles of equal length (a multiple of 16, not necessarily the kernel's compiled capacity) that fill
+    whole waves of CTAs (rows dealt to the warps in runs of ceil(nvalid / 16)), first from the 17-edges-per-atom
+    estimate, then calibrated to the real edge count."""
     r = reference_outputs
     fd = _case(r, key)
     eng = Engine(real_weights, 0)
@@ -115,7 +116,7 @@ def test_parity_planned_tile_lengths(real_weights, reference_outputs, key):
         if calibrated:
             eng.set_option("calibrate", 1)
         rows, cap = eng.get_option("tile_rows"), eng.get_option("tc_rows")
-        assert 16 <= rows <= cap <= 128
+        assert 16 <= rows <= cap <= 128 and rows % 16 == 0
         seen.append(rows)
         e, f = eng.forward_host(fd.pos)
         assert np.abs(f - f64).max() <= 2e-5 * np.abs(f64).max() + 5e-5, (calibrated, rows)
@@ -456,8 +457,33 @@ def test_fullsize_rigid_motion_equivariance(c4):
         q[:, 0] *= -1
     pos2 = (fd.pos.astype(np.float64) @ q.T + np.array([3.0, -2.0, 1.0])).astype(np.float32)
     e2, f2 = eng.forward_host(pos2)
+    ties2 = eng.vecln_near_ties()
+    eng.forward_host(fd.pos)
+    kink = np.union1d(fd.batch[ties2], fd.batch[eng.vecln_near_ties()])   # fragments on a VecLayerNorm argmax/argmin tie
+    assert len(kink) <= len(fd) // 20
+    keep = ~np.isin(fd.batch, kink)
     assert (np.abs(e2 - e) <= 3 * e_tol(e)).all()
-    assert np.abs(f2 - f @ q.T.astype(np.float32)).max() <= 3e-4      # fp32 positions re-rounded after the rotation
+    d = np.abs(f2 - f @ q.T.astype(np.float32)).max(1)
+    assert d[keep].max() <= 3e-4                      # fp32 positions re-rounded after the rotation
+    assert d.max() <= 5e-2                            # on a tie the argmax may flip: bounded jump, never garbage
+
+
+def test_vecln_tie_is_the_only_plan_dependence(c4, real_weights):
+    """Atom 11957 of this batch has two channel norms of its layer-4 vector features equal to 6e-7 relative: the
+    VecLayerNorm(max_min) argmax (reference src/ViSNet/model/utils.py:199-215) flips with the rounding order, and with it
+    the force on that one fragment.  Every other fragment agrees between the SIMT and the tensor-core node stage."""
+    fd, eng, e, f = c4
+    ties = eng.vecln_near_ties(rel_gap=5e-6)
+    assert 11957 in ties
+    eng2 = Engine(real_weights, 0)
+    eng2.set_option("node_tc", 0)
+    eng2.set_topology(fd.z, fd.batch)
+    e2, f2 = eng2.forward_host(fd.pos)
+    kink = np.union1d(fd.batch[eng.vecln_near_ties()], fd.batch[eng2.vecln_near_ties()])
+    keep = ~np.isin(fd.batch, kink)
+    d = np.abs(f2 - f).max(1)
+    assert d[keep].max() <= 3e-4 and d.max() <= 5e-2
+    assert (np.abs(e2 - e) <= 3 * e_tol(e)).all()
 
 
 def test_fullsize_fragment_order_independence(c4, real_weights):
