@@ -10,10 +10,15 @@
 namespace vb {
 
 // warps per CTA: 16 for the 4-node variant (small systems: more units in flight per node), 8 otherwise
-template <int NB> struct N2Cfg { static constexpr int WARPS = (NB <= 4) ? 16 : 8; static constexpr int THREADS = WARPS * 32; };
+template <int NB> struct N2Cfg {
+    static constexpr int WARPS = (NB <= 4) ? 16 : 8; static constexpr int THREADS = WARPS * 32;
+    static constexpr int KS = (NB <= 4) ? 2 : 1;       // K-split projection plan of the stand-alone kernels (see NodeFwd2Smem)
+};
 template <int NB> struct N2Rows { static constexpr int RB = (NB < 8) ? NB : 8; };   // rows per GEMM unit
 
-template <int NB>
+// KS = 2 (stand-alone 4-node kernels): every projection unit covers ALL rows of the CTA (one pass over each weight
+// chunk instead of one per row block) and half of K; the second K-half leaves a partial row in shared memory.
+template <int NB, int KS = 1>
 struct NodeFwd2Smem {
     static constexpr int LDA = D + LDS_PAD;       // 132
     static constexpr int LDO = 3 * D + LDS_PAD;   // 388
@@ -21,6 +26,9 @@ struct NodeFwd2Smem {
     float vs[3 * NB][LDA];                        // VecLayerNorm(vec) rows
     float os[NB][LDO];                            // o_proj output rows
     float osp[(NB <= 4) ? 3 : 1][NB][LDO];        // 4-node variant: K-quarter partials 1..3 of the o_proj rows
+    float px[(KS == 2) ? NB : 1][3 * D];          // KS = 2: second-K-half partials of the q|k|v rows,
+    float pv[(KS == 2) ? 3 * NB : 1][3 * D];      //         of the vec_proj rows
+    float pt[(KS == 2) ? 3 * NB : 1][2 * D];      //         and of the w_trg|w_src rows
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -29,11 +37,12 @@ struct NodeFwd2Smem {
 // Body shared by the stand-alone kernel below and by the fused per-layer kernel (k_fused.cuh): the N2Cfg<NB>::WARPS
 // warps with threadIdx.x < N2Cfg<NB>::THREADS run it for nodes [n0, n0 + NB); `sync` is a barrier among exactly those
 // threads (__syncthreads in the stand-alone kernel, a named barrier of the compute warps in the fused one).
-template <int NB, int NBUF = 4, typename SyncF>
+template <int NB, int NBUF = 4, int KS = 1, typename SyncF>
 __device__ __forceinline__ void node_fwd2_body(const ModelW& mw, const Workspace& ws, const int k, const int n0,
                                                float* dyn_smem, SyncF sync) {
     constexpr int N2_WARPS = N2Cfg<NB>::WARPS, N2_THREADS = N2Cfg<NB>::THREADS;
-    using S = NodeFwd2Smem<NB>;
+    static_assert(KS == 1 || (KS == 2 && NB <= 4 && N2_WARPS == 16), "the K-split projection plan is the 16-warp, <= 4-node one");
+    using S = NodeFwd2Smem<NB, KS>;
     constexpr int LDA = S::LDA;
     constexpr int N2_RB = N2Rows<NB>::RB;
     S& sm = *reinterpret_cast<S*>(dyn_smem);
@@ -121,37 +130,90 @@ __device__ __forceinline__ void node_fwd2_body(const ModelW& mw, const Workspace
     if (k >= L) return;
     sync();
     const LayerW& lw = mw.layer[k];
-    // GEMM units: [0, UQ): qkv ; [UQ, UQ+UV): vec_proj ; then w_trg|w_src
-    constexpr int UQ = 3 * (NB / N2_RB), UV = 3 * (3 * NB / N2_RB), UT = 2 * (3 * NB / N2_RB);
-    const int nunits = UQ + UV + ((k < L - 1) ? UT : 0);
-    for (int u = warp; u < nunits; u += N2_WARPS) {
-        float acc[N2_RB][4];
-        if (u < UQ) {
-            const int ch = u % 3, rb = u / 3;
-            acc_set_bias<N2_RB>(acc, lw.bqkv + ch * D, lane);
-            warp_gemm<N2_RB, D, LDA, (NB <= 8 ? NBUF : 2)>(acc, &sm.xs[rb * N2_RB][0], lw.WqkvT + ch * D, 3 * D, lane);
+    if constexpr (KS == 2) {
+        // 16 units, one per warp: (q|k|v chunk, K half) x3x2 on the NB scalar rows, (vec_proj chunk, K half) x3x2 and
+        // (w_trg|w_src chunk, K half) x2x2 on all 3*NB vector rows.  Every weight element is read once per CTA (the
+        // row-block plan below reads the vector weights once per 4 rows); half 1 parks its partial rows in shared
+        // memory, half 0 adds them (fixed order) and writes the result.
+        constexpr int RV = 3 * NB, KH = D / 2;
+        const int nunits = (k < L - 1) ? 16 : 12;
+        const int u = warp, kind = u < 6 ? 0 : (u < 12 ? 1 : 2);
+        const int v = kind == 0 ? u : (kind == 1 ? u - 6 : u - 12);
+        const int ch = kind == 2 ? (v & 1) : v % 3, half = kind == 2 ? (v >> 1) : v / 3;
+        const bool active = u < nunits;
+        float acc[RV][4];
+        float (&accx)[NB][4] = *reinterpret_cast<float (*)[NB][4]>(&acc[0][0]);
+        if (active) {
+            if (kind == 0) {
+                if (half == 0) acc_set_bias<NB>(accx, lw.bqkv + ch * D, lane);
+                else acc_zero<NB>(accx);
+                warp_gemm<NB, KH, LDA, NBUF>(accx, &sm.xs[0][half * KH], lw.WqkvT + (size_t)half * KH * 3 * D + ch * D, 3 * D, lane);
+                if (half == 1) {
 #pragma unroll
-            for (int r = 0; r < N2_RB; r++) {
-                const int nd = rb * N2_RB + r;
-                if (nd < nn) st4(ws.QKV[k] + (size_t)(n0 + nd) * 3 * D + ch * D + col, arr4(acc[r]));
+                    for (int r = 0; r < NB; r++) st4(&sm.px[r][ch * D + col], arr4(accx[r]));
+                }
+            } else {
+                acc_zero<RV>(acc);
+                if (kind == 1) warp_gemm<RV, KH, LDA, 2>(acc, &sm.vs[0][half * KH], lw.WvecT + (size_t)half * KH * 3 * D + ch * D, 3 * D, lane);
+                else           warp_gemm<RV, KH, LDA, 2>(acc, &sm.vs[0][half * KH], lw.WtuT + (size_t)half * KH * 2 * D + ch * D, 2 * D, lane);
+                if (half == 1) {
+#pragma unroll
+                    for (int r = 0; r < RV; r++) {
+                        if (kind == 1) st4(&sm.pv[r][ch * D + col], arr4(acc[r]));
+                        else           st4(&sm.pt[r][ch * D + col], arr4(acc[r]));
+                    }
+                }
             }
-        } else if (u < UQ + UV) {
-            const int v = u - UQ, ch = v % 3, rb = v / 3;
-            acc_zero<N2_RB>(acc);
-            warp_gemm<N2_RB, D, LDA, (NB <= 8 ? NBUF : 2)>(acc, &sm.vs[rb * N2_RB][0], lw.WvecT + ch * D, 3 * D, lane);
+        }
+        sync();
+        if (active && half == 0) {
+            if (kind == 0) {
 #pragma unroll
-            for (int r = 0; r < N2_RB; r++) {
-                const int row = rb * N2_RB + r;                  // = nd*3 + s
-                if (row / 3 < nn) st4(ws.V123[k] + ((size_t)n0 * 3 + row) * 3 * D + ch * D + col, arr4(acc[r]));
+                for (int r = 0; r < NB; r++)
+                    if (r < nn) st4(ws.QKV[k] + (size_t)(n0 + r) * 3 * D + ch * D + col, arr4(accx[r]) + ld4(&sm.px[r][ch * D + col]));
+            } else if (kind == 1) {
+#pragma unroll
+                for (int r = 0; r < RV; r++)
+                    if (r / 3 < nn) st4(ws.V123[k] + ((size_t)n0 * 3 + r) * 3 * D + ch * D + col, arr4(acc[r]) + ld4(&sm.pv[r][ch * D + col]));
+            } else {
+#pragma unroll
+                for (int r = 0; r < RV; r++)
+                    if (r / 3 < nn) st4(ws.TU[k] + ((size_t)n0 * 3 + r) * 2 * D + ch * D + col, arr4(acc[r]) + ld4(&sm.pt[r][ch * D + col]));
             }
-        } else {
-            const int v = u - UQ - UV, ch = v % 2, rb = v / 2;
-            acc_zero<N2_RB>(acc);
-            warp_gemm<N2_RB, D, LDA, (NB <= 8 ? NBUF : 2)>(acc, &sm.vs[rb * N2_RB][0], lw.WtuT + ch * D, 2 * D, lane);
-#pragma unroll
-            for (int r = 0; r < N2_RB; r++) {
-                const int row = rb * N2_RB + r;
-                if (row / 3 < nn) st4(ws.TU[k] + ((size_t)n0 * 3 + row) * 2 * D + ch * D + col, arr4(acc[r]));
+        }
+    } else {
+        // GEMM units: [0, UQ): qkv ; [UQ, UQ+UV): vec_proj ; then w_trg|w_src
+        constexpr int UQ = 3 * (NB / N2_RB), UV = 3 * (3 * NB / N2_RB), UT = 2 * (3 * NB / N2_RB);
+        const int nunits = UQ + UV + ((k < L - 1) ? UT : 0);
+        for (int u = warp; u < nunits; u += N2_WARPS) {
+            float acc[N2_RB][4];
+            if (u < UQ) {
+                const int ch = u % 3, rb = u / 3;
+                acc_set_bias<N2_RB>(acc, lw.bqkv + ch * D, lane);
+                warp_gemm<N2_RB, D, LDA, (NB <= 8 ? NBUF : 2)>(acc, &sm.xs[rb * N2_RB][0], lw.WqkvT + ch * D, 3 * D, lane);
+    #pragma unroll
+                for (int r = 0; r < N2_RB; r++) {
+                    const int nd = rb * N2_RB + r;
+                    if (nd < nn) st4(ws.QKV[k] + (size_t)(n0 + nd) * 3 * D + ch * D + col, arr4(acc[r]));
+                }
+            } else if (u < UQ + UV) {
+                const int v = u - UQ, ch = v % 3, rb = v / 3;
+                acc_zero<N2_RB>(acc);
+                warp_gemm<N2_RB, D, LDA, (NB <= 8 ? NBUF : 2)>(acc, &sm.vs[rb * N2_RB][0], lw.WvecT + ch * D, 3 * D, lane);
+    #pragma unroll
+                for (int r = 0; r < N2_RB; r++) {
+                    const int row = rb * N2_RB + r;                  // = nd*3 + s
+                    if (row / 3 < nn) st4(ws.V123[k] + ((size_t)n0 * 3 + row) * 3 * D + ch * D + col, arr4(acc[r]));
+                }
+            } else {
+                const int v = u - UQ - UV, ch = v % 2, rb = v / 2;
+                acc_zero<N2_RB>(acc);
+                warp_gemm<N2_RB, D, LDA, (NB <= 8 ? NBUF : 2)>(acc, &sm.vs[rb * N2_RB][0], lw.WtuT + ch * D, 2 * D, lane);
+    #pragma unroll
+                for (int r = 0; r < N2_RB; r++) {
+                    const int row = rb * N2_RB + r;
+                    if (row / 3 < nn) st4(ws.TU[k] + ((size_t)n0 * 3 + row) * 2 * D + ch * D + col, arr4(acc[r]));
+                }
             }
         }
     }
@@ -169,7 +231,7 @@ template <int NB>
 __global__ void __launch_bounds__(N2Cfg<NB>::THREADS) node_fwd2_kernel(NodeArgs a) {
     pdl_entry();
     extern __shared__ __align__(16) float dyn_smem[];
-    node_fwd2_body<NB, 4>(a.mw, a.ws, a.layer, (int)blockIdx.x * NB, dyn_smem, [] { __syncthreads(); });
+    node_fwd2_body<NB, 4, N2Cfg<NB>::KS>(a.mw, a.ws, a.layer, (int)blockIdx.x * NB, dyn_smem, [] { __syncthreads(); });
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -177,7 +239,9 @@ __global__ void __launch_bounds__(N2Cfg<NB>::THREADS) node_fwd2_kernel(NodeArgs 
 // chunk) is one unit writing a partial [8][128] product into its own shared slot; slots are summed in a
 // fixed order afterwards (deterministic).
 // ---------------------------------------------------------------------------------------------
-template <int NB>
+// KS = 2 (stand-alone 4-node kernels): units of (all rows of the CTA) x (half a 128-deep K chunk): each weight element is
+// read once per CTA, 16 (12 in the last layer) units = one per warp; the o_proj adjoint is cut into 12 units of K = 32.
+template <int NB, int KS = 1>
 struct NodeBwd2Smem {
     static constexpr int LD3 = 3 * D + LDS_PAD;   // 388
     static constexpr int LD2 = 2 * D + LDS_PAD;   // 260
@@ -186,18 +250,20 @@ struct NodeBwd2Smem {
     float gq[NB][LD3];                            // g_qkv rows -> later g_o rows
     float gvp[3 * NB][LD3];                       // [g_vdot*v2 | g_vdot*v1 | gvec*o1] rows
     float gtu[3 * NB][LD2];                       // [g_t | g_u] rows
-    float part_x[3][NB][D];                       // partial products of the scalar rows (3 K-chunks)
-    float part_v[5][3 * NB][D];                   // partial products of the vector rows (3 + 2 K-chunks)
+    float part_x[3 * KS][NB][D];                  // partial products of the scalar rows (3 K-chunks x KS)
+    float part_v[5 * KS][3 * NB][D];              // partial products of the vector rows ((3 + 2) K-chunks x KS); KS = 2: later
+                                                  // also the 12 K = 32 partials of the o_proj adjoint ([12][NB][D])
 };
 
 // Body (see node_fwd2_body).  GQKV / GVNMSG / GTU are the accumulators the edge adjoint of layer k added into; they are
 // consumed and re-zeroed here (the fused pipeline alternates between two sets, the stand-alone one uses ws.G*).
-template <int NB, int NBUF = 4, typename SyncF>
+template <int NB, int NBUF = 4, int KS = 1, typename SyncF>
 __device__ __forceinline__ void node_bwd2_body(const ModelW& mw, const Workspace& ws, const int k, const int n0,
                                                float* __restrict__ GQKV, float* __restrict__ GVNMSG, float* __restrict__ GTU,
                                                float* dyn_smem, SyncF sync) {
     constexpr int N2_WARPS = N2Cfg<NB>::WARPS;
-    using S = NodeBwd2Smem<NB>;
+    static_assert(KS == 1 || (KS == 2 && NB <= 4 && N2_WARPS == 16), "the K-split plan is the 16-warp, <= 4-node one");
+    using S = NodeBwd2Smem<NB, KS>;
     constexpr int LD3 = S::LD3, LD2 = S::LD2;
     constexpr int N2_RB = N2Rows<NB>::RB;
     S& sm = *reinterpret_cast<S*>(dyn_smem);
@@ -237,24 +303,47 @@ __device__ __forceinline__ void node_bwd2_body(const ModelW& mw, const Workspace
             }
         }
         sync();
-        // units: scalar rows x 3 K-chunks (Wqkv) ; vector rows x (3 K-chunks Wvec + 2 K-chunks Wtu)
-        constexpr int UX = 3 * S::NXB;
-        const int kv = has_tu ? 5 : 3;
-        const int nunits = UX + kv * S::NVB;
-        for (int u = warp; u < nunits; u += N2_WARPS) {
-            float acc[N2_RB][4];
-            acc_zero<N2_RB>(acc);
-            if (u < UX) {
-                const int kc = u % 3, rb = u / 3;
-                warp_gemm<N2_RB, D, LD3, NBUF>(acc, &sm.gq[rb * N2_RB][kc * D], lw.WqkvN + (size_t)kc * D * D, D, lane);
+        if constexpr (KS == 2) {
+            // one unit per warp: (K chunk, K half) on all scalar rows (6 units) / on all vector rows (10, or 6 without w_trg|w_src)
+            constexpr int RV = 3 * NB, KH = D / 2;
+            const int kv = has_tu ? 5 : 3;
+            const int u = warp;
+            if (u < 6) {
+                const int kc = u >> 1, half = u & 1;
+                float acc[NB][4];
+                acc_zero<NB>(acc);
+                warp_gemm<NB, KH, LD3, NBUF>(acc, &sm.gq[0][kc * D + half * KH], lw.WqkvN + ((size_t)kc * D + half * KH) * D, D, lane);
 #pragma unroll
-                for (int r = 0; r < N2_RB; r++) st4(&sm.part_x[kc][rb * N2_RB + r][col], arr4(acc[r]));
-            } else {
-                const int v = u - UX, kc = v % kv, rb = v / kv;
-                if (kc < 3) warp_gemm<N2_RB, D, LD3, NBUF>(acc, &sm.gvp[rb * N2_RB][kc * D], lw.WvecN + (size_t)kc * D * D, D, lane);
-                else        warp_gemm<N2_RB, D, LD2, NBUF>(acc, &sm.gtu[rb * N2_RB][(kc - 3) * D], lw.WtuN + (size_t)(kc - 3) * D * D, D, lane);
+                for (int r = 0; r < NB; r++) st4(&sm.part_x[u][r][col], arr4(acc[r]));
+            } else if (u < 6 + 2 * kv) {
+                const int v = u - 6, kc = v >> 1, half = v & 1;
+                float acc[RV][4];
+                acc_zero<RV>(acc);
+                if (kc < 3) warp_gemm<RV, KH, LD3, 2>(acc, &sm.gvp[0][kc * D + half * KH], lw.WvecN + ((size_t)kc * D + half * KH) * D, D, lane);
+                else        warp_gemm<RV, KH, LD2, 2>(acc, &sm.gtu[0][(kc - 3) * D + half * KH], lw.WtuN + ((size_t)(kc - 3) * D + half * KH) * D, D, lane);
 #pragma unroll
-                for (int r = 0; r < N2_RB; r++) st4(&sm.part_v[kc][rb * N2_RB + r][col], arr4(acc[r]));
+                for (int r = 0; r < RV; r++) st4(&sm.part_v[v][r][col], arr4(acc[r]));
+            }
+        } else {
+            // units: scalar rows x 3 K-chunks (Wqkv) ; vector rows x (3 K-chunks Wvec + 2 K-chunks Wtu)
+            constexpr int UX = 3 * S::NXB;
+            const int kv = has_tu ? 5 : 3;
+            const int nunits = UX + kv * S::NVB;
+            for (int u = warp; u < nunits; u += N2_WARPS) {
+                float acc[N2_RB][4];
+                acc_zero<N2_RB>(acc);
+                if (u < UX) {
+                    const int kc = u % 3, rb = u / 3;
+                    warp_gemm<N2_RB, D, LD3, NBUF>(acc, &sm.gq[rb * N2_RB][kc * D], lw.WqkvN + (size_t)kc * D * D, D, lane);
+    #pragma unroll
+                    for (int r = 0; r < N2_RB; r++) st4(&sm.part_x[kc][rb * N2_RB + r][col], arr4(acc[r]));
+                } else {
+                    const int v = u - UX, kc = v % kv, rb = v / kv;
+                    if (kc < 3) warp_gemm<N2_RB, D, LD3, NBUF>(acc, &sm.gvp[rb * N2_RB][kc * D], lw.WvecN + (size_t)kc * D * D, D, lane);
+                    else        warp_gemm<N2_RB, D, LD2, NBUF>(acc, &sm.gtu[rb * N2_RB][(kc - 3) * D], lw.WtuN + (size_t)(kc - 3) * D * D, D, lane);
+    #pragma unroll
+                    for (int r = 0; r < N2_RB; r++) st4(&sm.part_v[kc][rb * N2_RB + r][col], arr4(acc[r]));
+                }
             }
         }
         sync();
@@ -268,14 +357,22 @@ __device__ __forceinline__ void node_bwd2_body(const ModelW& mw, const Workspace
         for (int s = 0; s < 3; s++) gvec[s] = ok ? ld4(ws.GVEC + ((size_t)node * 3 + s) * D + col) : z4;
         if (has_a && ok) {
             const LayerW& lw = mw.layer[k];
-            const float4 gxn = (ld4(&sm.part_x[0][nd][col]) + ld4(&sm.part_x[1][nd][col])) + ld4(&sm.part_x[2][nd][col]);
+            const auto px = [&](int kc) {              // K chunk kc of the scalar rows (KS = 2: its two halves, fixed order)
+                if constexpr (KS == 2) return ld4(&sm.part_x[2 * kc][nd][col]) + ld4(&sm.part_x[2 * kc + 1][nd][col]);
+                else return ld4(&sm.part_x[kc][nd][col]);
+            };
+            const float4 gxn = (px(0) + px(1)) + px(2);
             float4 vin[3], gout[3], gv[3];
 #pragma unroll
             for (int s = 0; s < 3; s++) {
                 const int row = nd * 3 + s;
+                const auto pv = [&](int kc) {
+                    if constexpr (KS == 2) return ld4(&sm.part_v[2 * kc][row][col]) + ld4(&sm.part_v[2 * kc + 1][row][col]);
+                    else return ld4(&sm.part_v[kc][row][col]);
+                };
                 float4 g = ld4(GVNMSG + ((size_t)node * 3 + s) * D + col);
-                g = g + ((ld4(&sm.part_v[0][row][col]) + ld4(&sm.part_v[1][row][col])) + ld4(&sm.part_v[2][row][col]));
-                if (has_tu) g = g + (ld4(&sm.part_v[3][row][col]) + ld4(&sm.part_v[4][row][col]));
+                g = g + ((pv(0) + pv(1)) + pv(2));
+                if (has_tu) g = g + (pv(3) + pv(4));
                 gout[s] = g;
                 vin[s] = ld4(ws.V[k] + ((size_t)node * 3 + s) * D + col);
             }
@@ -310,28 +407,50 @@ __device__ __forceinline__ void node_bwd2_body(const ModelW& mw, const Workspace
     }
     if (!has_b) return;
     sync();
-    {
-        const LayerW& lw = mw.layer[k - 1];
+    const LayerW& lwo = mw.layer[k - 1];
+    if constexpr (KS == 2) {
+        // g_xa = g_o Wo: 12 units of K = 32 (3 chunks x 4 quarters), one per warp; partial rows in the (now free) part_v area
+        float (*po)[NB][D] = reinterpret_cast<float (*)[NB][D]>(&sm.part_v[0][0][0]);
+        if (warp < 12) {
+            const int kc = warp >> 2, q = warp & 3;
+            float acc[NB][4];
+            acc_zero<NB>(acc);
+            warp_gemm<NB, D / 4, LD3, NBUF>(acc, &sm.gq[0][kc * D + q * (D / 4)], lwo.WoN + ((size_t)kc * D + q * (D / 4)) * D, D, lane);
+#pragma unroll
+            for (int r = 0; r < NB; r++) st4(&po[warp][r][col], arr4(acc[r]));
+        }
+        sync();
+        for (int nd = warp; nd < nn; nd += N2_WARPS) {
+            float4 t[3];
+#pragma unroll
+            for (int kc = 0; kc < 3; kc++)
+                t[kc] = (ld4(&po[4 * kc][nd][col]) + ld4(&po[4 * kc + 1][nd][col])) + (ld4(&po[4 * kc + 2][nd][col]) + ld4(&po[4 * kc + 3][nd][col]));
+            st4(ws.GXA + (size_t)(n0 + nd) * D + col, (t[0] + t[1]) + t[2]);
+        }
+    } else {
         for (int u = warp; u < 3 * S::NXB; u += N2_WARPS) {
             const int kc = u % 3, rb = u / 3;
             float acc[N2_RB][4];
             acc_zero<N2_RB>(acc);
-            warp_gemm<N2_RB, D, LD3, NBUF>(acc, &sm.gq[rb * N2_RB][kc * D], lw.WoN + (size_t)kc * D * D, D, lane);
+            warp_gemm<N2_RB, D, LD3, NBUF>(acc, &sm.gq[rb * N2_RB][kc * D], lwo.WoN + (size_t)kc * D * D, D, lane);
 #pragma unroll
             for (int r = 0; r < N2_RB; r++) st4(&sm.part_x[kc][rb * N2_RB + r][col], arr4(acc[r]));
         }
+        sync();
+        for (int nd = warp; nd < nn; nd += N2_WARPS)
+            st4(ws.GXA + (size_t)(n0 + nd) * D + col,
+                (ld4(&sm.part_x[0][nd][col]) + ld4(&sm.part_x[1][nd][col])) + ld4(&sm.part_x[2][nd][col]));
     }
-    sync();
-    for (int nd = warp; nd < nn; nd += N2_WARPS)
-        st4(ws.GXA + (size_t)(n0 + nd) * D + col,
-            (ld4(&sm.part_x[0][nd][col]) + ld4(&sm.part_x[1][nd][col])) + ld4(&sm.part_x[2][nd][col]));
 }
 
 template <int NB>
 __global__ void __launch_bounds__(N2Cfg<NB>::THREADS) node_bwd2_kernel(NodeArgs a) {
     pdl_entry();
     extern __shared__ __align__(16) float dyn_smem[];
-    node_bwd2_body<NB, 4>(a.mw, a.ws, a.layer, (int)blockIdx.x * NB, a.ws.GQKV, a.ws.GVNMSG, a.ws.GTU, dyn_smem, [] { __syncthreads(); });
+    node_bwd2_body<NB, 4, N2Cfg<NB>::KS>(a.mw, a.ws, a.layer, (int)blockIdx.x * NB, a.ws.GQKV, a.ws.GVNMSG, a.ws.GTU, dyn_smem, [] { __syncthreads(); });
 }
+
+template <int NB> using NodeFwd2SmemK = NodeFwd2Smem<NB, N2Cfg<NB>::KS>;     // shared-memory blocks of the stand-alone kernels
+template <int NB> using NodeBwd2SmemK = NodeBwd2Smem<NB, N2Cfg<NB>::KS>;
 
 }  // namespace vb
