@@ -95,39 +95,72 @@ __device__ __forceinline__ void warp_gemm_loadw(float4 (&w)[4], const float* __r
 
 // Software-pipelined: the weight rows of the next k-groups are in flight while the current group is
 // multiplied (register ring of NBUF groups; NBUF = 4 for small R where the math does not cover L2 latency).
+// krot (a multiple of 4, taken modulo K; K a power of two when it is non-zero): the k loop starts at row krot of this
+// call's K range and wraps, so that CTAs walking the same weight chunk at the same time do not all ask the same L2 slices
+// for the same rows (the caller derives it from its block index; the summation order then depends on the block).
 template <int R, int K, int LDA, int NBUF = (R <= 4 ? 4 : 2)>
 __device__ __forceinline__ void warp_gemm(float (&acc)[R][4], const float* __restrict__ As,
-                                          const float* __restrict__ W, int ldw, int lane) {
+                                          const float* __restrict__ W, int ldw, int lane, int krot = 0) {
     static_assert(K % 16 == 0, "K must be a multiple of 16");
     const float* Wp = W + lane * 4;
+    const auto kk = [&](int k) { return (k + krot) & (K - 1 | -(int)((K & (K - 1)) != 0)); };   // non-power-of-two K: krot must be 0
     if constexpr (NBUF == 4) {
         float4 w0[4], w1[4], w2[4], w3[4];
-        warp_gemm_loadw(w0, Wp, ldw, 0);
-        warp_gemm_loadw(w1, Wp, ldw, 4);
-        warp_gemm_loadw(w2, Wp, ldw, 8);
+        warp_gemm_loadw(w0, Wp, ldw, kk(0));
+        warp_gemm_loadw(w1, Wp, ldw, kk(4));
+        warp_gemm_loadw(w2, Wp, ldw, kk(8));
 #pragma unroll 1
         for (int k = 0; k < K; k += 16) {
-            warp_gemm_loadw(w3, Wp, ldw, k + 12);
-            warp_gemm_group<R>(acc, As, LDA, k, w0);
-            if (k + 16 < K) warp_gemm_loadw(w0, Wp, ldw, k + 16);
-            warp_gemm_group<R>(acc, As, LDA, k + 4, w1);
-            if (k + 16 < K) warp_gemm_loadw(w1, Wp, ldw, k + 20);
-            warp_gemm_group<R>(acc, As, LDA, k + 8, w2);
-            if (k + 16 < K) warp_gemm_loadw(w2, Wp, ldw, k + 24);
-            warp_gemm_group<R>(acc, As, LDA, k + 12, w3);
+            warp_gemm_loadw(w3, Wp, ldw, kk(k + 12));
+            warp_gemm_group<R>(acc, As, LDA, kk(k), w0);
+            if (k + 16 < K) warp_gemm_loadw(w0, Wp, ldw, kk(k + 16));
+            warp_gemm_group<R>(acc, As, LDA, kk(k + 4), w1);
+            if (k + 16 < K) warp_gemm_loadw(w1, Wp, ldw, kk(k + 20));
+            warp_gemm_group<R>(acc, As, LDA, kk(k + 8), w2);
+            if (k + 16 < K) warp_gemm_loadw(w2, Wp, ldw, kk(k + 24));
+            warp_gemm_group<R>(acc, As, LDA, kk(k + 12), w3);
         }
     } else {
         float4 w0[4], w1[4];
-        warp_gemm_loadw(w0, Wp, ldw, 0);
+        warp_gemm_loadw(w0, Wp, ldw, kk(0));
 #pragma unroll 1
         for (int k = 0; k < K; k += 8) {
-            warp_gemm_loadw(w1, Wp, ldw, k + 4);
-            warp_gemm_group<R>(acc, As, LDA, k, w0);
-            if (k + 8 < K) warp_gemm_loadw(w0, Wp, ldw, k + 8);
-            warp_gemm_group<R>(acc, As, LDA, k + 4, w1);
+            warp_gemm_loadw(w1, Wp, ldw, kk(k + 4));
+            warp_gemm_group<R>(acc, As, LDA, kk(k), w0);
+            if (k + 8 < K) warp_gemm_loadw(w0, Wp, ldw, kk(k + 8));
+            warp_gemm_group<R>(acc, As, LDA, kk(k + 4), w1);
         }
     }
 }
+
+// Two-phase variant for the CTA-cooperative node kernels: prefetch() issues the first NPRE groups of weight rows -- they
+// do not depend on the A rows, so a warp that is idle while others finish the previous phase calls it BEFORE the barrier
+// that publishes A and the ~0.9 us L2 round trip overlaps that phase; run() consumes group g and refills its registers with
+// group g + NPRE.  K a power of two, K / 4 a multiple of NPRE; krot as in warp_gemm.
+template <int K, int NPRE>
+struct WarpGemmPre {
+    static_assert((K & (K - 1)) == 0 && K % (4 * NPRE) == 0, "K: power of two and a multiple of the ring");
+    float4 w[NPRE][4];
+    const float* Wp;
+    int ldw, krot;
+    __device__ __forceinline__ int kk(int k) const { return (k + krot) & (K - 1); }
+    __device__ __forceinline__ void prefetch(const float* __restrict__ W, int ldw_, int lane, int krot_) {
+        Wp = W + lane * 4; ldw = ldw_; krot = krot_;
+#pragma unroll
+        for (int g = 0; g < NPRE; g++) warp_gemm_loadw(w[g], Wp, ldw, kk(4 * g));
+    }
+    template <int R, int LDA>
+    __device__ __forceinline__ void run(float (&acc)[R][4], const float* __restrict__ As) {
+#pragma unroll 1
+        for (int k = 0; k < K; k += 4 * NPRE) {
+#pragma unroll
+            for (int g = 0; g < NPRE; g++) {
+                warp_gemm_group<R>(acc, As, LDA, kk(k + 4 * g), w[g]);
+                if (k + 4 * (g + NPRE) < K) warp_gemm_loadw(w[g], Wp, ldw, kk(k + 4 * (g + NPRE)));
+            }
+        }
+    }
+};
 
 // Narrow variant: 64 output columns, 2 per lane (head blocks).  W row-major [K][ldw].
 template <int R, int K, int LDA>

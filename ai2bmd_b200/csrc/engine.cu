@@ -126,7 +126,7 @@ struct vb_handle {
     size_t arena_bytes = 0;
     float* d_pos = nullptr;      // [N][3]
     float* d_energy = nullptr;   // [G]
-    unsigned long long* d_tl = nullptr;   // optional in-kernel timeline of the tcgen05 edge kernels [2L][TC_TL_SLOTS]
+    unsigned long long* d_tl = nullptr;   // optional in-kernel timelines [4L+2][TC_TL_SLOTS]: edge fwd l, edge bwd L+l, node fwd 2L+k, node bwd 3L+1+k
     int timeline = 0;
     float* d_forces = nullptr;   // [N][3]
     float *h_pos = nullptr, *h_energy = nullptr, *h_forces = nullptr;   // pinned staging
@@ -154,6 +154,8 @@ struct vb_handle {
     int tc_rows_opt = 0, tc_rows = 128;                  // kernel variant: capacity of a tcgen05 tile (32 / 64 / 96 / 128; MMA M stays 128)
     int tile_rows = 128;                                 // edges per tile actually used (<= tc_rows): whole waves of CTAs
     long long edges_plan = 0;                            // edge count the tile length was planned for (estimate or calibrated)
+    int krot = 1;      // rotate the K loops of the SIMT node GEMM units per CTA (L2 slice hot-spotting: all CTAs walk the same weights)
+    int node_nb = 0;   // nodes per CTA of the CTA-cooperative SIMT node kernels (0 = automatic)
     int node_impl = 1; // 0: warp-per-node kernels (k_node.cuh), 1: CTA-cooperative kernels (k_node2.cuh)
     int fused = 0, fused_opt = -1;   // 1: one launch per layer and direction (k_fused.cuh); -1 = choose by problem size
     int node_tc = 0, node_tc_opt = -1;   // 1: node stage on tensor cores (k_node_tc.cuh); -1 = choose by problem size
@@ -416,28 +418,51 @@ void launch_edge_bwd(Launcher& Lc, int l, int occ) {
 template <int NB>
 void launch_node_fwd2(Launcher& Lc, int k) {
     vb_handle* h = Lc.h;
-    NodeArgs a{k, h->mw, h->ws};
+    NodeArgs a{k, h->mw, h->ws, h->timeline ? h->d_tl + (size_t)2 * L * TC_TL_SLOTS + (size_t)k * N2_TL_SLOTS : nullptr, h->krot};
     Lc.launch(node_fwd2_kernel<NB>, dim3((h->ws.N + NB - 1) / NB), dim3(N2Cfg<NB>::THREADS), sizeof(NodeFwd2SmemK<NB>), a);
+    if (h->timeline == 2) Lc.launch(node_fwd2_kernel<NB>, dim3((h->ws.N + NB - 1) / NB), dim3(N2Cfg<NB>::THREADS), sizeof(NodeFwd2SmemK<NB>), a);
     Lc.check();
 }
 template <int NB>
 void launch_node_bwd2(Launcher& Lc, int k) {
     vb_handle* h = Lc.h;
-    NodeArgs a{k, h->mw, h->ws};
+    NodeArgs a{k, h->mw, h->ws, h->timeline ? h->d_tl + (size_t)2 * L * TC_TL_SLOTS + (size_t)(L + 1 + k) * N2_TL_SLOTS : nullptr, h->krot};
     Lc.launch(node_bwd2_kernel<NB>, dim3((h->ws.N + NB - 1) / NB), dim3(N2Cfg<NB>::THREADS), sizeof(NodeBwd2SmemK<NB>), a);
+    if (h->timeline == 2) Lc.launch(node_bwd2_kernel<NB>, dim3((h->ws.N + NB - 1) / NB), dim3(N2Cfg<NB>::THREADS), sizeof(NodeBwd2SmemK<NB>), a);
     Lc.check();
+}
+// nodes per CTA of the CTA-cooperative SIMT node kernels: the fewest (1..4) that still fit one wave, else 8
+int node_nb(const vb_handle* h) {
+    if (h->node_nb > 0) return h->node_nb;
+    for (int nb = 1; nb <= 4; nb++)
+        if ((h->ws.N + nb - 1) / nb <= h->sm_count) return nb;
+    return 8;
 }
 void node_fwd(Launcher& Lc, int k) {
     if (Lc.h->node_impl == 1) {
         if (Lc.h->npw == 2) launch_node_fwd2<16>(Lc, k);
-        else if ((Lc.h->ws.N + 3) / 4 <= Lc.h->sm_count) launch_node_fwd2<4>(Lc, k);   // one wave of 4-node, 16-warp CTAs
-        else launch_node_fwd2<8>(Lc, k);
+        else switch (node_nb(Lc.h)) {           // one wave of 16-warp CTAs with as few nodes each as that allows
+            case 1: launch_node_fwd2<1>(Lc, k); break;
+            case 2: launch_node_fwd2<2>(Lc, k); break;
+            case 3: launch_node_fwd2<3>(Lc, k); break;
+            case 4: launch_node_fwd2<4>(Lc, k); break;
+            default: launch_node_fwd2<8>(Lc, k);
+        }
         return;
     }
     Lc.h->npw == 2 ? launch_node_fwd<2>(Lc, k) : launch_node_fwd<1>(Lc, k);
 }
 void node_bwd(Launcher& Lc, int k) {
-    if (Lc.h->node_impl == 1) { (Lc.h->ws.N + 3) / 4 <= Lc.h->sm_count ? launch_node_bwd2<4>(Lc, k) : launch_node_bwd2<8>(Lc, k); return; }
+    if (Lc.h->node_impl == 1) {
+        switch (node_nb(Lc.h)) {
+            case 1: launch_node_bwd2<1>(Lc, k); break;
+            case 2: launch_node_bwd2<2>(Lc, k); break;
+            case 3: launch_node_bwd2<3>(Lc, k); break;
+            case 4: launch_node_bwd2<4>(Lc, k); break;
+            default: launch_node_bwd2<8>(Lc, k);
+        }
+        return;
+    }
     Lc.h->npw == 2 ? launch_node_bwd<2>(Lc, k) : launch_node_bwd<1>(Lc, k);
 }
 void head(Launcher& Lc) {
@@ -677,7 +702,7 @@ void enqueue_all(Launcher& Lc, const StepIO& io) {
         else Lc.launch(embed_node_kernel<1>, dim3(N), dim3(EMB_THREADS), 0, h->mw, ws);
         Lc.check();
     }
-    const int eblocks = std::max(1, std::min(ws.Ecap, h->sm_count * 16));
+    const int eblocks = std::max(1, std::min((ws.Ecap + 3) / 4, h->sm_count * 16));     // four edges per block and pass
     if (Lc.next("embed_edge")) { Lc.launch(embed_edge_kernel, dim3(eblocks), dim3(128), 0, h->mw, ws); Lc.check(); }
     if (h->fused) {
         // one launch per layer and direction: "fwdL" = edge stage L + node stage L+1, "bwdL" = node adjoint L+1 + edge adjoint L
@@ -765,6 +790,12 @@ int configure_kernels(vb_handle* h) {
     CUDA_TRY(h, opt_in_smem(node_tc_kernel<NT_BWDA>, TC_SMEM_BYTES));
     CUDA_TRY(h, opt_in_smem(node_tc_kernel<NT_BWDB>, TC_SMEM_BYTES));
 
+    CUDA_TRY(h, opt_in_smem(node_fwd2_kernel<1>, sizeof(NodeFwd2SmemK<1>)));
+    CUDA_TRY(h, opt_in_smem(node_bwd2_kernel<1>, sizeof(NodeBwd2SmemK<1>)));
+    CUDA_TRY(h, opt_in_smem(node_fwd2_kernel<2>, sizeof(NodeFwd2SmemK<2>)));
+    CUDA_TRY(h, opt_in_smem(node_bwd2_kernel<2>, sizeof(NodeBwd2SmemK<2>)));
+    CUDA_TRY(h, opt_in_smem(node_fwd2_kernel<3>, sizeof(NodeFwd2SmemK<3>)));
+    CUDA_TRY(h, opt_in_smem(node_bwd2_kernel<3>, sizeof(NodeBwd2SmemK<3>)));
     CUDA_TRY(h, opt_in_smem(node_fwd2_kernel<4>, sizeof(NodeFwd2SmemK<4>)));
     CUDA_TRY(h, opt_in_smem(node_bwd2_kernel<4>, sizeof(NodeBwd2SmemK<4>)));
     CUDA_TRY(h, opt_in_smem(node_fwd2_kernel<8>, sizeof(NodeFwd2SmemK<8>)));
@@ -1638,16 +1669,18 @@ int vb_set_option(vb_handle* h, const char* key, int64_t value) {
         if (e > 0) plan_tiles(h, e);
     }
     else if (k == "node_impl" && (value == 0 || value == 1)) h->node_impl = (int)value;
+    else if (k == "node_nb" && (value == 0 || value == 1 || value == 2 || value == 3 || value == 4 || value == 8)) h->node_nb = (int)value;
+    else if (k == "krot" && (value == 0 || value == 1)) h->krot = (int)value;
     else if (k == "fused" && (value == 0 || value == 1)) { h->fused = h->fused_opt = (int)value; if (value) h->node_tc = 0; set_gxa_parts(h); }
     else if (k == "node_tc" && (value == 0 || value == 1)) { h->node_tc = h->node_tc_opt = (int)value; if (value) h->fused = 0; set_gxa_parts(h); }
     else if (k == "comm_auto" && (value == 0 || value == 1)) h->comm_auto = (int)value;
     else if (k == "embed_batch" && value >= -1 && value <= 3) h->embed_batch_opt = (int)value;
-    else if (k == "timeline" && (value == 0 || value == 1)) {
+    else if (k == "timeline" && (value >= 0 && value <= 2)) {
         if (value && !h->d_tl) {
-            if (cudaSetDevice(h->device) != cudaSuccess || cudaMalloc(&h->d_tl, sizeof(unsigned long long) * 2 * L * TC_TL_SLOTS) != cudaSuccess) {
+            if (cudaSetDevice(h->device) != cudaSuccess || cudaMalloc(&h->d_tl, sizeof(unsigned long long) * (2 * L * TC_TL_SLOTS + (2 * L + 2) * N2_TL_SLOTS)) != cudaSuccess) {
                 h->set_error("vb_set_option: timeline buffer allocation failed"); return VB_ERR_CUDA;
             }
-            cudaMemset(h->d_tl, 0, sizeof(unsigned long long) * 2 * L * TC_TL_SLOTS);
+            cudaMemset(h->d_tl, 0, sizeof(unsigned long long) * (2 * L * TC_TL_SLOTS + (2 * L + 2) * N2_TL_SLOTS));
         }
         h->timeline = (int)value;
     }
@@ -1667,6 +1700,8 @@ int64_t vb_get_option(const vb_handle* h, const char* key) {
     if (k == "te_bwd") return h->te_bwd;
     if (k == "edge_tc") return h->edge_tc;
     if (k == "node_impl") return h->node_impl;
+    if (k == "node_nb") return h->has_topology ? node_nb(h) : h->node_nb;
+    if (k == "krot") return h->krot;
     if (k == "fused") return h->fused;
     if (k == "node_tc") return h->node_tc;
     if (k == "comm_auto") return h->comm_auto;
@@ -1796,6 +1831,7 @@ int64_t vb_debug_read(vb_handle* h, const char* name, int layer, void* host_dst,
     else if (k == "SP" && lay(L)) { src = ws.SP[layer]; bytes = E * 2 * D * 4; }
     else if (k == "ATT" && lay(L)) { src = ws.ATT[layer]; bytes = E * H * 4; }
     else if (k == "TL" && lay(2 * L) && h->d_tl) { src = h->d_tl + (size_t)layer * TC_TL_SLOTS; bytes = TC_TL_SLOTS * 8; }
+    else if (k == "TLN" && lay(2 * L + 2) && h->d_tl) { src = h->d_tl + (size_t)2 * L * TC_TL_SLOTS + (size_t)layer * N2_TL_SLOTS; bytes = N2_TL_SLOTS * 8; }
     else BUF("XA", ws.XA, N * D, 4)
     else BUF("VA", ws.VA, N * 3 * D, 4)
     else BUF("GX", ws.GX, N * D, 4)

@@ -239,16 +239,31 @@ __global__ void __launch_bounds__(128) embed_edge_kernel(ModelW mw, Workspace ws
     const float be = __ldg(mw.be + c);
     const int E = ws.rowptr[ws.N];
     const float* __restrict__ X = ws.X[0];
-    for (int e = blockIdx.x; e < E; e += gridDim.x) {
-        float ep = be;
+    // four edges per pass: their index loads, the two x-row gathers and the 32-deep fma chains are independent and overlap
+    constexpr int EU = 4;
+    for (int e0 = blockIdx.x * EU; e0 < E; e0 += gridDim.x * EU) {
+        int ii[EU], jj[EU];
+        float xs[EU], ep[EU];
+#pragma unroll
+        for (int u = 0; u < EU; u++) {
+            const int e = min(e0 + u, E - 1);
+            ii[u] = ws.edst[e]; jj[u] = ws.esrc[e];
+            ep[u] = be;
+        }
+#pragma unroll
+        for (int u = 0; u < EU; u++) xs[u] = X[(size_t)ii[u] * D + c] + X[(size_t)jj[u] * D + c];
 #pragma unroll
         for (int k = 0; k < NR; k += 4) {
-            const float4 rb = ld4(ws.rbf + (size_t)e * NR + k);
-            ep = fmaf(rb.x, we[k], ep); ep = fmaf(rb.y, we[k + 1], ep);
-            ep = fmaf(rb.z, we[k + 2], ep); ep = fmaf(rb.w, we[k + 3], ep);
+#pragma unroll
+            for (int u = 0; u < EU; u++) {
+                const float4 rb = ld4(ws.rbf + (size_t)min(e0 + u, E - 1) * NR + k);
+                ep[u] = fmaf(rb.x, we[k], ep[u]); ep[u] = fmaf(rb.y, we[k + 1], ep[u]);
+                ep[u] = fmaf(rb.z, we[k + 2], ep[u]); ep[u] = fmaf(rb.w, we[k + 3], ep[u]);
+            }
         }
-        const int i = ws.edst[e], j = ws.esrc[e];
-        ws.F[0][(size_t)e * D + c] = (X[(size_t)i * D + c] + X[(size_t)j * D + c]) * ep;
+#pragma unroll
+        for (int u = 0; u < EU; u++)
+            if (e0 + u < E) ws.F[0][(size_t)(e0 + u) * D + c] = xs[u] * ep[u];
     }
 }
 
@@ -262,7 +277,7 @@ __global__ void __launch_bounds__(EEB_WARPS * 32) embed_edge_bwd_kernel(ModelW m
     pdl_entry();
     __shared__ __align__(16) float WeT_s[NR][D];          // [k][c]
     __shared__ float WeN_s[D][NR + 1];                    // [c][k] (+1: conflict-free column walks)
-    __shared__ __align__(16) float gep_s[EEB_WARPS][D];
+    __shared__ __align__(16) float gep_s[EEB_WARPS][2][D];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, col = lane * 4;
     for (int idx = threadIdx.x; idx < D * NR; idx += blockDim.x) {
         const int c = idx / NR, k = idx % NR;
@@ -274,24 +289,44 @@ __global__ void __launch_bounds__(EEB_WARPS * 32) embed_edge_bwd_kernel(ModelW m
     const float4 be = ldg4(mw.be + col);
     const int E = ws.rowptr[ws.N];
     const float* __restrict__ X = ws.X[0];
-    for (int e = blockIdx.x * EEB_WARPS + warp; e < E; e += gridDim.x * EEB_WARPS) {
-        const int i = ws.edst[e], j = ws.esrc[e];
-        const float rk = __ldg(ws.rbf + (size_t)e * NR + lane);
-        const float4 gf = ld4(ws.GF + (size_t)e * D + col);
-        const float4 xs = ldg4(X + (size_t)i * D + col) + ldg4(X + (size_t)j * D + col);
-        float4 ep = be;
+    // two edges per warp and pass: phase B reads every weight once for both and runs four independent fma chains
+    for (int e0 = (blockIdx.x * EEB_WARPS + warp) * 2; e0 < E; e0 += gridDim.x * EEB_WARPS * 2) {
+        const bool two = e0 + 1 < E;
+        const int e1 = two ? e0 + 1 : e0;
+        const int i0 = ws.edst[e0], j0 = ws.esrc[e0], i1 = ws.edst[e1], j1 = ws.esrc[e1];
+        const float rk0 = __ldg(ws.rbf + (size_t)e0 * NR + lane), rk1 = __ldg(ws.rbf + (size_t)e1 * NR + lane);
+        const float4 gf0 = ld4(ws.GF + (size_t)e0 * D + col), gf1 = ld4(ws.GF + (size_t)e1 * D + col);
+        const float4 xs0 = ldg4(X + (size_t)i0 * D + col) + ldg4(X + (size_t)j0 * D + col);
+        const float4 xs1 = ldg4(X + (size_t)i1 * D + col) + ldg4(X + (size_t)j1 * D + col);
+        float4 ep0 = be, ep1 = be;
 #pragma unroll
-        for (int k = 0; k < NR; k++) ep = ep + ld4(&WeT_s[k][col]) * __shfl_sync(0xffffffffu, rk, k);
-        const float4 gfe = gf * ep;
-        red4(ws.GX + (size_t)i * D + col, gfe);
-        red4(ws.GX + (size_t)j * D + col, gfe);
+        for (int k = 0; k < NR; k++) {
+            const float4 w = ld4(&WeT_s[k][col]);
+            ep0 = ep0 + w * __shfl_sync(0xffffffffu, rk0, k);
+            ep1 = ep1 + w * __shfl_sync(0xffffffffu, rk1, k);
+        }
+        const float4 gfe0 = gf0 * ep0, gfe1 = gf1 * ep1;
+        red4(ws.GX + (size_t)i0 * D + col, gfe0);
+        red4(ws.GX + (size_t)j0 * D + col, gfe0);
+        if (two) {
+            red4(ws.GX + (size_t)i1 * D + col, gfe1);
+            red4(ws.GX + (size_t)j1 * D + col, gfe1);
+        }
         __syncwarp();
-        st4(&gep_s[warp][col], gf * xs);
+        st4(&gep_s[warp][0][col], gf0 * xs0);
+        st4(&gep_s[warp][1][col], gf1 * xs1);
         __syncwarp();
-        float g = 0.f;
+        float ga[2] = {0.f, 0.f}, gb[2] = {0.f, 0.f};
 #pragma unroll 8
-        for (int c = 0; c < D; c++) g = fmaf(gep_s[warp][c], WeN_s[c][lane], g);
-        ws.grbf[(size_t)e * NR + lane] = g;
+        for (int c = 0; c < D; c += 2) {
+            const float w0 = WeN_s[c][lane], w1 = WeN_s[c + 1][lane];
+            const float2 a = *reinterpret_cast<const float2*>(&gep_s[warp][0][c]);
+            const float2 b = *reinterpret_cast<const float2*>(&gep_s[warp][1][c]);
+            ga[0] = fmaf(a.x, w0, ga[0]); ga[1] = fmaf(a.y, w1, ga[1]);
+            gb[0] = fmaf(b.x, w0, gb[0]); gb[1] = fmaf(b.y, w1, gb[1]);
+        }
+        ws.grbf[(size_t)e0 * NR + lane] = ga[0] + ga[1];
+        if (two) ws.grbf[(size_t)e1 * NR + lane] = gb[0] + gb[1];
     }
 }
 
@@ -360,9 +395,14 @@ __global__ void __launch_bounds__(ENB_WARPS * 32) embed_node_bwd_kernel(ModelW m
         __syncwarp();
         st4(&gwe_s[warp][col], gwe * Ce);
         __syncwarp();
-        float g = 0.f;
-#pragma unroll 8
-        for (int cc = 0; cc < D; cc++) g = fmaf(gwe_s[warp][cc], WdN_s[cc][lane], g);
+        float g4[4] = {0.f, 0.f, 0.f, 0.f};               // four independent chains instead of one 128-deep one
+#pragma unroll 4
+        for (int cc = 0; cc < D; cc += 4) {
+            const float4 gw = ld4(&gwe_s[warp][cc]);
+            g4[0] = fmaf(gw.x, WdN_s[cc][lane], g4[0]); g4[1] = fmaf(gw.y, WdN_s[cc + 1][lane], g4[1]);
+            g4[2] = fmaf(gw.z, WdN_s[cc + 2][lane], g4[2]); g4[3] = fmaf(gw.w, WdN_s[cc + 3][lane], g4[3]);
+        }
+        const float g = (g4[0] + g4[1]) + (g4[2] + g4[3]);
         const float gC = ea.x + gc;
         const float grbf = grbf0 + g;
         const float ex = __expf(-alpha * r);

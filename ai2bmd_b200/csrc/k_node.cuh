@@ -17,7 +17,11 @@ struct NodeArgs {
     int layer;      // forward: stage k in 0..L ; backward: stage k in L..0
     ModelW mw;
     Workspace ws;
+    unsigned long long* tl = nullptr;   // optional timeline (SM clock stamps of every warp of CTA 0 at the phase boundaries of
+                                        // the CTA-cooperative kernels, k_node2.cuh: slot = stamp * 16 + warp); nullptr = off
+    int krot = 0;                       // 1: every CTA starts the K loops of its GEMM units at a different row (common.cuh)
 };
+constexpr int N2_TL_SLOTS = 256;
 
 // ---- small per-lane helpers ----------------------------------------------------------------------
 __device__ __forceinline__ float4 ln_forward(float4 x, const float* __restrict__ w, const float* __restrict__ b,

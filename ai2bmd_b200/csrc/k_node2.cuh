@@ -39,7 +39,9 @@ struct NodeFwd2Smem {
 // threads (__syncthreads in the stand-alone kernel, a named barrier of the compute warps in the fused one).
 template <int NB, int NBUF = 4, int KS = 1, typename SyncF>
 __device__ __forceinline__ void node_fwd2_body(const ModelW& mw, const Workspace& ws, const int k, const int n0,
-                                               float* dyn_smem, SyncF sync) {
+                                               float* dyn_smem, SyncF sync, unsigned long long* tl = nullptr, const int krot = 0) {
+#define N2_TL(i) do { if (tl != nullptr && n0 == 0 && (threadIdx.x & 31) == 0) tl[(i) * 16 + (threadIdx.x >> 5)] = (unsigned long long)clock64(); } while (0)
+    N2_TL(0);
     constexpr int N2_WARPS = N2Cfg<NB>::WARPS, N2_THREADS = N2Cfg<NB>::THREADS;
     static_assert(KS == 1 || (KS == 2 && NB <= 4 && N2_WARPS == 16), "the K-split projection plan is the 16-warp, <= 4-node one");
     using S = NodeFwd2Smem<NB, KS>;
@@ -55,22 +57,49 @@ __device__ __forceinline__ void node_fwd2_body(const ModelW& mw, const Workspace
             const int nd = idx >> 5, c4 = (idx & 31) * 4;
             st4(&sm.xs[nd][c4], nd < nn ? ld4(ws.XA + (size_t)(n0 + nd) * D + c4) : f4s(0.f));
         }
+        [[maybe_unused]] WarpGemmPre<D / 4, 4> go;               // KS = 2: weight rows of this warp's o_proj unit, issued before the barrier
+        if constexpr (KS == 2) {
+            if (warp < 12) go.prefetch(lw.WoT + (size_t)(warp / 3) * (D / 4) * 3 * D + (warp % 3) * D, 3 * D, lane, krot);
+        }
         sync();
+        N2_TL(1);
         // o = xa Wo^T + bo : units = 3 chunks x NB/8 row blocks (x 4 K-quarters in the 16-warp variant)
-        if constexpr (NB <= 4) {
-            for (int u = warp; u < 12; u += N2_WARPS) {
-                const int ch = u % 3, kq = u / 3;
+        if constexpr (KS == 2) {
+            if (warp < 12) {
+                const int ch = warp % 3, kq = warp / 3;
                 float acc[N2_RB][4];
                 if (kq == 0) acc_set_bias<N2_RB>(acc, lw.bo + ch * D, lane);
                 else acc_zero<N2_RB>(acc);
-                warp_gemm<N2_RB, D / 4, LDA, NBUF>(acc, &sm.xs[0][kq * (D / 4)], lw.WoT + (size_t)kq * (D / 4) * 3 * D + ch * D, 3 * D, lane);
+                go.template run<N2_RB, LDA>(acc, &sm.xs[0][kq * (D / 4)]);
 #pragma unroll
                 for (int r = 0; r < N2_RB; r++) {
                     if (kq == 0) st4(&sm.os[r][ch * D + col], arr4(acc[r]));
                     else st4(&sm.osp[kq - 1][r][ch * D + col], arr4(acc[r]));
                 }
             }
+            N2_TL(2);
             sync();
+            N2_TL(3);
+            for (int idx = threadIdx.x; idx < NB * 96; idx += N2_THREADS) {      // fixed-order sum of the K-quarters
+                const int r = idx / 96, c4 = (idx % 96) * 4;
+                st4(&sm.os[r][c4], (ld4(&sm.os[r][c4]) + ld4(&sm.osp[0][r][c4])) + (ld4(&sm.osp[1][r][c4]) + ld4(&sm.osp[2][r][c4])));
+            }
+        } else if constexpr (NB <= 4) {
+            for (int u = warp; u < 12; u += N2_WARPS) {
+                const int ch = u % 3, kq = u / 3;
+                float acc[N2_RB][4];
+                if (kq == 0) acc_set_bias<N2_RB>(acc, lw.bo + ch * D, lane);
+                else acc_zero<N2_RB>(acc);
+                warp_gemm<N2_RB, D / 4, LDA, NBUF>(acc, &sm.xs[0][kq * (D / 4)], lw.WoT + (size_t)kq * (D / 4) * 3 * D + ch * D, 3 * D, lane, krot);
+#pragma unroll
+                for (int r = 0; r < N2_RB; r++) {
+                    if (kq == 0) st4(&sm.os[r][ch * D + col], arr4(acc[r]));
+                    else st4(&sm.osp[kq - 1][r][ch * D + col], arr4(acc[r]));
+                }
+            }
+            N2_TL(2);
+            sync();
+            N2_TL(3);
             for (int idx = threadIdx.x; idx < NB * 96; idx += N2_THREADS) {      // fixed-order sum of the K-quarters
                 const int r = idx / 96, c4 = (idx % 96) * 4;
                 st4(&sm.os[r][c4], (ld4(&sm.os[r][c4]) + ld4(&sm.osp[0][r][c4])) + (ld4(&sm.osp[1][r][c4]) + ld4(&sm.osp[2][r][c4])));
@@ -86,6 +115,7 @@ __device__ __forceinline__ void node_fwd2_body(const ModelW& mw, const Workspace
             }
         }
         sync();
+        N2_TL(4);
     }
     // per-node phase: residual update, LayerNorm, VecLayerNorm (warp per node)
     for (int nd = warp; nd < NB; nd += N2_WARPS) {
@@ -127,35 +157,45 @@ __device__ __forceinline__ void node_fwd2_body(const ModelW& mw, const Workspace
             }
         }
     }
+    N2_TL(5);
     if (k >= L) return;
-    sync();
     const LayerW& lw = mw.layer[k];
+    // KS = 2 plan (16 units, one per warp): (q|k|v chunk, K half) x3x2 on the NB scalar rows, (vec_proj chunk, K half) x3x2
+    // and (w_trg|w_src chunk, K half) x2x2 on all 3*NB vector rows.  Every weight element is read once per CTA (the
+    // row-block plan below reads the vector weights once per 4 rows); half 1 parks its partial rows in shared memory,
+    // half 0 adds them (fixed order) and writes the result.  The first weight rows are requested before the barrier.
+    constexpr int RV = 3 * NB, KH = D / 2;
+    [[maybe_unused]] WarpGemmPre<KH, 2> gm;
+    [[maybe_unused]] const int nunits2 = (k < L - 1) ? 16 : 12;
+    [[maybe_unused]] const int kind = warp < 6 ? 0 : (warp < 12 ? 1 : 2);
+    [[maybe_unused]] const int uv = kind == 0 ? warp : (kind == 1 ? warp - 6 : warp - 12);
+    [[maybe_unused]] const int ch2 = kind == 2 ? (uv & 1) : uv % 3, half = kind == 2 ? (uv >> 1) : uv / 3;
+    [[maybe_unused]] const bool active = warp < nunits2;
     if constexpr (KS == 2) {
-        // 16 units, one per warp: (q|k|v chunk, K half) x3x2 on the NB scalar rows, (vec_proj chunk, K half) x3x2 and
-        // (w_trg|w_src chunk, K half) x2x2 on all 3*NB vector rows.  Every weight element is read once per CTA (the
-        // row-block plan below reads the vector weights once per 4 rows); half 1 parks its partial rows in shared
-        // memory, half 0 adds them (fixed order) and writes the result.
-        constexpr int RV = 3 * NB, KH = D / 2;
-        const int nunits = (k < L - 1) ? 16 : 12;
-        const int u = warp, kind = u < 6 ? 0 : (u < 12 ? 1 : 2);
-        const int v = kind == 0 ? u : (kind == 1 ? u - 6 : u - 12);
-        const int ch = kind == 2 ? (v & 1) : v % 3, half = kind == 2 ? (v >> 1) : v / 3;
-        const bool active = u < nunits;
+        if (active) {
+            const float* W = kind == 0 ? lw.WqkvT : (kind == 1 ? lw.WvecT : lw.WtuT);
+            const int ldw = kind == 2 ? 2 * D : 3 * D;
+            gm.prefetch(W + (size_t)half * KH * ldw + ch2 * D, ldw, lane, krot);
+        }
+    }
+    sync();
+    N2_TL(6);
+    if constexpr (KS == 2) {
+        const int ch = ch2;
         float acc[RV][4];
         float (&accx)[NB][4] = *reinterpret_cast<float (*)[NB][4]>(&acc[0][0]);
         if (active) {
             if (kind == 0) {
                 if (half == 0) acc_set_bias<NB>(accx, lw.bqkv + ch * D, lane);
                 else acc_zero<NB>(accx);
-                warp_gemm<NB, KH, LDA, NBUF>(accx, &sm.xs[0][half * KH], lw.WqkvT + (size_t)half * KH * 3 * D + ch * D, 3 * D, lane);
+                gm.template run<NB, LDA>(accx, &sm.xs[0][half * KH]);
                 if (half == 1) {
 #pragma unroll
                     for (int r = 0; r < NB; r++) st4(&sm.px[r][ch * D + col], arr4(accx[r]));
                 }
             } else {
                 acc_zero<RV>(acc);
-                if (kind == 1) warp_gemm<RV, KH, LDA, 2>(acc, &sm.vs[0][half * KH], lw.WvecT + (size_t)half * KH * 3 * D + ch * D, 3 * D, lane);
-                else           warp_gemm<RV, KH, LDA, 2>(acc, &sm.vs[0][half * KH], lw.WtuT + (size_t)half * KH * 2 * D + ch * D, 2 * D, lane);
+                gm.template run<RV, LDA>(acc, &sm.vs[0][half * KH]);
                 if (half == 1) {
 #pragma unroll
                     for (int r = 0; r < RV; r++) {
@@ -165,7 +205,9 @@ __device__ __forceinline__ void node_fwd2_body(const ModelW& mw, const Workspace
                 }
             }
         }
+        N2_TL(7);
         sync();
+        N2_TL(8);
         if (active && half == 0) {
             if (kind == 0) {
 #pragma unroll
@@ -217,7 +259,9 @@ __device__ __forceinline__ void node_fwd2_body(const ModelW& mw, const Workspace
             }
         }
     }
+    N2_TL(9);
     sync();     // V123 rows of this CTA are visible block-wide
+    N2_TL(10);
     for (int nd = warp; nd < nn; nd += N2_WARPS) {
         const size_t r3 = (size_t)(n0 + nd) * 3;
         float4 vd = f4s(0.f);
@@ -225,13 +269,15 @@ __device__ __forceinline__ void node_fwd2_body(const ModelW& mw, const Workspace
         for (int s = 0; s < 3; s++) vd = vd + ld4(ws.V123[k] + (r3 + s) * 3 * D + col) * ld4(ws.V123[k] + (r3 + s) * 3 * D + D + col);
         st4(ws.VDOT[k] + (size_t)(n0 + nd) * D + col, vd);
     }
+    N2_TL(11);
 }
 
 template <int NB>
 __global__ void __launch_bounds__(N2Cfg<NB>::THREADS) node_fwd2_kernel(NodeArgs a) {
     pdl_entry();
     extern __shared__ __align__(16) float dyn_smem[];
-    node_fwd2_body<NB, 4, N2Cfg<NB>::KS>(a.mw, a.ws, a.layer, (int)blockIdx.x * NB, dyn_smem, [] { __syncthreads(); });
+    node_fwd2_body<NB, 4, N2Cfg<NB>::KS>(a.mw, a.ws, a.layer, (int)blockIdx.x * NB, dyn_smem, [] { __syncthreads(); }, a.tl,
+                                         a.krot ? (int)blockIdx.x * 16 : 0);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -260,9 +306,10 @@ struct NodeBwd2Smem {
 template <int NB, int NBUF = 4, int KS = 1, typename SyncF>
 __device__ __forceinline__ void node_bwd2_body(const ModelW& mw, const Workspace& ws, const int k, const int n0,
                                                float* __restrict__ GQKV, float* __restrict__ GVNMSG, float* __restrict__ GTU,
-                                               float* dyn_smem, SyncF sync) {
+                                               float* dyn_smem, SyncF sync, unsigned long long* tl = nullptr, const int krot = 0) {
     constexpr int N2_WARPS = N2Cfg<NB>::WARPS;
     static_assert(KS == 1 || (KS == 2 && NB <= 4 && N2_WARPS == 16), "the K-split plan is the 16-warp, <= 4-node one");
+    N2_TL(0);
     using S = NodeBwd2Smem<NB, KS>;
     constexpr int LD3 = S::LD3, LD2 = S::LD2;
     constexpr int N2_RB = N2Rows<NB>::RB;
@@ -302,25 +349,37 @@ __device__ __forceinline__ void node_bwd2_body(const ModelW& mw, const Workspace
                 }
             }
         }
-        sync();
+        // KS = 2: one unit per warp, (K chunk, K half) on all scalar rows (6 units) / on all vector rows (10, or 6 without
+        // w_trg|w_src); the first weight rows are requested before the barrier (13 of the 16 warps have nothing to stage)
+        constexpr int RV = 3 * NB, KH = D / 2;
+        [[maybe_unused]] WarpGemmPre<KH, 2> gm;
+        [[maybe_unused]] const int kv2 = has_tu ? 5 : 3;
         if constexpr (KS == 2) {
-            // one unit per warp: (K chunk, K half) on all scalar rows (6 units) / on all vector rows (10, or 6 without w_trg|w_src)
-            constexpr int RV = 3 * NB, KH = D / 2;
-            const int kv = has_tu ? 5 : 3;
+            const int u = warp;
+            if (u < 6) gm.prefetch(lw.WqkvN + ((size_t)(u >> 1) * D + (u & 1) * KH) * D, D, lane, krot);
+            else if (u < 6 + 2 * kv2) {
+                const int v = u - 6, kc = v >> 1, hf = v & 1;
+                gm.prefetch((kc < 3 ? lw.WvecN + (size_t)kc * D * D : lw.WtuN + (size_t)(kc - 3) * D * D) + (size_t)hf * KH * D, D, lane, krot);
+            }
+        }
+        N2_TL(1);
+        sync();
+        N2_TL(2);
+        if constexpr (KS == 2) {
             const int u = warp;
             if (u < 6) {
                 const int kc = u >> 1, half = u & 1;
                 float acc[NB][4];
                 acc_zero<NB>(acc);
-                warp_gemm<NB, KH, LD3, NBUF>(acc, &sm.gq[0][kc * D + half * KH], lw.WqkvN + ((size_t)kc * D + half * KH) * D, D, lane);
+                gm.template run<NB, LD3>(acc, &sm.gq[0][kc * D + half * KH]);
 #pragma unroll
                 for (int r = 0; r < NB; r++) st4(&sm.part_x[u][r][col], arr4(acc[r]));
-            } else if (u < 6 + 2 * kv) {
+            } else if (u < 6 + 2 * kv2) {
                 const int v = u - 6, kc = v >> 1, half = v & 1;
                 float acc[RV][4];
                 acc_zero<RV>(acc);
-                if (kc < 3) warp_gemm<RV, KH, LD3, 2>(acc, &sm.gvp[0][kc * D + half * KH], lw.WvecN + ((size_t)kc * D + half * KH) * D, D, lane);
-                else        warp_gemm<RV, KH, LD2, 2>(acc, &sm.gtu[0][(kc - 3) * D + half * KH], lw.WtuN + ((size_t)(kc - 3) * D + half * KH) * D, D, lane);
+                if (kc < 3) gm.template run<RV, LD3>(acc, &sm.gvp[0][kc * D + half * KH]);
+                else        gm.template run<RV, LD2>(acc, &sm.gtu[0][(kc - 3) * D + half * KH]);
 #pragma unroll
                 for (int r = 0; r < RV; r++) st4(&sm.part_v[v][r][col], arr4(acc[r]));
             }
@@ -346,7 +405,9 @@ __device__ __forceinline__ void node_bwd2_body(const ModelW& mw, const Workspace
                 }
             }
         }
+        N2_TL(3);
         sync();
+        N2_TL(4);
     }
     // per-node phase
     for (int nd = warp; nd < NB; nd += N2_WARPS) {
@@ -355,6 +416,12 @@ __device__ __forceinline__ void node_bwd2_body(const ModelW& mw, const Workspace
         float4 gx = ok ? ld4(ws.GX + (size_t)node * D + col) : z4, gvec[3];
 #pragma unroll
         for (int s = 0; s < 3; s++) gvec[s] = ok ? ld4(ws.GVEC + ((size_t)node * 3 + s) * D + col) : z4;
+        float4 v3p[3] = {z4, z4, z4}, vdp = z4;             // layer k-1 rows of the g_o products: requested now, used last
+        if (has_b && ok) {
+#pragma unroll
+            for (int s = 0; s < 3; s++) v3p[s] = ld4(ws.V123[k - 1] + ((size_t)node * 3 + s) * 3 * D + 2 * D + col);
+            vdp = ld4(ws.VDOT[k - 1] + (size_t)node * D + col);
+        }
         if (has_a && ok) {
             const LayerW& lw = mw.layer[k];
             const auto px = [&](int kc) {              // K chunk kc of the scalar rows (KS = 2: its two halves, fixed order)
@@ -397,17 +464,22 @@ __device__ __forceinline__ void node_bwd2_body(const ModelW& mw, const Workspace
         if (has_b) {
             float4 go1 = z4;
 #pragma unroll
-            for (int s = 0; s < 3; s++)
-                go1 = go1 + gvec[s] * (ok ? ld4(ws.V123[k - 1] + ((size_t)node * 3 + s) * 3 * D + 2 * D + col) : z4);
+            for (int s = 0; s < 3; s++) go1 = go1 + gvec[s] * v3p[s];
             __syncwarp();
             st4(&sm.gq[nd][col], go1);
-            st4(&sm.gq[nd][D + col], gx * (ok ? ld4(ws.VDOT[k - 1] + (size_t)node * D + col) : z4));
+            st4(&sm.gq[nd][D + col], gx * vdp);
             st4(&sm.gq[nd][2 * D + col], gx);
         }
     }
+    N2_TL(5);
     if (!has_b) return;
-    sync();
     const LayerW& lwo = mw.layer[k - 1];
+    [[maybe_unused]] WarpGemmPre<D / 4, 4> go;
+    if constexpr (KS == 2) {
+        if (warp < 12) go.prefetch(lwo.WoN + ((size_t)(warp >> 2) * D + (warp & 3) * (D / 4)) * D, D, lane, krot);
+    }
+    sync();
+    N2_TL(6);
     if constexpr (KS == 2) {
         // g_xa = g_o Wo: 12 units of K = 32 (3 chunks x 4 quarters), one per warp; partial rows in the (now free) part_v area
         float (*po)[NB][D] = reinterpret_cast<float (*)[NB][D]>(&sm.part_v[0][0][0]);
@@ -415,11 +487,13 @@ __device__ __forceinline__ void node_bwd2_body(const ModelW& mw, const Workspace
             const int kc = warp >> 2, q = warp & 3;
             float acc[NB][4];
             acc_zero<NB>(acc);
-            warp_gemm<NB, D / 4, LD3, NBUF>(acc, &sm.gq[0][kc * D + q * (D / 4)], lwo.WoN + ((size_t)kc * D + q * (D / 4)) * D, D, lane);
+            go.template run<NB, LD3>(acc, &sm.gq[0][kc * D + q * (D / 4)]);
 #pragma unroll
             for (int r = 0; r < NB; r++) st4(&po[warp][r][col], arr4(acc[r]));
         }
+        N2_TL(7);
         sync();
+        N2_TL(8);
         for (int nd = warp; nd < nn; nd += N2_WARPS) {
             float4 t[3];
 #pragma unroll
@@ -427,6 +501,7 @@ __device__ __forceinline__ void node_bwd2_body(const ModelW& mw, const Workspace
                 t[kc] = (ld4(&po[4 * kc][nd][col]) + ld4(&po[4 * kc + 1][nd][col])) + (ld4(&po[4 * kc + 2][nd][col]) + ld4(&po[4 * kc + 3][nd][col]));
             st4(ws.GXA + (size_t)(n0 + nd) * D + col, (t[0] + t[1]) + t[2]);
         }
+        N2_TL(9);
     } else {
         for (int u = warp; u < 3 * S::NXB; u += N2_WARPS) {
             const int kc = u % 3, rb = u / 3;
@@ -447,8 +522,10 @@ template <int NB>
 __global__ void __launch_bounds__(N2Cfg<NB>::THREADS) node_bwd2_kernel(NodeArgs a) {
     pdl_entry();
     extern __shared__ __align__(16) float dyn_smem[];
-    node_bwd2_body<NB, 4, N2Cfg<NB>::KS>(a.mw, a.ws, a.layer, (int)blockIdx.x * NB, a.ws.GQKV, a.ws.GVNMSG, a.ws.GTU, dyn_smem, [] { __syncthreads(); });
+    node_bwd2_body<NB, 4, N2Cfg<NB>::KS>(a.mw, a.ws, a.layer, (int)blockIdx.x * NB, a.ws.GQKV, a.ws.GVNMSG, a.ws.GTU, dyn_smem, [] { __syncthreads(); }, a.tl,
+                                         a.krot ? (int)blockIdx.x * 16 : 0);
 }
+#undef N2_TL
 
 template <int NB> using NodeFwd2SmemK = NodeFwd2Smem<NB, N2Cfg<NB>::KS>;     // shared-memory blocks of the stand-alone kernels
 template <int NB> using NodeBwd2SmemK = NodeBwd2Smem<NB, N2Cfg<NB>::KS>;

@@ -1,6 +1,8 @@
 set -x
 mkdir -p gpurun_out
-timeout 600 python tools/stage_times.py --workload chig > gpurun_out/r02l_stages_chig.txt 2>&1
-grep -E "node_fwd[036]|node_bwd[036]|graph replay|sum" gpurun_out/r02l_stages_chig.txt
-timeout 1500 python -m pytest tests -m gpu -q -x > gpurun_out/r02l_pytest_gpu.log 2>&1
-tail -8 gpurun_out/r02l_pytest_gpu.log
+for w in chig c4; do
+for o in krot=1 krot=0; do
+  timeout 600 python tools/stage_times.py --workload $w --opts $o 2>&1 | grep -E "^workload|edge_fwd[03]|edge_bwd[03]|graph replay"
+done; done > gpurun_out/r02p_krot.txt 2>&1
+cat gpurun_out/r02p_krot.txt
+timeout 900 python -m pytest tests/test_stages_gpu.py tests/test_engine_gpu.py -m gpu -q -x 2>&1 | tail -5

@@ -34,6 +34,11 @@ BWD = {0: "kernel start", 1: "setup done", 2: "meta loaded", 3: "s1-half SIMT do
        22: "g_f written", 31: "teardown done"}
 
 
+NFWD = {0: "start", 1: "xa rows staged", 2: "o_proj unit done", 4: "K-quarters summed", 5: "per-node phase done",
+        7: "projection unit done", 9: "results written", 11: "vec_dot done"}
+NBWD = {0: "start", 1: "A rows staged", 3: "adjoint unit done", 5: "per-node phase done", 7: "o_proj adjoint unit done", 9: "g_xa written"}
+
+
 def show(title, tl, names, mhz, jobs):
     t0 = int(tl[0])
     print(f"--- {title} ---")
@@ -55,6 +60,8 @@ def main():
     ap.add_argument("--workload", default="chig")
     ap.add_argument("--layer", type=int, default=2)
     ap.add_argument("--mhz", type=float, default=0.0)
+    ap.add_argument("--opts", default="", help="comma list key=value for vb_set_option")
+    ap.add_argument("--twice", action="store_true", help="launch every SIMT node kernel twice (results invalid): second launch = warm instruction cache")
     args = ap.parse_args()
     mhz = args.mhz
     if not mhz:
@@ -69,7 +76,10 @@ def main():
     sd = load_state_dict(WEIGHTS)
     eng = Engine(sd, 0)
     eng.set_option("edge_tc", 3)
-    eng.set_option("timeline", 1)
+    eng.set_option("timeline", 2 if args.twice else 1)
+    for kv in filter(None, args.opts.split(",")):
+        kk, vv = kv.split("=")
+        eng.set_option(kk, int(vv))
     eng.set_topology(fd.z, fd.batch, n_graphs=len(fd))
     pos = np.ascontiguousarray(fd.pos, dtype=np.float32)
     for _ in range(3):
@@ -81,7 +91,16 @@ def main():
     tb = eng.debug_read("TL", nl + args.layer, (64,), dtype=np.uint64)
     show("edge_fwd_tc", tf, FWD, mhz, 5)
     show("edge_bwd_tc", tb, BWD, mhz, 5)
-
+    if eng.get_option("node_tc") == 0 and eng.get_option("fused") == 0:
+        for title, idx, names in ((f"node_fwd2 stage {args.layer}", args.layer, NFWD), (f"node_bwd2 stage {args.layer}", nl + 1 + args.layer, NBWD)):
+            tl = eng.debug_read("TLN", idx, (16, 16), dtype=np.uint64).astype(np.int64)     # [stamp][warp]
+            t0 = tl[0][tl[0] > 0].min()
+            print(f"--- {title} (nodes per CTA {eng.get_option('node_nb')}): per stamp, first / last warp to pass it ---")
+            for i in sorted(names):
+                row = tl[i][tl[i] > 0]
+                if len(row):
+                    per = " ".join(f"{(x - t0) / mhz:5.1f}" if x > 0 else "    -" for x in tl[i])
+                    print(f"  [{i:2d}] {names[i]:<34} {(row.min() - t0) / mhz:7.2f} .. {(row.max() - t0) / mhz:7.2f} us   | {per}")
 
 if __name__ == "__main__":
     main()
