@@ -332,8 +332,8 @@ void layout_workspace(vb_handle* h, char* base, ArenaPlan& plan, int*& z, int*& 
     carve(plan, base, ws.GTU2, N * 6 * D);
     carve(plan, base, ws.eatom, N);
     carve(plan, base, h->d_pos, N * 3);
-    carve(plan, base, h->d_energy, G);
-    carve(plan, base, h->d_forces, N * 3);
+    carve(plan, base, h->d_forces, N * 3 + G);          // forces, then the fragment energies: one D2H copy brings both back
+    h->d_energy = h->d_forces ? h->d_forces + N * 3 : nullptr;
 }
 
 // ---- launch sequence --------------------------------------------------------------------------------
@@ -1031,7 +1031,7 @@ void vb_destroy(vb_handle* h) {
     cudaFree(h->arena);
     h->free_map();
     cudaFree(h->d_flags);
-    cudaFreeHost(h->h_pos); cudaFreeHost(h->h_energy); cudaFreeHost(h->h_forces);
+    cudaFreeHost(h->h_pos); cudaFreeHost(h->h_forces);
     delete h;
 }
 
@@ -1063,7 +1063,7 @@ int vb_set_topology(vb_handle* h, int64_t n_atoms, int64_t n_graphs, const int64
     h->free_caph();               // ... and the hydrogen-refinement terms
     h->has_topology = false;
     cudaFree(h->arena); h->arena = nullptr;
-    cudaFreeHost(h->h_pos); cudaFreeHost(h->h_energy); cudaFreeHost(h->h_forces);
+    cudaFreeHost(h->h_pos); cudaFreeHost(h->h_forces);
     h->h_pos = h->h_energy = h->h_forces = nullptr;
     h->ws = Workspace{};
     h->edges_plan = 0;
@@ -1091,8 +1091,8 @@ int vb_set_topology(vb_handle* h, int64_t n_atoms, int64_t n_graphs, const int64
     CUDA_TRY(h, cudaMemcpy(dfo, frag_of.data(), sizeof(int) * n_atoms, cudaMemcpyHostToDevice));
     CUDA_TRY(h, cudaMemcpy(dfs, frag_start.data(), sizeof(int) * (n_graphs + 1), cudaMemcpyHostToDevice));
     CUDA_TRY(h, cudaMallocHost(&h->h_pos, sizeof(float) * 3 * n_atoms));
-    CUDA_TRY(h, cudaMallocHost(&h->h_forces, sizeof(float) * 3 * n_atoms));
-    CUDA_TRY(h, cudaMallocHost(&h->h_energy, sizeof(float) * n_graphs));
+    CUDA_TRY(h, cudaMallocHost(&h->h_forces, sizeof(float) * (3 * n_atoms + n_graphs)));   // forces, then energies (one copy)
+    h->h_energy = h->h_forces + 3 * n_atoms;
     choose_defaults(h);
     record_stages(h);
     h->has_topology = true;
@@ -1137,8 +1137,7 @@ int vb_forward_host(vb_handle* h, const float* pos_host, float* energy_host, flo
     int rc = run_cached(h, st, K_HOST, io, [&](cudaStream_t s) -> int {
         CUDA_TRY(h, cudaMemcpyAsync(h->d_pos, h->h_pos, sizeof(float) * 3 * N, cudaMemcpyHostToDevice, s));
         if (int r = enqueue_eval(h, s, io)) return r;
-        CUDA_TRY(h, cudaMemcpyAsync(h->h_energy, h->d_energy, sizeof(float) * G, cudaMemcpyDeviceToHost, s));
-        CUDA_TRY(h, cudaMemcpyAsync(h->h_forces, h->d_forces, sizeof(float) * 3 * N, cudaMemcpyDeviceToHost, s));
+        CUDA_TRY(h, cudaMemcpyAsync(h->h_forces, h->d_forces, sizeof(float) * (3 * N + G), cudaMemcpyDeviceToHost, s));   // forces + energies
         return (int)VB_OK;
     });
     if (rc != VB_OK) return rc;

@@ -202,7 +202,11 @@ class Engine:
             raise ValueError(f"pos must be [{self.n_atoms},3]")
         e = np.empty((self.n_graphs,), dtype=np.float32)
         f = np.empty((self.n_atoms, 3), dtype=np.float32)
-        self._check(self.lib.vb_forward_host(self.h, pos.ctypes.data, e.ctypes.data, f.ctypes.data), "vb_forward_host")
+        # __array_interface__ instead of .ctypes.data: no ctypes helper object per array (this call is the per-step path)
+        rc = self.lib.vb_forward_host(self.h, pos.__array_interface__["data"][0], e.__array_interface__["data"][0],
+                                      f.__array_interface__["data"][0])
+        if rc < 0:
+            self._check(rc, "vb_forward_host")
         return e, f
 
     def forward_device(self, pos_ptr: int, energy_ptr: int, forces_ptr: int, stream_ptr: int = 0):

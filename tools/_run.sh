@@ -1,8 +1,12 @@
 set -x
 mkdir -p gpurun_out
-for w in chig c4; do
-for o in krot=1 krot=0; do
-  timeout 600 python tools/stage_times.py --workload $w --opts $o 2>&1 | grep -E "^workload|edge_fwd[03]|edge_bwd[03]|graph replay"
-done; done > gpurun_out/r02p_krot.txt 2>&1
-cat gpurun_out/r02p_krot.txt
-timeout 900 python -m pytest tests/test_stages_gpu.py tests/test_engine_gpu.py -m gpu -q -x 2>&1 | tail -5
+python bench.py --steps 200 --warmup 10 > gpurun_out/r02q_bench_chig.json 2> gpurun_out/r02q_bench_chig.err
+python - <<'PY'
+import json
+d=json.loads([l for l in open("gpurun_out/r02q_bench_chig.json") if l.startswith("{")][0])
+print("value", d["value"], "ms", d["ms_per_step"], "warm", d.get("value_l2_warm"), "e2e", d["e2e"]["value"], "md", d["md_device"]["value"] if d.get("md_device") else None, "parity", d.get("parity"), "acc", d.get("accuracy"))
+PY
+for w in trpcage ww; do for o in node_tc=1 node_tc=0 node_tc=0,node_nb=4; do
+  timeout 600 python tools/stage_times.py --workload $w --opts $o 2>&1 | grep -E "^workload|graph replay"
+done; done
+timeout 1500 python -m pytest tests -m gpu -q -x 2>&1 | tail -5
