@@ -420,7 +420,6 @@ void launch_node_fwd2(Launcher& Lc, int k) {
     vb_handle* h = Lc.h;
     NodeArgs a{k, h->mw, h->ws, h->timeline ? h->d_tl + (size_t)2 * L * TC_TL_SLOTS + (size_t)k * N2_TL_SLOTS : nullptr, h->krot};
     Lc.launch(node_fwd2_kernel<NB>, dim3((h->ws.N + NB - 1) / NB), dim3(N2Cfg<NB>::THREADS), sizeof(NodeFwd2SmemK<NB>), a);
-    if (h->timeline == 2) Lc.launch(node_fwd2_kernel<NB>, dim3((h->ws.N + NB - 1) / NB), dim3(N2Cfg<NB>::THREADS), sizeof(NodeFwd2SmemK<NB>), a);
     Lc.check();
 }
 template <int NB>
@@ -428,7 +427,6 @@ void launch_node_bwd2(Launcher& Lc, int k) {
     vb_handle* h = Lc.h;
     NodeArgs a{k, h->mw, h->ws, h->timeline ? h->d_tl + (size_t)2 * L * TC_TL_SLOTS + (size_t)(L + 1 + k) * N2_TL_SLOTS : nullptr, h->krot};
     Lc.launch(node_bwd2_kernel<NB>, dim3((h->ws.N + NB - 1) / NB), dim3(N2Cfg<NB>::THREADS), sizeof(NodeBwd2SmemK<NB>), a);
-    if (h->timeline == 2) Lc.launch(node_bwd2_kernel<NB>, dim3((h->ws.N + NB - 1) / NB), dim3(N2Cfg<NB>::THREADS), sizeof(NodeBwd2SmemK<NB>), a);
     Lc.check();
 }
 // nodes per CTA of the CTA-cooperative SIMT node kernels: the fewest (1..4) that still fit one wave, else 8
@@ -699,7 +697,7 @@ void enqueue_all(Launcher& Lc, const StepIO& io) {
     const bool batch_bwd = h->embed_batch_opt >= 0 ? (h->embed_batch_opt & 2) != 0 : N > 8 * h->sm_count;
     if (Lc.next("embed_node")) {
         if (batch) Lc.launch(embed_node_kernel<8>, dim3((N + 7) / 8), dim3(EMB_THREADS), 0, h->mw, ws);
-        else Lc.launch(embed_node_kernel<1>, dim3(N), dim3(EMB_THREADS), 0, h->mw, ws);
+        else Lc.launch(embed_node_small_kernel, dim3((N + EMS_NB - 1) / EMS_NB), dim3(EMS_THREADS), 0, h->mw, ws);
         Lc.check();
     }
     const int eblocks = std::max(1, std::min((ws.Ecap + 3) / 4, h->sm_count * 16));     // four edges per block and pass
@@ -1674,7 +1672,7 @@ int vb_set_option(vb_handle* h, const char* key, int64_t value) {
     else if (k == "node_tc" && (value == 0 || value == 1)) { h->node_tc = h->node_tc_opt = (int)value; if (value) h->fused = 0; set_gxa_parts(h); }
     else if (k == "comm_auto" && (value == 0 || value == 1)) h->comm_auto = (int)value;
     else if (k == "embed_batch" && value >= -1 && value <= 3) h->embed_batch_opt = (int)value;
-    else if (k == "timeline" && (value >= 0 && value <= 2)) {
+    else if (k == "timeline" && (value == 0 || value == 1)) {
         if (value && !h->d_tl) {
             if (cudaSetDevice(h->device) != cudaSuccess || cudaMalloc(&h->d_tl, sizeof(unsigned long long) * (2 * L * TC_TL_SLOTS + (2 * L + 2) * N2_TL_SLOTS)) != cudaSuccess) {
                 h->set_error("vb_set_option: timeline buffer allocation failed"); return VB_ERR_CUDA;

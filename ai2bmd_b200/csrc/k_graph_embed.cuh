@@ -111,7 +111,7 @@ __global__ void __launch_bounds__(128) edge_geom_kernel(int N, const float* __re
             ws.esrc[e] = j;
             ws.edst[e] = i;
             st4(ws.geom + (size_t)e * 8, f4(r, C, dx, dy));
-            st4(ws.geom + (size_t)e * 8 + 4, f4(dz, inv_r, 0.f, 0.f));
+            st4(ws.geom + (size_t)e * 8 + 4, f4(dz, inv_r, __int_as_float(ws.z[j]), 0.f));   // [6]: z of the source atom (embed_node)
             st4(ws.eacc + (size_t)e * 4, f4s(0.f));
         }
     }
@@ -226,37 +226,135 @@ __global__ void __launch_bounds__(EMB_THREADS) embed_node_kernel(ModelW mw, Work
     }
 }
 
-// K5: edge embedding  f0_e[c] = (x_i[c] + x_j[c]) * (rbf_e . We[c,:] + be[c]).   thread = channel.
+// Small-system variant of K4: FOUR nodes per CTA of 512 threads = 128 channels x 4 slices.  Slice q aggregates node q (all of
+// its <= 32 edges, rbf rows and edge metadata staged in shared memory by the whole CTA), then multiplies K-slice q of the
+// combine weight for all four nodes, so a CTA reads the 128 KB weight once for four nodes.  With one node per CTA the ~400
+// CTAs of a small protein all pulled the same 128 KB through L2 at the same time and that, not latency, bounded the kernel
+// (23 us for 391 atoms, identical before and after a rewrite that cut its dependent load rounds from ~20 to 5); for the
+// same reason every CTA starts its walk over the weight rows at a different row.
+constexpr int EMS_THREADS = 4 * D, EMS_NB = 4;
+__global__ void __launch_bounds__(EMS_THREADS) embed_node_small_kernel(ModelW mw, Workspace ws) {
+    pdl_entry();
+    __shared__ __align__(16) float rbf_s[EMS_NB][KNB][NR];
+    __shared__ __align__(16) float cat[EMS_NB][2 * D];
+    __shared__ float part[3][EMS_NB][D];
+    __shared__ int sj[EMS_NB][KNB];
+    __shared__ int sz[EMS_NB][KNB];
+    __shared__ float sC[EMS_NB][KNB];
+    __shared__ int se0[EMS_NB], sdg[EMS_NB];
+    const int c = threadIdx.x & (D - 1), q = threadIdx.x >> 7;
+    const int n0 = blockIdx.x * EMS_NB;
+    float wd[NR];
+#pragma unroll
+    for (int k = 0; k < NR; k++) wd[k] = __ldg(mw.WdT + k * D + c);     // coalesced (the [c][k] image costs 32 sectors per request)
+    const float bd = __ldg(mw.bd + c);
+    // combine weight rows of this slice (k in [64 q, 64 q + 64), walked from a row that differs from CTA to CTA): the first
+    // half is requested now, the second as soon as the registers of the neighbour rows are free -- neither waits for the
+    // aggregation
+    const int kb = q * (D / 2), rot = ((int)blockIdx.x * 16) & (D / 2 - 1);
+    float wc[32];
+#pragma unroll
+    for (int u = 0; u < 32; u++) wc[u] = __ldg(mw.WcT + (size_t)(kb + ((rot + u) & (D / 2 - 1))) * D + c);
+    const int i = n0 + q;                                    // this slice's node
+    const bool ok = i < ws.N;
+    const int e0 = ok ? ws.rowptr[i] : 0, dg = ok ? ws.rowptr[i + 1] - e0 : 0;
+    const float x0 = ok ? __ldg(mw.emb + ws.z[i] * D + c) : 0.f;
+    if (c < dg) {
+        const float4 g0 = ld4(ws.geom + (size_t)(e0 + c) * 8);
+        const float4 g1 = ld4(ws.geom + (size_t)(e0 + c) * 8 + 4);
+        sj[q][c] = ws.esrc[e0 + c];
+        sC[q][c] = g0.y;
+        sz[q][c] = __float_as_int(g1.z);                  // z of the source atom, left there by edge_geom
+    }
+    for (int idx = c; idx < dg * NR; idx += D) (&rbf_s[q][0][0])[idx] = ws.rbf[(size_t)e0 * NR + idx];
+    __syncthreads();
+    float acc = 0.f;
+    {
+        float nbv[KNB];                                      // all neighbour-embedding rows of the node in flight at once
+#pragma unroll
+        for (int k2 = 0; k2 < KNB; k2++) nbv[k2] = (k2 < dg && sj[q][k2] != i) ? __ldg(mw.nb_emb + sz[q][k2] * D + c) : 0.f;
+#pragma unroll
+        for (int k2 = 0; k2 < KNB; k2++) {
+            if (k2 < dg && sj[q][k2] != i) {                // (uniform per slice)
+                float dp = bd;
+#pragma unroll
+                for (int k = 0; k < NR; k += 4) {
+                    const float4 rb = ld4(&rbf_s[q][k2][k]);
+                    dp = fmaf(rb.x, wd[k], dp); dp = fmaf(rb.y, wd[k + 1], dp);
+                    dp = fmaf(rb.z, wd[k + 2], dp); dp = fmaf(rb.w, wd[k + 3], dp);
+                }
+                acc = fmaf(dp * sC[q][k2], nbv[k2], acc);
+            }
+        }
+    }
+    float wc2[32];
+#pragma unroll
+    for (int u = 0; u < 32; u++) wc2[u] = __ldg(mw.WcT + (size_t)(kb + ((rot + 32 + u) & (D / 2 - 1))) * D + c);
+    cat[q][c] = x0;
+    cat[q][D + c] = acc;
+    __syncthreads();
+    // x = [emb | agg] Wc^T + bc : slice q multiplies its 64 k's for the four nodes
+    float o[EMS_NB] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int u = 0; u < 32; u++) {
+        const int k = kb + ((rot + u) & (D / 2 - 1));
+#pragma unroll
+        for (int nd = 0; nd < EMS_NB; nd++) o[nd] = fmaf(cat[nd][k], wc[u], o[nd]);
+    }
+#pragma unroll
+    for (int u = 0; u < 32; u++) {
+        const int k = kb + ((rot + 32 + u) & (D / 2 - 1));
+#pragma unroll
+        for (int nd = 0; nd < EMS_NB; nd++) o[nd] = fmaf(cat[nd][k], wc2[u], o[nd]);
+    }
+    if (q > 0) {
+#pragma unroll
+        for (int nd = 0; nd < EMS_NB; nd++) part[q - 1][nd][c] = o[nd];
+    }
+    __syncthreads();
+    if (q == 0) {
+        const float bcv = __ldg(mw.bc + c);
+#pragma unroll
+        for (int nd = 0; nd < EMS_NB; nd++)
+            if (n0 + nd < ws.N) ws.X[0][(size_t)(n0 + nd) * D + c] = (bcv + ((o[nd] + part[0][nd][c]) + part[1][nd][c])) + part[2][nd][c];
+    }
+}
+
+// K5: edge embedding  f0_e[c] = (x_i[c] + x_j[c]) * (rbf_e . We[c,:] + be[c]).   thread = channel, four edges per pass.
+// The four rbf rows reach the block as ONE coalesced load per thread (shared memory, read back as broadcasts): the former
+// 32 same-address global loads per thread and edge kept the load queue full and every chain waiting (ncu: 52 % of the
+// samples at the first fma).
 __global__ void __launch_bounds__(128) embed_edge_kernel(ModelW mw, Workspace ws) {
     pdl_entry();
+    constexpr int EU = 4;
+    __shared__ __align__(16) float rbf_s[EU][NR];
     const int c = threadIdx.x;
     float we[NR];
 #pragma unroll
-    for (int k = 0; k < NR; k += 4) {
-        const float4 w = ldg4(mw.WeN + c * NR + k);
-        we[k] = w.x; we[k + 1] = w.y; we[k + 2] = w.z; we[k + 3] = w.w;
-    }
+    for (int k = 0; k < NR; k++) we[k] = __ldg(mw.WeT + k * D + c);     // coalesced
     const float be = __ldg(mw.be + c);
     const int E = ws.rowptr[ws.N];
     const float* __restrict__ X = ws.X[0];
-    // four edges per pass: their index loads, the two x-row gathers and the 32-deep fma chains are independent and overlap
-    constexpr int EU = 4;
     for (int e0 = blockIdx.x * EU; e0 < E; e0 += gridDim.x * EU) {
+        {
+            const int e = e0 + (c >> 5);
+            rbf_s[c >> 5][c & 31] = (e < E) ? ws.rbf[(size_t)e * NR + (c & 31)] : 0.f;
+        }
         int ii[EU], jj[EU];
-        float xs[EU], ep[EU];
 #pragma unroll
         for (int u = 0; u < EU; u++) {
             const int e = min(e0 + u, E - 1);
             ii[u] = ws.edst[e]; jj[u] = ws.esrc[e];
-            ep[u] = be;
         }
+        float xs[EU], ep[EU];
 #pragma unroll
-        for (int u = 0; u < EU; u++) xs[u] = X[(size_t)ii[u] * D + c] + X[(size_t)jj[u] * D + c];
+        for (int u = 0; u < EU; u++) { xs[u] = X[(size_t)ii[u] * D + c] + X[(size_t)jj[u] * D + c]; ep[u] = be; }
+        __syncthreads();
 #pragma unroll
         for (int k = 0; k < NR; k += 4) {
 #pragma unroll
             for (int u = 0; u < EU; u++) {
-                const float4 rb = ld4(ws.rbf + (size_t)min(e0 + u, E - 1) * NR + k);
+                const float4 rb = ld4(&rbf_s[u][k]);
                 ep[u] = fmaf(rb.x, we[k], ep[u]); ep[u] = fmaf(rb.y, we[k + 1], ep[u]);
                 ep[u] = fmaf(rb.z, we[k + 2], ep[u]); ep[u] = fmaf(rb.w, we[k + 3], ep[u]);
             }
@@ -264,6 +362,7 @@ __global__ void __launch_bounds__(128) embed_edge_kernel(ModelW mw, Workspace ws
 #pragma unroll
         for (int u = 0; u < EU; u++)
             if (e0 + u < E) ws.F[0][(size_t)(e0 + u) * D + c] = xs[u] * ep[u];
+        __syncthreads();                                    // rbf_s is rewritten by the next pass
     }
 }
 
@@ -279,11 +378,9 @@ __global__ void __launch_bounds__(EEB_WARPS * 32) embed_edge_bwd_kernel(ModelW m
     __shared__ float WeN_s[D][NR + 1];                    // [c][k] (+1: conflict-free column walks)
     __shared__ __align__(16) float gep_s[EEB_WARPS][2][D];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, col = lane * 4;
-    for (int idx = threadIdx.x; idx < D * NR; idx += blockDim.x) {
-        const int c = idx / NR, k = idx % NR;
-        const float w = __ldg(mw.WeN + idx);
-        WeT_s[k][c] = w;
-        WeN_s[c][k] = w;
+    for (int idx = threadIdx.x; idx < D * NR; idx += blockDim.x) {        // both images copied with consecutive addresses
+        WeT_s[idx / D][idx % D] = __ldg(mw.WeT + idx);                    // (the former in-kernel transpose wrote 32-way bank conflicts)
+        WeN_s[idx / NR][idx % NR] = __ldg(mw.WeN + idx);
     }
     __syncthreads();
     const float4 be = ldg4(mw.be + col);
@@ -350,10 +447,8 @@ __global__ void __launch_bounds__(ENB_WARPS * 32) embed_node_bwd_kernel(ModelW m
     __shared__ float fi_s[ENB_WARPS][3];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, col = lane * 4;
     for (int idx = threadIdx.x; idx < D * NR; idx += ENB_WARPS * 32) {      // once per CTA (a CTA walks several nodes of a batch)
-        const int cc = idx / NR, k = idx % NR;
-        const float w = __ldg(mw.WdN + idx);
-        WdT_s[k][cc] = w;
-        WdN_s[cc][k] = w;
+        WdT_s[idx / D][idx % D] = __ldg(mw.WdT + idx);
+        WdN_s[idx / NR][idx % NR] = __ldg(mw.WdN + idx);
     }
     const float alpha = 5.0f / mw.cutoff;
     const float mu = __ldg(mw.rbf_means + lane), beta = __ldg(mw.rbf_betas + lane);
@@ -377,16 +472,36 @@ __global__ void __launch_bounds__(ENB_WARPS * 32) embed_node_bwd_kernel(ModelW m
     for (int w = 0; w < ENB_WARPS; w++) g_agg = g_agg + ld4(&gagg_s[w][col]);
     float fix = 0.f, fiy = 0.f, fiz = 0.f;
     const int e1 = ws.rowptr[i + 1];
-    for (int e = ws.rowptr[i] + warp; e < e1; e += ENB_WARPS) {
-        const int j = ws.esrc[e];
-        if (j == i) continue;     // self-loops carry no geometry and are masked out of the neighbour embedding
-        const float4 g0 = ld4(ws.geom + (size_t)e * 8);
-        const float4 g1 = ld4(ws.geom + (size_t)e * 8 + 4);
+    // the (at most 4) edges of this warp: every row they need is requested before the first is used -- two L2 round trips
+    // for the node instead of three per edge (edge data, then the neighbour-embedding rows by the z that edge_geom left in geom[6])
+    constexpr int EPW = KNB / ENB_WARPS;
+    float4 g0r[EPW], g1r[EPW], ear[EPW], nbr[EPW];
+    float rkr[EPW], grr[EPW];
+    int jr[EPW];
+#pragma unroll
+    for (int t = 0; t < EPW; t++) {
+        const int e = ws.rowptr[i] + warp + t * ENB_WARPS;
+        const bool on = e < e1;
+        const int ec = on ? e : e1 - 1;                      // (e1 > rowptr[i]: every atom has its self loop)
+        jr[t] = on ? ws.esrc[ec] : i;
+        g0r[t] = ld4(ws.geom + (size_t)ec * 8);
+        g1r[t] = ld4(ws.geom + (size_t)ec * 8 + 4);
+        rkr[t] = __ldg(ws.rbf + (size_t)ec * NR + lane);
+        ear[t] = ld4(ws.eacc + (size_t)ec * 4);
+        grr[t] = ws.grbf[(size_t)ec * NR + lane];
+    }
+#pragma unroll
+    for (int t = 0; t < EPW; t++) nbr[t] = ldg4(mw.nb_emb + __float_as_int(g1r[t].z) * D + col);
+#pragma unroll
+    for (int t = 0; t < EPW; t++) {
+        const int j = jr[t];
+        if (j == i) continue;     // self-loops carry no geometry and are masked out of the neighbour embedding (also: no edge)
+        const float4 g0 = g0r[t], g1 = g1r[t];
         const float r = g0.x, Ce = g0.y, dx = g0.z, dy = g0.w, dz = g1.x, inv_r = g1.y;
-        const float rk = __ldg(ws.rbf + (size_t)e * NR + lane);
-        const float4 nbj = ldg4(mw.nb_emb + ws.z[j] * D + col);
-        const float4 ea = ld4(ws.eacc + (size_t)e * 4);
-        const float grbf0 = ws.grbf[(size_t)e * NR + lane];
+        const float rk = rkr[t];
+        const float4 nbj = nbr[t];
+        const float4 ea = ear[t];
+        const float grbf0 = grr[t];
         float4 dp = bd;
 #pragma unroll
         for (int k = 0; k < NR; k++) dp = dp + ld4(&WdT_s[k][col]) * __shfl_sync(0xffffffffu, rk, k);
@@ -406,10 +521,10 @@ __global__ void __launch_bounds__(ENB_WARPS * 32) embed_node_bwd_kernel(ModelW m
         const float gC = ea.x + gc;
         const float grbf = grbf0 + g;
         const float ex = __expf(-alpha * r);
-        const float t = ex - mu;
-        const float gk = __expf(-beta * t * t);
+        const float tt = ex - mu;
+        const float gk = __expf(-beta * tt * tt);
         const float dC = cutoff_dfn(r, mw.cutoff);
-        const float drbf = dC * gk + Ce * gk * (2.0f * beta * alpha) * t * ex;
+        const float drbf = dC * gk + Ce * gk * (2.0f * beta * alpha) * tt * ex;
         const float g_r = gC * dC + warp_sum(grbf * drbf);
         if (lane == 0) {
             const float gdd = ea.y * dx + ea.z * dy + ea.w * dz;

@@ -15,9 +15,9 @@ namespace vb {
     X(emb, 100 * D)        /* representation_model.embedding.weight                     */        \
     X(nb_emb, 100 * D)     /* neighbor_embedding.embedding.weight                        */        \
     X(rbf_means, NR) X(rbf_betas, NR)                                                              \
-    X(WdN, D * NR) X(bd, D)            /* neighbor_embedding.distance_proj [128,32]      */        \
+    X(WdN, D * NR) X(WdT, NR * D) X(bd, D) /* neighbor_embedding.distance_proj [128,32] (+ transposed) */     \
     X(WcT, 2 * D * D) X(bc, D) X(WcN, D * 2 * D) /* neighbor_embedding.combine [128,256] */        \
-    X(WeN, D * NR) X(be, D)            /* edge_embedding.edge_proj [128,32]              */        \
+    X(WeN, D * NR) X(WeT, NR * D) X(be, D) /* edge_embedding.edge_proj [128,32] (+ transposed) */             \
     X(on_w, D) X(on_b, D) X(von_w, D)  /* out_norm, vec_out_norm                         */        \
     X(h0_W1T, D * D) X(h0_W1N, D * D)          /* head block 0 vec1_proj [128,128]       */        \
     X(h0_W2T, D * 64) X(h0_W2N, 64 * D)        /* head block 0 vec2_proj [64,128]        */        \

@@ -47,10 +47,12 @@ def _named_arrays(sd: Dict[str, np.ndarray]) -> Dict[str, np.ndarray]:
     out["rbf_means"] = f(rm + "distance_expansion.means")
     out["rbf_betas"] = f(rm + "distance_expansion.betas")
     out["WdN"] = f(rm + "neighbor_embedding.distance_proj.weight")
+    out["WdT"] = out["WdN"].T
     out["bd"] = f(rm + "neighbor_embedding.distance_proj.bias")
     wc = f(rm + "neighbor_embedding.combine.weight")
     out["WcT"], out["bc"], out["WcN"] = wc.T, f(rm + "neighbor_embedding.combine.bias"), wc
     out["WeN"] = f(rm + "edge_embedding.edge_proj.weight")
+    out["WeT"] = out["WeN"].T
     out["be"] = f(rm + "edge_embedding.edge_proj.bias")
     out["on_w"], out["on_b"] = f(rm + "out_norm.weight"), f(rm + "out_norm.bias")
     out["von_w"] = f(rm + "vec_out_norm.weight")

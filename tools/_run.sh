@@ -1,12 +1,17 @@
 set -x
-mkdir -p gpurun_out
-python bench.py --steps 200 --warmup 10 > gpurun_out/r02q_bench_chig.json 2> gpurun_out/r02q_bench_chig.err
-python - <<'PY'
-import json
-d=json.loads([l for l in open("gpurun_out/r02q_bench_chig.json") if l.startswith("{")][0])
-print("value", d["value"], "ms", d["ms_per_step"], "warm", d.get("value_l2_warm"), "e2e", d["e2e"]["value"], "md", d["md_device"]["value"] if d.get("md_device") else None, "parity", d.get("parity"), "acc", d.get("accuracy"))
-PY
-for w in trpcage ww; do for o in node_tc=1 node_tc=0 node_tc=0,node_nb=4; do
-  timeout 600 python tools/stage_times.py --workload $w --opts $o 2>&1 | grep -E "^workload|graph replay"
-done; done
-timeout 1500 python -m pytest tests -m gpu -q -x 2>&1 | tail -5
+out=gpurun_out
+mkdir -p $out
+timeout 600 python tools/stage_times.py --workload chig 2>&1 | grep -E "embed|graph replay"
+cap() {
+  rep=/tmp/s_$1
+  timeout 300 ncu --set full --clock-control none --import-source on -k regex:$1 --launch-skip $2 -c 1 -f -o $rep \
+    python bench.py --workload chig --steps 2 --warmup 1 --skip-cpu-baseline > $out/ncu_$1.log 2>&1
+  python tools/ncu_summary.py full $rep.ncu-rep $out/r02t_$1_chig_full.txt > /dev/null 2>&1
+  python tools/ncu_lines.py $rep.ncu-rep 16 > $out/r02t_$1_chig_lines.txt 2>&1
+  rm -f $rep.ncu-rep
+}
+cap embed_node_small 3
+cap embed_node_bwd 3
+for k in embed_node_small embed_node_bwd; do
+  echo "=== $k"; grep -E "duration|registers|warps_active|issue_active|stalled|inst_executed|dram|lts__t|l1tex" $out/r02t_${k}_chig_full.txt | head -16; head -16 $out/r02t_${k}_chig_lines.txt | cut -c1-170
+done

@@ -61,7 +61,6 @@ def main():
     ap.add_argument("--layer", type=int, default=2)
     ap.add_argument("--mhz", type=float, default=0.0)
     ap.add_argument("--opts", default="", help="comma list key=value for vb_set_option")
-    ap.add_argument("--twice", action="store_true", help="launch every SIMT node kernel twice (results invalid): second launch = warm instruction cache")
     args = ap.parse_args()
     mhz = args.mhz
     if not mhz:
@@ -76,7 +75,7 @@ def main():
     sd = load_state_dict(WEIGHTS)
     eng = Engine(sd, 0)
     eng.set_option("edge_tc", 3)
-    eng.set_option("timeline", 2 if args.twice else 1)
+    eng.set_option("timeline", 1)
     for kv in filter(None, args.opts.split(",")):
         kk, vv = kv.split("=")
         eng.set_option(kk, int(vv))
