@@ -697,7 +697,8 @@ void enqueue_all(Launcher& Lc, const StepIO& io) {
     const bool batch_bwd = h->embed_batch_opt >= 0 ? (h->embed_batch_opt & 2) != 0 : N > 8 * h->sm_count;
     if (Lc.next("embed_node")) {
         if (batch) Lc.launch(embed_node_kernel<8>, dim3((N + 7) / 8), dim3(EMB_THREADS), 0, h->mw, ws);
-        else Lc.launch(embed_node_small_kernel, dim3((N + EMS_NB - 1) / EMS_NB), dim3(EMS_THREADS), 0, h->mw, ws);
+        else Lc.launch(embed_node_small_kernel, dim3((N + EMS_NB - 1) / EMS_NB), dim3(EMS_THREADS), 0, h->mw, ws,
+                       h->timeline ? h->d_tl + (size_t)2 * L * TC_TL_SLOTS + (size_t)(2 * L + 2) * N2_TL_SLOTS : (unsigned long long*)nullptr);
         Lc.check();
     }
     const int eblocks = std::max(1, std::min((ws.Ecap + 3) / 4, h->sm_count * 16));     // four edges per block and pass
@@ -1674,10 +1675,10 @@ int vb_set_option(vb_handle* h, const char* key, int64_t value) {
     else if (k == "embed_batch" && value >= -1 && value <= 3) h->embed_batch_opt = (int)value;
     else if (k == "timeline" && (value == 0 || value == 1)) {
         if (value && !h->d_tl) {
-            if (cudaSetDevice(h->device) != cudaSuccess || cudaMalloc(&h->d_tl, sizeof(unsigned long long) * (2 * L * TC_TL_SLOTS + (2 * L + 2) * N2_TL_SLOTS)) != cudaSuccess) {
+            if (cudaSetDevice(h->device) != cudaSuccess || cudaMalloc(&h->d_tl, sizeof(unsigned long long) * (2 * L * TC_TL_SLOTS + (2 * L + 3) * N2_TL_SLOTS)) != cudaSuccess) {
                 h->set_error("vb_set_option: timeline buffer allocation failed"); return VB_ERR_CUDA;
             }
-            cudaMemset(h->d_tl, 0, sizeof(unsigned long long) * (2 * L * TC_TL_SLOTS + (2 * L + 2) * N2_TL_SLOTS));
+            cudaMemset(h->d_tl, 0, sizeof(unsigned long long) * (2 * L * TC_TL_SLOTS + (2 * L + 3) * N2_TL_SLOTS));
         }
         h->timeline = (int)value;
     }
@@ -1828,7 +1829,7 @@ int64_t vb_debug_read(vb_handle* h, const char* name, int layer, void* host_dst,
     else if (k == "SP" && lay(L)) { src = ws.SP[layer]; bytes = E * 2 * D * 4; }
     else if (k == "ATT" && lay(L)) { src = ws.ATT[layer]; bytes = E * H * 4; }
     else if (k == "TL" && lay(2 * L) && h->d_tl) { src = h->d_tl + (size_t)layer * TC_TL_SLOTS; bytes = TC_TL_SLOTS * 8; }
-    else if (k == "TLN" && lay(2 * L + 2) && h->d_tl) { src = h->d_tl + (size_t)2 * L * TC_TL_SLOTS + (size_t)layer * N2_TL_SLOTS; bytes = N2_TL_SLOTS * 8; }
+    else if (k == "TLN" && lay(2 * L + 3) && h->d_tl) { src = h->d_tl + (size_t)2 * L * TC_TL_SLOTS + (size_t)layer * N2_TL_SLOTS; bytes = N2_TL_SLOTS * 8; }
     else BUF("XA", ws.XA, N * D, 4)
     else BUF("VA", ws.VA, N * 3 * D, 4)
     else BUF("GX", ws.GX, N * D, 4)

@@ -705,9 +705,9 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) edge_bwd_tc_kernel(const __gri
                     const size_t j = sh.meta.src[row];
                     const float Ce = sh.meta.C[row];
                     const float av = avr[u], sa = silu_(av), A = sa * Ce;
-                    const float4 gm = ld4(&sh.tile[row][col]) + gxa[u];
+                    const bool mine = rb + u < rpw;                 // a slot past the run is the next warp's row: no shared accesses
+                    const float4 gm = mine ? ld4(&sh.tile[row][col]) + gxa[u] : f4s(0.f);   // (its owner rewrites it in this phase)
                     const float4 dv = silu4(pdvr[u]);
-                    const bool mine = rb + u < rpw;                 // a slot past the run is the next warp's row: no shared writes
                     if (mine) st4(&sh.tile[row][col], ok ? gm * vjr[u] * A * dsilu4(pdvr[u]) : f4s(0.f));      // g_Pdv
                     const float gA = quad_sum(hsum4(gm * vjr[u] * dv));
                     if (mine && (lane & 3) == 0) sh.gattn[row][hd] = gA * Ce * dsilu_(av);

@@ -233,8 +233,11 @@ __global__ void __launch_bounds__(EMB_THREADS) embed_node_kernel(ModelW mw, Work
 // (23 us for 391 atoms, identical before and after a rewrite that cut its dependent load rounds from ~20 to 5); for the
 // same reason every CTA starts its walk over the weight rows at a different row.
 constexpr int EMS_THREADS = 4 * D, EMS_NB = 4;
-__global__ void __launch_bounds__(EMS_THREADS) embed_node_small_kernel(ModelW mw, Workspace ws) {
+__global__ void __launch_bounds__(EMS_THREADS) embed_node_small_kernel(ModelW mw, Workspace ws, unsigned long long* tl) {
+#define EMS_TL(i) do { if (tl != nullptr && blockIdx.x == 0 && (threadIdx.x & 31) == 0) tl[(i) * 16 + (threadIdx.x >> 5)] = (unsigned long long)clock64(); } while (0)
+    EMS_TL(0);
     pdl_entry();
+    EMS_TL(1);
     __shared__ __align__(16) float rbf_s[EMS_NB][KNB][NR];
     __shared__ __align__(16) float cat[EMS_NB][2 * D];
     __shared__ float part[3][EMS_NB][D];
@@ -267,23 +270,37 @@ __global__ void __launch_bounds__(EMS_THREADS) embed_node_small_kernel(ModelW mw
         sz[q][c] = __float_as_int(g1.z);                  // z of the source atom, left there by edge_geom
     }
     for (int idx = c; idx < dg * NR; idx += D) (&rbf_s[q][0][0])[idx] = ws.rbf[(size_t)e0 * NR + idx];
+    if (c == 0) sdg[q] = dg;
+    EMS_TL(2);
     __syncthreads();
-    float acc = 0.f;
+    // slice q takes the edges q, q + 4, ... of ALL four nodes (a slice per node would wait for the node with the most
+    // neighbours); the eight 32-deep products of a node are independent chains (select instead of branch)
+    float accn[EMS_NB] = {0.f, 0.f, 0.f, 0.f};
     {
-        float nbv[KNB];                                      // all neighbour-embedding rows of the node in flight at once
+        constexpr int EPQ = KNB / 4;
+        float nbv[EMS_NB][EPQ];
 #pragma unroll
-        for (int k2 = 0; k2 < KNB; k2++) nbv[k2] = (k2 < dg && sj[q][k2] != i) ? __ldg(mw.nb_emb + sz[q][k2] * D + c) : 0.f;
+        for (int nd = 0; nd < EMS_NB; nd++)
 #pragma unroll
-        for (int k2 = 0; k2 < KNB; k2++) {
-            if (k2 < dg && sj[q][k2] != i) {                // (uniform per slice)
+            for (int t = 0; t < EPQ; t++) {
+                const int k2 = q + 4 * t;
+                nbv[nd][t] = (k2 < sdg[nd] && sj[nd][k2] != n0 + nd) ? __ldg(mw.nb_emb + sz[nd][k2] * D + c) : 0.f;
+            }
+#pragma unroll
+        for (int nd = 0; nd < EMS_NB; nd++) {
+            if (q >= sdg[nd]) continue;                     // (uniform per slice: none of this slice's edges exist)
+#pragma unroll
+            for (int t = 0; t < EPQ; t++) {
+                const int k2 = q + 4 * t;
+                const bool on = k2 < sdg[nd] && sj[nd][k2] != n0 + nd;
                 float dp = bd;
 #pragma unroll
                 for (int k = 0; k < NR; k += 4) {
-                    const float4 rb = ld4(&rbf_s[q][k2][k]);
+                    const float4 rb = ld4(&rbf_s[nd][on ? k2 : 0][k]);
                     dp = fmaf(rb.x, wd[k], dp); dp = fmaf(rb.y, wd[k + 1], dp);
                     dp = fmaf(rb.z, wd[k + 2], dp); dp = fmaf(rb.w, wd[k + 3], dp);
                 }
-                acc = fmaf(dp * sC[q][k2], nbv[k2], acc);
+                accn[nd] += on ? dp * sC[nd][k2] * nbv[nd][t] : 0.f;
             }
         }
     }
@@ -291,7 +308,16 @@ __global__ void __launch_bounds__(EMS_THREADS) embed_node_small_kernel(ModelW mw
 #pragma unroll
     for (int u = 0; u < 32; u++) wc2[u] = __ldg(mw.WcT + (size_t)(kb + ((rot + 32 + u) & (D / 2 - 1))) * D + c);
     cat[q][c] = x0;
-    cat[q][D + c] = acc;
+    if (q > 0) {
+#pragma unroll
+        for (int nd = 0; nd < EMS_NB; nd++) part[q - 1][nd][c] = accn[nd];
+    }
+    __syncthreads();
+    if (q == 0) {
+#pragma unroll
+        for (int nd = 0; nd < EMS_NB; nd++) cat[nd][D + c] = ((accn[nd] + part[0][nd][c]) + part[1][nd][c]) + part[2][nd][c];
+    }
+    EMS_TL(3);
     __syncthreads();
     // x = [emb | agg] Wc^T + bc : slice q multiplies its 64 k's for the four nodes
     float o[EMS_NB] = {0.f, 0.f, 0.f, 0.f};
@@ -311,6 +337,7 @@ __global__ void __launch_bounds__(EMS_THREADS) embed_node_small_kernel(ModelW mw
 #pragma unroll
         for (int nd = 0; nd < EMS_NB; nd++) part[q - 1][nd][c] = o[nd];
     }
+    EMS_TL(4);
     __syncthreads();
     if (q == 0) {
         const float bcv = __ldg(mw.bc + c);
@@ -318,6 +345,8 @@ __global__ void __launch_bounds__(EMS_THREADS) embed_node_small_kernel(ModelW mw
         for (int nd = 0; nd < EMS_NB; nd++)
             if (n0 + nd < ws.N) ws.X[0][(size_t)(n0 + nd) * D + c] = (bcv + ((o[nd] + part[0][nd][c]) + part[1][nd][c])) + part[2][nd][c];
     }
+    EMS_TL(5);
+#undef EMS_TL
 }
 
 // K5: edge embedding  f0_e[c] = (x_i[c] + x_j[c]) * (rbf_e . We[c,:] + be[c]).   thread = channel, four edges per pass.

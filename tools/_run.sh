@@ -1,17 +1,14 @@
 set -x
 out=gpurun_out
 mkdir -p $out
-timeout 600 python tools/stage_times.py --workload chig 2>&1 | grep -E "embed|graph replay"
-cap() {
-  rep=/tmp/s_$1
-  timeout 300 ncu --set full --clock-control none --import-source on -k regex:$1 --launch-skip $2 -c 1 -f -o $rep \
-    python bench.py --workload chig --steps 2 --warmup 1 --skip-cpu-baseline > $out/ncu_$1.log 2>&1
-  python tools/ncu_summary.py full $rep.ncu-rep $out/r02t_$1_chig_full.txt > /dev/null 2>&1
-  python tools/ncu_lines.py $rep.ncu-rep 16 > $out/r02t_$1_chig_lines.txt 2>&1
-  rm -f $rep.ncu-rep
-}
-cap embed_node_small 3
-cap embed_node_bwd 3
-for k in embed_node_small embed_node_bwd; do
-  echo "=== $k"; grep -E "duration|registers|warps_active|issue_active|stalled|inst_executed|dram|lts__t|l1tex" $out/r02t_${k}_chig_full.txt | head -16; head -16 $out/r02t_${k}_chig_lines.txt | cut -c1-170
-done
+nvidia-smi -L > $out/r02w_gpus.txt
+timeout 600 python tools/stage_times.py --workload chig 2>&1 | grep -E "embed_node|graph replay"
+timeout 600 python -m pytest tests/test_stages_gpu.py -m gpu -q -x 2>&1 | tail -2
+timeout 900 python -m pytest tests/test_multigpu.py -m gpu -x -q > $out/r02w_pytest_multigpu_2gpu.log 2>&1
+tail -3 $out/r02w_pytest_multigpu_2gpu.log
+timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 100 --warmup 5 > $out/r02w_bench_chig_n2.json 2> $out/r02w_bench_chig_n2.err
+python - <<'PY'
+import json
+d=json.loads([l for l in open("gpurun_out/r02w_bench_chig_n2.json") if l.startswith("{")][0])
+print("n2 value", d["value"], "e2e", d["e2e"]["value"], "md", (d.get("md_device") or {}).get("value"), "comm", d.get("comm"), "scale_c4", d.get("scale_c4"), "parity", (d.get("parity") or {}).get("parity_ok"))
+PY

@@ -33,6 +33,9 @@ for w in chig c4; do
 done
 capture node_tc_kernel c4 20 4
 capture node_bwd2 chig 8 2
+capture node_fwd2 chig 8 2
+capture embed_node_small chig 3 1
+capture embed_node_bwd chig 3 1
 for t in memcheck racecheck; do
   timeout 600 compute-sanitizer --tool $t python tools/sanitize_run.py 3 4 node_tc=1 > $out/${tag}_${t}_nodetc.log 2>&1
 done

@@ -91,7 +91,9 @@ def main():
     show("edge_fwd_tc", tf, FWD, mhz, 5)
     show("edge_bwd_tc", tb, BWD, mhz, 5)
     if eng.get_option("node_tc") == 0 and eng.get_option("fused") == 0:
-        for title, idx, names in ((f"node_fwd2 stage {args.layer}", args.layer, NFWD), (f"node_bwd2 stage {args.layer}", nl + 1 + args.layer, NBWD)):
+        EMB = {0: "start", 1: "previous kernel complete (pdl)", 2: "loads issued, rows staged", 3: "aggregation done", 4: "combine done", 5: "x written"}
+        for title, idx, names in ((f"node_fwd2 stage {args.layer}", args.layer, NFWD), (f"node_bwd2 stage {args.layer}", nl + 1 + args.layer, NBWD),
+                                  ("embed_node_small", 2 * nl + 2, EMB)):
             tl = eng.debug_read("TLN", idx, (16, 16), dtype=np.uint64).astype(np.int64)     # [stamp][warp]
             t0 = tl[0][tl[0] > 0].min()
             print(f"--- {title} (nodes per CTA {eng.get_option('node_nb')}): per stamp, first / last warp to pass it ---")
