@@ -214,9 +214,11 @@ def make_cpu_model(sd, sample):
     best, best_t = cands[0], float("inf")
     for c in cands:
         torch.set_num_threads(c)
-        t0 = time.perf_counter()
-        model.dl_potential_loader(sample)
-        dt = time.perf_counter() - t0
+        dt = float("inf")
+        for _ in range(2):                              # best of two: a single timing picked 8 threads (2.8 steps/s) where 16 give 4.0
+            t0 = time.perf_counter()
+            model.dl_potential_loader(sample)
+            dt = min(dt, time.perf_counter() - t0)
         if dt < best_t:
             best, best_t = c, dt
         if dt > 4 * best_t:
@@ -233,7 +235,7 @@ def run_reference(args):
         return
     fd, pm, desc = load_workload(args.workload, args.fragments)
     sd = load_weights()
-    calib = fd if len(fd) <= 8 else fd[0:8]
+    calib = fd if len(fd) <= 64 else fd[0:8]              # the whole workload when it is small: the thread optimum depends on the batch
     model, threads, avail = make_cpu_model(sd, calib)
     t0 = time.perf_counter()
     model.dl_potential_loader(fd)
@@ -563,7 +565,7 @@ def run_ours(args):
     cpu = None
     if not args.skip_cpu_baseline:
         sample = fd if len(fd.z) <= 800 else fd[0:24]
-        model_cpu, threads, avail = make_cpu_model(sd, sample if len(sample) <= 8 else sample[0:8])
+        model_cpu, threads, avail = make_cpu_model(sd, sample if len(sample) <= 64 else sample[0:8])
         n_eval = 3
         model_cpu.dl_potential_loader(sample)
         t0 = time.perf_counter()
