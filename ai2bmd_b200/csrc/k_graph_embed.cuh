@@ -244,7 +244,7 @@ __global__ void __launch_bounds__(EMS_THREADS) embed_node_small_kernel(ModelW mw
     __shared__ int sj[EMS_NB][KNB];
     __shared__ int sz[EMS_NB][KNB];
     __shared__ float sC[EMS_NB][KNB];
-    __shared__ int se0[EMS_NB], sdg[EMS_NB];
+    __shared__ int sdg[EMS_NB];
     const int c = threadIdx.x & (D - 1), q = threadIdx.x >> 7;
     const int n0 = blockIdx.x * EMS_NB;
     float wd[NR];
