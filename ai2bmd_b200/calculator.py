@@ -65,7 +65,8 @@ class ViSNetModel:
         return (z.size, hash(z.tobytes()), hash(batch.tobytes())), z, batch
 
     def _ensure_topology(self, frag: FragmentData):
-        # an MD loop hands over the same z / batch arrays every step: identity of the two arrays short-cuts the hash
+        # the same READ-ONLY z / batch arrays as last time cannot have changed: identity short-cuts the hash.  Writable arrays
+        # are hashed every call (the reference re-uploads z and batch every call, so in-place edits must keep working)
         seen = getattr(self, "_topo_arrays", None)
         if seen is not None and seen[0] is frag.z and seen[1] is frag.batch:
             return
@@ -74,7 +75,9 @@ class ViSNetModel:
             self.engine.set_topology(z, batch, n_graphs=len(frag))
             self._topo_key = key
             self._calibrated = False
-        self._topo_arrays = (frag.z, frag.batch)
+        frozen = (isinstance(frag.z, np.ndarray) and isinstance(frag.batch, np.ndarray)
+                  and not frag.z.flags.writeable and not frag.batch.flags.writeable)
+        self._topo_arrays = (frag.z, frag.batch) if frozen else None
 
     def dl_potential_loader(self, frag_data: FragmentData) -> Tuple[np.ndarray, np.ndarray]:
         """``FragmentData -> (e[G,1] float32 eV, f[N,3] float32 eV/A)`` as numpy arrays."""

@@ -353,3 +353,31 @@ def test_example_fragments_never_exceed_the_neighbour_cap():
     for name in ("chig", "trpcage", "ww", "abd"):
         fd, _ = load_fragments(name)
         assert neighbour_cap_margin(fd) >= 0, f"{name}: an atom has more than 32 candidates: atom order now matters"
+
+
+def test_topology_check_follows_in_place_edits_of_writable_arrays():
+    """``dl_potential_loader`` must notice a changed z / batch even when the caller reuses the same array objects (the
+    reference re-uploads both every call, visnet_calculator.py:47-52); only read-only arrays may be trusted by identity."""
+    from ai2bmd_b200.calculator import ViSNetModel
+    from ai2bmd_b200.fragment_data import FragmentData
+
+    class FakeEngine:
+        def __init__(self):
+            self.topologies = 0
+
+        def set_topology(self, z, batch, n_graphs=None):
+            self.topologies += 1
+
+    m = ViSNetModel.__new__(ViSNetModel)
+    m.engine, m._topo_key = FakeEngine(), None
+    z = np.array([6, 1, 1, 8], dtype=np.int64)
+    batch = np.zeros(4, dtype=np.int64)
+    fd = FragmentData(z, np.zeros((4, 3), np.float32), np.array([0]), np.array([4]), batch)
+    m._ensure_topology(fd); m._ensure_topology(fd)
+    assert m.engine.topologies == 1
+    z[1] = 7                                             # same object, new content
+    m._ensure_topology(fd)
+    assert m.engine.topologies == 2
+    z.flags.writeable = False; batch.flags.writeable = False
+    m._ensure_topology(fd); m._ensure_topology(fd)      # frozen arrays: identity is enough from now on
+    assert m.engine.topologies == 2 and m._topo_arrays is not None
